@@ -1,0 +1,590 @@
+// btb200_api.cu -- the extern "C" ABI declared in include/btb200.h.
+// Host orchestration only: all arithmetic on the sample path runs in the
+// kernels of rx_kernels.cu; there is no CPU fallback.
+#include "../../include/btb200.h"
+#include "plan.hpp"
+#include "rx_kernels.cuh"
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+using namespace btb200;
+
+namespace {
+constexpr int kNumEvents = 8;
+constexpr uint32_t kDefaultMaxSlots = 64;
+constexpr unsigned kHitCap = 1u << 18;
+constexpr unsigned long long kArenaCap = 256ull << 20;
+}
+
+struct btb200_ctx {
+  btb200_config cfg{};
+  Plan plan;
+  Geom G{};
+  DevTables T{};
+  DevBatch W{};
+  int device = 0, sm_count = 0;
+  uint32_t max_slots = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[kNumEvents + 1]{};
+  // device allocations
+  std::vector<void *> allocs;
+  c32 *d_x = nullptr;
+  size_t x_cap = 0;          // samples
+  c32 *d_phc = nullptr, *d_phn = nullptr;
+  float *d_soft = nullptr;
+  // pinned host
+  double *h_energy = nullptr, *h_noise = nullptr;
+  int *h_pass = nullptr;
+  unsigned *h_counts = nullptr;      // [0] hits, [2..3] arena_used (64-bit)
+  DevHit *h_hits = nullptr;
+  uint8_t *h_arena = nullptr;
+  c32 *h_ph = nullptr;               // chained-mode phase staging
+  size_t h_ph_cap = 0;
+  // stream state
+  std::vector<Rotator> rot_c, rot_n;
+  MmState mm{};
+  bool pending = false;
+  uint32_t pend_slots = 0;
+  uint64_t pend_first_slot = 0;
+  uint32_t last_slots = 0;
+  float timing[8]{};
+  uint64_t launches = 0;
+  int impl = IMPL_TUNED;
+  std::string last_error;
+};
+
+namespace {
+
+thread_local std::string g_create_error;
+
+#define CK(call)                                                                          \
+  do {                                                                                    \
+    cudaError_t e_ = (call);                                                              \
+    if (e_ != cudaSuccess) {                                                              \
+      char buf_[512];                                                                     \
+      std::snprintf(buf_, sizeof buf_, "%s -> %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+      ctx->last_error = buf_;                                                             \
+      return BTB200_ERR_CUDA;                                                             \
+    }                                                                                     \
+  } while (0)
+
+template <class T>
+int dev_alloc(btb200_ctx *ctx, T **p, size_t count)
+{
+  void *v = nullptr;
+  cudaError_t e = cudaMalloc(&v, std::max<size_t>(count, 1) * sizeof(T));
+  if (e != cudaSuccess) {
+    ctx->last_error = std::string("cudaMalloc: ") + cudaGetErrorString(e);
+    return e == cudaErrorMemoryAllocation ? BTB200_ERR_NOMEM : BTB200_ERR_CUDA;
+  }
+  ctx->allocs.push_back(v);
+  *p = (T *)v;
+  return 0;
+}
+
+template <class T>
+int upload_raw(btb200_ctx *ctx, const T **dst, const void *src, size_t count)
+{
+  T *p = nullptr;
+  int rc = dev_alloc(ctx, &p, count);
+  if (rc) return rc;
+  CK(cudaMemcpy(p, src, count * sizeof(T), cudaMemcpyHostToDevice));
+  *dst = p;
+  return 0;
+}
+template <class T>
+int upload(btb200_ctx *ctx, const T **dst, const std::vector<T> &src)
+{
+  return upload_raw<T>(ctx, dst, src.data(), src.size());
+}
+
+void reset_stream_state(btb200_ctx *ctx)
+{
+  const Plan &P = ctx->plan;
+  ctx->rot_c.assign(P.nch, Rotator{});
+  ctx->rot_n.assign(P.nch, Rotator{});
+  for (int c = 0; c < P.nch; c++) {
+    ctx->rot_c[c].incr = P.chan_incr[c];
+    ctx->rot_n[c].incr = P.noise_incr[c];
+  }
+  ctx->mm = MmState{P.mu0, P.omega_mid, 0.0f};
+}
+
+int setup(btb200_ctx *ctx)
+{
+  const Plan &P = ctx->plan;
+  Geom &G = ctx->G;
+  G.S = P.S; G.H = P.H; G.D = P.D; G.Nc = P.Nc; G.Nn = P.Nn; G.fcs = P.fcs; G.fns = P.fns;
+  G.nch = P.nch; G.n_ddc = P.n_ddc; G.n_noise = P.n_noise; G.n_dem = P.n_dem; G.gps = P.grid_per_slot;
+  G.n_dem_pad = (P.n_dem + 3) & ~3;
+  G.bw = (P.n_dem + 31) / 32 + 4;
+  G.ch_lo = P.ch_lo;
+  G.demod_gain = P.demod_gain;
+  G.mm = MmConst{P.gain_mu, P.gain_omega, P.omega_mid, P.omega_lim};
+  G.mu0 = P.mu0;
+  G.squelch_db = P.squelch_db;
+  G.search = ctx->cfg.search;
+  G.stateless = ctx->cfg.mm_mode == BTB200_MM_STATELESS;
+
+  CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  for (auto &e : ctx->ev) CK(cudaEventCreate(&e));
+
+  int rc;
+  if ((rc = upload_raw<c32>(ctx, &ctx->T.chan_rtaps, P.chan_rtaps.data(), P.chan_rtaps.size()))) return rc;
+  if ((rc = upload_raw<c32>(ctx, &ctx->T.noise_rtaps, P.noise_rtaps.data(), P.noise_rtaps.size()))) return rc;
+  if ((rc = upload(ctx, &ctx->T.mmse, P.mmse))) return rc;
+  if ((rc = upload(ctx, &ctx->T.atan_tab, P.atan_tab))) return rc;
+  if ((rc = upload(ctx, &ctx->T.ac_lut, P.ac_lut))) return rc;
+  std::vector<uint8_t> hdr(4 * 256);
+  for (int w = 0; w < 4; w++)
+    for (int v = 0; v < 256; v++) hdr[w * 256 + v] = (uint8_t)le_hdr_dist((uint32_t)v, w);
+  if ((rc = upload(ctx, &ctx->T.le_hdr_lut, hdr))) return rc;
+  if ((rc = upload(ctx, &ctx->T.le_index, P.le_index))) return rc;
+  std::vector<uint32_t> white(P.nch, 0);
+  for (int c = 0; c < P.nch; c++)
+    for (int i = 0; i < 16; i++) white[c] |= (uint32_t)P.le_white16[(size_t)c * 16 + i] << i;
+  if ((rc = upload(ctx, &ctx->T.le_white, white))) return rc;
+
+  const size_t B = ctx->max_slots;
+  const size_t nch = P.nch;
+  ctx->x_cap = (B - 1) * (size_t)P.S + P.H;
+  if ((rc = dev_alloc(ctx, &ctx->d_x, ctx->x_cap))) return rc;
+  DevBatch &W = ctx->W;
+  if ((rc = dev_alloc(ctx, &W.Y, ((B - 1) * P.grid_per_slot + P.n_ddc) * nch))) return rc;
+  if ((rc = dev_alloc(ctx, &W.Nz, B * P.n_noise * nch))) return rc;
+  const size_t bp = G.stateless ? 1 : B;
+  if ((rc = dev_alloc(ctx, &ctx->d_phc, bp * P.n_ddc * nch))) return rc;
+  if ((rc = dev_alloc(ctx, &ctx->d_phn, bp * P.n_noise * nch))) return rc;
+  if ((rc = dev_alloc(ctx, &W.energy, B * nch))) return rc;
+  if ((rc = dev_alloc(ctx, &W.noise, B * nch))) return rc;
+  if ((rc = dev_alloc(ctx, &W.pass, B * nch))) return rc;
+  if ((rc = dev_alloc(ctx, &W.dem, B * nch * G.n_dem_pad))) return rc;
+  if (ctx->cfg.keep_stages) { if ((rc = dev_alloc(ctx, &ctx->d_soft, B * nch * G.n_dem_pad))) return rc; }
+  if ((rc = dev_alloc(ctx, &W.bits, B * nch * G.bw))) return rc;
+  if ((rc = dev_alloc(ctx, &W.nsym, B * nch))) return rc;
+  if ((rc = dev_alloc(ctx, &W.mm_state, 1))) return rc;
+  if ((rc = dev_alloc(ctx, &W.hits, kHitCap))) return rc;
+  unsigned *cnt = nullptr;
+  if ((rc = dev_alloc(ctx, &cnt, 4))) return rc;
+  W.hit_count = cnt;
+  W.arena_used = reinterpret_cast<unsigned long long *>(cnt + 2);
+  if ((rc = dev_alloc(ctx, &W.arena, kArenaCap))) return rc;
+  W.hit_cap = kHitCap;
+  W.arena_cap = kArenaCap;
+  W.soft = ctx->d_soft;
+  W.phc = ctx->d_phc;
+  W.phn = ctx->d_phn;
+  W.bp_stride = G.stateless ? 0 : 1;
+
+  CK(cudaMallocHost(&ctx->h_energy, B * nch * sizeof(double)));
+  CK(cudaMallocHost(&ctx->h_noise, B * nch * sizeof(double)));
+  CK(cudaMallocHost(&ctx->h_pass, B * nch * sizeof(int)));
+  CK(cudaMallocHost(&ctx->h_counts, 4 * sizeof(unsigned)));
+  CK(cudaMallocHost(&ctx->h_hits, (size_t)kHitCap * sizeof(DevHit)));
+  CK(cudaMallocHost(&ctx->h_arena, kArenaCap));
+  ctx->h_ph_cap = bp * (size_t)P.n_ddc * nch;
+  CK(cudaMallocHost(&ctx->h_ph, ctx->h_ph_cap * sizeof(c32)));
+
+  reset_stream_state(ctx);
+  if (G.stateless) {
+    // one rotator table per DDC object, restarted at phase 1 for every window
+    std::vector<Rotator> rc_ = ctx->rot_c, rn_ = ctx->rot_n;
+    for (int c = 0; c < P.nch; c++) rc_[c].generate(reinterpret_cast<cf32 *>(ctx->h_ph) + c, P.n_ddc, P.nch);
+    CK(cudaMemcpy(ctx->d_phc, ctx->h_ph, (size_t)P.n_ddc * nch * sizeof(c32), cudaMemcpyHostToDevice));
+    for (int c = 0; c < P.nch; c++) rn_[c].generate(reinterpret_cast<cf32 *>(ctx->h_ph) + c, P.n_noise, P.nch);
+    CK(cudaMemcpy(ctx->d_phn, ctx->h_ph, (size_t)P.n_noise * nch * sizeof(c32), cudaMemcpyHostToDevice));
+  }
+  return 0;
+}
+
+void teardown(btb200_ctx *ctx)
+{
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  for (void *p : ctx->allocs) cudaFree(p);
+  for (void *p : {(void *)ctx->h_energy, (void *)ctx->h_noise, (void *)ctx->h_pass, (void *)ctx->h_counts,
+                  (void *)ctx->h_hits, (void *)ctx->h_arena, (void *)ctx->h_ph})
+    if (p) cudaFreeHost(p);
+  for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *btb200_version(void) { return "btb200 0.1 (sm_100a)"; }
+
+const char *btb200_strerror(int err)
+{
+  switch (err) {
+    case BTB200_OK: return "ok";
+    case BTB200_ERR_ARG: return "bad argument or configuration";
+    case BTB200_ERR_NO_DEVICE: return "no CUDA device (this library has no CPU fallback)";
+    case BTB200_ERR_CUDA: return "CUDA error";
+    case BTB200_ERR_NOMEM: return "out of device memory";
+    case BTB200_ERR_SHORT_INPUT: return "input shorter than (n_slots-1)*S + H samples";
+    case BTB200_ERR_TOO_MANY: return "n_slots exceeds max_slots_per_call";
+    case BTB200_ERR_BAD_STEP: return "bad step";
+    case BTB200_ERR_MM_RANGE: return "interpolator index out of range";
+    default: return "unknown error";
+  }
+}
+
+const char *btb200_last_error(const btb200_ctx *ctx) { return ctx ? ctx->last_error.c_str() : g_create_error.c_str(); }
+
+int btb200_create(const btb200_config *cfg, btb200_ctx **out)
+{
+  if (!cfg || !out || cfg->abi_version != BTB200_ABI_VERSION) return BTB200_ERR_ARG;
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev <= 0 || cfg->device < 0 || cfg->device >= ndev) {
+    g_create_error = e != cudaSuccess ? cudaGetErrorString(e) : "no such device";
+    return BTB200_ERR_NO_DEVICE;
+  }
+  btb200_ctx *ctx = new (std::nothrow) btb200_ctx();
+  if (!ctx) return BTB200_ERR_NOMEM;
+  ctx->cfg = *cfg;
+  if (ctx->cfg.search == 0) ctx->cfg.search = BTB200_SEARCH_BR | BTB200_SEARCH_LE;
+  if (ctx->cfg.extra_history_symbols == 0) ctx->cfg.extra_history_symbols = 3125;
+  ctx->max_slots = cfg->max_slots_per_call ? cfg->max_slots_per_call : kDefaultMaxSlots;
+  ctx->device = cfg->device;
+  if (ctx->plan.design(cfg->sample_rate, cfg->center_freq, cfg->squelch_threshold,
+                       (int)ctx->cfg.extra_history_symbols) != 0 ||
+      (cfg->mm_mode != BTB200_MM_CHAINED && cfg->mm_mode != BTB200_MM_STATELESS)) {
+    delete ctx;
+    return BTB200_ERR_ARG;
+  }
+  int rc = BTB200_OK;
+  if (cudaSetDevice(ctx->device) != cudaSuccess) rc = BTB200_ERR_NO_DEVICE;
+  if (!rc) {
+    cudaDeviceProp prop{};
+    cudaGetDeviceProperties(&prop, ctx->device);
+    ctx->sm_count = prop.multiProcessorCount;
+    rc = setup(ctx);
+  }
+  if (rc) {
+    g_create_error = ctx->last_error;
+    teardown(ctx);
+    delete ctx;
+    return rc;
+  }
+  *out = ctx;
+  return BTB200_OK;
+}
+
+void btb200_destroy(btb200_ctx *ctx)
+{
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  teardown(ctx);
+  delete ctx;
+}
+
+int btb200_get_info(const btb200_ctx *ctx, btb200_info *o)
+{
+  if (!ctx || !o) return BTB200_ERR_ARG;
+  const Plan &P = ctx->plan;
+  o->samples_per_slot = P.S; o->history = P.H; o->decimation = P.D;
+  o->chan_taps = P.Nc; o->noise_taps = P.Nn;
+  o->first_channel_sample = P.fcs; o->first_noise_sample = P.fns;
+  o->channel_low = P.ch_lo; o->channel_high = P.ch_hi; o->n_channels = P.nch;
+  o->ddc_out_per_window = P.n_ddc; o->noise_out_per_window = P.n_noise;
+  o->demod_gain = P.demod_gain; o->omega_mid = P.omega_mid;
+  o->max_slots_per_call = ctx->max_slots; o->sm_count = ctx->sm_count;
+  return BTB200_OK;
+}
+
+int btb200_host_alloc(void **ptr, size_t bytes)
+{
+  if (!ptr) return BTB200_ERR_ARG;
+  return cudaMallocHost(ptr, bytes) == cudaSuccess ? BTB200_OK : BTB200_ERR_NOMEM;
+}
+void btb200_host_free(void *ptr) { if (ptr) cudaFreeHost(ptr); }
+
+int btb200_get_mm_state(const btb200_ctx *ctx, float mm[3])
+{
+  if (!ctx || !mm) return BTB200_ERR_ARG;
+  mm[0] = ctx->mm.mu; mm[1] = ctx->mm.omega; mm[2] = ctx->mm.last;
+  return BTB200_OK;
+}
+int btb200_set_mm_state(btb200_ctx *ctx, const float mm[3])
+{
+  if (!ctx || !mm) return BTB200_ERR_ARG;
+  ctx->mm = MmState{mm[0], mm[1], mm[2]};
+  return BTB200_OK;
+}
+int btb200_reset(btb200_ctx *ctx)
+{
+  if (!ctx) return BTB200_ERR_ARG;
+  reset_stream_state(ctx);
+  ctx->pending = false;
+  return BTB200_OK;
+}
+
+int btb200_submit(btb200_ctx *ctx, const float *iq, int iq_on_device, size_t n_samples,
+                  uint64_t first_slot, uint32_t n_slots)
+{
+  if (!ctx || !iq || n_slots == 0) return BTB200_ERR_ARG;
+  if (ctx->pending) return BTB200_ERR_ARG;
+  if (n_slots > ctx->max_slots) return BTB200_ERR_TOO_MANY;
+  const Plan &P = ctx->plan;
+  const Geom &G = ctx->G;
+  const size_t need = (size_t)(n_slots - 1) * P.S + P.H;
+  if (n_samples < need) return BTB200_ERR_SHORT_INPUT;
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  DevBatch W = ctx->W;
+  W.B = (int)n_slots;
+  const size_t nbc = (size_t)n_slots * P.nch;
+
+  CK(cudaEventRecord(ctx->ev[0], s));
+  if (iq_on_device) {
+    W.x = reinterpret_cast<const c32 *>(iq);
+  } else {
+    CK(cudaMemcpyAsync(ctx->d_x, iq, need * sizeof(c32), cudaMemcpyHostToDevice, s));
+    W.x = ctx->d_x;
+  }
+  if (!G.stateless) {
+    // free-running rotators: the phases of this batch's windows, generated with
+    // the same libm calls as the reference's rotator (hypotf renormalisation)
+    cf32 *hp = reinterpret_cast<cf32 *>(ctx->h_ph);
+    for (uint32_t b = 0; b < n_slots; b++)
+      for (int c = 0; c < P.nch; c++)
+        ctx->rot_c[c].generate(hp + ((size_t)b * P.n_ddc) * P.nch + c, P.n_ddc, P.nch);
+    CK(cudaMemcpyAsync(ctx->d_phc, hp, (size_t)n_slots * P.n_ddc * P.nch * sizeof(c32), cudaMemcpyHostToDevice, s));
+    CK(cudaStreamSynchronize(s));
+    for (uint32_t b = 0; b < n_slots; b++)
+      for (int c = 0; c < P.nch; c++)
+        ctx->rot_n[c].generate(hp + ((size_t)b * P.n_noise) * P.nch + c, P.n_noise, P.nch);
+    CK(cudaMemcpyAsync(ctx->d_phn, hp, (size_t)n_slots * P.n_noise * P.nch * sizeof(c32), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(W.mm_state, &ctx->mm, sizeof(MmState), cudaMemcpyHostToDevice, s));
+  }
+  CK(cudaMemsetAsync(W.hit_count, 0, 4 * sizeof(unsigned), s));
+  CK(cudaEventRecord(ctx->ev[1], s));
+  launch_chan_fir(G, ctx->T, W, ctx->impl, s);
+  CK(cudaEventRecord(ctx->ev[2], s));
+  launch_noise_fir(G, ctx->T, W, ctx->impl, s);
+  CK(cudaEventRecord(ctx->ev[3], s));
+  launch_energy(G, ctx->T, W, G.stateless ? 1 : 0, s);
+  CK(cudaMemcpyAsync(ctx->h_energy, W.energy, nbc * sizeof(double), cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(ctx->h_noise, W.noise, nbc * sizeof(double), cudaMemcpyDeviceToHost, s));
+  if (!G.stateless) {
+    // chained mode: the squelch decides which windows advance the shared M&M
+    // state, so it is settled with the reference's own libm arithmetic first
+    CK(cudaStreamSynchronize(s));
+    for (size_t i = 0; i < nbc; i++) {
+      const double snr = 10.0 * std::log10(ctx->h_energy[i] / ctx->h_noise[i]);
+      ctx->h_pass[i] = (snr >= P.squelch_db) ? 1 : 0;
+    }
+    CK(cudaMemcpyAsync(W.pass, ctx->h_pass, nbc * sizeof(int), cudaMemcpyHostToDevice, s));
+  }
+  CK(cudaEventRecord(ctx->ev[4], s));
+  launch_demod(G, ctx->T, W, s);
+  launch_mm(G, ctx->T, W, s);
+  CK(cudaEventRecord(ctx->ev[5], s));
+  launch_search(G, ctx->T, W, s);
+  launch_gather(G, W, s);
+  CK(cudaEventRecord(ctx->ev[6], s));
+  CK(cudaMemcpyAsync(ctx->h_counts, W.hit_count, 4 * sizeof(unsigned), cudaMemcpyDeviceToHost, s));
+  if (!G.stateless) CK(cudaMemcpyAsync(&ctx->mm, W.mm_state, sizeof(MmState), cudaMemcpyDeviceToHost, s));
+  CK(cudaEventRecord(ctx->ev[7], s));
+  CK(cudaGetLastError());
+  ctx->launches += kernel_launches_per_batch();
+  ctx->pending = true;
+  ctx->pend_slots = n_slots;
+  ctx->pend_first_slot = first_slot;
+  return BTB200_OK;
+}
+
+int btb200_collect(btb200_ctx *ctx, btb200_hits *out)
+{
+  if (!ctx || !ctx->pending) return BTB200_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  const Plan &P = ctx->plan;
+  ctx->pending = false;
+  CK(cudaStreamSynchronize(s));
+  unsigned nh = ctx->h_counts[0];
+  unsigned long long used;
+  std::memcpy(&used, ctx->h_counts + 2, sizeof used);
+  unsigned dropped = 0;
+  if (nh > kHitCap) { dropped = nh - kHitCap; nh = kHitCap; }
+  if (used > kArenaCap) used = kArenaCap;
+  if (nh) CK(cudaMemcpyAsync(ctx->h_hits, ctx->W.hits, (size_t)nh * sizeof(DevHit), cudaMemcpyDeviceToHost, s));
+  if (used && out && out->symbols) CK(cudaMemcpyAsync(ctx->h_arena, ctx->W.arena, used, cudaMemcpyDeviceToHost, s));
+  CK(cudaEventRecord(ctx->ev[8], s));
+  CK(cudaStreamSynchronize(s));
+  ctx->last_slots = ctx->pend_slots;
+  for (int i = 0; i < 7; i++) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev[i], ctx->ev[i + 1]);
+    ctx->timing[i] = ms;
+  }
+  {
+    // [0] H2D [1] chan FIR [2] noise FIR [3] energy [4] demod+mm [5] search [6] D2H, [7] total
+    float d2h = 0, tot = 0;
+    cudaEventElapsedTime(&d2h, ctx->ev[6], ctx->ev[8]);
+    cudaEventElapsedTime(&tot, ctx->ev[0], ctx->ev[8]);
+    ctx->timing[6] = d2h;
+    ctx->timing[7] = tot;
+  }
+  if (!out) return BTB200_OK;
+
+  // order = the reference's visiting order: slot, channel, BR before LE, ascending offset
+  std::vector<unsigned> order(nh);
+  for (unsigned i = 0; i < nh; i++) order[i] = i;
+  const DevHit *hh = ctx->h_hits;
+  std::sort(order.begin(), order.end(), [hh](unsigned a, unsigned b) {
+    const DevHit &x = hh[a], &y = hh[b];
+    if (x.b != y.b) return x.b < y.b;
+    if (x.chi != y.chi) return x.chi < y.chi;
+    if (x.kind != y.kind) return x.kind < y.kind;
+    return x.offset < y.offset;
+  });
+  out->count = 0;
+  out->overflow = dropped;
+  out->symbols_used = 0;
+  for (unsigned oi = 0; oi < nh; oi++) {
+    const DevHit &h = hh[order[oi]];
+    const size_t bc = (size_t)h.b * P.nch + h.chi;
+    // the value ac() prints, with the reference's own arithmetic (multi_block.cc:293)
+    const double snr = 10.0 * std::log10(ctx->h_energy[bc] / ctx->h_noise[bc]);
+    if (!(snr >= P.squelch_db)) continue;          // guard-band window the exact compare rejects
+    if (out->count >= out->cap) { out->overflow++; continue; }
+    btb200_hit &o = out->hits[out->count];
+    o.slot = (uint32_t)(ctx->pend_first_slot + (uint64_t)h.b);
+    o.channel = (uint16_t)(P.ch_lo + h.chi);
+    o.kind = (uint16_t)h.kind;
+    o.offset = h.offset;
+    o.n_symbols = h.n_symbols;
+    o.lap = h.lap;
+    o.flags = (std::fabs(snr - P.squelch_db) <= 1e-6) ? 1u : 0u;
+    o.snr = snr;
+    o.sym_offset = 0;
+    o.sym_count = 0;
+    o.reserved = 0;
+    if (out->symbols && h.sym_count && out->symbols_used + h.sym_count <= out->symbols_cap) {
+      std::memcpy(out->symbols + out->symbols_used, ctx->h_arena + h.sym_offset, h.sym_count);
+      o.sym_offset = out->symbols_used;
+      o.sym_count = h.sym_count;
+      out->symbols_used += h.sym_count;
+    }
+    out->count++;
+  }
+  return BTB200_OK;
+}
+
+int btb200_process(btb200_ctx *ctx, const float *iq, size_t n_samples, uint64_t first_slot,
+                   uint32_t n_slots, btb200_hits *out)
+{
+  int rc = btb200_submit(ctx, iq, 0, n_samples, first_slot, n_slots);
+  if (rc) return rc;
+  return btb200_collect(ctx, out);
+}
+
+int btb200_process_device(btb200_ctx *ctx, const float *d_iq, size_t n_samples, uint64_t first_slot,
+                          uint32_t n_slots, btb200_hits *out)
+{
+  int rc = btb200_submit(ctx, d_iq, 1, n_samples, first_slot, n_slots);
+  if (rc) return rc;
+  return btb200_collect(ctx, out);
+}
+
+int btb200_last_timing(const btb200_ctx *ctx, float ms[8])
+{
+  if (!ctx || !ms) return BTB200_ERR_ARG;
+  std::memcpy(ms, ctx->timing, sizeof ctx->timing);
+  return BTB200_OK;
+}
+
+uint64_t btb200_launch_count(const btb200_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int64_t btb200_get_stage(btb200_ctx *ctx, int stage, uint32_t b, uint32_t chi, void *dst, size_t cap)
+{
+  if (!ctx || !dst) return BTB200_ERR_ARG;
+  const Plan &P = ctx->plan;
+  const Geom &G = ctx->G;
+  if (cudaSetDevice(ctx->device) != cudaSuccess) return BTB200_ERR_NO_DEVICE;
+  auto host_copy = [&](const void *src, size_t bytes) -> int64_t {
+    if (bytes > cap) return BTB200_ERR_ARG;
+    std::memcpy(dst, src, bytes);
+    return (int64_t)bytes;
+  };
+  if (stage >= BTB200_STAGE_CHAN_TAPS) {
+    if ((int)chi >= P.nch) return BTB200_ERR_ARG;
+    switch (stage) {
+      case BTB200_STAGE_CHAN_TAPS: return host_copy(&P.chan_rtaps[(size_t)chi * P.Nc], (size_t)P.Nc * 8);
+      case BTB200_STAGE_NOISE_TAPS: return host_copy(&P.noise_rtaps[(size_t)chi * P.Nn], (size_t)P.Nn * 8);
+      case BTB200_STAGE_MMSE_TABLE: return host_copy(P.mmse.data(), P.mmse.size() * 4);
+      case BTB200_STAGE_ATAN_TABLE: return host_copy(P.atan_tab.data(), P.atan_tab.size() * 4);
+      case BTB200_STAGE_AC_LUT: return host_copy(P.ac_lut.data(), P.ac_lut.size() * 8);
+      default: return BTB200_ERR_ARG;
+    }
+  }
+  if (b >= ctx->last_slots || (int)chi >= P.nch) return BTB200_ERR_ARG;
+  const size_t bc = (size_t)b * P.nch + chi;
+  auto dev_copy = [&](const void *src, size_t bytes) -> int64_t {
+    if (bytes > cap) return BTB200_ERR_ARG;
+    if (cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost) != cudaSuccess) return BTB200_ERR_CUDA;
+    return (int64_t)bytes;
+  };
+  switch (stage) {
+    case BTB200_STAGE_ENERGY: return host_copy(&ctx->h_energy[bc], 8);
+    case BTB200_STAGE_NOISE: return host_copy(&ctx->h_noise[bc], 8);
+    case BTB200_STAGE_SNR: {
+      const double snr = 10.0 * std::log10(ctx->h_energy[bc] / ctx->h_noise[bc]);
+      return host_copy(&snr, 8);
+    }
+    case BTB200_STAGE_PASS: return dev_copy(ctx->W.pass + bc, 4);
+    case BTB200_STAGE_NSYM: return dev_copy(ctx->W.nsym + bc, 4);
+    case BTB200_STAGE_BITS: {
+      int nsym = 0;
+      if (cudaMemcpy(&nsym, ctx->W.nsym + bc, 4, cudaMemcpyDeviceToHost) != cudaSuccess) return BTB200_ERR_CUDA;
+      if ((size_t)nsym > cap) return BTB200_ERR_ARG;
+      std::vector<uint32_t> row(G.bw);
+      if (cudaMemcpy(row.data(), ctx->W.bits + bc * G.bw, (size_t)G.bw * 4, cudaMemcpyDeviceToHost) != cudaSuccess)
+        return BTB200_ERR_CUDA;
+      uint8_t *o = (uint8_t *)dst;
+      for (int i = 0; i < nsym; i++) o[i] = (row[i >> 5] >> (i & 31)) & 1;
+      return nsym;
+    }
+    case BTB200_STAGE_DDC: {
+      // rotated DDC output of the window = Y[b*gps + i][chi] * phase[i] (same fp32 ops as the kernels)
+      if ((size_t)P.n_ddc * 8 > cap) return BTB200_ERR_ARG;
+      std::vector<c32> y(P.n_ddc), ph(P.n_ddc);
+      const size_t pitch = (size_t)P.nch * sizeof(c32);
+      if (cudaMemcpy2D(y.data(), sizeof(c32), ctx->W.Y + ((size_t)b * P.grid_per_slot) * P.nch + chi, pitch,
+                       sizeof(c32), P.n_ddc, cudaMemcpyDeviceToHost) != cudaSuccess) return BTB200_ERR_CUDA;
+      const size_t bp = G.stateless ? 0 : b;
+      if (cudaMemcpy2D(ph.data(), sizeof(c32), ctx->d_phc + (bp * P.n_ddc) * P.nch + chi, pitch,
+                       sizeof(c32), P.n_ddc, cudaMemcpyDeviceToHost) != cudaSuccess) return BTB200_ERR_CUDA;
+      c32 *o = (c32 *)dst;
+      for (int i = 0; i < P.n_ddc; i++) o[i] = crot(y[i], ph[i]);
+      return (int64_t)P.n_ddc * 8;
+    }
+    case BTB200_STAGE_DEMOD: return dev_copy(ctx->W.dem + bc * G.n_dem_pad, (size_t)P.n_dem * 4);
+    case BTB200_STAGE_SOFT: {
+      if (!ctx->d_soft) return BTB200_ERR_ARG;
+      int nsym = 0;
+      if (cudaMemcpy(&nsym, ctx->W.nsym + bc, 4, cudaMemcpyDeviceToHost) != cudaSuccess) return BTB200_ERR_CUDA;
+      return dev_copy(ctx->d_soft + bc * G.n_dem_pad, (size_t)nsym * 4);
+    }
+    default: return BTB200_ERR_ARG;
+  }
+}
+
+// test hook: select baseline (0) or tuned (1) kernels
+BTB200_API int btb200_set_impl(btb200_ctx *ctx, int impl)
+{
+  if (!ctx) return BTB200_ERR_ARG;
+  ctx->impl = impl;
+  return BTB200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,64 @@
+// plan.hpp -- host-side design step of the B200 receive path.
+//
+// Everything multi_block's constructor derives from (sample_rate, center_freq)
+// -- lib/multi_block.cc:40-120, 299-342 of the reference -- plus the GNU Radio
+// 3.7 design arithmetic it calls (firdes::low_pass, freq_xlating_fir_filter_ccf
+// tap rotation and rotator, mmse_fir_interpolator_ff taps, fast_atan2f table;
+// SURVEY.md Appendix A).  Computed once on the host in the same precision and
+// operation order as the reference so the uploaded tables are bit-identical.
+#pragma once
+#include <cstdint>
+#include <vector>
+
+namespace btb200 {
+
+struct cf32 { float re, im; };
+
+struct Plan {
+  // make() arguments
+  double fs = 0, fc = 0, squelch_db = 0;
+  int extra_symbols = 3125;
+  // derived geometry
+  int S = 0;              // samples per slot
+  int H = 0;              // history = window length
+  int D = 1;              // DDC decimation
+  int Nc = 0, Nn = 0;     // prototype lengths
+  int fcs = 0, fns = 0;   // first channel / noise sample inside the window
+  int ch_lo = 0, ch_hi = -1, nch = 0;
+  int n_ddc = 0;          // channel DDC outputs per window
+  int n_noise = 0;        // noise DDC outputs per window
+  int n_dem = 0;          // demod outputs per window (n_ddc - 1)
+  int grid_per_slot = 0;  // S / D: decimated grid points per slot
+  float demod_gain = 0;
+  // M&M constants (lib/multi_block.cc:91-96)
+  float gain_mu = 0, gain_omega = 0, omega_mid = 0, omega_lim = 0, mu0 = 0;
+  // tables
+  std::vector<float> chan_proto, noise_proto;
+  std::vector<cf32>  chan_rtaps;    // [nch][Nc], reversed: rtaps[k] multiplies x[n0+k]
+  std::vector<cf32>  noise_rtaps;   // [nch][Nn]
+  std::vector<cf32>  chan_incr, noise_incr;   // rotator increments [nch]
+  std::vector<float> mmse;          // [129][8]
+  std::vector<float> atan_tab;      // [257]
+  std::vector<uint64_t> ac_lut;     // [3][256] affine sync-word tables, then constant
+  std::vector<uint8_t>  le_white16; // [nch][16] whitening bits for the LE header, per channel
+  std::vector<int8_t>   le_index;   // [nch] LE channel index or -1
+
+  int design(double fs, double fc, double squelch_db, int extra_symbols);   // 0 or negative error
+};
+
+// Free-running rotator of one DDC object (GNU Radio's gr::blocks::rotator):
+// phase multiplies output i, then advances; renormalised every 512 outputs.
+struct Rotator {
+  cf32 phase{1.0f, 0.0f};
+  cf32 incr{1.0f, 0.0f};
+  unsigned counter = 0;
+  void reset() { phase = {1.0f, 0.0f}; counter = 0; }
+  // writes the n phases that multiply the next n outputs, advancing the state
+  void generate(cf32 *dst, int n, int stride);
+};
+
+// 64-bit sync word of a LAP, bit i = access-code symbol 4+i
+// (restates classic_packet::acgen, lib/packet_impl.cc:309-364)
+uint64_t sync_word(uint32_t lap);
+
+}  // namespace btb200

@@ -1,0 +1,53 @@
+// rx_kernels.cuh -- launch interface of the sm_100a kernels (rx_kernels.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include "rx_bodies.cuh"
+
+namespace btb200 {
+
+struct DevTables {
+  const c32 *chan_rtaps;     // [nch][Nc]
+  const c32 *noise_rtaps;    // [nch][Nn]
+  const float *mmse;         // [129*8]
+  const float *atan_tab;     // [257]
+  const uint64_t *ac_lut;    // [769]
+  const uint8_t *le_hdr_lut; // [4*256]
+  const int8_t *le_index;    // [nch]
+  const uint32_t *le_white;  // [nch] 16 whitening bits
+};
+
+struct DevBatch {
+  const c32 *x;              // input
+  c32 *Y;                    // [G][nch]
+  c32 *Nz;                   // [B][n_noise][nch]
+  const c32 *phc, *phn;      // rotator tables
+  int bp_stride;             // 0: one table for every window (stateless), 1: per-window tables
+  double *energy, *noise;    // [B][nch]
+  int *pass;                 // [B][nch]  (device decision, or host-provided in chained mode)
+  float *dem;                // [B][nch][n_dem_pad]
+  float *soft;               // optional [B][nch][n_dem_pad]
+  uint32_t *bits;            // [B][nch][bw]
+  int *nsym;                 // [B][nch]
+  MmState *mm_state;         // [1] chained-mode state in/out
+  DevHit *hits;              // [hit_cap]
+  unsigned *hit_count;       // [1]
+  unsigned long long *arena_used;   // [1]
+  uint8_t *arena;            // [arena_cap]
+  unsigned hit_cap;
+  unsigned long long arena_cap;
+  int B;
+};
+
+// implementation selectors (tests compare tuned kernels against the v1 baseline)
+enum { IMPL_BASELINE = 0, IMPL_TUNED = 1 };
+
+void launch_chan_fir(const Geom &G, const DevTables &T, const DevBatch &W, int impl, cudaStream_t s);
+void launch_noise_fir(const Geom &G, const DevTables &T, const DevBatch &W, int impl, cudaStream_t s);
+void launch_energy(const Geom &G, const DevTables &T, const DevBatch &W, int device_gate, cudaStream_t s);
+void launch_demod(const Geom &G, const DevTables &T, const DevBatch &W, cudaStream_t s);
+void launch_mm(const Geom &G, const DevTables &T, const DevBatch &W, cudaStream_t s);
+void launch_search(const Geom &G, const DevTables &T, const DevBatch &W, cudaStream_t s);
+void launch_gather(const Geom &G, const DevBatch &W, cudaStream_t s);
+int  kernel_launches_per_batch();
+
+}  // namespace btb200

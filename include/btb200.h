@@ -1,0 +1,219 @@
+/*
+ * btb200.h -- C ABI of the B200-native gr-bluetooth multi-channel receive path.
+ *
+ * This is the drop-in boundary: everything the reference does between
+ * "GNU Radio hands work() a window of IQ" and "ac()/aa() get a symbol pointer"
+ * runs behind these entry points, in hand-written sm_100a kernels.  Plain
+ * pointers and sizes only.  No CPU fallback: every entry point fails with
+ * BTB200_ERR_NO_DEVICE / BTB200_ERR_CUDA when no usable GPU is present.
+ *
+ * What each entry point replaces in the reference (paths under
+ * /root/reference):
+ *
+ *   btb200_create        gr::bluetooth::multi_block::multi_block()
+ *                        lib/multi_block.cc:40-120, set_channels() :306-342,
+ *                        set_symbol_history() :299-303 (tap design, channel
+ *                        plan, DDC objects, history) -- reached through
+ *                        multi_sniffer::make() lib/multi_sniffer_impl.cc:42-48,
+ *                        multi_LAP::make() lib/multi_LAP_impl.cc:40-43,
+ *                        multi_hopper::make() lib/multi_hopper_impl.cc:36-40.
+ *   btb200_process       the body of multi_sniffer_impl::work()
+ *                        lib/multi_sniffer_impl.cc:82-166 for n_slots
+ *                        consecutive calls: channel_samples()
+ *                        lib/multi_block.cc:180-228, check_snr() :253-296,
+ *                        channel_symbols() :230-251 (demod :158-168, mm_cr
+ *                        :128-155, slicer :171-178), classic_packet::sniff_ac
+ *                        lib/packet_impl.cc:247-268 + check_ac :471-510 +
+ *                        acgen :309-364, le_packet::sniff_aa :1452-1527.
+ *                        Each returned hit is one ac()/aa() invocation
+ *                        (lib/multi_sniffer_impl.cc:117,139) with its
+ *                        arguments.
+ *   btb200_process_device same, input already resident in HBM.
+ *   btb200_get/set_mm_state  the three floats of M&M state that persist
+ *                        across work() calls: include/gr_bluetooth/multi_block.h:86-93.
+ *   btb200_get_stage     no reference counterpart: debug taps for parity tests.
+ */
+#ifndef BTB200_H
+#define BTB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BTB200_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define BTB200_API __attribute__((visibility("default")))
+#else
+#define BTB200_API
+#endif
+
+/* error codes (negative); the reference abort()s or throws instead
+ * (lib/multi_sniffer_impl.cc:36-40) */
+enum {
+  BTB200_OK              = 0,
+  BTB200_ERR_ARG         = -1,   /* bad argument / configuration */
+  BTB200_ERR_NO_DEVICE   = -2,   /* no CUDA device: there is NO CPU fallback */
+  BTB200_ERR_CUDA        = -3,   /* CUDA runtime error, see btb200_last_error() */
+  BTB200_ERR_NOMEM       = -4,
+  BTB200_ERR_SHORT_INPUT = -5,   /* n_samples < (n_slots-1)*S + H */
+  BTB200_ERR_TOO_MANY    = -6,   /* n_slots > max_slots_per_call */
+  BTB200_ERR_BAD_STEP    = -7,   /* the reference's "Bad step" abort (multi_sniffer_impl.cc:119) */
+  BTB200_ERR_MM_RANGE    = -8    /* interpolator index out of range (GNU Radio would throw) */
+};
+
+/* how clock-recovery / rotator state is carried from one channel-window to the next */
+enum {
+  /* reference behaviour: one M&M state shared by all channels and all work()
+   * calls (include/gr_bluetooth/multi_block.h:86-93), DDC rotators free-running.
+   * Serial by construction; bit-exact with the reference on whole files. */
+  BTB200_MM_CHAINED   = 0,
+  /* every channel-window starts from the constructor state
+   * (lib/multi_block.cc:91-98), rotators restart at phase 1.  Windows become
+   * pure functions of their samples: parallel, shardable, bit-exact with the
+   * oracle run in the same mode. */
+  BTB200_MM_STATELESS = 1
+};
+
+enum {
+  BTB200_SEARCH_BR = 1,          /* classic_packet::sniff_ac */
+  BTB200_SEARCH_LE = 2           /* le_packet::sniff_aa */
+};
+
+/* which block's window geometry / search */
+enum {
+  BTB200_BLOCK_SNIFFER = 0,      /* history += 3125 symbols (multi_sniffer_impl.cc:61) */
+  BTB200_BLOCK_LAP     = 1       /* history += 68 symbols   (multi_LAP_impl.cc:54)     */
+};
+
+typedef struct {
+  uint32_t abi_version;          /* BTB200_ABI_VERSION */
+  double   sample_rate;          /* make() arg 1 */
+  double   center_freq;          /* make() arg 2 */
+  double   squelch_threshold;    /* make() arg 3, dB */
+  uint32_t extra_history_symbols;/* 3125 or 68 */
+  int32_t  mm_mode;              /* BTB200_MM_* */
+  int32_t  search;               /* BTB200_SEARCH_* bit mask */
+  int32_t  device;               /* CUDA device ordinal */
+  uint32_t max_slots_per_call;   /* sizes device buffers; 0 = default */
+  uint32_t keep_stages;          /* 1: keep demod/soft-symbol buffers for btb200_get_stage */
+  uint32_t reserved[5];
+} btb200_config;
+
+/* derived constants (lib/multi_block.cc:56-119, 299-342) */
+typedef struct {
+  int32_t samples_per_slot;      /* S */
+  int32_t history;               /* H = window length in samples */
+  int32_t decimation;            /* D */
+  int32_t chan_taps, noise_taps; /* Nc, Nn */
+  int32_t first_channel_sample, first_noise_sample;
+  int32_t channel_low, channel_high, n_channels;
+  int32_t ddc_out_per_window;    /* 7494 @100 Msps */
+  int32_t noise_out_per_window;  /* 850 */
+  float   demod_gain;
+  float   omega_mid;
+  uint32_t max_slots_per_call;
+  int32_t sm_count;
+} btb200_info;
+
+/* one ac()/aa() invocation of the reference (multi_sniffer_impl.cc:117,139) */
+typedef struct {
+  uint32_t slot;                 /* work() call index == clkn (multi_sniffer_impl.cc:173) */
+  uint16_t channel;              /* classic channel 0..78 */
+  uint16_t kind;                 /* 0: BR access code, 1: LE access address */
+  int32_t  offset;               /* symbol index in the window where the packet starts */
+  int32_t  n_symbols;            /* the "len - i" argument of ac()/aa() */
+  uint32_t lap;                  /* BR: LAP (symbols 38..61); LE: AA (symbols 8..39) */
+  uint32_t flags;                /* bit0: squelch compare re-evaluated on the host (guard band) */
+  double   snr;                  /* dB, the value ac() prints */
+  uint64_t sym_offset;           /* into btb200_hits.symbols */
+  uint32_t sym_count;            /* min(n_symbols, 3125 + 376) symbols copied, one per byte, air order */
+  uint32_t reserved;
+} btb200_hit;
+
+typedef struct {
+  btb200_hit *hits;              /* caller-allocated */
+  uint32_t    cap;
+  uint32_t    count;             /* out; ordered by (slot, channel, kind, offset) = reference visiting order */
+  uint32_t    overflow;          /* out: hits dropped because cap was too small */
+  uint8_t    *symbols;           /* caller-allocated arena, may be NULL (no symbols wanted) */
+  uint64_t    symbols_cap;
+  uint64_t    symbols_used;      /* out */
+} btb200_hits;
+
+typedef struct btb200_ctx btb200_ctx;
+
+BTB200_API int  btb200_create(const btb200_config *cfg, btb200_ctx **out);
+BTB200_API void btb200_destroy(btb200_ctx *ctx);
+BTB200_API int  btb200_get_info(const btb200_ctx *ctx, btb200_info *out);
+
+/*
+ * Process n_slots consecutive work() calls.  iq points at the first sample of
+ * the first call's window -- exactly what GNU Radio passes as input_items[0]
+ * to a sync_block with history H -- and must hold at least
+ * (n_slots-1)*S + H complex64 samples (interleaved re,im).  first_slot is the
+ * call index of the first window (the reference's d_cumulative_count / S).
+ * Host memory (pageable or pinned) for btb200_process, device memory for
+ * btb200_process_device.
+ */
+BTB200_API int  btb200_process(btb200_ctx *ctx, const float *iq, size_t n_samples,
+                    uint64_t first_slot, uint32_t n_slots, btb200_hits *out);
+BTB200_API int  btb200_process_device(btb200_ctx *ctx, const float *d_iq, size_t n_samples,
+                           uint64_t first_slot, uint32_t n_slots, btb200_hits *out);
+
+/* split form for overlap / benchmarking: enqueue everything on the ctx stream,
+ * then wait and collect.  btb200_process == submit + collect. */
+BTB200_API int  btb200_submit(btb200_ctx *ctx, const float *iq, int iq_on_device, size_t n_samples,
+                   uint64_t first_slot, uint32_t n_slots);
+BTB200_API int  btb200_collect(btb200_ctx *ctx, btb200_hits *out);
+
+/* pinned host buffers for the H2D path */
+BTB200_API int  btb200_host_alloc(void **ptr, size_t bytes);
+BTB200_API void btb200_host_free(void *ptr);
+
+/* M&M state carried between calls in BTB200_MM_CHAINED: {mu, omega, last_sample} */
+BTB200_API int  btb200_get_mm_state(const btb200_ctx *ctx, float mm[3]);
+BTB200_API int  btb200_set_mm_state(btb200_ctx *ctx, const float mm[3]);
+/* restart the stream (slot counter, rotators, M&M) */
+BTB200_API int  btb200_reset(btb200_ctx *ctx);
+
+/* debug taps of the LAST processed batch (parity tests).  slot_in_batch and
+ * chan_index (channel - channel_low) select a channel-window; dst receives up
+ * to cap bytes; returns bytes written or a negative error. */
+enum {
+  BTB200_STAGE_ENERGY   = 1,     /* f64  on-channel mean |y|^2               */
+  BTB200_STAGE_NOISE    = 2,     /* f64  off-channel mean |y|^2              */
+  BTB200_STAGE_SNR      = 3,     /* f64  10*log10(on/off) (host libm)        */
+  BTB200_STAGE_PASS     = 4,     /* i32  squelch decision                    */
+  BTB200_STAGE_NSYM     = 5,     /* i32  symbols produced                    */
+  BTB200_STAGE_BITS     = 6,     /* u8[nsym] sliced symbols                  */
+  BTB200_STAGE_DDC      = 7,     /* c64[ddc_out_per_window] rotated DDC out  */
+  BTB200_STAGE_DEMOD    = 8,     /* f32[ddc_out-1] (needs keep_stages)       */
+  BTB200_STAGE_SOFT     = 9,     /* f32[nsym]      (needs keep_stages)       */
+  BTB200_STAGE_CHAN_TAPS  = 20,  /* c64[Nc] reversed band-pass taps of chan_index */
+  BTB200_STAGE_NOISE_TAPS = 21,  /* c64[Nn]                                  */
+  BTB200_STAGE_MMSE_TABLE = 22,  /* f32[129*8]                               */
+  BTB200_STAGE_ATAN_TABLE = 23,  /* f32[257]                                 */
+  BTB200_STAGE_AC_LUT     = 24   /* u64[3*256+1] affine sync-word tables + constant */
+};
+BTB200_API int64_t btb200_get_stage(btb200_ctx *ctx, int stage, uint32_t slot_in_batch,
+                         uint32_t chan_index, void *dst, size_t cap);
+
+/* timing of the last batch, milliseconds, CUDA events on the ctx stream:
+ * [0] H2D copy, [1] channel FIR, [2] noise FIR, [3] energy/squelch,
+ * [4] demod+clock recovery, [5] access-code search, [6] D2H + host, [7] total device */
+BTB200_API int  btb200_last_timing(const btb200_ctx *ctx, float ms[8]);
+/* number of kernel launches issued by this ctx so far */
+BTB200_API uint64_t btb200_launch_count(const btb200_ctx *ctx);
+
+BTB200_API const char *btb200_strerror(int err);
+BTB200_API const char *btb200_last_error(const btb200_ctx *ctx);   /* detail of the last CUDA failure */
+BTB200_API const char *btb200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BTB200_H */

@@ -1,0 +1,139 @@
+// tests/emul/emul.cpp -- TEST HARNESS, not product code.
+//
+// Runs the per-thread bodies of the baseline kernels (gr-bluetooth_b200/csrc/
+// rx_bodies.cuh, rx_math.cuh) and the host design step (plan.cpp) on the CPU, in
+// the same order the CUDA launch code drives them, so the kernel logic can be
+// checked against the oracle in the CPU-only test tier.  Never linked into
+// libbtb200.so; the product has no CPU path.
+#include "../../gr-bluetooth_b200/csrc/plan.hpp"
+#include "../../gr-bluetooth_b200/csrc/rx_bodies.cuh"
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+using namespace btb200;
+
+extern "C" {
+
+struct emul_hit { int32_t slot; int16_t channel; int16_t kind; int32_t offset; int32_t n_symbols; uint32_t lap; double snr; };
+
+struct emul_out {
+  double *energy, *noise;      // [B][nch]
+  int32_t *nsym;               // [B][nch]
+  uint8_t *bits;               // [B][nch][stride]
+  int32_t bits_stride;
+  emul_hit *hits; int32_t hits_cap; int32_t nhits;
+  float mm[3];                 // chained state in/out
+};
+
+int emul_plan_info(double fs, double fc, double snr, int extra, int32_t out[16])
+{
+  Plan P;
+  if (P.design(fs, fc, snr, extra)) return -1;
+  int32_t v[16] = {P.S, P.H, P.D, P.Nc, P.Nn, P.fcs, P.fns, P.ch_lo, P.ch_hi, P.nch, P.n_ddc, P.n_noise, P.n_dem, P.grid_per_slot, 0, 0};
+  std::memcpy(out, v, sizeof v);
+  return 0;
+}
+
+// tables for direct comparison with the oracle's
+int emul_plan_tables(double fs, double fc, int extra, int chi, float *chan_rtaps, float *noise_rtaps,
+                     float *mmse, float *atan_tab, uint64_t *ac_lut, float *incr4)
+{
+  Plan P;
+  if (P.design(fs, fc, 10.0, extra)) return -1;
+  std::memcpy(chan_rtaps, &P.chan_rtaps[(size_t)chi * P.Nc], (size_t)P.Nc * 8);
+  std::memcpy(noise_rtaps, &P.noise_rtaps[(size_t)chi * P.Nn], (size_t)P.Nn * 8);
+  std::memcpy(mmse, P.mmse.data(), P.mmse.size() * 4);
+  std::memcpy(atan_tab, P.atan_tab.data(), 257 * 4);
+  std::memcpy(ac_lut, P.ac_lut.data(), 769 * 8);
+  incr4[0] = P.chan_incr[chi].re; incr4[1] = P.chan_incr[chi].im;
+  incr4[2] = P.noise_incr[chi].re; incr4[3] = P.noise_incr[chi].im;
+  return 0;
+}
+
+uint64_t emul_sync_word(uint32_t lap) { return sync_word(lap); }
+
+// x: (B-1)*S+H complex samples; rot_state (chained): rotators continue from rot_calls previous calls
+int emul_run(double fs, double fc, double snr_db, int extra, int stateless, int search,
+             const float *xf, int B, int first_slot, emul_out *o)
+{
+  Plan P;
+  if (P.design(fs, fc, snr_db, extra)) return -1;
+  Geom G{};
+  G.S = P.S; G.H = P.H; G.D = P.D; G.Nc = P.Nc; G.Nn = P.Nn; G.fcs = P.fcs; G.fns = P.fns;
+  G.nch = P.nch; G.n_ddc = P.n_ddc; G.n_noise = P.n_noise; G.n_dem = P.n_dem; G.gps = P.grid_per_slot;
+  G.n_dem_pad = (P.n_dem + 3) & ~3;
+  G.bw = (P.n_dem + 31) / 32 + 4;
+  G.ch_lo = P.ch_lo; G.demod_gain = P.demod_gain;
+  G.mm = MmConst{P.gain_mu, P.gain_omega, P.omega_mid, P.omega_lim};
+  G.mu0 = P.mu0; G.squelch_db = P.squelch_db; G.search = search; G.stateless = stateless;
+  const c32 *x = reinterpret_cast<const c32 *>(xf);
+  const int nch = P.nch;
+  const long Gtot = (long)(B - 1) * G.gps + G.n_ddc;
+  std::vector<c32> Y((size_t)Gtot * nch), Nz((size_t)B * G.n_noise * nch);
+  for (long g = 0; g < Gtot; g++)
+    for (int c = 0; c < nch; c++)
+      Y[(size_t)g * nch + c] = chan_fir_point(G, x, reinterpret_cast<const c32 *>(&P.chan_rtaps[(size_t)c * P.Nc]), g);
+  for (int b = 0; b < B; b++)
+    for (int j = 0; j < G.n_noise; j++)
+      for (int c = 0; c < nch; c++)
+        Nz[((size_t)b * G.n_noise + j) * nch + c] =
+            noise_fir_point(G, x, reinterpret_cast<const c32 *>(&P.noise_rtaps[(size_t)c * P.Nn]), b, j);
+  // rotator tables
+  const int Bp = stateless ? 1 : B;
+  std::vector<c32> phc((size_t)Bp * G.n_ddc * nch), phn((size_t)Bp * G.n_noise * nch);
+  std::vector<Rotator> rc(nch), rn(nch);
+  for (int c = 0; c < nch; c++) { rc[c].incr = P.chan_incr[c]; rn[c].incr = P.noise_incr[c]; }
+  if (!stateless) {
+    // advance the free-running rotators over the first_slot calls before this batch
+    std::vector<cf32> scratch((size_t)std::max(G.n_ddc, G.n_noise));
+    for (int k = 0; k < first_slot; k++)
+      for (int c = 0; c < nch; c++) { rc[c].generate(scratch.data(), G.n_ddc, 1); rn[c].generate(scratch.data(), G.n_noise, 1); }
+  }
+  for (int b = 0; b < Bp; b++)
+    for (int c = 0; c < nch; c++) {
+      rc[c].generate(reinterpret_cast<cf32 *>(&phc[((size_t)b * G.n_ddc) * nch + c]), G.n_ddc, nch);
+      rn[c].generate(reinterpret_cast<cf32 *>(&phn[((size_t)b * G.n_noise) * nch + c]), G.n_noise, nch);
+    }
+  uint8_t hdr[4 * 256];
+  for (int w = 0; w < 4; w++) for (int v = 0; v < 256; v++) hdr[w * 256 + v] = (uint8_t)le_hdr_dist((uint32_t)v, w);
+  std::vector<float> dem((size_t)G.n_dem_pad);
+  std::vector<uint32_t> row((size_t)G.bw);
+  MmState chained{o->mm[0], o->mm[1], o->mm[2]};
+  o->nhits = 0;
+  for (int b = 0; b < B; b++)
+    for (int c = 0; c < nch; c++) {
+      const size_t bc = (size_t)b * nch + c;
+      double on, off;
+      window_energy(G, Y.data(), Nz.data(), phc.data(), phn.data(), b, c, stateless ? 0 : b, &on, &off);
+      o->energy[bc] = on; o->noise[bc] = off;
+      const double snr = 10.0 * std::log10(on / off);
+      o->nsym[bc] = 0;
+      if (!(snr >= snr_db)) continue;
+      for (int i = 0; i < G.n_dem; i++)
+        dem[i] = window_demod_point(G, Y.data(), phc.data(), P.atan_tab.data(), b, c, stateless ? 0 : b, i);
+      MmState st = stateless ? MmState{G.mu0, G.mm.omega_mid, 0.0f} : chained;
+      const int nsym = window_mm(G, P.mmse.data(), dem.data(), st, row.data(), nullptr);
+      if (!stateless) chained = st;
+      o->nsym[bc] = nsym;
+      if (o->bits)
+        for (int i = 0; i < nsym && i < o->bits_stride; i++)
+          o->bits[bc * o->bits_stride + i] = (row[i >> 5] >> (i & 31)) & 1;
+      uint32_t white = 0;
+      for (int i = 0; i < 16; i++) white |= (uint32_t)P.le_white16[(size_t)c * 16 + i] << i;
+      auto emit = [&](int kind, int offset, int n_symbols, uint32_t lap) {
+        if (o->nhits < o->hits_cap) {
+          emul_hit &h = o->hits[o->nhits];
+          h.slot = first_slot + b; h.channel = (int16_t)(P.ch_lo + c); h.kind = (int16_t)kind;
+          h.offset = offset; h.n_symbols = n_symbols; h.lap = lap; h.snr = snr;
+        }
+        o->nhits++;
+      };
+      window_search(G, P.ac_lut.data(), hdr, row.data(), nsym, P.le_index[c], white, emit);
+    }
+  o->mm[0] = chained.mu; o->mm[1] = chained.omega; o->mm[2] = chained.last;
+  return 0;
+}
+
+}  // extern "C"

@@ -17,6 +17,7 @@ LIB_PATH = os.path.join(_HERE, "libbtb200.so")
 ABI_VERSION = 1
 MM_CHAINED, MM_STATELESS = 0, 1
 SEARCH_BR, SEARCH_LE = 1, 2
+SQUELCH_DEFAULT, SQUELCH_EAGER, SQUELCH_LAZY = 0, 1, 2
 
 STAGE = dict(energy=1, noise=2, snr=3, pass_=4, nsym=5, bits=6, ddc=7, demod=8, soft=9,
              chan_taps=20, noise_taps=21, mmse_table=22, atan_table=23, ac_lut=24)
@@ -34,7 +35,7 @@ class Config(C.Structure):
                 ("squelch_threshold", C.c_double), ("extra_history_symbols", C.c_uint32),
                 ("mm_mode", C.c_int32), ("search", C.c_int32), ("device", C.c_int32),
                 ("max_slots_per_call", C.c_uint32), ("keep_stages", C.c_uint32),
-                ("reserved", C.c_uint32 * 5)]
+                ("squelch_mode", C.c_uint32), ("reserved", C.c_uint32 * 4)]
 
 
 class Info(C.Structure):
@@ -131,12 +132,13 @@ class multi_block:
     EXTRA_SYMBOLS = 3125
 
     def __init__(self, sample_rate, center_freq, squelch_threshold, *, mm_mode=MM_CHAINED,
-                 search=SEARCH_BR | SEARCH_LE, device=0, max_slots=64, keep_stages=False):
+                 search=SEARCH_BR | SEARCH_LE, device=0, max_slots=64, keep_stages=False,
+                 squelch=SQUELCH_DEFAULT):
         self._L = lib()
         cfg = Config(abi_version=ABI_VERSION, sample_rate=sample_rate, center_freq=center_freq,
                      squelch_threshold=squelch_threshold, extra_history_symbols=self.EXTRA_SYMBOLS,
                      mm_mode=mm_mode, search=search, device=device, max_slots_per_call=max_slots,
-                     keep_stages=int(keep_stages))
+                     keep_stages=int(keep_stages), squelch_mode=squelch)
         self._ctx = C.c_void_p()
         rc = self._L.btb200_create(C.byref(cfg), C.byref(self._ctx))
         if rc:

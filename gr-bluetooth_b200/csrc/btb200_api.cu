@@ -37,6 +37,16 @@ struct btb200_ctx {
   size_t x_cap = 0;          // samples
   c32 *d_phc = nullptr, *d_phn = nullptr;
   float *d_soft = nullptr;
+  float *d_dem = nullptr;
+  // lazy squelch (stateless): exact energies only for windows with hits
+  bool lazy = false;
+  c32 *d_NzL = nullptr;
+  int *d_groups = nullptr, *d_list = nullptr;
+  double *d_eon = nullptr, *d_eoff = nullptr;
+  int *h_groups = nullptr, *h_list = nullptr;
+  double *h_eon = nullptr, *h_eoff = nullptr;
+  size_t list_cap = 0, group_cap = 0;
+  DevBatch pendW{};
   // pinned host
   double *h_energy = nullptr, *h_noise = nullptr;
   int *h_pass = nullptr;
@@ -140,6 +150,25 @@ int setup(btb200_ctx *ctx)
   if ((rc = upload(ctx, &ctx->T.mmse, P.mmse))) return rc;
   if ((rc = upload(ctx, &ctx->T.atan_tab, P.atan_tab))) return rc;
   if ((rc = upload(ctx, &ctx->T.ac_lut, P.ac_lut))) return rc;
+  {
+    // channel-group-interleaved tap banks for the tiled FIR: [group][k][16], zero taps for padding channels
+    const int ng = (P.nch + 15) / 16;
+    std::vector<c32> tg((size_t)ng * P.Nc * 16, c32{0.0f, 0.0f});
+    for (int c = 0; c < P.nch; c++)
+      for (int k = 0; k < P.Nc; k++) {
+        const cf32 t = P.chan_rtaps[(size_t)c * P.Nc + k];
+        tg[((size_t)(c / 16) * P.Nc + k) * 16 + (c % 16)] = c32{t.re, t.im};
+      }
+    if ((rc = upload(ctx, &ctx->T.chan_tg, tg))) return rc;
+    tg.assign((size_t)ng * P.Nn * 16, c32{0.0f, 0.0f});
+    for (int c = 0; c < P.nch; c++)
+      for (int k = 0; k < P.Nn; k++) {
+        const cf32 t = P.noise_rtaps[(size_t)c * P.Nn + k];
+        tg[((size_t)(c / 16) * P.Nn + k) * 16 + (c % 16)] = c32{t.re, t.im};
+      }
+    if ((rc = upload(ctx, &ctx->T.noise_tg, tg))) return rc;
+    if (fir_setup(ctx->device) != 0) { ctx->last_error = "cannot opt in to large dynamic shared memory"; return BTB200_ERR_CUDA; }
+  }
   std::vector<uint8_t> hdr(4 * 256);
   for (int w = 0; w < 4; w++)
     for (int v = 0; v < 256; v++) hdr[w * 256 + v] = (uint8_t)le_hdr_dist((uint32_t)v, w);
@@ -152,18 +181,31 @@ int setup(btb200_ctx *ctx)
 
   const size_t B = ctx->max_slots;
   const size_t nch = P.nch;
+  const uint32_t sq = ctx->cfg.squelch_mode;    // 0 default (lazy), 1 eager, 2 lazy
+  ctx->lazy = G.stateless && sq != 1;
   ctx->x_cap = (B - 1) * (size_t)P.S + P.H;
   if ((rc = dev_alloc(ctx, &ctx->d_x, ctx->x_cap))) return rc;
   DevBatch &W = ctx->W;
   if ((rc = dev_alloc(ctx, &W.Y, ((B - 1) * P.grid_per_slot + P.n_ddc) * nch))) return rc;
-  if ((rc = dev_alloc(ctx, &W.Nz, B * P.n_noise * nch))) return rc;
+  if (!ctx->lazy) { if ((rc = dev_alloc(ctx, &W.Nz, B * P.n_noise * nch))) return rc; }
+  else {
+    ctx->group_cap = B * ((nch + LAZY_CG - 1) / LAZY_CG);
+    ctx->list_cap = B * nch;
+    if ((rc = dev_alloc(ctx, &ctx->d_NzL, ctx->group_cap * P.n_noise * LAZY_CG))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->d_groups, ctx->group_cap * (1 + LAZY_CG)))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->d_list, ctx->list_cap * 4))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->d_eon, ctx->list_cap))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->d_eoff, ctx->list_cap))) return rc;
+  }
   const size_t bp = G.stateless ? 1 : B;
   if ((rc = dev_alloc(ctx, &ctx->d_phc, bp * P.n_ddc * nch))) return rc;
   if ((rc = dev_alloc(ctx, &ctx->d_phn, bp * P.n_noise * nch))) return rc;
   if ((rc = dev_alloc(ctx, &W.energy, B * nch))) return rc;
   if ((rc = dev_alloc(ctx, &W.noise, B * nch))) return rc;
   if ((rc = dev_alloc(ctx, &W.pass, B * nch))) return rc;
-  if ((rc = dev_alloc(ctx, &W.dem, B * nch * G.n_dem_pad))) return rc;
+  // demod floats only travel through HBM in chained mode (separate demod kernel) or for debug taps
+  if (!G.stateless || ctx->cfg.keep_stages) { if ((rc = dev_alloc(ctx, &ctx->d_dem, B * nch * G.n_dem_pad))) return rc; }
+  W.dem = ctx->d_dem;
   if (ctx->cfg.keep_stages) { if ((rc = dev_alloc(ctx, &ctx->d_soft, B * nch * G.n_dem_pad))) return rc; }
   if ((rc = dev_alloc(ctx, &W.bits, B * nch * G.bw))) return rc;
   if ((rc = dev_alloc(ctx, &W.nsym, B * nch))) return rc;
@@ -187,6 +229,12 @@ int setup(btb200_ctx *ctx)
   CK(cudaMallocHost(&ctx->h_counts, 4 * sizeof(unsigned)));
   CK(cudaMallocHost(&ctx->h_hits, (size_t)kHitCap * sizeof(DevHit)));
   CK(cudaMallocHost(&ctx->h_arena, kArenaCap));
+  if (ctx->lazy) {
+    CK(cudaMallocHost(&ctx->h_groups, ctx->group_cap * (1 + LAZY_CG) * sizeof(int)));
+    CK(cudaMallocHost(&ctx->h_list, ctx->list_cap * 4 * sizeof(int)));
+    CK(cudaMallocHost(&ctx->h_eon, ctx->list_cap * sizeof(double)));
+    CK(cudaMallocHost(&ctx->h_eoff, ctx->list_cap * sizeof(double)));
+  }
   ctx->h_ph_cap = bp * (size_t)P.n_ddc * nch;
   CK(cudaMallocHost(&ctx->h_ph, ctx->h_ph_cap * sizeof(c32)));
 
@@ -207,7 +255,8 @@ void teardown(btb200_ctx *ctx)
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   for (void *p : ctx->allocs) cudaFree(p);
   for (void *p : {(void *)ctx->h_energy, (void *)ctx->h_noise, (void *)ctx->h_pass, (void *)ctx->h_counts,
-                  (void *)ctx->h_hits, (void *)ctx->h_arena, (void *)ctx->h_ph})
+                  (void *)ctx->h_hits, (void *)ctx->h_arena, (void *)ctx->h_ph, (void *)ctx->h_groups,
+                  (void *)ctx->h_list, (void *)ctx->h_eon, (void *)ctx->h_eoff})
     if (p) cudaFreeHost(p);
   for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -367,38 +416,51 @@ int btb200_submit(btb200_ctx *ctx, const float *iq, int iq_on_device, size_t n_s
   }
   CK(cudaMemsetAsync(W.hit_count, 0, 4 * sizeof(unsigned), s));
   CK(cudaEventRecord(ctx->ev[1], s));
-  launch_chan_fir(G, ctx->T, W, ctx->impl, s);
+  launch_chan_fir(G, ctx->T, W, ctx->impl, s); ctx->launches++;
   CK(cudaEventRecord(ctx->ev[2], s));
-  launch_noise_fir(G, ctx->T, W, ctx->impl, s);
-  CK(cudaEventRecord(ctx->ev[3], s));
-  launch_energy(G, ctx->T, W, G.stateless ? 1 : 0, s);
-  CK(cudaMemcpyAsync(ctx->h_energy, W.energy, nbc * sizeof(double), cudaMemcpyDeviceToHost, s));
-  CK(cudaMemcpyAsync(ctx->h_noise, W.noise, nbc * sizeof(double), cudaMemcpyDeviceToHost, s));
-  if (!G.stateless) {
-    // chained mode: the squelch decides which windows advance the shared M&M
-    // state, so it is settled with the reference's own libm arithmetic first
-    CK(cudaStreamSynchronize(s));
-    for (size_t i = 0; i < nbc; i++) {
-      const double snr = 10.0 * std::log10(ctx->h_energy[i] / ctx->h_noise[i]);
-      ctx->h_pass[i] = (snr >= P.squelch_db) ? 1 : 0;
+  if (ctx->lazy) {
+    // lazy squelch: every window is demodulated and searched; the squelch (and the snr
+    // ac() prints) is settled exactly, afterwards, for the windows that produced hits
+    CK(cudaEventRecord(ctx->ev[3], s));
+    launch_fill_pass(W, (int)nbc, 1, s); ctx->launches++;
+  } else {
+    launch_noise_fir(G, ctx->T, W, ctx->impl, s); ctx->launches++;
+    CK(cudaEventRecord(ctx->ev[3], s));
+    launch_energy(G, ctx->T, W, G.stateless ? 1 : 0, s); ctx->launches++;
+    CK(cudaMemcpyAsync(ctx->h_energy, W.energy, nbc * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(ctx->h_noise, W.noise, nbc * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (!G.stateless) {
+      // chained mode: the squelch decides which windows advance the shared M&M
+      // state, so it is settled with the reference's own libm arithmetic first
+      CK(cudaStreamSynchronize(s));
+      for (size_t i = 0; i < nbc; i++) {
+        const double snr = 10.0 * std::log10(ctx->h_energy[i] / ctx->h_noise[i]);
+        ctx->h_pass[i] = (snr >= P.squelch_db) ? 1 : 0;
+      }
+      CK(cudaMemcpyAsync(W.pass, ctx->h_pass, nbc * sizeof(int), cudaMemcpyHostToDevice, s));
     }
-    CK(cudaMemcpyAsync(W.pass, ctx->h_pass, nbc * sizeof(int), cudaMemcpyHostToDevice, s));
   }
   CK(cudaEventRecord(ctx->ev[4], s));
-  launch_demod(G, ctx->T, W, s);
-  launch_mm(G, ctx->T, W, s);
+  if (G.stateless && (ctx->impl != IMPL_BASELINE || !W.dem)) {
+    launch_dmm_stateless(G, ctx->T, W, s); ctx->launches++;
+  } else {
+    launch_demod(G, ctx->T, W, s);
+    launch_mm(G, ctx->T, W, s);
+    ctx->launches += 2;
+  }
   CK(cudaEventRecord(ctx->ev[5], s));
   launch_search(G, ctx->T, W, s);
   launch_gather(G, W, s);
+  ctx->launches += 2;
   CK(cudaEventRecord(ctx->ev[6], s));
   CK(cudaMemcpyAsync(ctx->h_counts, W.hit_count, 4 * sizeof(unsigned), cudaMemcpyDeviceToHost, s));
   if (!G.stateless) CK(cudaMemcpyAsync(&ctx->mm, W.mm_state, sizeof(MmState), cudaMemcpyDeviceToHost, s));
   CK(cudaEventRecord(ctx->ev[7], s));
   CK(cudaGetLastError());
-  ctx->launches += kernel_launches_per_batch();
   ctx->pending = true;
   ctx->pend_slots = n_slots;
   ctx->pend_first_slot = first_slot;
+  ctx->pendW = W;
   return BTB200_OK;
 }
 
@@ -418,6 +480,46 @@ int btb200_collect(btb200_ctx *ctx, btb200_hits *out)
   if (used > kArenaCap) used = kArenaCap;
   if (nh) CK(cudaMemcpyAsync(ctx->h_hits, ctx->W.hits, (size_t)nh * sizeof(DevHit), cudaMemcpyDeviceToHost, s));
   if (used && out && out->symbols) CK(cudaMemcpyAsync(ctx->h_arena, ctx->W.arena, used, cudaMemcpyDeviceToHost, s));
+  if (ctx->lazy) {
+    const size_t nbc = (size_t)ctx->pend_slots * P.nch;
+    for (size_t i = 0; i < nbc; i++) ctx->h_energy[i] = ctx->h_noise[i] = std::nan("");
+    if (nh) {
+      CK(cudaStreamSynchronize(s));
+      // unique hit windows, in (slot, channel) order
+      std::vector<uint32_t> keys(nh);
+      for (unsigned i = 0; i < nh; i++) keys[i] = (uint32_t)ctx->h_hits[i].b * (uint32_t)P.nch + (uint32_t)ctx->h_hits[i].chi;
+      std::sort(keys.begin(), keys.end());
+      keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
+      int ng = 0, nl = 0;
+      int cur_b = -1, fill = LAZY_CG;
+      for (uint32_t k : keys) {
+        const int b = (int)(k / P.nch), c = (int)(k % P.nch);
+        if (b != cur_b || fill == LAZY_CG) {
+          int *g = ctx->h_groups + (size_t)ng * (1 + LAZY_CG);
+          g[0] = b;
+          for (int i = 0; i < LAZY_CG; i++) g[1 + i] = -1;
+          ng++; fill = 0; cur_b = b;
+        }
+        ctx->h_groups[(size_t)(ng - 1) * (1 + LAZY_CG) + 1 + fill] = c;
+        int *l = ctx->h_list + (size_t)nl * 4;
+        l[0] = b; l[1] = c; l[2] = ng - 1; l[3] = fill;
+        nl++; fill++;
+      }
+      CK(cudaMemcpyAsync(ctx->d_groups, ctx->h_groups, (size_t)ng * (1 + LAZY_CG) * sizeof(int), cudaMemcpyHostToDevice, s));
+      CK(cudaMemcpyAsync(ctx->d_list, ctx->h_list, (size_t)nl * 4 * sizeof(int), cudaMemcpyHostToDevice, s));
+      launch_noise_fir_list(ctx->G, ctx->T, ctx->pendW, ctx->d_groups, ng, ctx->d_NzL, s);
+      launch_energy_list(ctx->G, ctx->pendW, ctx->d_list, nl, ctx->d_NzL, ctx->d_eon, ctx->d_eoff, s);
+      ctx->launches += 2;
+      CK(cudaMemcpyAsync(ctx->h_eon, ctx->d_eon, (size_t)nl * sizeof(double), cudaMemcpyDeviceToHost, s));
+      CK(cudaMemcpyAsync(ctx->h_eoff, ctx->d_eoff, (size_t)nl * sizeof(double), cudaMemcpyDeviceToHost, s));
+      CK(cudaStreamSynchronize(s));
+      for (int l = 0; l < nl; l++) {
+        const size_t bc = (size_t)ctx->h_list[(size_t)l * 4] * P.nch + ctx->h_list[(size_t)l * 4 + 1];
+        ctx->h_energy[bc] = ctx->h_eon[l];
+        ctx->h_noise[bc] = ctx->h_eoff[l];
+      }
+    }
+  }
   CK(cudaEventRecord(ctx->ev[8], s));
   CK(cudaStreamSynchronize(s));
   ctx->last_slots = ctx->pend_slots;
@@ -568,7 +670,9 @@ int64_t btb200_get_stage(btb200_ctx *ctx, int stage, uint32_t b, uint32_t chi, v
       for (int i = 0; i < P.n_ddc; i++) o[i] = crot(y[i], ph[i]);
       return (int64_t)P.n_ddc * 8;
     }
-    case BTB200_STAGE_DEMOD: return dev_copy(ctx->W.dem + bc * G.n_dem_pad, (size_t)P.n_dem * 4);
+    case BTB200_STAGE_DEMOD:
+      if (!ctx->d_dem) return BTB200_ERR_ARG;
+      return dev_copy(ctx->d_dem + bc * G.n_dem_pad, (size_t)P.n_dem * 4);
     case BTB200_STAGE_SOFT: {
       if (!ctx->d_soft) return BTB200_ERR_ARG;
       int nsym = 0;

@@ -8,6 +8,8 @@ namespace btb200 {
 struct DevTables {
   const c32 *chan_rtaps;     // [nch][Nc]
   const c32 *noise_rtaps;    // [nch][Nn]
+  const c32 *chan_tg;        // [ngroups][Nc][16]  channel-group-interleaved taps for the tiled FIR
+  const c32 *noise_tg;       // [ngroups][Nn][16]
   const float *mmse;         // [129*8]
   const float *atan_tab;     // [257]
   const uint64_t *ac_lut;    // [769]
@@ -48,6 +50,14 @@ void launch_demod(const Geom &G, const DevTables &T, const DevBatch &W, cudaStre
 void launch_mm(const Geom &G, const DevTables &T, const DevBatch &W, cudaStream_t s);
 void launch_search(const Geom &G, const DevTables &T, const DevBatch &W, cudaStream_t s);
 void launch_gather(const Geom &G, const DevBatch &W, cudaStream_t s);
-int  kernel_launches_per_batch();
+void launch_dmm_stateless(const Geom &G, const DevTables &T, const DevBatch &W, cudaStream_t s);
+void launch_fill_pass(const DevBatch &W, int n, int v, cudaStream_t s);
+// lazy squelch: noise FIR for listed (slot, <=LAZY_CG channels) groups, then exact energies of listed windows
+constexpr int LAZY_CG = 4;
+void launch_noise_fir_list(const Geom &G, const DevTables &T, const DevBatch &W, const int *groups, int n_groups,
+                           c32 *NzL, cudaStream_t s);
+void launch_energy_list(const Geom &G, const DevBatch &W, const int *list4, int n_list, const c32 *NzL,
+                        double *e_on, double *e_off, cudaStream_t s);
+int  fir_setup(int device);   // opt in to large dynamic shared memory
 
 }  // namespace btb200

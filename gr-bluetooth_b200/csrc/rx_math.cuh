@@ -19,7 +19,7 @@
 
 namespace btb200 {
 
-struct c32 { float re, im; };
+struct alignas(8) c32 { float re, im; };
 
 // x * t accumulated the way std::complex<float> does it with contraction off:
 // (a*c - b*d, a*d + b*c), then acc += product.     [gr_arith.h: gra_dot_cc]

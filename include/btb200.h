@@ -78,6 +78,18 @@ enum {
   BTB200_MM_STATELESS = 1
 };
 
+/* when the SNR squelch (lib/multi_block.cc:253-296) is evaluated in stateless mode */
+enum {
+  BTB200_SQUELCH_DEFAULT = 0,    /* lazy */
+  /* eager: noise DDC + energies for every channel-window before demodulation, like the reference */
+  BTB200_SQUELCH_EAGER   = 1,
+  /* lazy: every window is demodulated and searched (no state is shared between windows, so a
+   * squelched window cannot influence another); the exact squelch arithmetic -- 20001-tap noise
+   * DDC at 100 Msps -- runs only for windows that produced a hit, and hits from windows the
+   * reference would have squelched are dropped.  Same hit list, bit for bit. */
+  BTB200_SQUELCH_LAZY    = 2
+};
+
 enum {
   BTB200_SEARCH_BR = 1,          /* classic_packet::sniff_ac */
   BTB200_SEARCH_LE = 2           /* le_packet::sniff_aa */
@@ -100,7 +112,8 @@ typedef struct {
   int32_t  device;               /* CUDA device ordinal */
   uint32_t max_slots_per_call;   /* sizes device buffers; 0 = default */
   uint32_t keep_stages;          /* 1: keep demod/soft-symbol buffers for btb200_get_stage */
-  uint32_t reserved[5];
+  uint32_t squelch_mode;         /* BTB200_SQUELCH_* (stateless mode only; chained is always eager) */
+  uint32_t reserved[4];
 } btb200_config;
 
 /* derived constants (lib/multi_block.cc:56-119, 299-342) */

@@ -204,8 +204,9 @@ int setup(btb200_ctx *ctx)
   if ((rc = dev_alloc(ctx, &W.noise, B * nch))) return rc;
   if ((rc = dev_alloc(ctx, &W.pass, B * nch))) return rc;
   // demod floats only travel through HBM in chained mode (separate demod kernel) or for debug taps
-  if (!G.stateless || ctx->cfg.keep_stages) { if ((rc = dev_alloc(ctx, &ctx->d_dem, B * nch * G.n_dem_pad))) return rc; }
-  W.dem = ctx->d_dem;
+  // demod floats: [b][c][i] rows in chained mode (separate kernels), transposed [b][i][c] in stateless mode
+  if ((rc = dev_alloc(ctx, &ctx->d_dem, B * nch * G.n_dem_pad))) return rc;
+  W.dem = G.stateless ? nullptr : ctx->d_dem;
   if (ctx->cfg.keep_stages) { if ((rc = dev_alloc(ctx, &ctx->d_soft, B * nch * G.n_dem_pad))) return rc; }
   if ((rc = dev_alloc(ctx, &W.bits, B * nch * G.bw))) return rc;
   if ((rc = dev_alloc(ctx, &W.nsym, B * nch))) return rc;
@@ -441,15 +442,18 @@ int btb200_submit(btb200_ctx *ctx, const float *iq, int iq_on_device, size_t n_s
     }
   }
   CK(cudaEventRecord(ctx->ev[4], s));
-  if (G.stateless && (ctx->impl != IMPL_BASELINE || !W.dem)) {
-    launch_dmm_stateless(G, ctx->T, W, s); ctx->launches++;
+  if (G.stateless && ctx->impl == IMPL_TILED_SCALAR) {
+    launch_dmm_stateless(G, ctx->T, W, s); ctx->launches++;       // fused demod+M&M variant
+  } else if (G.stateless) {
+    launch_demod_mm_v2(G, ctx->T, W, ctx->d_dem, s); ctx->launches += 2;
   } else {
     launch_demod(G, ctx->T, W, s);
     launch_mm(G, ctx->T, W, s);
     ctx->launches += 2;
   }
   CK(cudaEventRecord(ctx->ev[5], s));
-  launch_search(G, ctx->T, W, s);
+  if (ctx->impl == IMPL_BASELINE) launch_search(G, ctx->T, W, s);
+  else launch_search_warp(G, ctx->T, W, s);
   launch_gather(G, W, s);
   ctx->launches += 2;
   CK(cudaEventRecord(ctx->ev[6], s));
@@ -671,7 +675,13 @@ int64_t btb200_get_stage(btb200_ctx *ctx, int stage, uint32_t b, uint32_t chi, v
       return (int64_t)P.n_ddc * 8;
     }
     case BTB200_STAGE_DEMOD:
-      if (!ctx->d_dem) return BTB200_ERR_ARG;
+      if (!ctx->d_dem || ctx->impl == IMPL_TILED_SCALAR) return BTB200_ERR_ARG;
+      if (G.stateless) {          // transposed [b][i][c]
+        if ((size_t)P.n_dem * 4 > cap) return BTB200_ERR_ARG;
+        if (cudaMemcpy2D(dst, 4, ctx->d_dem + ((size_t)b * G.n_dem_pad) * P.nch + chi, (size_t)P.nch * 4, 4, P.n_dem,
+                         cudaMemcpyDeviceToHost) != cudaSuccess) return BTB200_ERR_CUDA;
+        return (int64_t)P.n_dem * 4;
+      }
       return dev_copy(ctx->d_dem + bc * G.n_dem_pad, (size_t)P.n_dem * 4);
     case BTB200_STAGE_SOFT: {
       if (!ctx->d_soft) return BTB200_ERR_ARG;

@@ -239,6 +239,112 @@ __global__ void __launch_bounds__(W * 32, (CG == 16) ? 1 : 2) k_fir_tiled(FirJob
   }
 }
 
+// ===========================================================================
+// Packed-FP32 variant of the tiled FIR (Blackwell FMUL2/FADD2: two fp32 lanes per
+// instruction).  tools/ubench_f32x2.cu measures the 2-register-operand packed forms
+// (mul.rn.f32x2, add/sub.rn.f32x2) at the full issue rate on B200, i.e. twice the
+// scalar FMUL/FADD throughput, while each half still rounds exactly like the
+// scalar instruction -- so the oracle's one-rounding-per-operation order is kept.
+//
+// A thread pairs output r with output r+R/2: the staged input entry e holds
+// (re[e], re[e+DELTA], im[e], im[e+DELTA]) with DELTA = the sample distance between
+// the two outputs, so ONE LDS.128 feeds both; the tap entry is (c, c, d, d).
+//   RE pair: (a*c) - (b*d)   IM pair: (a*d) + (b*c)   then acc += ...   = 8 packed
+// instructions per 2 complex MACs (scalar: 16).
+// ===========================================================================
+typedef unsigned long long u64;
+// NOTE on ptxas 12.9: it contracts mul.rn.f32x2 feeding add/sub.rn.f32x2 into one FFMA2 even
+// though the operations carry an explicit .rn (it does not do that for scalar mul.rn/add.rn).
+// That would change the rounding.  A product must therefore never be the direct operand of a
+// packed add/sub: "x - p" is written fma(p, -1, x) (exact: p*(-1) is exact, one rounding),
+// which ptxas keeps as FFMA2 with an immediate and cannot merge with the FMUL2 that made p.
+// The SASS is checked for this in tests/test_build.py.
+__device__ __forceinline__ u64 pk_mul(u64 a, u64 b) { u64 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ u64 pk_add(u64 a, u64 b) { u64 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+// x - p, p a product
+__device__ __forceinline__ u64 pk_xsubp(u64 x, u64 p)
+{ u64 d; asm("{.reg .b64 m1; mov.b64 m1, 0xbf800000bf800000; fma.rn.f32x2 %0, %2, m1, %1;}" : "=l"(d) : "l"(x), "l"(p)); return d; }
+__device__ __forceinline__ u64 pk_neg(u64 a) { return a ^ 0x8000000080000000ull; }
+__device__ __forceinline__ float pk_lo(u64 v) { return __uint_as_float((unsigned)(v & 0xffffffffull)); }
+__device__ __forceinline__ float pk_hi(u64 v) { return __uint_as_float((unsigned)(v >> 32)); }
+
+template <int R, int W>
+__global__ void __launch_bounds__(W * 32, 1) k_fir_packed(FirJob J)
+{
+  constexpr int CG = 16, NH = 2, TJ = NH * R * W, RP = R / 2;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float4 *ts = reinterpret_cast<float4 *>(smem_raw);     // [KT][16]  (c, c, d, d)
+  float4 *xs = ts + (size_t)J.KT * CG;                   // [HS]      (re[e], re[e+DELTA], im[e], im[e+DELTA])
+  long s0;
+  int nj;
+  c32 *outp;
+  if (J.mode == 0) {
+    const long g0 = (long)blockIdx.x * TJ;
+    const long left = J.Gtot - g0;
+    nj = left < TJ ? (int)left : TJ;
+    s0 = J.fcs + g0 * J.D;
+    outp = J.out + g0 * J.nch;
+  } else {
+    const int b = blockIdx.x / J.tiles_per_slot, jt = blockIdx.x - b * J.tiles_per_slot;
+    const int j0 = jt * TJ;
+    nj = (J.n_noise - j0) < TJ ? (J.n_noise - j0) : TJ;
+    s0 = (long)b * J.S + J.fns + (long)j0 * J.D;
+    outp = J.out + ((long)b * J.n_noise + j0) * J.nch;
+  }
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, cg = lane & 15, h = lane >> 4;
+  const int jj0 = NH * w + h;
+  const int rstride = NH * W * J.D;            // samples between consecutive outputs of a thread
+  const int delta = RP * rstride;              // samples between the two outputs of a pair
+  const int hs_base = (RP * NH * W - 1) * J.D; // entries = hs_base + kt
+  u64 are[RP], aim[RP];
+#pragma unroll
+  for (int r = 0; r < RP; r++) { are[r] = 0ull; aim[r] = 0ull; }
+  for (int k0 = 0; k0 < J.N; k0 += J.KT) {
+    const int kt = (J.N - k0) < J.KT ? (J.N - k0) : J.KT;
+    __syncthreads();
+    const c32 *tg = J.taps + ((size_t)blockIdx.y * J.N + k0) * CG;
+    for (int i = threadIdx.x; i < kt * CG; i += W * 32) { const c32 t = tg[i]; ts[i] = make_float4(t.re, t.re, t.im, t.im); }
+    const int hs = hs_base + kt;
+    const long base = s0 + k0;
+    for (int i = threadIdx.x; i < hs; i += W * 32) {
+      const long n0 = base + i, n1 = n0 + delta;
+      const c32 v0 = (n0 < J.n_x) ? J.x[n0] : c32{0.0f, 0.0f};
+      const c32 v1 = (n1 < J.n_x) ? J.x[n1] : c32{0.0f, 0.0f};
+      xs[i] = make_float4(v0.re, v1.re, v0.im, v1.im);
+    }
+    __syncthreads();
+    const float4 *xp = xs + jj0 * J.D;
+    const float4 *tp = ts + cg;
+#pragma unroll 4
+    for (int k = 0; k < kt; k++) {
+      const ulonglong2 T = *reinterpret_cast<const ulonglong2 *>(tp + k * CG);     // .x = (c,c)  .y = (d,d)
+      const u64 ncc = pk_neg(T.x);                                                   // (-c,-c), exact
+#pragma unroll
+      for (int r = 0; r < RP; r++) {
+        const ulonglong2 V = *reinterpret_cast<const ulonglong2 *>(xp + r * rstride + k);   // .x = (a,a')  .y = (b,b')
+        const u64 pr = pk_xsubp(pk_mul(V.x, T.x), pk_mul(V.y, T.y));  // a*c - b*d
+        const u64 pi = pk_xsubp(pk_mul(V.x, T.y), pk_mul(V.y, ncc));  // a*d - (b*(-c)) = a*d + b*c, same roundings
+        are[r] = pk_add(are[r], pr);
+        aim[r] = pk_add(aim[r], pi);
+      }
+    }
+  }
+  const int c = (int)blockIdx.y * CG + cg;
+  if (c < J.nch) {
+#pragma unroll
+    for (int r = 0; r < RP; r++) {
+      const int ja = jj0 + r * NH * W, jb = ja + RP * NH * W;
+      if (ja < nj) outp[(long)ja * J.nch + c] = c32{pk_lo(are[r]), pk_lo(aim[r])};
+      if (jb < nj) outp[(long)jb * J.nch + c] = c32{pk_hi(are[r]), pk_hi(aim[r])};
+    }
+  }
+}
+
+static size_t fir_packed_smem(int R, int W, int D, int KT) { return ((size_t)KT * 16 + (size_t)((R / 2) * 2 * W - 1) * D + KT) * sizeof(float4); }
+
+template <int BLK>
+__global__ void k_dmm_stateless(Geom G, DevBatch W, const float *__restrict__ mmse_g, const float *__restrict__ atan_g);
+
 static size_t fir_smem(int CG, int R, int W, int D, int KT) { return ((size_t)KT * CG + (size_t)((32 / CG) * R * W - 1) * D + KT) * sizeof(c32); }
 static int g_max_smem = 48 * 1024;
 
@@ -247,9 +353,17 @@ int fir_setup(int device)
   int v = 0;
   if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, device) != cudaSuccess) return -1;
   g_max_smem = v;
-  if (cudaFuncSetAttribute(k_fir_tiled<16, 8, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, v) != cudaSuccess) return -1;
-  if (cudaFuncSetAttribute(k_fir_tiled<16, 8, 14>, cudaFuncAttributeMaxDynamicSharedMemorySize, v) != cudaSuccess) return -1;
-  if (cudaFuncSetAttribute(k_fir_tiled<4, 8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, v) != cudaSuccess) return -1;
+  auto opt_in = [&](const void *fn) {
+    cudaFuncAttributes fa{};
+    if (cudaFuncGetAttributes(&fa, fn) != cudaSuccess) return false;
+    return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, v - (int)fa.sharedSizeBytes) == cudaSuccess;
+  };
+  if (!opt_in((const void *)k_fir_tiled<16, 8, 16>)) return -1;
+  if (!opt_in((const void *)k_fir_tiled<16, 8, 14>)) return -1;
+  if (!opt_in((const void *)k_fir_tiled<4, 8, 4>)) return -1;
+  if (!opt_in((const void *)k_dmm_stateless<64>)) return -1;
+  if (!opt_in((const void *)k_fir_packed<8, 16>)) return -1;
+  if (!opt_in((const void *)k_fir_packed<8, 14>)) return -1;
   return 0;
 }
 
@@ -257,7 +371,7 @@ int fir_setup(int device)
 static int pick_kt(int CG, int R, int W, int D, int N, int blocks_per_sm)
 {
   int kt = (N + 31) & ~31;
-  const size_t budget = (size_t)(g_max_smem + 1024) / blocks_per_sm - 2048;
+  const size_t budget = (size_t)(g_max_smem + 1024) / blocks_per_sm - 2048;   // 1 KB/block reserved + static
   while (kt > 32 && fir_smem(CG, R, W, D, kt) > budget) kt -= 32;
   return kt;
 }
@@ -270,13 +384,32 @@ static int pick_kt(int CG, int R, int W, int D, int N, int blocks_per_sm)
 // ever looks 8 samples ahead), so the demod floats never travel through HBM.
 // Same arithmetic, in the same order, as window_demod_point + window_mm.
 // ===========================================================================
+// Y rows and rotator phases are prefetched into per-thread shared-memory rings with
+// cp.async (LDGSTS), PFD rows ahead of the clock-recovery position: the loop is a serial
+// dependency chain per window, so without the prefetch every step would expose a DRAM
+// round trip (Y does not fit in L2).
+__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc)
+{
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
 template <int BLK>
 __global__ void __launch_bounds__(BLK) k_dmm_stateless(Geom G, DevBatch W, const float *__restrict__ mmse_g,
                                                        const float *__restrict__ atan_g)
 {
-  __shared__ float s_mmse[129 * 8];
-  __shared__ float s_atan[257];
-  __shared__ float ring[16][BLK];
+  constexpr int RD = 64;          // ring depth (rows)
+  constexpr int PFD = 48;         // prefetch distance (rows) beyond the 8-sample interpolator window
+  constexpr int LAG = 6;          // cp.async groups allowed in flight (advance <= 4 rows/step -> PFD/4 >= LAG)
+  extern __shared__ __align__(16) unsigned char dmm_smem[];
+  c32 (*ry)[BLK] = reinterpret_cast<c32 (*)[BLK]>(dmm_smem);                         // [RD][BLK]
+  c32 (*rp)[BLK] = reinterpret_cast<c32 (*)[BLK]>(dmm_smem + sizeof(c32) * RD * BLK);
+  float (*ring)[BLK] = reinterpret_cast<float (*)[BLK]>(dmm_smem + 2 * sizeof(c32) * RD * BLK);   // [16][BLK]
+  float *s_mmse = reinterpret_cast<float *>(dmm_smem + 2 * sizeof(c32) * RD * BLK + sizeof(float) * 16 * BLK);
+  float *s_atan = s_mmse + 129 * 8;
   for (int i = threadIdx.x; i < 129 * 8; i += BLK) s_mmse[i] = mmse_g[i];
   for (int i = threadIdx.x; i < 257; i += BLK) s_atan[i] = atan_g[i];
   __syncthreads();
@@ -293,23 +426,30 @@ __global__ void __launch_bounds__(BLK) k_dmm_stateless(Geom G, DevBatch W, const
   unsigned ii = 0;
   int oo = 0;
   const unsigned ni = (unsigned)(G.n_dem - 8);
-  int pnext = 0;                 // demod indices [pnext-16, pnext) live in the ring
-  int prev_idx = -1;
+  int pnext = 0;                 // demod indices [pnext-16, pnext) live in the demod ring
+  int pf = 0;                    // rows [pf-RD, pf) are in (or on their way to) the Y/phase rings
   c32 zprev{0.0f, 0.0f};
   uint32_t word = 0;
   const int tid = threadIdx.x;
+  bool first = true;
   while (oo < G.n_dem && ii < ni) {
-    if ((int)ii < pnext - 16) { pnext = (int)ii; prev_idx = -1; }       // stepped far backwards: refill
+    // 1. keep the prefetch PFD rows ahead (row d feeds demod d and d+1)
+    int want = (int)ii + 8 + PFD;
+    if (want > G.n_ddc) want = G.n_ddc;
+    for (; pf < want; pf++) {
+      cp_async8(&ry[pf & (RD - 1)][tid], y + (long)pf * G.nch);
+      cp_async8(&rp[pf & (RD - 1)][tid], p + (long)pf * G.nch);
+    }
+    cp_async_commit();
+    if (first) { cp_async_wait<0>(); first = false; } else cp_async_wait<LAG>();
+    // 2. demod values up to ii+7 (a backward step of the loop never exceeds the 16-deep ring:
+    //    mu + omega + gain_mu*mm_val >= -1 for |demod| <= gain*pi)
     while (pnext < (int)ii + 8) {
       const int d = pnext;
       float val = 0.0f;                                                 // demod_out[0] is never written
-      if (d > 0) {
-        const c32 zc = crot(y[(long)d * G.nch], p[(long)d * G.nch]);
-        if (prev_idx != d - 1) zprev = crot(y[(long)(d - 1) * G.nch], p[(long)(d - 1) * G.nch]);
-        val = demod_point(s_atan, G.demod_gain, zc, zprev);
-        zprev = zc;
-        prev_idx = d;
-      }
+      const c32 zc = crot(ry[d & (RD - 1)][tid], rp[d & (RD - 1)][tid]);
+      if (d > 0) val = demod_point(s_atan, G.demod_gain, zc, zprev);
+      zprev = zc;
       ring[d & 15][tid] = val;
       if (dem_row) dem_row[d] = val;
       pnext++;
@@ -324,9 +464,212 @@ __global__ void __launch_bounds__(BLK) k_dmm_stateless(Geom G, DevBatch W, const
     ii += (unsigned)mm_update(G.mm, st, out);
     oo++;
   }
+  cp_async_wait<0>();
   if (oo & 31) bits_row[oo >> 5] = word;
   for (int w = (oo + 31) >> 5; w < G.bw; w++) bits_row[w] = 0;
   W.nsym[idx] = oo;
+}
+
+// ===========================================================================
+// Stateless pipeline, second generation: demod of every window in parallel (transposed
+// [b][i][c] so that clock recovery reads channel-contiguous rows), then one thread per
+// window for the inherently serial Mueller & Mueller chain with a cp.async ring on the
+// demod floats, then a warp per window for the access-code search.
+// ===========================================================================
+__global__ void k_demod_all(Geom G, DevBatch W, const float *__restrict__ atan_g, float *__restrict__ demT)
+{
+  __shared__ float s_atan[257];
+  for (int i = threadIdx.x; i < 257; i += blockDim.x) s_atan[i] = atan_g[i];
+  __syncthreads();
+  const int b = blockIdx.y;
+  const long e = (long)blockIdx.x * blockDim.x + threadIdx.x;        // i*nch + c
+  if (e >= (long)G.n_dem * G.nch) return;
+  const int i = (int)(e / G.nch), c = (int)(e - (long)i * G.nch);
+  if (!W.pass[b * G.nch + c]) return;
+  float val = 0.0f;
+  if (i > 0) {
+    const c32 *y = W.Y + ((long)b * G.gps) * G.nch;
+    const c32 *p = W.phc + (long)(b * W.bp_stride) * G.n_ddc * G.nch;
+    const c32 cur = crot(y[e], p[e]);
+    const c32 prev = crot(y[e - G.nch], p[e - G.nch]);
+    val = demod_point(s_atan, G.demod_gain, cur, prev);
+  }
+  demT[((long)b * G.n_dem_pad) * G.nch + e] = val;
+}
+
+__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gsrc)
+{
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(gsrc));
+}
+
+template <int BLK>
+__global__ void __launch_bounds__(BLK) k_mm_stateless_v2(Geom G, DevBatch W, const float *__restrict__ mmse_g,
+                                                         const float *__restrict__ demT)
+{
+  constexpr int RD = 128;          // ring depth (demod samples)
+  constexpr int BURST = 16;        // samples fetched per refill
+  constexpr int MINAHEAD = 48;     // refill when fewer than this many samples are in flight ahead of ii+8
+  __shared__ float ring[RD][BLK];
+  __shared__ float s_mmse[8][132]; // transposed, padded: lanes with different imu hit different banks
+  for (int i = threadIdx.x; i < 129 * 8; i += BLK) s_mmse[7 - (i & 7)][i >> 3] = mmse_g[i];   // [k][imu] = taps[imu][7-k]
+  __syncthreads();
+  const int idx = blockIdx.x * BLK + threadIdx.x;
+  if (idx >= W.B * G.nch) return;
+  if (!W.pass[idx]) { W.nsym[idx] = 0; return; }
+  const int b = idx / G.nch, c = idx - b * G.nch;
+  const float *__restrict__ dem = demT + ((long)b * G.n_dem_pad) * G.nch + c;    // dem[i*nch]
+  uint32_t *__restrict__ bits_row = W.bits + (long)idx * G.bw;
+  float *soft_row = W.soft ? W.soft + (long)idx * G.n_dem_pad : nullptr;
+  MmState st{G.mu0, G.mm.omega_mid, 0.0f};
+  unsigned ii = 0;
+  int oo = 0;
+  const unsigned ni = (unsigned)(G.n_dem - 8);
+  int pf = 0;                      // samples [pf-RD, pf) are in (or on their way to) the ring
+  uint32_t word = 0;
+  const int tid = threadIdx.x;
+  // prime the ring
+  for (; pf < 8 + MINAHEAD + BURST && pf < G.n_dem; pf++) cp_async4(&ring[pf & (RD - 1)][tid], dem + (long)pf * G.nch);
+  cp_async_commit();
+  cp_async_wait<0>();
+  while (oo < G.n_dem && ii < ni) {
+    if (pf < (int)ii + 8 + MINAHEAD) {
+#pragma unroll
+      for (int j = 0; j < BURST; j++) {
+        const int q = pf + j;
+        if (q < G.n_dem) cp_async4(&ring[q & (RD - 1)][tid], dem + (long)q * G.nch);
+      }
+      pf += BURST;
+    }
+    cp_async_commit();
+    cp_async_wait<4>();            // a burst lands >= MINAHEAD/5 > 4 steps before it is consumed
+#if defined(__CUDA_ARCH__)
+    int imu = __float2int_rn(st.mu * 128.0f);
+#else
+    int imu = 0;
+#endif
+    imu = imu < 0 ? 0 : (imu > 128 ? 128 : imu);
+    float out = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 8; k++) out = out + ring[(ii + k) & (RD - 1)][tid] * s_mmse[k][imu];
+    if (soft_row) soft_row[oo] = out;
+    if (!(out < 0)) word |= 1u << (oo & 31);
+    if ((oo & 31) == 31) { bits_row[oo >> 5] = word; word = 0; }
+    ii += (unsigned)mm_update(G.mm, st, out);
+    oo++;
+  }
+  cp_async_wait<0>();
+  if (oo & 31) bits_row[oo >> 5] = word;
+  for (int w = (oo + 31) >> 5; w < G.bw; w++) bits_row[w] = 0;
+  W.nsym[idx] = oo;
+}
+
+// Access-code search, one warp per channel-window (lib/multi_sniffer_impl.cc:107-148 +
+// lib/packet_impl.cc:247-268, 471-510, 1452-1527): the 32 lanes test 32 consecutive lags of
+// the packed symbol row (64-bit sliding window, preamble/Barker gate, affine sync-word LUT,
+// popcount threshold), warp ballots collect one flag per lag, then the first-hit / skip
+// rule of the reference is replayed on the flag words.
+__global__ void k_search_warp(Geom G, DevTables T, DevBatch W)
+{
+  const int idx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (idx >= W.B * G.nch) return;
+  const int nsym = W.nsym[idx];
+  if (nsym <= 0) return;
+  const int b = idx / G.nch, c = idx - b * G.nch;
+  const uint32_t *__restrict__ row = W.bits + (long)idx * G.bw;
+  const uint32_t wl = row[lane < G.bw ? lane : 0];           // words 0..31 cover lags 0..(625+72)
+  const int le_idx = T.le_index[c];
+  const uint32_t le_white = T.le_white[c];
+  uint32_t br_mask = 0, le_mask = 0;                         // lane q keeps the flags of lags 32q..32q+31
+  for (int q = 0; q < 20; q++) {
+    const uint32_t w0 = __shfl_sync(0xffffffffu, wl, q), w1 = __shfl_sync(0xffffffffu, wl, q + 1);
+    const uint32_t w2 = __shfl_sync(0xffffffffu, wl, q + 2), w3 = __shfl_sync(0xffffffffu, wl, q + 3);
+    const uint64_t a = w0 | ((uint64_t)w1 << 32), bb = w2 | ((uint64_t)w3 << 32);
+    const uint64_t lo = lane ? (a >> lane) | (bb << (64 - lane)) : a;
+    const uint32_t hi = (uint32_t)(bb >> lane) & 0xff;
+    const int lag = 32 * q + lane;
+    uint32_t lap;
+    const bool fb = (G.search & 1) && lag < 625 && br_lag_test(T.ac_lut, lo, hi, &lap);
+    const bool fl = (G.search & 2) && le_idx >= 0 && lag < 625 && le_lag_test(T.le_hdr_lut, lo, le_white, le_idx >= 37);
+    const uint32_t mb = __ballot_sync(0xffffffffu, fb), ml = __ballot_sync(0xffffffffu, fl);
+    if (lane == q) { br_mask = mb; le_mask = ml; }
+  }
+  // replay of the search loops (warp-uniform control flow; lane 0 emits)
+  HitEmitter em{G, W, b, c, nsym};
+  int len = nsym;
+  if (G.search & 1) {
+    const int limit0 = (len - 68 < 625) ? len - 68 : 625;
+    int start = 0;
+    while (limit0 - start >= 0) {
+      int found = -1;
+      for (int wi = start >> 5; wi < 20 && found < 0; wi++) {
+        uint32_t m = __shfl_sync(0xffffffffu, br_mask, wi);
+        if (wi == (start >> 5)) m &= ~0u << (start & 31);
+        if (m) found = wi * 32 + __ffs(m) - 1;
+      }
+      if (found < 0 || found >= limit0) break;
+      if (lane == 0) {
+        uint64_t lo; uint32_t hi;
+        bits_window(row, found, &lo, &hi);
+        em(0, found, nsym - found, (uint32_t)(lo >> 38) & 0xffffff);
+      }
+      start = found + 68;
+    }
+    len = nsym - start;
+  }
+  if ((G.search & 2) && le_idx >= 0) {
+    const int limit0 = (len - 68 < 625) ? len - 68 : 625;
+    const int len_le = len;
+    int start = 0;
+    while (limit0 - start >= 0) {
+      int found = -1;
+      for (int wi = start >> 5; wi < 20 && found < 0; wi++) {
+        uint32_t m = __shfl_sync(0xffffffffu, le_mask, wi);
+        if (wi == (start >> 5)) m &= ~0u << (start & 31);
+        if (m) found = wi * 32 + __ffs(m) - 1;
+      }
+      if (found < 0 || found >= limit0) break;
+      if (lane == 0) {
+        uint64_t lo; uint32_t hi;
+        bits_window(row, found, &lo, &hi);
+        em(1, found, len_le - found, (uint32_t)(lo >> 8));
+      }
+      start = found + 40;
+    }
+  }
+}
+
+// Exact energies of LISTED channel-windows (lazy squelch), one warp per window: the 32 lanes
+// rotate and square 32 consecutive outputs, the fp64 sum is then taken strictly in index
+// order (every lane carries the same chain) -- bit-identical to window_energy().
+__global__ void k_energy_list_warp(Geom G, DevBatch W, const int4 *__restrict__ list, int n_list,
+                                   const c32 *__restrict__ NzL, int cgw, double *__restrict__ e_on, double *__restrict__ e_off)
+{
+  const int l = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (l >= n_list) return;
+  const int4 it = list[l];
+  const int b = it.x, c = it.y;
+  const c32 *y = W.Y + ((long)b * G.gps) * G.nch + c;
+  const c32 *p = W.phc + c;
+  double e = 0.0;
+  for (int i0 = 0; i0 < G.n_ddc; i0 += 32) {
+    const int i = i0 + lane;
+    const float m = (i < G.n_ddc) ? mag2(crot(y[(long)i * G.nch], p[(long)i * G.nch])) : 0.0f;
+    const int cnt = (G.n_ddc - i0) < 32 ? (G.n_ddc - i0) : 32;
+    for (int j = 0; j < cnt; j++) e += (double)__shfl_sync(0xffffffffu, m, j);
+  }
+  const c32 *z = NzL + ((long)it.z * G.n_noise) * cgw + it.w;
+  const c32 *q = W.phn + c;
+  double n = 0.0;
+  for (int j0 = 0; j0 < G.n_noise; j0 += 32) {
+    const int j = j0 + lane;
+    const float m = (j < G.n_noise) ? mag2(crot(z[(long)j * cgw], q[(long)j * G.nch])) : 0.0f;
+    const int cnt = (G.n_noise - j0) < 32 ? (G.n_noise - j0) : 32;
+    for (int k = 0; k < cnt; k++) n += (double)__shfl_sync(0xffffffffu, m, k);
+  }
+  if (lane == 0) { e_on[l] = e / G.n_ddc; e_off[l] = n / G.n_noise; }
 }
 
 // every window passes (lazy squelch: the squelch is settled afterwards, exactly, for hit windows only)
@@ -356,6 +699,14 @@ __global__ void k_energy_list(Geom G, DevBatch W, const int4 *__restrict__ list,
   e_off[l] = n / G.n_noise;
 }
 
+static int pick_kt_packed(int R, int W, int D, int N)
+{
+  int kt = (N + 31) & ~31;
+  const size_t budget = (size_t)g_max_smem - 1024;
+  while (kt > 32 && fir_packed_smem(R, W, D, kt) > budget) kt -= 32;
+  return kt;
+}
+
 // ===========================================================================
 // launchers
 // ===========================================================================
@@ -371,10 +722,16 @@ void launch_chan_fir(const Geom &G, const DevTables &T, const DevBatch &W, int i
   constexpr int R = 8, Wp = 16, TJ = 2 * R * Wp;   // 16 channels x 256 outputs per block
   FirJob J{};
   J.x = W.x; J.n_x = (long)(W.B - 1) * G.S + G.H; J.taps = T.chan_tg; J.out = W.Y;
-  J.N = G.Nc; J.D = G.D; J.nch = G.nch; J.KT = pick_kt(16, R, Wp, G.D, G.Nc, 1);
+  J.N = G.Nc; J.D = G.D; J.nch = G.nch;
   J.mode = 0; J.Gtot = Gtot; J.fcs = G.fcs;
   dim3 grid(cdiv(Gtot, TJ), (unsigned)((G.nch + 15) / 16));
-  k_fir_tiled<16, R, Wp><<<grid, Wp * 32, fir_smem(16, R, Wp, G.D, J.KT), s>>>(J);
+  if (impl == IMPL_TILED_SCALAR) {
+    J.KT = pick_kt(16, R, Wp, G.D, G.Nc, 1);
+    k_fir_tiled<16, R, Wp><<<grid, Wp * 32, fir_smem(16, R, Wp, G.D, J.KT), s>>>(J);
+  } else {
+    J.KT = pick_kt_packed(R, Wp, G.D, G.Nc);
+    k_fir_packed<R, Wp><<<grid, Wp * 32, fir_packed_smem(R, Wp, G.D, J.KT), s>>>(J);
+  }
 }
 
 void launch_noise_fir(const Geom &G, const DevTables &T, const DevBatch &W, int impl, cudaStream_t s)
@@ -388,10 +745,15 @@ void launch_noise_fir(const Geom &G, const DevTables &T, const DevBatch &W, int 
   FirJob J{};
   J.x = W.x; J.n_x = (long)(W.B - 1) * G.S + G.H; J.taps = T.noise_tg; J.out = W.Nz;
   J.N = G.Nn; J.D = G.D; J.nch = G.nch;
-  J.KT = pick_kt(16, R, Wp, G.D, G.Nn < 512 ? G.Nn : 512, 1);
   J.mode = 1; J.S = G.S; J.fns = G.fns; J.n_noise = G.n_noise; J.tiles_per_slot = (G.n_noise + TJ - 1) / TJ;
   dim3 grid((unsigned)(W.B * J.tiles_per_slot), (unsigned)((G.nch + 15) / 16));
-  k_fir_tiled<16, R, Wp><<<grid, Wp * 32, fir_smem(16, R, Wp, G.D, J.KT), s>>>(J);
+  if (impl == IMPL_TILED_SCALAR) {
+    J.KT = pick_kt(16, R, Wp, G.D, G.Nn < 512 ? G.Nn : 512, 1);
+    k_fir_tiled<16, R, Wp><<<grid, Wp * 32, fir_smem(16, R, Wp, G.D, J.KT), s>>>(J);
+  } else {
+    J.KT = pick_kt_packed(R, Wp, G.D, G.Nn < 256 ? G.Nn : 256);
+    k_fir_packed<R, Wp><<<grid, Wp * 32, fir_packed_smem(R, Wp, G.D, J.KT), s>>>(J);
+  }
 }
 
 void launch_energy(const Geom &G, const DevTables &T, const DevBatch &W, int device_gate, cudaStream_t s)
@@ -422,10 +784,24 @@ void launch_gather(const Geom &G, const DevBatch &W, cudaStream_t s)
   k_gather<<<148, 128, 0, s>>>(G, W);
 }
 
+void launch_demod_mm_v2(const Geom &G, const DevTables &T, const DevBatch &W, float *demT, cudaStream_t s)
+{
+  dim3 grid(cdiv((long)G.n_dem * G.nch, 256), (unsigned)W.B);
+  k_demod_all<<<grid, 256, 0, s>>>(G, W, T.atan_tab, demT);
+  constexpr int BLK = 64;
+  k_mm_stateless_v2<BLK><<<cdiv((long)W.B * G.nch, BLK), BLK, 0, s>>>(G, W, T.mmse, demT);
+}
+
+void launch_search_warp(const Geom &G, const DevTables &T, const DevBatch &W, cudaStream_t s)
+{
+  k_search_warp<<<cdiv((long)W.B * G.nch * 32, 256), 256, 0, s>>>(G, T, W);
+}
+
 void launch_dmm_stateless(const Geom &G, const DevTables &T, const DevBatch &W, cudaStream_t s)
 {
   constexpr int BLK = 64;
-  k_dmm_stateless<BLK><<<cdiv((long)W.B * G.nch, BLK), BLK, 0, s>>>(G, W, T.mmse, T.atan_tab);
+  const size_t smem = 2 * sizeof(c32) * 64 * BLK + sizeof(float) * 16 * BLK + sizeof(float) * (129 * 8 + 257);
+  k_dmm_stateless<BLK><<<cdiv((long)W.B * G.nch, BLK), BLK, smem, s>>>(G, W, T.mmse, T.atan_tab);
 }
 
 void launch_fill_pass(const DevBatch &W, int n, int v, cudaStream_t s)
@@ -450,7 +826,7 @@ void launch_noise_fir_list(const Geom &G, const DevTables &T, const DevBatch &W,
 void launch_energy_list(const Geom &G, const DevBatch &W, const int *list4, int n_list, const c32 *NzL,
                         double *e_on, double *e_off, cudaStream_t s)
 {
-  k_energy_list<<<cdiv(n_list, 32), 32, 0, s>>>(G, W, reinterpret_cast<const int4 *>(list4), n_list, NzL, LAZY_CG, e_on, e_off);
+  k_energy_list_warp<<<cdiv((long)n_list * 32, 128), 128, 0, s>>>(G, W, reinterpret_cast<const int4 *>(list4), n_list, NzL, LAZY_CG, e_on, e_off);
 }
 
 }  // namespace btb200

@@ -41,7 +41,7 @@ struct DevBatch {
 };
 
 // implementation selectors (tests compare tuned kernels against the v1 baseline)
-enum { IMPL_BASELINE = 0, IMPL_TUNED = 1 };
+enum { IMPL_BASELINE = 0, IMPL_TUNED = 1, IMPL_TILED_SCALAR = 2 };
 
 void launch_chan_fir(const Geom &G, const DevTables &T, const DevBatch &W, int impl, cudaStream_t s);
 void launch_noise_fir(const Geom &G, const DevTables &T, const DevBatch &W, int impl, cudaStream_t s);
@@ -50,6 +50,8 @@ void launch_demod(const Geom &G, const DevTables &T, const DevBatch &W, cudaStre
 void launch_mm(const Geom &G, const DevTables &T, const DevBatch &W, cudaStream_t s);
 void launch_search(const Geom &G, const DevTables &T, const DevBatch &W, cudaStream_t s);
 void launch_gather(const Geom &G, const DevBatch &W, cudaStream_t s);
+void launch_demod_mm_v2(const Geom &G, const DevTables &T, const DevBatch &W, float *demT, cudaStream_t s);
+void launch_search_warp(const Geom &G, const DevTables &T, const DevBatch &W, cudaStream_t s);
 void launch_dmm_stateless(const Geom &G, const DevTables &T, const DevBatch &W, cudaStream_t s);
 void launch_fill_pass(const DevBatch &W, int n, int v, cudaStream_t s);
 // lazy squelch: noise FIR for listed (slot, <=LAZY_CG channels) groups, then exact energies of listed windows

@@ -1,0 +1,65 @@
+"""CPU tier: properties of the compiled sm_100a code that the exactness argument relies on
+(DESIGN.md "Exactness"): no fused multiply-add where the oracle rounds twice."""
+import os
+import re
+import subprocess
+
+import pytest
+
+from conftest import ROOT
+
+LIB = os.path.join(ROOT, "gr-bluetooth_b200", "libbtb200.so")
+
+
+@pytest.fixture(scope="module")
+def sass():
+    if not os.path.exists(LIB):
+        pytest.skip("libbtb200.so not built")
+    out = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True).stdout
+    funcs = {}
+    cur = None
+    for line in out.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            cur = m.group(1)
+            funcs[cur] = []
+        elif cur and "/*" in line:
+            funcs[cur].append(line)
+    return funcs
+
+
+def body(funcs, key):
+    names = [n for n in funcs if key in n]
+    assert names, key
+    return [l for n in names for l in funcs[n]]
+
+
+def test_built_for_sm100a():
+    out = subprocess.run(["cuobjdump", "-lelf", LIB], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+
+
+def test_exact_fir_kernels_have_no_fused_multiply_add(sass):
+    for key in ("k_fir_tiled", "k_chan_fir_v1", "k_noise_fir_v1"):
+        lines = body(sass, key)
+        assert any(" FMUL " in l for l in lines) and any(" FADD " in l for l in lines)
+        assert not any(re.search(r"\bFFMA\b", l) for l in lines), key
+
+
+def test_packed_fir_keeps_separate_roundings(sass):
+    """ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2; the kernel avoids that pattern.
+    Every FFMA2 left must be the 'x - p' form with the -1 immediate (exact), and the
+    instruction mix per complex MAC pair is 4 FMUL2 : 2 FFMA2 : 2 FADD2."""
+    lines = body(sass, "k_fir_packed")
+    ffma2 = [l for l in lines if " FFMA2 " in l]
+    assert ffma2 and all(", -1, " in l for l in ffma2)
+    nmul = sum(" FMUL2 " in l for l in lines)
+    nadd = sum(" FADD2 " in l for l in lines)
+    assert nmul == 2 * len(ffma2) and nadd == len(ffma2)
+    assert not any(re.search(r"\bFFMA\b", l) for l in lines)
+    assert any("LDS.128" in l for l in lines)
+
+
+def test_no_fmad_flag_in_makefile():
+    mk = open(os.path.join(ROOT, "gr-bluetooth_b200", "Makefile")).read()
+    assert "--fmad=false" in mk and "-ffp-contract=off" in mk

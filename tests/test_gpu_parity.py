@@ -54,7 +54,7 @@ def test_uploaded_tables_equal_oracle(fs, fc, extra):
 
 @pytest.mark.parametrize("name", list(FILES))
 @pytest.mark.parametrize("mode", ["chained", "stateless", "stateless-lazy"])
-@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("impl", [0, 1, 2])
 def test_excerpt_bit_exact(name, mode, impl):
     """Committed excerpts of the bundled captures: energies (f64), every sliced symbol of every
     channel-window, and the ac()/aa() call list, identical to the reference's own code.
@@ -107,6 +107,19 @@ def test_stage_floats_bit_exact(name):
     """Rotated DDC output, demod floats and soft symbols of the heavy-captured windows."""
     ex = load_excerpt(name, "chained")
     blk = g.multi_sniffer(ex["fs"], ex["fc"], 10.0, mm_mode=g.MM_CHAINED, max_slots=8, keep_stages=True)
+    _stage_check(blk, ex)
+
+
+@pytest.mark.parametrize("name", ["headset3", "headset2"])
+def test_stage_floats_bit_exact_stateless(name):
+    """Same for the stateless pipeline (parallel demod kernel + clock-recovery kernel)."""
+    ex = load_excerpt(name, "stateless")
+    blk = g.multi_sniffer(ex["fs"], ex["fc"], 10.0, mm_mode=g.MM_STATELESS, max_slots=8, keep_stages=True,
+                          squelch=g.SQUELCH_EAGER)
+    _stage_check(blk, ex)
+
+
+def _stage_check(blk, ex):
     P = O.Plan(ex["fs"], ex["fc"])
     S, H = P.S, P.H
     x = np.concatenate([np.zeros(H - 1, np.complex64), ex["iq"]])

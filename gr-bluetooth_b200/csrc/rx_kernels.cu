@@ -156,7 +156,7 @@ struct FirJob {
 };
 
 template <int CG, int R, int W>
-__global__ void __launch_bounds__(W * 32, (CG == 16) ? 1 : 2) k_fir_tiled(FirJob J)
+__global__ void __launch_bounds__(W * 32, (CG == 16) ? 1 : 2) k_fir_tiled(FirJob J)   // small groups: 2 blocks/SM
 {
   constexpr int NH = 32 / CG;                 // output sub-groups per warp
   constexpr int TJ = NH * R * W;
@@ -344,6 +344,8 @@ static size_t fir_packed_smem(int R, int W, int D, int KT) { return ((size_t)KT 
 
 template <int BLK>
 __global__ void k_dmm_stateless(Geom G, DevBatch W, const float *__restrict__ mmse_g, const float *__restrict__ atan_g);
+template <int BLK>
+__global__ void k_mm_stateless_v2(Geom G, DevBatch W, const float *__restrict__ mmse_g, const float *__restrict__ demT);
 
 static size_t fir_smem(int CG, int R, int W, int D, int KT) { return ((size_t)KT * CG + (size_t)((32 / CG) * R * W - 1) * D + KT) * sizeof(c32); }
 static int g_max_smem = 48 * 1024;
@@ -360,8 +362,9 @@ int fir_setup(int device)
   };
   if (!opt_in((const void *)k_fir_tiled<16, 8, 16>)) return -1;
   if (!opt_in((const void *)k_fir_tiled<16, 8, 14>)) return -1;
-  if (!opt_in((const void *)k_fir_tiled<4, 8, 4>)) return -1;
   if (!opt_in((const void *)k_dmm_stateless<64>)) return -1;
+  if (!opt_in((const void *)k_mm_stateless_v2<64>)) return -1;
+  if (!opt_in((const void *)k_fir_tiled<LAZY_CG, LAZY_R, LAZY_W>)) return -1;
   if (!opt_in((const void *)k_fir_packed<8, 16>)) return -1;
   if (!opt_in((const void *)k_fir_packed<8, 14>)) return -1;
   return 0;
@@ -476,25 +479,37 @@ __global__ void __launch_bounds__(BLK) k_dmm_stateless(Geom G, DevBatch W, const
 // window for the inherently serial Mueller & Mueller chain with a cp.async ring on the
 // demod floats, then a warp per window for the access-code search.
 // ===========================================================================
-__global__ void k_demod_all(Geom G, DevBatch W, const float *__restrict__ atan_g, float *__restrict__ demT)
+// block (x: tile of DM_TI output indices, y: slot, z: 32-channel group); warp w handles the run
+// i0 + w*DM_RUN .. of DM_RUN consecutive outputs for its 32 channels, carrying the previous
+// rotated sample, so each DDC output is rotated once and all loads/stores are channel-contiguous.
+constexpr int DM_WARPS = 8, DM_RUN = 16, DM_TI = DM_WARPS * DM_RUN;
+__global__ void __launch_bounds__(DM_WARPS * 32) k_demod_all(Geom G, DevBatch W, const float *__restrict__ atan_g,
+                                                             float *__restrict__ demT)
 {
   __shared__ float s_atan[257];
   for (int i = threadIdx.x; i < 257; i += blockDim.x) s_atan[i] = atan_g[i];
   __syncthreads();
   const int b = blockIdx.y;
-  const long e = (long)blockIdx.x * blockDim.x + threadIdx.x;        // i*nch + c
-  if (e >= (long)G.n_dem * G.nch) return;
-  const int i = (int)(e / G.nch), c = (int)(e - (long)i * G.nch);
+  const int c = blockIdx.z * 32 + (threadIdx.x & 31);
+  const int w = threadIdx.x >> 5;
+  if (c >= G.nch) return;
   if (!W.pass[b * G.nch + c]) return;
-  float val = 0.0f;
-  if (i > 0) {
-    const c32 *y = W.Y + ((long)b * G.gps) * G.nch;
-    const c32 *p = W.phc + (long)(b * W.bp_stride) * G.n_ddc * G.nch;
-    const c32 cur = crot(y[e], p[e]);
-    const c32 prev = crot(y[e - G.nch], p[e - G.nch]);
-    val = demod_point(s_atan, G.demod_gain, cur, prev);
+  const int i0 = blockIdx.x * DM_TI + w * DM_RUN;
+  if (i0 >= G.n_dem) return;
+  const int i1 = (i0 + DM_RUN < G.n_dem) ? i0 + DM_RUN : G.n_dem;
+  const c32 *y = W.Y + ((long)b * G.gps) * G.nch + c;
+  const c32 *p = W.phc + (long)(b * W.bp_stride) * G.n_ddc * G.nch + c;
+  float *d = demT + ((long)b * G.n_dem_pad) * G.nch + c;
+  c32 prev{0.0f, 0.0f};
+  int i = i0;
+  if (i == 0) { d[0] = 0.0f; prev = crot(y[0], p[0]); i = 1; }          // demod_out[0] is never written by the reference
+  else prev = crot(y[(long)(i - 1) * G.nch], p[(long)(i - 1) * G.nch]);
+#pragma unroll 4
+  for (; i < i1; i++) {
+    const c32 cur = crot(y[(long)i * G.nch], p[(long)i * G.nch]);
+    d[(long)i * G.nch] = demod_point(s_atan, G.demod_gain, cur, prev);
+    prev = cur;
   }
-  demT[((long)b * G.n_dem_pad) * G.nch + e] = val;
 }
 
 __device__ __forceinline__ void cp_async4(void *smem_dst, const void *gsrc)
@@ -507,18 +522,21 @@ template <int BLK>
 __global__ void __launch_bounds__(BLK) k_mm_stateless_v2(Geom G, DevBatch W, const float *__restrict__ mmse_g,
                                                          const float *__restrict__ demT)
 {
-  constexpr int RD = 128;          // ring depth (demod samples)
-  constexpr int BURST = 16;        // samples fetched per refill
-  constexpr int MINAHEAD = 48;     // refill when fewer than this many samples are in flight ahead of ii+8
-  __shared__ float ring[RD][BLK];
-  __shared__ float s_mmse[8][132]; // transposed, padded: lanes with different imu hit different banks
+  constexpr int RD = 256;          // ring depth (demod samples per window)
+  constexpr int AHEAD = 88;        // refill target: ii + 8 + AHEAD
+  constexpr int PERIOD = 8;        // refill every PERIOD steps (warp-uniform: all lanes share the step counter)
+  // The loop advances ii by at most 5 samples per step (|demod| <= gain*pi bounds mm_val), so a refill
+  // at step t covers everything consumed before step t+2*PERIOD: the group in flight is never read.
+  extern __shared__ __align__(16) unsigned char mm_smem[];
+  float (*ring)[BLK] = reinterpret_cast<float (*)[BLK]>(mm_smem);                        // [RD][BLK]
+  float (*s_mmse)[132] = reinterpret_cast<float (*)[132]>(mm_smem + sizeof(float) * RD * BLK);   // [8][132]
   for (int i = threadIdx.x; i < 129 * 8; i += BLK) s_mmse[7 - (i & 7)][i >> 3] = mmse_g[i];   // [k][imu] = taps[imu][7-k]
   __syncthreads();
   const int idx = blockIdx.x * BLK + threadIdx.x;
   if (idx >= W.B * G.nch) return;
   if (!W.pass[idx]) { W.nsym[idx] = 0; return; }
   const int b = idx / G.nch, c = idx - b * G.nch;
-  const float *__restrict__ dem = demT + ((long)b * G.n_dem_pad) * G.nch + c;    // dem[i*nch]
+  const float *gp = demT + ((long)b * G.n_dem_pad) * G.nch + c;    // next sample to prefetch
   uint32_t *__restrict__ bits_row = W.bits + (long)idx * G.bw;
   float *soft_row = W.soft ? W.soft + (long)idx * G.n_dem_pad : nullptr;
   MmState st{G.mu0, G.mm.omega_mid, 0.0f};
@@ -526,28 +544,27 @@ __global__ void __launch_bounds__(BLK) k_mm_stateless_v2(Geom G, DevBatch W, con
   int oo = 0;
   const unsigned ni = (unsigned)(G.n_dem - 8);
   int pf = 0;                      // samples [pf-RD, pf) are in (or on their way to) the ring
+  int ready = 0;                   // samples below `ready` have landed
   uint32_t word = 0;
   const int tid = threadIdx.x;
-  // prime the ring
-  for (; pf < 8 + MINAHEAD + BURST && pf < G.n_dem; pf++) cp_async4(&ring[pf & (RD - 1)][tid], dem + (long)pf * G.nch);
-  cp_async_commit();
-  cp_async_wait<0>();
-  while (oo < G.n_dem && ii < ni) {
-    if (pf < (int)ii + 8 + MINAHEAD) {
-#pragma unroll
-      for (int j = 0; j < BURST; j++) {
-        const int q = pf + j;
-        if (q < G.n_dem) cp_async4(&ring[q & (RD - 1)][tid], dem + (long)q * G.nch);
-      }
-      pf += BURST;
-    }
+  const int nch = G.nch;
+  {
+    int want = 8 + AHEAD; if (want > G.n_dem) want = G.n_dem;
+    for (; pf < want; pf++, gp += nch) cp_async4(&ring[pf & (RD - 1)][tid], gp);
     cp_async_commit();
-    cp_async_wait<4>();            // a burst lands >= MINAHEAD/5 > 4 steps before it is consumed
-#if defined(__CUDA_ARCH__)
+    cp_async_wait<0>();
+    ready = pf;
+  }
+  while (oo < G.n_dem && ii < ni) {
+    if ((oo & (PERIOD - 1)) == 0 && oo) {
+      cp_async_wait<0>();          // the previous refill (issued PERIOD steps ago) has long landed
+      ready = pf;
+      int want = (int)ii + 8 + AHEAD; if (want > G.n_dem) want = G.n_dem;
+      for (; pf < want; pf++, gp += nch) cp_async4(&ring[pf & (RD - 1)][tid], gp);
+      cp_async_commit();
+    }
+    if ((int)ii + 8 > ready) { cp_async_wait<0>(); ready = pf; }     // never taken for bounded inputs
     int imu = __float2int_rn(st.mu * 128.0f);
-#else
-    int imu = 0;
-#endif
     imu = imu < 0 ? 0 : (imu > 128 ? 128 : imu);
     float out = 0.0f;
 #pragma unroll
@@ -786,10 +803,11 @@ void launch_gather(const Geom &G, const DevBatch &W, cudaStream_t s)
 
 void launch_demod_mm_v2(const Geom &G, const DevTables &T, const DevBatch &W, float *demT, cudaStream_t s)
 {
-  dim3 grid(cdiv((long)G.n_dem * G.nch, 256), (unsigned)W.B);
-  k_demod_all<<<grid, 256, 0, s>>>(G, W, T.atan_tab, demT);
+  dim3 grid(cdiv(G.n_dem, DM_TI), (unsigned)W.B, (unsigned)((G.nch + 31) / 32));
+  k_demod_all<<<grid, DM_WARPS * 32, 0, s>>>(G, W, T.atan_tab, demT);
   constexpr int BLK = 64;
-  k_mm_stateless_v2<BLK><<<cdiv((long)W.B * G.nch, BLK), BLK, 0, s>>>(G, W, T.mmse, demT);
+  const size_t smem = sizeof(float) * 256 * BLK + sizeof(float) * 8 * 132;
+  k_mm_stateless_v2<BLK><<<cdiv((long)W.B * G.nch, BLK), BLK, smem, s>>>(G, W, T.mmse, demT);
 }
 
 void launch_search_warp(const Geom &G, const DevTables &T, const DevBatch &W, cudaStream_t s)
@@ -812,7 +830,7 @@ void launch_fill_pass(const DevBatch &W, int n, int v, cudaStream_t s)
 void launch_noise_fir_list(const Geom &G, const DevTables &T, const DevBatch &W, const int *groups, int n_groups,
                            c32 *NzL, cudaStream_t s)
 {
-  constexpr int CG = LAZY_CG, R = 8, Wp = 4, TJ = (32 / CG) * R * Wp;
+  constexpr int CG = LAZY_CG, R = LAZY_R, Wp = LAZY_W, TJ = (32 / CG) * R * Wp;
   FirJob J{};
   J.x = W.x; J.n_x = (long)(W.B - 1) * G.S + G.H; J.taps = T.noise_rtaps; J.out = NzL;
   J.N = G.Nn; J.D = G.D; J.nch = G.nch;

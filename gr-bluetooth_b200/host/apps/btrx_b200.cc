@@ -1,0 +1,85 @@
+// btrx_b200 -- command-line receiver with the flag surface of the reference's apps/btrx
+// (Python 2 + GNU Radio there; options at apps/btrx:23-58).  File input only: it plays the
+// role of the GNU Radio scheduler for one block -- zero history in front of the stream, then
+// work() until the file is consumed.
+//   -f/--freq Hz   -r/--rate sps   -i/--input-file FILE   -S (all-piconet sniffer, default)
+//   -L (LAP printer)   -s/--snr dB   -N/--nsamples n   -2/--input-shorts
+#include "gr_bluetooth/multi_sniffer.h"
+#include "gr_bluetooth/multi_LAP.h"
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+static double parse_eng(const char *s)
+{
+  char *end = nullptr;
+  double v = std::strtod(s, &end);
+  if (end && (*end == 'M' || *end == 'm')) v *= 1e6;
+  else if (end && (*end == 'k' || *end == 'K')) v *= 1e3;
+  else if (end && (*end == 'G' || *end == 'g')) v *= 1e9;
+  return v;
+}
+
+int main(int argc, char **argv)
+{
+  double freq = 2476e6, rate = 2e6, snr = 10;
+  std::string in;
+  long nsamples = -1;
+  bool shorts = false, lap_mode = false;
+  for (int i = 1; i < argc; i++) {
+    std::string a = argv[i];
+    auto next = [&]() -> const char * { return i + 1 < argc ? argv[++i] : ""; };
+    if (a == "-f" || a == "--freq") freq = parse_eng(next());
+    else if (a == "-r" || a == "--rate") rate = parse_eng(next());
+    else if (a == "-i" || a == "--input-file") in = next();
+    else if (a == "-s" || a == "--snr") snr = std::atof(next());
+    else if (a == "-N" || a == "--nsamples") nsamples = (long)parse_eng(next());
+    else if (a == "-2" || a == "--input-shorts") shorts = true;
+    else if (a == "-S" || a == "--sniff-all") lap_mode = false;
+    else if (a == "-L" || a == "--lap") lap_mode = true;
+    else { std::fprintf(stderr, "unknown option %s\n", a.c_str()); return 2; }
+  }
+  if (in.empty()) { std::fprintf(stderr, "usage: btrx_b200 -f FREQ -r RATE -i FILE [-S|-L] [-s SNR] [-N n] [-2]\n"); return 2; }
+  FILE *f = std::fopen(in.c_str(), "rb");
+  if (!f) { std::perror(in.c_str()); return 2; }
+  std::fseek(f, 0, SEEK_END);
+  long total = std::ftell(f) / (shorts ? 4 : 8);
+  std::fseek(f, 0, SEEK_SET);
+  if (nsamples >= 0 && nsamples < total) total = nsamples;
+
+  boost::shared_ptr<gr::bluetooth::multi_block> blk;
+  try {
+    if (lap_mode) blk = gr::bluetooth::multi_LAP::make(rate, freq, snr);
+    else blk = gr::bluetooth::multi_sniffer::make(rate, freq, snr, false);
+  } catch (const std::exception &e) {
+    std::fprintf(stderr, "btrx_b200: %s\n", e.what());
+    return 1;
+  }
+  const long H = blk->history(), S = (long)blk->samples_per_slot();
+  std::vector<gr_complex> buf((size_t)(H - 1 + total));
+  if (shorts) {
+    std::vector<short> tmp((size_t)total * 2);
+    if (std::fread(tmp.data(), 4, (size_t)total, f) != (size_t)total) return 2;
+    for (long i = 0; i < total; i++) buf[(size_t)(H - 1 + i)] = gr_complex(tmp[2 * i], tmp[2 * i + 1]);
+  } else if (std::fread(&buf[(size_t)(H - 1)], 8, (size_t)total, f) != (size_t)total) return 2;
+  std::fclose(f);
+
+  gr_vector_const_void_star inv(1);
+  gr_vector_void_star outv;
+  long consumed = 0;                    // new samples consumed so far
+  const long ncalls = (total + S - 1) / S;
+  long k = 0;
+  while (k < ncalls) {
+    // offer the block as many whole slots as it batches; the last window must end inside the stream
+    long n = (long)blk->batch_slots();
+    if (k + n > ncalls) n = ncalls - k;
+    inv[0] = &buf[(size_t)consumed];
+    const int got = blk->work((int)((n - 1) * S + 1), inv, outv);
+    consumed += got;
+    k += got / S;
+  }
+  std::fflush(stdout);
+  return 0;
+}

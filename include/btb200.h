@@ -101,7 +101,7 @@ enum {
   BTB200_BLOCK_LAP     = 1       /* history += 68 symbols   (multi_LAP_impl.cc:54)     */
 };
 
-typedef struct {
+typedef struct btb200_config {
   uint32_t abi_version;          /* BTB200_ABI_VERSION */
   double   sample_rate;          /* make() arg 1 */
   double   center_freq;          /* make() arg 2 */
@@ -117,7 +117,7 @@ typedef struct {
 } btb200_config;
 
 /* derived constants (lib/multi_block.cc:56-119, 299-342) */
-typedef struct {
+typedef struct btb200_info {
   int32_t samples_per_slot;      /* S */
   int32_t history;               /* H = window length in samples */
   int32_t decimation;            /* D */
@@ -133,7 +133,7 @@ typedef struct {
 } btb200_info;
 
 /* one ac()/aa() invocation of the reference (multi_sniffer_impl.cc:117,139) */
-typedef struct {
+typedef struct btb200_hit {
   uint32_t slot;                 /* work() call index == clkn (multi_sniffer_impl.cc:173) */
   uint16_t channel;              /* classic channel 0..78 */
   uint16_t kind;                 /* 0: BR access code, 1: LE access address */
@@ -147,7 +147,7 @@ typedef struct {
   uint32_t reserved;
 } btb200_hit;
 
-typedef struct {
+typedef struct btb200_hits {
   btb200_hit *hits;              /* caller-allocated */
   uint32_t    cap;
   uint32_t    count;             /* out; ordered by (slot, channel, kind, offset) = reference visiting order */

@@ -159,7 +159,8 @@ def run_ours(args):
 
     B = args.slots
     iq, truth, lead, S = synth_batch(B, seed=1234 + rank)          # every rank its own time shard
-    blk = g.multi_sniffer.make(FS, FC, SNR_DB, False, mm_mode=g.MM_STATELESS, device=local, max_slots=B)
+    blk = g.multi_sniffer.make(FS, FC, SNR_DB, False, mm_mode=g.MM_STATELESS, device=local, max_slots=B,
+                               snr_mode=g.SNR_FAST_GUARDED if args.snr_mode == "fast" else g.SNR_EXACT)
     H = blk.history()
     w0 = lead * S - (H - 1)
     n_in = (B - 1) * S + H
@@ -238,7 +239,7 @@ def run_ours(args):
                 "config": {"workload": "multi_sniffer 79-ch, synthetic 100 Msps IQ (BASELINE configs[2]), "
                                        "stateless mode, %d slots (%.1f M samples, %.0f MiB) per step per GPU"
                                        % (B, B * S / 1e6, n_in * 8 / 2**20),
-                           "fs": FS, "fc": FC, "channels": blk.info.n_channels, "slots_per_step": B,
+                           "fs": FS, "fc": FC, "channels": blk.info.n_channels, "slots_per_step": B, "snr_mode": args.snr_mode,
                            "l2": "flushed between timed iterations (256 MiB write); input %.0f MiB > L2" % (n_in * 8 / 2**20),
                            "timing": "CUDA events on the ctx stream, max over ranks", "sharding": "time shards, no collective"},
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(n_in * 8), "d2h_bytes_per_step": d2h},
@@ -265,6 +266,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--slots", type=int, default=64, help="slots (625 us each) per step per GPU")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--snr-mode", default="exact", choices=["exact", "fast"],
+                    help="exact: reference arithmetic for every printed snr; fast: guarded polyphase estimate")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -18,8 +18,9 @@ ABI_VERSION = 1
 MM_CHAINED, MM_STATELESS = 0, 1
 SEARCH_BR, SEARCH_LE = 1, 2
 SQUELCH_DEFAULT, SQUELCH_EAGER, SQUELCH_LAZY = 0, 1, 2
+SNR_EXACT, SNR_FAST_GUARDED = 0, 1
 
-STAGE = dict(energy=1, noise=2, snr=3, pass_=4, nsym=5, bits=6, ddc=7, demod=8, soft=9,
+STAGE = dict(noise_fast=10, energy=1, noise=2, snr=3, pass_=4, nsym=5, bits=6, ddc=7, demod=8, soft=9,
              chan_taps=20, noise_taps=21, mmse_table=22, atan_table=23, ac_lut=24)
 
 
@@ -35,7 +36,7 @@ class Config(C.Structure):
                 ("squelch_threshold", C.c_double), ("extra_history_symbols", C.c_uint32),
                 ("mm_mode", C.c_int32), ("search", C.c_int32), ("device", C.c_int32),
                 ("max_slots_per_call", C.c_uint32), ("keep_stages", C.c_uint32),
-                ("squelch_mode", C.c_uint32), ("reserved", C.c_uint32 * 4)]
+                ("squelch_mode", C.c_uint32), ("snr_mode", C.c_uint32), ("reserved", C.c_uint32 * 3)]
 
 
 class Info(C.Structure):
@@ -133,12 +134,12 @@ class multi_block:
 
     def __init__(self, sample_rate, center_freq, squelch_threshold, *, mm_mode=MM_CHAINED,
                  search=SEARCH_BR | SEARCH_LE, device=0, max_slots=64, keep_stages=False,
-                 squelch=SQUELCH_DEFAULT):
+                 squelch=SQUELCH_DEFAULT, snr_mode=SNR_EXACT):
         self._L = lib()
         cfg = Config(abi_version=ABI_VERSION, sample_rate=sample_rate, center_freq=center_freq,
                      squelch_threshold=squelch_threshold, extra_history_symbols=self.EXTRA_SYMBOLS,
                      mm_mode=mm_mode, search=search, device=device, max_slots_per_call=max_slots,
-                     keep_stages=int(keep_stages), squelch_mode=squelch)
+                     keep_stages=int(keep_stages), squelch_mode=squelch, snr_mode=snr_mode)
         self._ctx = C.c_void_p()
         rc = self._L.btb200_create(C.byref(cfg), C.byref(self._ctx))
         if rc:
@@ -272,7 +273,7 @@ class multi_block:
 
     def stage(self, name, slot_in_batch=0, chan_index=0):
         I = self.info
-        sizes = dict(energy=(8, np.float64), noise=(8, np.float64), snr=(8, np.float64), pass_=(4, np.int32),
+        sizes = dict(noise_fast=(8, np.float64), energy=(8, np.float64), noise=(8, np.float64), snr=(8, np.float64), pass_=(4, np.int32),
                      nsym=(4, np.int32), bits=(I.ddc_out_per_window, np.uint8),
                      ddc=(I.ddc_out_per_window * 8, np.complex64), demod=(I.ddc_out_per_window * 4, np.float32),
                      soft=(I.ddc_out_per_window * 4, np.float32), chan_taps=(I.chan_taps * 8, np.complex64),

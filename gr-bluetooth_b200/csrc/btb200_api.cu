@@ -4,6 +4,7 @@
 #include "../../include/btb200.h"
 #include "plan.hpp"
 #include "rx_kernels.cuh"
+#include "rx_fast.cuh"
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -49,6 +50,12 @@ struct btb200_ctx {
   double *h_eon = nullptr, *h_eoff = nullptr;
   size_t list_cap = 0, group_cap = 0;
   DevBatch pendW{};
+  // fast guarded snr
+  bool fast_snr = false;
+  FastNoisePlan F{};
+  double *h_esum = nullptr;
+  double phi = 0;                    // common fractional MHz offset of the noise DDCs
+  std::vector<double> fast_off;      // [B][nch] fast off-channel energy of the last batch
   // pinned host
   double *h_energy = nullptr, *h_noise = nullptr;
   int *h_pass = nullptr;
@@ -125,6 +132,58 @@ void reset_stream_state(btb200_ctx *ctx)
     ctx->rot_n[c].incr = P.noise_incr[c];
   }
   ctx->mm = MmState{P.mu0, P.omega_mid, 0.0f};
+}
+
+
+// Tables of the fast noise estimator (rx_fast.cu).  Returns 0; leaves ctx->fast_snr false when the
+// configuration does not fit the polyphase model (non-integer MHz rate, D not dividing M).
+int setup_fast(btb200_ctx *ctx)
+{
+  const Plan &P = ctx->plan;
+  const double Md = P.fs / 1e6;
+  const int M = (int)std::llround(Md);
+  if (std::fabs(Md - M) > 1e-9 || M < 1 || M % P.D != 0) return 0;
+  // noise DDC offsets in MHz: a_c + phi, a_c integer, phi common to all channels
+  const double f0 = (2402e6 + P.ch_lo * 1e6 + 790000.0 - P.fc) / 1e6;
+  const double a0 = std::floor(f0);
+  const double phi = f0 - a0;
+  // phasor period: phi/M as a fraction with denominator 1000*M
+  const long num = std::llround(phi * 1000.0);
+  if (std::fabs(phi * 1000.0 - num) > 1e-6) return 0;
+  long den = 1000L * M, g = num ? num : den;
+  for (long a = den, b = g; b;) { long t = a % b; a = b; b = t; g = a; }
+  const long period = den / (num ? g : den);
+  if (period > (1 << 20)) return 0;
+  FastNoisePlan &F = ctx->F;
+  F.M = M; F.C = M / P.D; F.Q = (P.Nn + M - 1) / M; F.period = (int)period;
+  F.nchp = (P.nch + 15) & ~15;
+  std::vector<float> hpad((size_t)(F.Q + 16) * M, 0.0f);
+  for (int k = 0; k < P.Nn; k++) hpad[(size_t)(k / M + 8) * M + (k % M)] = P.noise_proto[P.Nn - 1 - k];   // h'[k] = h[N-1-k]
+  std::vector<c32> ph((size_t)period);
+  for (long n = 0; n < period; n++) {
+    const double a = -2.0 * M_PI * phi * (double)n / M;
+    ph[(size_t)n] = c32{(float)std::cos(a), (float)std::sin(a)};
+  }
+  std::vector<c32> tw((size_t)M * F.nchp, c32{0.0f, 0.0f});
+  for (int c = 0; c < P.nch; c++) {
+    const long ac = (long)a0 + c;
+    for (int r = 0; r < M; r++) {
+      const long m = ((ac * r) % M + M) % M;
+      const double a = -2.0 * M_PI * (double)m / M;
+      tw[(size_t)r * F.nchp + c] = c32{(float)std::cos(a), (float)std::sin(a)};
+    }
+  }
+  int rc;
+  if ((rc = upload(ctx, &F.hpad, hpad))) return rc;
+  if ((rc = upload(ctx, &F.phasor, ph))) return rc;
+  if ((rc = upload(ctx, &F.twid, tw))) return rc;
+  const size_t B = ctx->max_slots;
+  if ((rc = dev_alloc(ctx, &F.U, B * P.n_noise * (size_t)M))) return rc;
+  if ((rc = dev_alloc(ctx, &F.esum, B * P.nch))) return rc;
+  CK(cudaMallocHost(&ctx->h_esum, B * P.nch * sizeof(double)));
+  ctx->phi = phi;
+  ctx->fast_snr = true;
+  return 0;
 }
 
 int setup(btb200_ctx *ctx)
@@ -242,6 +301,10 @@ int setup(btb200_ctx *ctx)
   ctx->h_ph_cap = bp * (size_t)P.n_ddc * nch;
   CK(cudaMallocHost(&ctx->h_ph, ctx->h_ph_cap * sizeof(c32)));
 
+  if (ctx->lazy && ctx->cfg.snr_mode == BTB200_SNR_FAST_GUARDED) {
+    int rcf = setup_fast(ctx);
+    if (rcf) return rcf;
+  }
   reset_stream_state(ctx);
   if (G.stateless) {
     // one rotator table per DDC object, restarted at phase 1 for every window
@@ -260,7 +323,7 @@ void teardown(btb200_ctx *ctx)
   for (void *p : ctx->allocs) cudaFree(p);
   for (void *p : {(void *)ctx->h_energy, (void *)ctx->h_noise, (void *)ctx->h_pass, (void *)ctx->h_counts,
                   (void *)ctx->h_hits, (void *)ctx->h_arena, (void *)ctx->h_ph, (void *)ctx->h_groups,
-                  (void *)ctx->h_list, (void *)ctx->h_eon, (void *)ctx->h_eoff})
+                  (void *)ctx->h_list, (void *)ctx->h_eon, (void *)ctx->h_eoff, (void *)ctx->h_esum})
     if (p) cudaFreeHost(p);
   for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
   for (auto &e : ctx->evl) if (e) cudaEventDestroy(e);
@@ -426,6 +489,10 @@ int btb200_submit(btb200_ctx *ctx, const float *iq, int iq_on_device, size_t n_s
   if (ctx->lazy) {
     // lazy squelch: every window is demodulated and searched; the squelch (and the snr
     // ac() prints) is settled exactly, afterwards, for the windows that produced hits
+    if (ctx->fast_snr) {
+      launch_noise_fast(ctx->F, W.x, W.B, G.S, G.fns, G.D, G.n_noise, G.nch, s); ctx->launches += 2;
+      CK(cudaMemcpyAsync(ctx->h_esum, ctx->F.esum, nbc * sizeof(double), cudaMemcpyDeviceToHost, s));
+    }
     CK(cudaEventRecord(ctx->ev[3], s));
     launch_fill_pass(W, (int)nbc, 1, s); ctx->launches++;
   } else {
@@ -489,9 +556,14 @@ int btb200_collect(btb200_ctx *ctx, btb200_hits *out)
   if (nh) CK(cudaMemcpyAsync(ctx->h_hits, ctx->W.hits, (size_t)nh * sizeof(DevHit), cudaMemcpyDeviceToHost, s));
   if (used && out && out->symbols) CK(cudaMemcpyAsync(ctx->h_arena, ctx->W.arena, used, cudaMemcpyDeviceToHost, s));
   ctx->lazy_timed = false;
+  std::vector<uint8_t> est_flag;       // per listed window: 1 = snr from the fast estimate
   if (ctx->lazy) {
     const size_t nbc = (size_t)ctx->pend_slots * P.nch;
     for (size_t i = 0; i < nbc; i++) ctx->h_energy[i] = ctx->h_noise[i] = std::nan("");
+    if (ctx->fast_snr) {
+      ctx->fast_off.resize(nbc);
+      for (size_t i = 0; i < nbc; i++) ctx->fast_off[i] = ctx->h_esum[i] / P.n_noise;
+    }
     if (nh) {
       CK(cudaStreamSynchronize(s));
       // unique hit windows, in (slot, channel) order
@@ -499,37 +571,75 @@ int btb200_collect(btb200_ctx *ctx, btb200_hits *out)
       for (unsigned i = 0; i < nh; i++) keys[i] = (uint32_t)ctx->h_hits[i].b * (uint32_t)P.nch + (uint32_t)ctx->h_hits[i].chi;
       std::sort(keys.begin(), keys.end());
       keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
-      int ng = 0, nl = 0;
-      int cur_b = -1, fill = LAZY_CG;
-      for (uint32_t k : keys) {
-        const int b = (int)(k / P.nch), c = (int)(k % P.nch);
-        if (b != cur_b || fill == LAZY_CG) {
-          int *g = ctx->h_groups + (size_t)ng * (1 + LAZY_CG);
-          g[0] = b;
-          for (int i = 0; i < LAZY_CG; i++) g[1 + i] = -1;
-          ng++; fill = 0; cur_b = b;
+      const int nl_all = (int)keys.size();
+      // pass 1 (fast mode): exact on-channel energy of every hit window, off-channel from the estimate
+      std::vector<uint32_t> need_exact;
+      if (ctx->fast_snr) {
+        for (int l = 0; l < nl_all; l++) {
+          int *q = ctx->h_list + (size_t)l * 4;
+          q[0] = (int)(keys[l] / P.nch); q[1] = (int)(keys[l] % P.nch); q[2] = 0; q[3] = 0;
         }
-        ctx->h_groups[(size_t)(ng - 1) * (1 + LAZY_CG) + 1 + fill] = c;
-        int *l = ctx->h_list + (size_t)nl * 4;
-        l[0] = b; l[1] = c; l[2] = ng - 1; l[3] = fill;
-        nl++; fill++;
+        CK(cudaMemcpyAsync(ctx->d_list, ctx->h_list, (size_t)nl_all * 4 * sizeof(int), cudaMemcpyHostToDevice, s));
+        CK(cudaEventRecord(ctx->evl[0], s));
+        CK(cudaEventRecord(ctx->evl[1], s));
+        launch_energy_list(ctx->G, ctx->pendW, ctx->d_list, nl_all, nullptr, ctx->d_eon, ctx->d_eoff, s);
+        ctx->launches++;
+        CK(cudaEventRecord(ctx->evl[2], s));
+        ctx->lazy_timed = true;
+        CK(cudaMemcpyAsync(ctx->h_eon, ctx->d_eon, (size_t)nl_all * sizeof(double), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        const double guard = 5e-3;
+        for (int l = 0; l < nl_all; l++) {
+          const size_t bc = keys[l];
+          const double on = ctx->h_eon[l], off = ctx->fast_off[bc];
+          const double snr = 10.0 * std::log10(on / off);
+          bool sure = std::isfinite(snr) && std::fabs(snr - P.squelch_db) > guard;
+          if (sure) {
+            const double d = snr * 10.0, t = d - std::floor(d);        // %.1f rounds at x.x5
+            if (std::fabs(t - 0.5) <= 10.0 * guard) sure = false;
+          }
+          if (sure) { ctx->h_energy[bc] = on; ctx->h_noise[bc] = off; }
+          else need_exact.push_back(keys[l]);
+        }
+      } else {
+        need_exact = keys;
       }
-      CK(cudaMemcpyAsync(ctx->d_groups, ctx->h_groups, (size_t)ng * (1 + LAZY_CG) * sizeof(int), cudaMemcpyHostToDevice, s));
-      CK(cudaMemcpyAsync(ctx->d_list, ctx->h_list, (size_t)nl * 4 * sizeof(int), cudaMemcpyHostToDevice, s));
-      CK(cudaEventRecord(ctx->evl[0], s));
-      launch_noise_fir_list(ctx->G, ctx->T, ctx->pendW, ctx->d_groups, ng, ctx->d_NzL, s);
-      CK(cudaEventRecord(ctx->evl[1], s));
-      launch_energy_list(ctx->G, ctx->pendW, ctx->d_list, nl, ctx->d_NzL, ctx->d_eon, ctx->d_eoff, s);
-      CK(cudaEventRecord(ctx->evl[2], s));
-      ctx->lazy_timed = true;
-      ctx->launches += 2;
-      CK(cudaMemcpyAsync(ctx->h_eon, ctx->d_eon, (size_t)nl * sizeof(double), cudaMemcpyDeviceToHost, s));
-      CK(cudaMemcpyAsync(ctx->h_eoff, ctx->d_eoff, (size_t)nl * sizeof(double), cudaMemcpyDeviceToHost, s));
-      CK(cudaStreamSynchronize(s));
-      for (int l = 0; l < nl; l++) {
-        const size_t bc = (size_t)ctx->h_list[(size_t)l * 4] * P.nch + ctx->h_list[(size_t)l * 4 + 1];
-        ctx->h_energy[bc] = ctx->h_eon[l];
-        ctx->h_noise[bc] = ctx->h_eoff[l];
+      if (!need_exact.empty()) {
+        int ng = 0, nl = 0;
+        int cur_b = -1, fill = LAZY_CG;
+        for (uint32_t k : need_exact) {
+          const int b = (int)(k / P.nch), c = (int)(k % P.nch);
+          if (b != cur_b || fill == LAZY_CG) {
+            int *g = ctx->h_groups + (size_t)ng * (1 + LAZY_CG);
+            g[0] = b;
+            for (int i = 0; i < LAZY_CG; i++) g[1 + i] = -1;
+            ng++; fill = 0; cur_b = b;
+          }
+          ctx->h_groups[(size_t)(ng - 1) * (1 + LAZY_CG) + 1 + fill] = c;
+          int *l = ctx->h_list + (size_t)nl * 4;
+          l[0] = b; l[1] = c; l[2] = ng - 1; l[3] = fill;
+          nl++; fill++;
+        }
+        CK(cudaMemcpyAsync(ctx->d_groups, ctx->h_groups, (size_t)ng * (1 + LAZY_CG) * sizeof(int), cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(ctx->d_list, ctx->h_list, (size_t)nl * 4 * sizeof(int), cudaMemcpyHostToDevice, s));
+        if (!ctx->fast_snr) CK(cudaEventRecord(ctx->evl[0], s));
+        launch_noise_fir_list(ctx->G, ctx->T, ctx->pendW, ctx->d_groups, ng, ctx->d_NzL, s);
+        if (!ctx->fast_snr) CK(cudaEventRecord(ctx->evl[1], s));
+        launch_energy_list(ctx->G, ctx->pendW, ctx->d_list, nl, ctx->d_NzL, ctx->d_eon, ctx->d_eoff, s);
+        if (!ctx->fast_snr) { CK(cudaEventRecord(ctx->evl[2], s)); ctx->lazy_timed = true; }
+        ctx->launches += 2;
+        CK(cudaMemcpyAsync(ctx->h_eon, ctx->d_eon, (size_t)nl * sizeof(double), cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(ctx->h_eoff, ctx->d_eoff, (size_t)nl * sizeof(double), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        for (int l = 0; l < nl; l++) {
+          const size_t bc = (size_t)ctx->h_list[(size_t)l * 4] * P.nch + ctx->h_list[(size_t)l * 4 + 1];
+          ctx->h_energy[bc] = ctx->h_eon[l];
+          ctx->h_noise[bc] = ctx->h_eoff[l];
+        }
+      }
+      if (ctx->fast_snr) {
+        est_flag.assign(nbc, 1);
+        for (uint32_t k : need_exact) est_flag[k] = 0;
       }
     }
   }
@@ -587,6 +697,7 @@ int btb200_collect(btb200_ctx *ctx, btb200_hits *out)
     o.n_symbols = h.n_symbols;
     o.lap = h.lap;
     o.flags = (std::fabs(snr - P.squelch_db) <= 1e-6) ? 1u : 0u;
+    if (!est_flag.empty() && est_flag[bc]) o.flags |= 2u;
     o.snr = snr;
     o.sym_offset = 0;
     o.sym_count = 0;
@@ -659,6 +770,9 @@ int64_t btb200_get_stage(btb200_ctx *ctx, int stage, uint32_t b, uint32_t chi, v
   switch (stage) {
     case BTB200_STAGE_ENERGY: return host_copy(&ctx->h_energy[bc], 8);
     case BTB200_STAGE_NOISE: return host_copy(&ctx->h_noise[bc], 8);
+    case BTB200_STAGE_NOISE_FAST:
+      if (!ctx->fast_snr || ctx->fast_off.size() <= bc) return BTB200_ERR_ARG;
+      return host_copy(&ctx->fast_off[bc], 8);
     case BTB200_STAGE_SNR: {
       const double snr = 10.0 * std::log10(ctx->h_energy[bc] / ctx->h_noise[bc]);
       return host_copy(&snr, 8);

@@ -677,6 +677,7 @@ __global__ void k_energy_list_warp(Geom G, DevBatch W, const int4 *__restrict__ 
     const int cnt = (G.n_ddc - i0) < 32 ? (G.n_ddc - i0) : 32;
     for (int j = 0; j < cnt; j++) e += (double)__shfl_sync(0xffffffffu, m, j);
   }
+  if (!NzL) { if (lane == 0) { e_on[l] = e / G.n_ddc; e_off[l] = 0.0; } return; }    // on-channel only
   const c32 *z = NzL + ((long)it.z * G.n_noise) * cgw + it.w;
   const c32 *q = W.phn + c;
   double n = 0.0;

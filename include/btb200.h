@@ -90,6 +90,18 @@ enum {
   BTB200_SQUELCH_LAZY    = 2
 };
 
+/* how the off-channel (noise) energy behind the squelch / printed snr is obtained (lazy squelch) */
+enum {
+  /* exact: the reference's 20001-tap noise DDC in the oracle's operation order, for every hit window;
+   * hit.snr is bit-identical to the reference's double */
+  BTB200_SNR_EXACT        = 0,
+  /* fast, guarded: a polyphase + DFT estimate (fp32, FMA, ~1e-4 dB from the exact value) decides the
+   * squelch and provides hit.snr whenever it is farther than the guard band (5e-3 dB) from the
+   * squelch threshold and from every %.1f rounding boundary; otherwise the exact value is computed.
+   * Same hit list and same printed snr=%.1f as BTB200_SNR_EXACT; hit.flags bit1 marks estimated snr. */
+  BTB200_SNR_FAST_GUARDED = 1
+};
+
 enum {
   BTB200_SEARCH_BR = 1,          /* classic_packet::sniff_ac */
   BTB200_SEARCH_LE = 2           /* le_packet::sniff_aa */
@@ -113,7 +125,8 @@ typedef struct btb200_config {
   uint32_t max_slots_per_call;   /* sizes device buffers; 0 = default */
   uint32_t keep_stages;          /* 1: keep demod/soft-symbol buffers for btb200_get_stage */
   uint32_t squelch_mode;         /* BTB200_SQUELCH_* (stateless mode only; chained is always eager) */
-  uint32_t reserved[4];
+  uint32_t snr_mode;             /* BTB200_SNR_* (lazy squelch only) */
+  uint32_t reserved[3];
 } btb200_config;
 
 /* derived constants (lib/multi_block.cc:56-119, 299-342) */
@@ -140,7 +153,7 @@ typedef struct btb200_hit {
   int32_t  offset;               /* symbol index in the window where the packet starts */
   int32_t  n_symbols;            /* the "len - i" argument of ac()/aa() */
   uint32_t lap;                  /* BR: LAP (symbols 38..61); LE: AA (symbols 8..39) */
-  uint32_t flags;                /* bit0: squelch compare re-evaluated on the host (guard band) */
+  uint32_t flags;                /* bit0: snr within 1e-6 dB of the threshold; bit1: snr from the fast noise estimate */
   double   snr;                  /* dB, the value ac() prints */
   uint64_t sym_offset;           /* into btb200_hits.symbols */
   uint32_t sym_count;            /* min(n_symbols, 3125 + 376) symbols copied, one per byte, air order */
@@ -206,6 +219,7 @@ enum {
   BTB200_STAGE_DDC      = 7,     /* c64[ddc_out_per_window] rotated DDC out  */
   BTB200_STAGE_DEMOD    = 8,     /* f32[ddc_out-1] (needs keep_stages)       */
   BTB200_STAGE_SOFT     = 9,     /* f32[nsym]      (needs keep_stages)       */
+  BTB200_STAGE_NOISE_FAST = 10,  /* f64  fast estimate of the off-channel energy (BTB200_SNR_FAST_GUARDED) */
   BTB200_STAGE_CHAN_TAPS  = 20,  /* c64[Nc] reversed band-pass taps of chan_index */
   BTB200_STAGE_NOISE_TAPS = 21,  /* c64[Nn]                                  */
   BTB200_STAGE_MMSE_TABLE = 22,  /* f32[129*8]                               */

@@ -270,3 +270,78 @@ def test_cpp_blocks_btrx_b200(tmp_path):
         return head, l.rstrip().endswith("ID")
     assert [key(l) for l in got_lines] == [key(l) for l in ref_lines] and len(ref_lines) >= 4
     assert out.stdout.splitlines()[0] == ex["stdout"].splitlines()[0]       # "history set to ..." line
+
+
+# ---------------------------------------------------------------------------------------------
+# BTB200_SNR_FAST_GUARDED: polyphase + DFT noise estimate with a guard band and exact fall-back.
+# Tolerances (the only floating-point tolerances in this suite):
+FAST_NOISE_TOL_DB = 1.0e-3      # |fast - exact| off-channel energy, asserted over every window checked
+FAST_GUARD_DB = 5.0e-3          # guard band inside which the library computes the exact value instead
+
+
+@pytest.mark.parametrize("fs,fc,nslots", [(100e6, 2441e6, 11), (8e6, 2476.5e6, 40), (30e6, 2414e6, 11)])
+def test_fast_noise_estimate_accuracy(fs, fc, nslots):
+    iq, truth = synth_small(fs, fc, nslots, 23, [0x9E8B33, 0x24D952, 0x123456])
+    P = O.Plan(fs, fc)
+    first = 7
+    B = nslots - first
+    S, H = P.S, P.H
+    w0 = first * S - (H - 1)
+    seg = iq[w0:w0 + (B - 1) * S + H]
+    exact = g.multi_sniffer(fs, fc, 10.0, mm_mode=g.MM_STATELESS, max_slots=B, squelch=g.SQUELCH_EAGER)
+    fast = g.multi_sniffer(fs, fc, 10.0, mm_mode=g.MM_STATELESS, max_slots=B, squelch=g.SQUELCH_LAZY,
+                           snr_mode=g.SNR_FAST_GUARDED)
+    exact.process(seg, first, B)
+    fast.process(seg, first, B)
+    worst = 0.0
+    for b in range(B):
+        for chi in range(P.nch):
+            e = exact.stage("noise", b, chi)[0]
+            f = fast.stage("noise_fast", b, chi)[0]
+            worst = max(worst, abs(10 * np.log10(f / e)))
+    print("fast noise estimate: worst |delta| = %.2e dB over %d windows" % (worst, B * P.nch))
+    assert worst < FAST_NOISE_TOL_DB
+    exact.close(); fast.close()
+
+
+def _fast_vs_oracle(hits, ohits):
+    a = [(int(h["slot"]), int(h["channel"]), int(h["kind"]), int(h["offset"]), int(h["n_symbols"]), int(h["lap"]),
+          "%.1f" % h["snr"]) for h in hits]
+    b = [(int(h["slot"]), int(h["channel"]), int(h["kind"]), int(h["offset"]), int(h["len"]), int(h["lap"]),
+          "%.1f" % h["snr"]) for h in ohits]
+    assert a == b
+    d = np.abs(hits["snr"] - ohits["snr"])
+    assert np.all(d < FAST_GUARD_DB)
+    est = (hits["flags"] & 2) != 0
+    assert np.all(d[~est] == 0.0)           # exact fall-back values are the oracle's doubles
+    return int(est.sum()), len(hits)
+
+
+@pytest.mark.parametrize("fs,fc,nslots", [(100e6, 2441e6, 13), (30e6, 2414e6, 13)])
+def test_fast_guarded_hits_equal_oracle_synthetic(fs, fc, nslots):
+    iq, truth = synth_small(fs, fc, nslots, 31, [0x9E8B33, 0x24D952, 0x123456])
+    P = O.Plan(fs, fc)
+    first = 7
+    B = nslots - first
+    o = P.run(iq, first_call=first, num_calls=B, stateless=True, threads=8)
+    blk = g.multi_sniffer(fs, fc, 10.0, mm_mode=g.MM_STATELESS, max_slots=B, snr_mode=g.SNR_FAST_GUARDED)
+    S, H = P.S, P.H
+    w0 = first * S - (H - 1)
+    hits, _, _ = blk.process(iq[w0:w0 + (B - 1) * S + H], first, B)
+    n_est, n = _fast_vs_oracle(hits, o["hits"])
+    assert n > 5 and n_est > 0.5 * n        # most hits never needed the exact noise DDC
+    blk.close()
+
+
+@pytest.mark.parametrize("name", list(FILES))
+def test_fast_guarded_hits_equal_oracle_captures(name):
+    iq = full_capture(name)
+    if iq is None:
+        iq = load_excerpt(name, "stateless")["iq"]
+    fs, fc = FILES[name]
+    P = O.Plan(fs, fc)
+    o = P.run(iq, stateless=True, threads=8)
+    blk = g.multi_sniffer(fs, fc, 10.0, mm_mode=g.MM_STATELESS, max_slots=64, snr_mode=g.SNR_FAST_GUARDED)
+    hits = blk.run_stream(iq)
+    _fast_vs_oracle(hits, o["hits"])
+    blk.close()

@@ -39,31 +39,38 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons during the timed region."""
+    """nvidia-smi clocks/throttle reasons DURING the timed region (one streaming nvidia-smi -lms process)."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.rows, self.stop, self.th = index, [], False, None
+        self.index, self.rows, self.proc, self.th = index, [], None, None
 
     def _run(self):
-        while not self.stop:
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, timeout=5).stdout.decode()
-                self.rows.append([c.strip() for c in out.strip().split(",")])
-            except Exception:
-                pass
-            time.sleep(0.2)
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.decode(errors="replace").strip().split(",")])
 
     def __enter__(self):
-        self.th = threading.Thread(target=self._run, daemon=True)
-        self.th.start()
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL)
+            self.th = threading.Thread(target=self._run, daemon=True)
+            self.th.start()
+            time.sleep(0.15)          # first sample is out before the timed region starts
+        except Exception:
+            self.proc = None
         return self
 
     def __exit__(self, *a):
-        self.stop = True
-        self.th.join(timeout=6)
+        if self.proc:
+            time.sleep(0.05)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+            self.th.join(timeout=5)
 
     def summary(self):
         sm = [int(r[0]) for r in self.rows if len(r) >= 6 and r[0].isdigit()]
@@ -144,6 +151,9 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+FP32_NONFUSED_PEAK = 35.6e12     # thread-level FMUL/FADD per second measured on this pool's B200 by tools/ubench_f32x2.cu
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -159,15 +169,7 @@ def run_ours(args):
 
     B = args.slots
     iq, truth, lead, S = synth_batch(B, seed=1234 + rank)          # every rank its own time shard
-    blk = g.multi_sniffer.make(FS, FC, SNR_DB, False, mm_mode=g.MM_STATELESS, device=local, max_slots=B,
-                               snr_mode=g.SNR_FAST_GUARDED if args.snr_mode == "fast" else g.SNR_EXACT)
-    H = blk.history()
-    w0 = lead * S - (H - 1)
-    n_in = (B - 1) * S + H
-    pinned = g.PinnedBuffer(n_in)
-    pinned.array[:] = iq[w0:w0 + n_in]
-    d_iq = torch.from_numpy(pinned.array.view(np.float32).copy()).to(dev)     # resident copy for `value`
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)             # > 126 MB L2
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     def barrier():
         torch.cuda.synchronize()
@@ -175,85 +177,132 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step_resident():
-        return blk.process_device(d_iq.data_ptr(), n_in, lead, B)
+    def allmax(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
-    def step_e2e():
-        return blk.process(pinned.array, lead, B)
+    def measure(snr_mode, steps, warmup):
+        mk = lambda: g.multi_sniffer.make(FS, FC, SNR_DB, False, mm_mode=g.MM_STATELESS, device=local, max_slots=B,
+                                          snr_mode=g.SNR_FAST_GUARDED if snr_mode == "fast" else g.SNR_EXACT)
+        blks = [mk(), mk()]                       # two contexts: the e2e loop overlaps H2D of batch k+1 with batch k
+        blk = blks[0]
+        H = blk.history()
+        w0 = lead * S - (H - 1)
+        n_in = (B - 1) * S + H
+        pinned = [g.PinnedBuffer(n_in), g.PinnedBuffer(n_in)]
+        for p in pinned:
+            p.array[:] = iq[w0:w0 + n_in]
+        d_iq = torch.from_numpy(pinned[0].array.view(np.float32).copy()).to(dev)     # resident copy for `value`
 
-    # ---- device-resident throughput (`value`) ----
-    for _ in range(args.warmup):
-        hits, _, _ = step_resident()
-    stage_ms = {}
-    barrier()
-    l0 = blk.launch_count()
-    with ClockSampler(local) as clk:
-        t0 = time.perf_counter()
-        dev_ms = 0.0
-        for _ in range(args.steps):
-            flush.zero_()                                   # L2 flush between timed iterations
-            step_resident()
-            tm = blk.last_timing()
-            dev_ms += tm["total"]
-            for k, v in tm.items():
-                stage_ms[k] = stage_ms.get(k, 0.0) + v / args.steps
+        # ---- device-resident throughput (`value`) ----
+        for _ in range(warmup):
+            hits, _, _ = blk.process_device(d_iq.data_ptr(), n_in, lead, B)
+        stage_ms = {}
         barrier()
-        wall = time.perf_counter() - t0
-    launches = blk.launch_count() - l0
-    # device time of the K steps (CUDA events on the ctx stream), max over ranks
-    t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms = float(t.item())
-    total_samples = world * args.steps * B * S
-    value = total_samples / (dev_ms / 1e3) / 1e6
+        l0 = blk.launch_count()
+        with ClockSampler(local) as clk:
+            dev_ms = 0.0
+            for _ in range(steps):
+                flush.zero_()                                   # L2 flush between timed iterations
+                hits, _, _ = blk.process_device(d_iq.data_ptr(), n_in, lead, B)
+                tm = blk.last_timing()
+                dev_ms += tm["total"]
+                for k, v in tm.items():
+                    stage_ms[k] = stage_ms.get(k, 0.0) + v / steps
+            barrier()
+        launches = blk.launch_count() - l0
+        dev_ms = allmax(dev_ms)                   # CUDA events on the ctx stream, max over ranks
+        total_samples = world * steps * B * S
+        value = total_samples / (dev_ms / 1e3) / 1e6
 
-    # ---- end to end through the public call with host buffers ----
-    for _ in range(max(1, args.warmup // 2)):
-        step_e2e()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        hits, _, _ = step_e2e()
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_val = total_samples / float(t.item()) / 1e6
-    d2h = int(2 * 8 * B * blk.info.n_channels + 16 + len(hits) * 40)
+        # ---- end to end through the public calls with HOST buffers: btb200_submit (H2D copy + kernels)
+        #      / btb200_collect (hits + symbols D2H), double-buffered over two contexts ----
+        def e2e_loop(n):
+            blks[0].submit(pinned[0].ptr.value, False, n_in, lead, B)
+            for i in range(1, n):
+                blks[i & 1].submit(pinned[i & 1].ptr.value, False, n_in, lead, B)
+                blks[(i - 1) & 1].collect(want_symbols=True)
+            return blks[(n - 1) & 1].collect(want_symbols=True)
+        e2e_loop(2)
+        barrier()
+        t0 = time.perf_counter()
+        ehits, esyms, _ = e2e_loop(steps)
+        barrier()
+        e2e_s = allmax(time.perf_counter() - t0)
+        e2e_val = total_samples / e2e_s / 1e6
+        d2h = int(len(ehits) * 56 + len(esyms) + 16 + (8 * B * blk.info.n_channels if snr_mode == "fast" else 0))
+        nwin = len({(int(h["slot"]), int(h["channel"])) for h in hits})
+        res = dict(value=value, ms_per_step=dev_ms / steps, e2e=e2e_val, e2e_ms_per_step=e2e_s / steps * 1e3,
+                   stage_ms={k: round(v, 3) for k, v in stage_ms.items()}, launches=int(launches), clocks=clk.summary(),
+                   h2d=int(n_in * 8), d2h=d2h, hits=hits, n_in=n_in, hit_windows=nwin, info=blk.info)
+        for bk in blks:
+            bk.close()
+        for p in pinned:
+            p.close()
+        del d_iq
+        torch.cuda.empty_cache()
+        return res
 
-    line = None
+    main = measure(args.snr_mode, args.steps, args.warmup)
+    alt = None
+    if not args.no_alt:
+        other = "fast" if args.snr_mode == "exact" else "exact"
+        alt = measure(other, max(2, args.steps // 2), 2)
+
     if rank == 0:
+        I = main["info"]
         peak, peak_src = measured_peaks()
-        dom = max(("chan_fir", "noise_fir", "energy", "demod_mm", "search"), key=lambda k: stage_ms[k])
-        dom_s = stage_ms[dom] / 1e3
+        st = main["stage_ms"]
+        dom = max(("chan_fir", "noise_fir", "energy", "demod_mm", "search"), key=lambda k: st[k])
+        dom_s = st[dom] / 1e3
         achieved = ALGO_BYTES_PER_SAMPLE * B * S / dom_s / 1e9
+        # fp32 work of the two FIR stages (complex MAC = 4 FMUL + 4 FADD, no FMA on the exact path)
+        gtot = (B - 1) * (S // I.decimation) + I.ddc_out_per_window
+        cmac = {"chan_fir": gtot * I.n_channels * I.chan_taps,
+                "noise_fir": main["hit_windows"] * I.noise_out_per_window * I.noise_taps}
+        fp32 = {k: {"cmac_per_launch": int(v), "fp32_ops_per_s": 8 * v / (st[k] / 1e3),
+                    "frac_of_nonfused_peak": 8 * v / (st[k] / 1e3) / FP32_NONFUSED_PEAK}
+                for k, v in cmac.items() if st.get(k, 0) > 0.05}
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "r1_traffic.json")
+        if os.path.exists(tp):
+            tj = json.load(open(tp))
+            if tj.get("slots") == B and dom in tj.get("dram_bytes_per_launch", {}):
+                traffic = tj["dram_bytes_per_launch"][dom]
+        hits = main["hits"]
         found = {(int(h["channel"]), int(h["lap"])) for h in hits if h["kind"] == 0}
         expect = {(t_["channel"], t_["lap"]) for t_ in truth if t_["slot"] <= B - 2}
         threads = os.cpu_count() or 1
         cb = cpu_baseline(threads, max(threads, 8)) if not args.no_cpu else None
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        line = {"metric": METRIC, "value": main["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": "multi_sniffer 79-ch, synthetic 100 Msps IQ (BASELINE configs[2]), "
                                        "stateless mode, %d slots (%.1f M samples, %.0f MiB) per step per GPU"
-                                       % (B, B * S / 1e6, n_in * 8 / 2**20),
-                           "fs": FS, "fc": FC, "channels": blk.info.n_channels, "slots_per_step": B, "snr_mode": args.snr_mode,
-                           "l2": "flushed between timed iterations (256 MiB write); input %.0f MiB > L2" % (n_in * 8 / 2**20),
-                           "timing": "CUDA events on the ctx stream, max over ranks", "sharding": "time shards, no collective"},
-                "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(n_in * 8), "d2h_bytes_per_step": d2h},
-                "gpu_launches": int(launches),
-                "clocks": clk.summary(),
+                                       % (B, B * S / 1e6, main["n_in"] * 8 / 2**20),
+                           "fs": FS, "fc": FC, "channels": I.n_channels, "slots_per_step": B, "snr_mode": args.snr_mode,
+                           "l2": "flushed between timed iterations (256 MiB write); input %.0f MiB" % (main["n_in"] * 8 / 2**20),
+                           "timing": "value: CUDA events on the ctx stream; e2e: wall clock between barriers; max over ranks",
+                           "sharding": "time shards, no collective"},
+                "e2e": {"value": main["e2e"], "unit": UNIT, "h2d_bytes_per_step": main["h2d"], "d2h_bytes_per_step": main["d2h"],
+                        "ms_per_step": main["e2e_ms_per_step"],
+                        "api": "btb200_submit/btb200_collect with pinned host buffers, two contexts double-buffered"},
+                "gpu_launches": main["launches"],
+                "clocks": main["clocks"],
                 "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                             "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                             "note": "path is fp32-ALU bound (exact-order FIRs), not HBM bound; see DESIGN.md"},
-                "stage_ms": {k: round(v, 3) for k, v in stage_ms.items()},
-                "wall_s_value_loop": wall,
-                "detect": {"truth_bursts": len(expect), "found": len(expect & found)},
+                             "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                             "note": "the path is bound by the non-fused fp32 rate (exact-order FIRs), not by HBM: see `fp32`"},
+                "fp32": {"peak_ops_per_s": FP32_NONFUSED_PEAK, "peak_source": "tools/ubench_f32x2.cu on this pool (FMUL+FADD)",
+                         "kernels": fp32},
+                "stage_ms": st,
+                "detect": {"truth_bursts": len(expect), "found": len(expect & found), "hit_windows": main["hit_windows"]},
                 "cpu_baseline": cb}
+        if alt is not None:
+            line["alt_snr_mode"] = {"snr_mode": "fast" if args.snr_mode == "exact" else "exact", "value": alt["value"],
+                                    "e2e": alt["e2e"], "stage_ms": alt["stage_ms"], "unit": UNIT}
         print(json.dumps(line))
-    blk.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -264,7 +313,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--slots", type=int, default=64, help="slots (625 us each) per step per GPU")
+    ap.add_argument("--slots", type=int, default=512, help="slots (625 us each) per step per GPU")
+    ap.add_argument("--no-alt", action="store_true", help="skip the second measurement in the other snr mode")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--snr-mode", default="exact", choices=["exact", "fast"],
                     help="exact: reference arithmetic for every printed snr; fast: guarded polyphase estimate")

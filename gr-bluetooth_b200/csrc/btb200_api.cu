@@ -251,7 +251,7 @@ int setup(btb200_ctx *ctx)
   if ((rc = dev_alloc(ctx, &W.Y, ((B - 1) * P.grid_per_slot + P.n_ddc) * nch))) return rc;
   if (!ctx->lazy) { if ((rc = dev_alloc(ctx, &W.Nz, B * P.n_noise * nch))) return rc; }
   else {
-    ctx->group_cap = B * ((nch + LAZY_CG - 1) / LAZY_CG);
+    ctx->group_cap = B * ((nch + 1) / 2);
     ctx->list_cap = B * nch;
     if ((rc = dev_alloc(ctx, &ctx->d_NzL, ctx->group_cap * P.n_noise * LAZY_CG))) return rc;
     if ((rc = dev_alloc(ctx, &ctx->d_groups, ctx->group_cap * (1 + LAZY_CG)))) return rc;
@@ -606,21 +606,22 @@ int btb200_collect(btb200_ctx *ctx, btb200_hits *out)
       }
       if (!need_exact.empty()) {
         int ng = 0, nl = 0;
-        int cur_b = -1, fill = LAZY_CG;
+        const int CGR = lazy_group_channels();
+        int cur_b = -1, fill = CGR;
         for (uint32_t k : need_exact) {
           const int b = (int)(k / P.nch), c = (int)(k % P.nch);
-          if (b != cur_b || fill == LAZY_CG) {
-            int *g = ctx->h_groups + (size_t)ng * (1 + LAZY_CG);
+          if (b != cur_b || fill == CGR) {
+            int *g = ctx->h_groups + (size_t)ng * (1 + CGR);
             g[0] = b;
-            for (int i = 0; i < LAZY_CG; i++) g[1 + i] = -1;
+            for (int i = 0; i < CGR; i++) g[1 + i] = -1;
             ng++; fill = 0; cur_b = b;
           }
-          ctx->h_groups[(size_t)(ng - 1) * (1 + LAZY_CG) + 1 + fill] = c;
+          ctx->h_groups[(size_t)(ng - 1) * (1 + CGR) + 1 + fill] = c;
           int *l = ctx->h_list + (size_t)nl * 4;
           l[0] = b; l[1] = c; l[2] = ng - 1; l[3] = fill;
           nl++; fill++;
         }
-        CK(cudaMemcpyAsync(ctx->d_groups, ctx->h_groups, (size_t)ng * (1 + LAZY_CG) * sizeof(int), cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(ctx->d_groups, ctx->h_groups, (size_t)ng * (1 + CGR) * sizeof(int), cudaMemcpyHostToDevice, s));
         CK(cudaMemcpyAsync(ctx->d_list, ctx->h_list, (size_t)nl * 4 * sizeof(int), cudaMemcpyHostToDevice, s));
         if (!ctx->fast_snr) CK(cudaEventRecord(ctx->evl[0], s));
         launch_noise_fir_list(ctx->G, ctx->T, ctx->pendW, ctx->d_groups, ng, ctx->d_NzL, s);

@@ -2,6 +2,7 @@
 // --fmad=false (see rx_math.cuh): every fp32 operation rounds once.
 #include "rx_kernels.cuh"
 #include <cstdio>
+#include <cstdlib>
 
 namespace btb200 {
 
@@ -364,7 +365,6 @@ int fir_setup(int device)
   if (!opt_in((const void *)k_fir_tiled<16, 8, 14>)) return -1;
   if (!opt_in((const void *)k_dmm_stateless<64>)) return -1;
   if (!opt_in((const void *)k_mm_stateless_v2<64>)) return -1;
-  if (!opt_in((const void *)k_fir_tiled<LAZY_CG, LAZY_R, LAZY_W>)) return -1;
   if (!opt_in((const void *)k_fir_packed<8, 16>)) return -1;
   if (!opt_in((const void *)k_fir_packed<8, 14>)) return -1;
   return 0;
@@ -828,24 +828,62 @@ void launch_fill_pass(const DevBatch &W, int n, int v, cudaStream_t s)
   k_fill_pass<<<cdiv(n, 256), 256, 0, s>>>(W.pass, n, v);
 }
 
-void launch_noise_fir_list(const Geom &G, const DevTables &T, const DevBatch &W, const int *groups, int n_groups,
-                           c32 *NzL, cudaStream_t s)
+// Deferred noise FIR over listed (slot, <=cg channels) groups.  Configurations (channels per
+// group, outputs per thread, warps, blocks per SM) are selectable for tuning (BTB200_LAZY_CFG).
+template <int CG, int R, int Wp, int BPS>
+static void launch_list_cfg(const Geom &G, const DevTables &T, const DevBatch &W, const int *groups, int n_groups,
+                            c32 *NzL, cudaStream_t s)
 {
-  constexpr int CG = LAZY_CG, R = LAZY_R, Wp = LAZY_W, TJ = (32 / CG) * R * Wp;
+  constexpr int TJ = (32 / CG) * R * Wp;
+  static bool opted = false;
+  if (!opted) {
+    cudaFuncAttributes fa{};
+    cudaFuncGetAttributes(&fa, (const void *)k_fir_tiled<CG, R, Wp>);
+    cudaFuncSetAttribute((const void *)k_fir_tiled<CG, R, Wp>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         g_max_smem - (int)fa.sharedSizeBytes);
+    opted = true;
+  }
   FirJob J{};
   J.x = W.x; J.n_x = (long)(W.B - 1) * G.S + G.H; J.taps = T.noise_rtaps; J.out = NzL;
   J.N = G.Nn; J.D = G.D; J.nch = G.nch;
-  J.KT = pick_kt(CG, R, Wp, G.D, G.Nn < 512 ? G.Nn : 512, 2);
+  J.KT = pick_kt(CG, R, Wp, G.D, G.Nn < 512 ? G.Nn : 512, BPS);
   J.mode = 2; J.S = G.S; J.fns = G.fns; J.n_noise = G.n_noise; J.tiles_per_slot = (G.n_noise + TJ - 1) / TJ;
   J.groups = groups;
   dim3 grid((unsigned)(n_groups * J.tiles_per_slot), 1);
   k_fir_tiled<CG, R, Wp><<<grid, Wp * 32, fir_smem(CG, R, Wp, G.D, J.KT), s>>>(J);
 }
 
+int lazy_group_channels()
+{
+  static int cg = -1;
+  if (cg < 0) {
+    const char *e = getenv("BTB200_LAZY_CFG");
+    const int cfg = e ? atoi(e) : 5;
+    cg = (cfg >= 3) ? 2 : 4;
+  }
+  return cg;
+}
+
+void launch_noise_fir_list(const Geom &G, const DevTables &T, const DevBatch &W, const int *groups, int n_groups,
+                           c32 *NzL, cudaStream_t s)
+{
+  static int cfg = -1;
+  if (cfg < 0) { const char *e = getenv("BTB200_LAZY_CFG"); cfg = e ? atoi(e) : 5; }     // 5 measured fastest on B200
+  switch (cfg) {
+    case 0: launch_list_cfg<4, 8, 4, 2>(G, T, W, groups, n_groups, NzL, s); break;   // 256 outputs, 8 warps/SM
+    case 1: launch_list_cfg<4, 4, 8, 2>(G, T, W, groups, n_groups, NzL, s); break;   // 256 outputs, 16 warps/SM
+    case 2: launch_list_cfg<4, 6, 6, 1>(G, T, W, groups, n_groups, NzL, s); break;   // 288 outputs, 6 warps/SM
+    case 3: launch_list_cfg<2, 9, 2, 1>(G, T, W, groups, n_groups, NzL, s); break;   // 288 outputs, 2 warps/SM
+    case 4: launch_list_cfg<2, 6, 3, 1>(G, T, W, groups, n_groups, NzL, s); break;   // 288 outputs, 3 warps/SM
+    default:
+    case 5: launch_list_cfg<2, 4, 4, 2>(G, T, W, groups, n_groups, NzL, s); break;   // 256 outputs, 8 warps/SM
+  }
+}
+
 void launch_energy_list(const Geom &G, const DevBatch &W, const int *list4, int n_list, const c32 *NzL,
                         double *e_on, double *e_off, cudaStream_t s)
 {
-  k_energy_list_warp<<<cdiv((long)n_list * 32, 128), 128, 0, s>>>(G, W, reinterpret_cast<const int4 *>(list4), n_list, NzL, LAZY_CG, e_on, e_off);
+  k_energy_list_warp<<<cdiv((long)n_list * 32, 128), 128, 0, s>>>(G, W, reinterpret_cast<const int4 *>(list4), n_list, NzL, lazy_group_channels(), e_on, e_off);
 }
 
 }  // namespace btb200

@@ -55,7 +55,8 @@ void launch_search_warp(const Geom &G, const DevTables &T, const DevBatch &W, cu
 void launch_dmm_stateless(const Geom &G, const DevTables &T, const DevBatch &W, cudaStream_t s);
 void launch_fill_pass(const DevBatch &W, int n, int v, cudaStream_t s);
 // lazy squelch: noise FIR for listed (slot, <=LAZY_CG channels) groups, then exact energies of listed windows
-constexpr int LAZY_CG = 4, LAZY_R = 8, LAZY_W = 4;   // 4 channels x (8 x 8 x 4 = 256) outputs per block, 2 blocks per SM
+constexpr int LAZY_CG = 4;            // upper bound of channels per group (buffer sizing)
+int lazy_group_channels();           // channels per group of the selected configuration   // 4 channels x (8 x 8 x 4 = 256) outputs per block, 2 blocks per SM
 void launch_noise_fir_list(const Geom &G, const DevTables &T, const DevBatch &W, const int *groups, int n_groups,
                            c32 *NzL, cudaStream_t s);
 void launch_energy_list(const Geom &G, const DevBatch &W, const int *list4, int n_list, const c32 *NzL,

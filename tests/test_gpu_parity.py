@@ -345,3 +345,24 @@ def test_fast_guarded_hits_equal_oracle_captures(name):
     hits = blk.run_stream(iq)
     _fast_vs_oracle(hits, o["hits"])
     blk.close()
+
+
+@pytest.mark.parametrize("name", list(FILES))
+def test_gpu_front_end_plus_reference_host_layer_reproduces_reference_stdout(name, kats, tmp_path):
+    """BASELINE config 1 ("pass = identical stdout"): tests/refhost feeds every hit the CUDA path
+    returns (chained mode, through the C ABI) into the REFERENCE's own ac()/aa() host layer
+    (packet_impl.cc / piconet_impl.cc compiled verbatim).  The complete stdout -- UAP/CLK discovery,
+    payload decodes, BLE lines -- must have the md5 of the reference running alone."""
+    import hashlib
+    import subprocess
+    from conftest import ROOT
+    exe = os.path.join(ROOT, "tests", "refhost", "_build", "refhost")
+    iq = full_capture(name)
+    if not os.path.exists(exe) or iq is None:
+        pytest.skip("refhost harness or full capture not staged")
+    fs, fc = FILES[name]
+    path = tmp_path / (name + ".cfile")
+    iq.tofile(path)
+    out = subprocess.run([exe, repr(fs), repr(fc), str(path), "48"], capture_output=True, timeout=600)
+    assert out.returncode == 0, out.stderr.decode()[-2000:]
+    assert hashlib.md5(out.stdout).hexdigest() == kats["stdout_md5"][name]

@@ -154,6 +154,8 @@ struct FirJob {
   long Gtot; int fcs;
   int S, fns, n_noise, tiles_per_slot;
   const int *groups;    // mode 2: [ngroups][1+CG] = slot, channel indices (-1 = unused)
+  int group_fast;       // modes 0/1: blockIdx.x = channel group, blockIdx.y = tile, so the groups that share an
+                        // input span run back to back and the span is read from DRAM once (L2 serves the rest)
 };
 
 template <int CG, int R, int W>
@@ -168,15 +170,17 @@ __global__ void __launch_bounds__(W * 32, (CG == 16) ? 1 : 2) k_fir_tiled(FirJob
   long s0;
   int nj, ostride;
   c32 *outp;
+  const unsigned bx = J.group_fast ? blockIdx.y : blockIdx.x;     // tile index
+  const unsigned by = J.group_fast ? blockIdx.x : blockIdx.y;     // channel group
   if (J.mode == 0) {
-    const long g0 = (long)blockIdx.x * TJ;
+    const long g0 = (long)bx * TJ;
     const long left = J.Gtot - g0;
     nj = left < TJ ? (int)left : TJ;
     s0 = J.fcs + g0 * J.D;
     outp = J.out + g0 * J.nch;
     ostride = J.nch;
   } else {
-    const int q = blockIdx.x / J.tiles_per_slot, jt = blockIdx.x - q * J.tiles_per_slot;
+    const int q = bx / J.tiles_per_slot, jt = bx - q * J.tiles_per_slot;
     const int j0 = jt * TJ;
     nj = (J.n_noise - j0) < TJ ? (J.n_noise - j0) : TJ;
     int b = q;
@@ -207,7 +211,7 @@ __global__ void __launch_bounds__(W * 32, (CG == 16) ? 1 : 2) k_fir_tiled(FirJob
         ts[k * CG + ci] = (ch >= 0) ? J.taps[(size_t)ch * J.N + k0 + k] : c32{0.0f, 0.0f};
       }
     } else {
-      const c32 *tg = J.taps + ((size_t)blockIdx.y * J.N + k0) * CG;
+      const c32 *tg = J.taps + ((size_t)by * J.N + k0) * CG;
       for (int i = threadIdx.x; i < kt * CG; i += W * 32) ts[i] = tg[i];
     }
     const int sp = (TJ - 1) * J.D + kt;
@@ -229,7 +233,7 @@ __global__ void __launch_bounds__(W * 32, (CG == 16) ? 1 : 2) k_fir_tiled(FirJob
       }
     }
   }
-  const int c = (J.mode == 2) ? cg : (int)blockIdx.y * CG + cg;
+  const int c = (J.mode == 2) ? cg : (int)by * CG + cg;
   const bool live = (J.mode == 2) ? true : (c < J.nch);
   if (live) {
 #pragma unroll
@@ -279,14 +283,16 @@ __global__ void __launch_bounds__(W * 32, 1) k_fir_packed(FirJob J)
   long s0;
   int nj;
   c32 *outp;
+  const unsigned bx = J.group_fast ? blockIdx.y : blockIdx.x;     // tile index
+  const unsigned by = J.group_fast ? blockIdx.x : blockIdx.y;     // channel group
   if (J.mode == 0) {
-    const long g0 = (long)blockIdx.x * TJ;
+    const long g0 = (long)bx * TJ;
     const long left = J.Gtot - g0;
     nj = left < TJ ? (int)left : TJ;
     s0 = J.fcs + g0 * J.D;
     outp = J.out + g0 * J.nch;
   } else {
-    const int b = blockIdx.x / J.tiles_per_slot, jt = blockIdx.x - b * J.tiles_per_slot;
+    const int b = bx / J.tiles_per_slot, jt = bx - b * J.tiles_per_slot;
     const int j0 = jt * TJ;
     nj = (J.n_noise - j0) < TJ ? (J.n_noise - j0) : TJ;
     s0 = (long)b * J.S + J.fns + (long)j0 * J.D;
@@ -303,7 +309,7 @@ __global__ void __launch_bounds__(W * 32, 1) k_fir_packed(FirJob J)
   for (int k0 = 0; k0 < J.N; k0 += J.KT) {
     const int kt = (J.N - k0) < J.KT ? (J.N - k0) : J.KT;
     __syncthreads();
-    const c32 *tg = J.taps + ((size_t)blockIdx.y * J.N + k0) * CG;
+    const c32 *tg = J.taps + ((size_t)by * J.N + k0) * CG;
     for (int i = threadIdx.x; i < kt * CG; i += W * 32) { const c32 t = tg[i]; ts[i] = make_float4(t.re, t.re, t.im, t.im); }
     const int hs = hs_base + kt;
     const long base = s0 + k0;
@@ -330,7 +336,7 @@ __global__ void __launch_bounds__(W * 32, 1) k_fir_packed(FirJob J)
       }
     }
   }
-  const int c = (int)blockIdx.y * CG + cg;
+  const int c = (int)by * CG + cg;
   if (c < J.nch) {
 #pragma unroll
     for (int r = 0; r < RP; r++) {
@@ -742,7 +748,9 @@ void launch_chan_fir(const Geom &G, const DevTables &T, const DevBatch &W, int i
   J.x = W.x; J.n_x = (long)(W.B - 1) * G.S + G.H; J.taps = T.chan_tg; J.out = W.Y;
   J.N = G.Nc; J.D = G.D; J.nch = G.nch;
   J.mode = 0; J.Gtot = Gtot; J.fcs = G.fcs;
-  dim3 grid(cdiv(Gtot, TJ), (unsigned)((G.nch + 15) / 16));
+  const unsigned ntile = cdiv(Gtot, TJ), ngrp = (unsigned)((G.nch + 15) / 16);
+  J.group_fast = ntile <= 65535u;
+  dim3 grid(J.group_fast ? ngrp : ntile, J.group_fast ? ntile : ngrp);
   if (impl == IMPL_TILED_SCALAR) {
     J.KT = pick_kt(16, R, Wp, G.D, G.Nc, 1);
     k_fir_tiled<16, R, Wp><<<grid, Wp * 32, fir_smem(16, R, Wp, G.D, J.KT), s>>>(J);
@@ -764,7 +772,9 @@ void launch_noise_fir(const Geom &G, const DevTables &T, const DevBatch &W, int 
   J.x = W.x; J.n_x = (long)(W.B - 1) * G.S + G.H; J.taps = T.noise_tg; J.out = W.Nz;
   J.N = G.Nn; J.D = G.D; J.nch = G.nch;
   J.mode = 1; J.S = G.S; J.fns = G.fns; J.n_noise = G.n_noise; J.tiles_per_slot = (G.n_noise + TJ - 1) / TJ;
-  dim3 grid((unsigned)(W.B * J.tiles_per_slot), (unsigned)((G.nch + 15) / 16));
+  const unsigned ntile = (unsigned)(W.B * J.tiles_per_slot), ngrp = (unsigned)((G.nch + 15) / 16);
+  J.group_fast = ntile <= 65535u;
+  dim3 grid(J.group_fast ? ngrp : ntile, J.group_fast ? ntile : ngrp);
   if (impl == IMPL_TILED_SCALAR) {
     J.KT = pick_kt(16, R, Wp, G.D, G.Nn < 512 ? G.Nn : 512, 1);
     k_fir_tiled<16, R, Wp><<<grid, Wp * 32, fir_smem(16, R, Wp, G.D, J.KT), s>>>(J);

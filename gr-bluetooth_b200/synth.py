@@ -56,8 +56,35 @@ def gfsk(bits, sps, bt=0.5, h=0.32):
     return np.exp(1j * phase)
 
 
+LE_ADV_CHANNELS = {0: 37, 24: 38, 78: 39}       # classic channel number -> LE advertising index
+LE_ADV_AA = 0x8E89BED6
+
+
+def ble_whiten(bits, chan_idx):
+    """BLE data whitening (Core spec vol 6 part B 3.2): LFSR x^7 + x^4 + 1, position 0 = 1,
+    positions 1..6 = channel index MSB..LSB, output from position 6."""
+    reg = [1] + [(chan_idx >> (5 - i)) & 1 for i in range(6)]
+    out = np.empty(len(bits), np.uint8)
+    for i, b in enumerate(bits):
+        o = reg[6]
+        out[i] = b ^ o
+        reg = [o, reg[0], reg[1], reg[2], reg[3] ^ o, reg[4], reg[5]]
+    return out
+
+
+def ble_adv_packet(chan_idx, rng):
+    """Air-order bits of an ADV_IND: preamble, access address, whitened (header + payload + CRC bits)."""
+    aa = [(LE_ADV_AA >> i) & 1 for i in range(32)]
+    pre = [0, 1] * 4 if aa[0] == 0 else [1, 0] * 4
+    n_data = int(rng.integers(0, 20))
+    hdr0, hdr1 = 0x00, 6 + n_data                    # PDU type 0, TxAdd = RxAdd = 0; length
+    pdu = [hdr0, hdr1] + [int(v) for v in rng.integers(0, 256, 6 + n_data)] + [int(v) for v in rng.integers(0, 256, 3)]
+    bits = np.array([(byte >> i) & 1 for byte in pdu for i in range(8)], np.uint8)
+    return np.concatenate([np.array(pre + aa, np.uint8), ble_whiten(bits, chan_idx)])
+
+
 def generate(fs, fc, nslots, seed=1234, laps=None, occupancy=0.05, snr_db=17.0, sigma=50.0,
-             burst_seed=5678, return_f64=False):
+             burst_seed=5678, return_f64=False, le_adv_occupancy=0.0):
     """-> (iq complex64 [nslots*S], truth list of dict(slot, channel, lap, start_sample, nsym))."""
     laps = DEFAULT_LAPS if laps is None else laps
     S = int(625 * fs / 1e6)
@@ -78,6 +105,20 @@ def generate(fs, fc, nslots, seed=1234, laps=None, occupancy=0.05, snr_db=17.0, 
         for ch in range(lo, hi + 1):
             if brng.random() >= occupancy:
                 continue
+            if le_adv_occupancy > 0 and ch in LE_ADV_CHANNELS and brng.random() < le_adv_occupancy / occupancy:
+                # a BLE advertising packet (h = 0.5) on an advertising channel
+                bits = ble_adv_packet(LE_ADV_CHANNELS[ch], brng)
+                bits = np.concatenate([bits[:2] ^ 1, bits])             # two ramp-up symbols
+                start = slot * S + int(brng.uniform(0, 200e-6) * fs)
+                sig = gfsk(bits, sps, h=0.5)
+                k = np.arange(len(sig))
+                f_off = (2402e6 + ch * 1e6 - fc) / fs
+                sig = amp * sig * np.exp(2j * np.pi * f_off * (start + k)) * np.exp(2j * np.pi * brng.random())
+                end = min(start + len(sig), n)
+                if end > start:
+                    iq[start:end] += sig[:end - start].astype(np.complex64)
+                    truth.append(dict(slot=slot, channel=ch, lap=LE_ADV_AA, start_sample=start, nsym=len(bits), kind=1))
+                continue
             lap = int(laps[int(brng.integers(0, len(laps)))])
             hdr = np.repeat(brng.integers(0, 2, 18).astype(np.uint8), 3)
             pay = brng.integers(0, 2, int(brng.integers(0, 367))).astype(np.uint8)
@@ -92,5 +133,5 @@ def generate(fs, fc, nslots, seed=1234, laps=None, occupancy=0.05, snr_db=17.0, 
             if end <= start:
                 continue
             iq[start:end] += sig[:end - start].astype(np.complex64)
-            truth.append(dict(slot=slot, channel=ch, lap=lap, start_sample=start, nsym=len(bits)))
+            truth.append(dict(slot=slot, channel=ch, lap=lap, start_sample=start, nsym=len(bits), kind=0))
     return iq, truth

@@ -1,0 +1,55 @@
+#!/usr/bin/env python
+"""Turns gpurun_out/*.ncu-rep + launch list into profiles/r1_ncu.md and profiles/r1_traffic.json."""
+import csv, io, json, subprocess, sys
+from collections import defaultdict
+
+UNIT = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+rnd = sys.argv[1] if len(sys.argv) > 1 else "r1"
+rows = list(csv.reader(open("profiles/%s_launches.csv" % rnd)))
+hdr = [i for i, r in enumerate(rows) if "Kernel Name" in r][0]
+H = rows[hdr]; ki = H.index("Kernel Name"); vi = H.index("Metric Value")
+d = defaultdict(list)
+for r in rows[hdr + 1:]:
+    if len(r) > vi:
+        d[r[ki]].append(float(r[vi].replace(",", "")))
+tot = sum(sum(v) for v in d.values())
+md = ["# Round %s profiles (B200, sm_100a)\n" % rnd[1:], "## Launch list\n",
+      "Command: `ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file %s_launches.csv python bench.py --steps 2 --warmup 1 --no-alt --no-cpu`" % rnd,
+      "(512 slots = 32 M samples per step, exact snr mode, stateless + lazy squelch; cold-cache, serialised: compare SHARES).",
+      "Raw list: `profiles/%s_launches.csv`.\n" % rnd,
+      "| kernel | launches | mean ms | share of GPU time |", "|---|---|---|---|"]
+for k, v in sorted(d.items(), key=lambda kv: -sum(kv[1])):
+    md.append("| `%s` | %d | %.3f | %.1f %% |" % (k[:90], len(v), sum(v) / len(v) / 1e6, 100 * sum(v) / tot))
+
+keys = ["gpu__time_duration.sum", "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+        "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "launch__registers_per_thread", "smsp__inst_executed.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__cycles_elapsed.avg"]
+traffic = {}
+md += ["\n## `ncu --set full` summaries\n",
+       "Commands: `ncu --set full --clock-control none --import-source on -k regex:<kernels> ... python bench.py --steps 1 --no-alt --no-cpu [--snr-mode fast]` (512 slots per launch).\n"]
+for rep in sys.argv[2:]:
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rr = list(csv.reader(io.StringIO(out)))
+    H, U, body = rr[0], rr[1], rr[2:]
+    for r in body:
+        name = r[H.index("Kernel Name")]
+        md.append("### `%s`\n" % name)
+        md.append("| metric | value | unit |\n|---|---|---|")
+        for k in keys:
+            if k in H:
+                md.append("| %s | %s | %s |" % (k, r[H.index(k)], U[H.index(k)]))
+        md.append("")
+        def b(k):
+            i = H.index(k)
+            return float(r[i]) * UNIT.get(U[i], 1)
+        t = int(b("dram__bytes_read.sum") + b("dram__bytes_write.sum"))
+        for key, tag in (("k_fir_packed", "chan_fir"), ("k_fir_tiled", "noise_fir"), ("k_mm_stateless", "demod_mm")):
+            if key in name:
+                traffic[tag] = t
+json.dump({"slots": 512, "dram_bytes_per_launch": traffic,
+           "source": "ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum per launch, see profiles/%s_ncu.md" % rnd},
+          open("profiles/%s_traffic.json" % rnd, "w"), indent=1)
+open("profiles/%s_ncu.md" % rnd, "w").write("\n".join(md))
+print(traffic)

@@ -158,8 +158,8 @@ struct FirJob {
                         // input span run back to back and the span is read from DRAM once (L2 serves the rest)
 };
 
-template <int CG, int R, int W>
-__global__ void __launch_bounds__(W * 32, (CG == 16) ? 1 : 2) k_fir_tiled(FirJob J)   // small groups: 2 blocks/SM
+template <int CG, int R, int W, bool SKEW = false, int MINB = ((CG == 16) ? 1 : 2)>
+__global__ void __launch_bounds__(W * 32, MINB) k_fir_tiled(FirJob J)
 {
   constexpr int NH = 32 / CG;                 // output sub-groups per warp
   constexpr int TJ = NH * R * W;
@@ -216,20 +216,48 @@ __global__ void __launch_bounds__(W * 32, (CG == 16) ? 1 : 2) k_fir_tiled(FirJob
     }
     const int sp = (TJ - 1) * J.D + kt;
     const long base = s0 + k0;
-    for (int i = threadIdx.x; i < sp; i += W * 32) {
-      const long n = base + i;
-      xs[i] = (n < J.n_x) ? J.x[n] : c32{0.0f, 0.0f};
+    if (SKEW) {
+      // one pad element per D samples: sample i sits at i + i/D, so the NH outputs a warp reads at once
+      // (D samples apart) are D+1 slots apart and fall into distinct banks even when 2D is a multiple of 32
+      for (int i = threadIdx.x; i < sp; i += W * 32) {
+        const long n = base + i;
+        xs[i + i / J.D] = (n < J.n_x) ? J.x[n] : c32{0.0f, 0.0f};
+      }
+    } else {
+      for (int i = threadIdx.x; i < sp; i += W * 32) {
+        const long n = base + i;
+        xs[i] = (n < J.n_x) ? J.x[n] : c32{0.0f, 0.0f};
+      }
     }
     __syncthreads();
-    const c32 *xp = xs + jj0 * J.D;
     const c32 *tp = ts + cg;
-#pragma unroll 4
-    for (int k = 0; k < kt; k++) {
-      const c32 t = tp[k * CG];
+    if (SKEW) {
+      const int D1 = J.D + 1;
+      const c32 *xp = xs + jj0 * D1;
+      const int rs = NH * W * D1;
+      for (int kq = 0, k = 0; k < kt; kq++) {
+        const int kn = (kt - k) < J.D ? (kt - k) : J.D;
+        const c32 *xq = xp + kq * D1;
+#pragma unroll 5
+        for (int kp = 0; kp < kn; kp++, k++) {
+          const c32 t = tp[k * CG];
 #pragma unroll
-      for (int r = 0; r < R; r++) {
-        const c32 v = xp[r * rstride + k];
-        cmac(ar[r], ai[r], v.re, v.im, t.re, t.im);
+          for (int r = 0; r < R; r++) {
+            const c32 v = xq[r * rs + kp];
+            cmac(ar[r], ai[r], v.re, v.im, t.re, t.im);
+          }
+        }
+      }
+    } else {
+      const c32 *xp = xs + jj0 * J.D;
+#pragma unroll 4
+      for (int k = 0; k < kt; k++) {
+        const c32 t = tp[k * CG];
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+          const c32 v = xp[r * rstride + k];
+          cmac(ar[r], ai[r], v.re, v.im, t.re, t.im);
+        }
       }
     }
   }
@@ -273,15 +301,16 @@ __device__ __forceinline__ u64 pk_neg(u64 a) { return a ^ 0x8000000080000000ull;
 __device__ __forceinline__ float pk_lo(u64 v) { return __uint_as_float((unsigned)(v & 0xffffffffull)); }
 __device__ __forceinline__ float pk_hi(u64 v) { return __uint_as_float((unsigned)(v >> 32)); }
 
-template <int R, int W>
-__global__ void __launch_bounds__(W * 32, 1) k_fir_packed(FirJob J)
+template <int CG, int R, int W, bool SKEW = false, int MINB = 1>
+__global__ void __launch_bounds__(W * 32, MINB) k_fir_packed(FirJob J)
 {
-  constexpr int CG = 16, NH = 2, TJ = NH * R * W, RP = R / 2;
+  constexpr int NH = 32 / CG, TJ = NH * R * W, RP = R / 2;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float4 *ts = reinterpret_cast<float4 *>(smem_raw);     // [KT][16]  (c, c, d, d)
+  float4 *ts = reinterpret_cast<float4 *>(smem_raw);     // [KT][CG]  (c, c, d, d)
   float4 *xs = ts + (size_t)J.KT * CG;                   // [HS]      (re[e], re[e+DELTA], im[e], im[e+DELTA])
+  __shared__ int s_ch[CG];
   long s0;
-  int nj;
+  int nj, ostride;
   c32 *outp;
   const unsigned bx = J.group_fast ? blockIdx.y : blockIdx.x;     // tile index
   const unsigned by = J.group_fast ? blockIdx.x : blockIdx.y;     // channel group
@@ -291,14 +320,24 @@ __global__ void __launch_bounds__(W * 32, 1) k_fir_packed(FirJob J)
     nj = left < TJ ? (int)left : TJ;
     s0 = J.fcs + g0 * J.D;
     outp = J.out + g0 * J.nch;
+    ostride = J.nch;
   } else {
-    const int b = bx / J.tiles_per_slot, jt = bx - b * J.tiles_per_slot;
+    const int q = bx / J.tiles_per_slot, jt = bx - q * J.tiles_per_slot;
     const int j0 = jt * TJ;
     nj = (J.n_noise - j0) < TJ ? (J.n_noise - j0) : TJ;
+    int b = q;
+    if (J.mode == 2) {
+      b = J.groups[q * (1 + CG)];
+      if (threadIdx.x < CG) s_ch[threadIdx.x] = J.groups[q * (1 + CG) + 1 + threadIdx.x];
+      outp = J.out + ((long)q * J.n_noise + j0) * CG;
+      ostride = CG;
+    } else {
+      outp = J.out + ((long)b * J.n_noise + j0) * J.nch;
+      ostride = J.nch;
+    }
     s0 = (long)b * J.S + J.fns + (long)j0 * J.D;
-    outp = J.out + ((long)b * J.n_noise + j0) * J.nch;
   }
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, cg = lane & 15, h = lane >> 4;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, cg = lane % CG, h = lane / CG;
   const int jj0 = NH * w + h;
   const int rstride = NH * W * J.D;            // samples between consecutive outputs of a thread
   const int delta = RP * rstride;              // samples between the two outputs of a pair
@@ -309,52 +348,92 @@ __global__ void __launch_bounds__(W * 32, 1) k_fir_packed(FirJob J)
   for (int k0 = 0; k0 < J.N; k0 += J.KT) {
     const int kt = (J.N - k0) < J.KT ? (J.N - k0) : J.KT;
     __syncthreads();
-    const c32 *tg = J.taps + ((size_t)by * J.N + k0) * CG;
-    for (int i = threadIdx.x; i < kt * CG; i += W * 32) { const c32 t = tg[i]; ts[i] = make_float4(t.re, t.re, t.im, t.im); }
+    if (J.mode == 2) {
+      for (int i = threadIdx.x; i < kt * CG; i += W * 32) {
+        const int ci = i / kt, k = i - ci * kt;
+        const int ch = s_ch[ci];
+        const c32 t = (ch >= 0) ? J.taps[(size_t)ch * J.N + k0 + k] : c32{0.0f, 0.0f};
+        ts[k * CG + ci] = make_float4(t.re, t.re, t.im, t.im);
+      }
+    } else {
+      const c32 *tg = J.taps + ((size_t)by * J.N + k0) * CG;
+      for (int i = threadIdx.x; i < kt * CG; i += W * 32) { const c32 t = tg[i]; ts[i] = make_float4(t.re, t.re, t.im, t.im); }
+    }
     const int hs = hs_base + kt;
     const long base = s0 + k0;
     for (int i = threadIdx.x; i < hs; i += W * 32) {
       const long n0 = base + i, n1 = n0 + delta;
       const c32 v0 = (n0 < J.n_x) ? J.x[n0] : c32{0.0f, 0.0f};
       const c32 v1 = (n1 < J.n_x) ? J.x[n1] : c32{0.0f, 0.0f};
-      xs[i] = make_float4(v0.re, v1.re, v0.im, v1.im);
+      xs[SKEW ? i + i / J.D : i] = make_float4(v0.re, v1.re, v0.im, v1.im);
     }
     __syncthreads();
-    const float4 *xp = xs + jj0 * J.D;
     const float4 *tp = ts + cg;
-#pragma unroll 4
-    for (int k = 0; k < kt; k++) {
-      const ulonglong2 T = *reinterpret_cast<const ulonglong2 *>(tp + k * CG);     // .x = (c,c)  .y = (d,d)
-      const u64 ncc = pk_neg(T.x);                                                   // (-c,-c), exact
+    if (SKEW) {
+      const int D1 = J.D + 1;
+      const float4 *xp = xs + jj0 * D1;
+      const int rs = NH * W * D1;
+      for (int kq = 0, k = 0; k < kt; kq++) {
+        const int kn = (kt - k) < J.D ? (kt - k) : J.D;
+        const float4 *xq = xp + kq * D1;
+#pragma unroll 5
+        for (int kp = 0; kp < kn; kp++, k++) {
+          const ulonglong2 T = *reinterpret_cast<const ulonglong2 *>(tp + k * CG);
+          const u64 ncc = pk_neg(T.x);
 #pragma unroll
-      for (int r = 0; r < RP; r++) {
-        const ulonglong2 V = *reinterpret_cast<const ulonglong2 *>(xp + r * rstride + k);   // .x = (a,a')  .y = (b,b')
-        const u64 pr = pk_xsubp(pk_mul(V.x, T.x), pk_mul(V.y, T.y));  // a*c - b*d
-        const u64 pi = pk_xsubp(pk_mul(V.x, T.y), pk_mul(V.y, ncc));  // a*d - (b*(-c)) = a*d + b*c, same roundings
-        are[r] = pk_add(are[r], pr);
-        aim[r] = pk_add(aim[r], pi);
+          for (int r = 0; r < RP; r++) {
+            const ulonglong2 V = *reinterpret_cast<const ulonglong2 *>(xq + r * rs + kp);
+            const u64 pr = pk_xsubp(pk_mul(V.x, T.x), pk_mul(V.y, T.y));
+            const u64 pi = pk_xsubp(pk_mul(V.x, T.y), pk_mul(V.y, ncc));
+            are[r] = pk_add(are[r], pr);
+            aim[r] = pk_add(aim[r], pi);
+          }
+        }
+      }
+    } else {
+      const float4 *xp = xs + jj0 * J.D;
+#pragma unroll 4
+      for (int k = 0; k < kt; k++) {
+        const ulonglong2 T = *reinterpret_cast<const ulonglong2 *>(tp + k * CG);     // .x = (c,c)  .y = (d,d)
+        const u64 ncc = pk_neg(T.x);                                                   // (-c,-c), exact
+#pragma unroll
+        for (int r = 0; r < RP; r++) {
+          const ulonglong2 V = *reinterpret_cast<const ulonglong2 *>(xp + r * rstride + k);   // .x = (a,a')  .y = (b,b')
+          const u64 pr = pk_xsubp(pk_mul(V.x, T.x), pk_mul(V.y, T.y));  // a*c - b*d
+          const u64 pi = pk_xsubp(pk_mul(V.x, T.y), pk_mul(V.y, ncc));  // a*d - (b*(-c)) = a*d + b*c, same roundings
+          are[r] = pk_add(are[r], pr);
+          aim[r] = pk_add(aim[r], pi);
+        }
       }
     }
   }
-  const int c = (int)by * CG + cg;
-  if (c < J.nch) {
+  const int c = (J.mode == 2) ? cg : (int)by * CG + cg;
+  if (J.mode == 2 || c < J.nch) {
 #pragma unroll
     for (int r = 0; r < RP; r++) {
       const int ja = jj0 + r * NH * W, jb = ja + RP * NH * W;
-      if (ja < nj) outp[(long)ja * J.nch + c] = c32{pk_lo(are[r]), pk_lo(aim[r])};
-      if (jb < nj) outp[(long)jb * J.nch + c] = c32{pk_hi(are[r]), pk_hi(aim[r])};
+      if (ja < nj) outp[(long)ja * ostride + c] = c32{pk_lo(are[r]), pk_lo(aim[r])};
+      if (jb < nj) outp[(long)jb * ostride + c] = c32{pk_hi(are[r]), pk_hi(aim[r])};
     }
   }
 }
 
-static size_t fir_packed_smem(int R, int W, int D, int KT) { return ((size_t)KT * 16 + (size_t)((R / 2) * 2 * W - 1) * D + KT) * sizeof(float4); }
+static size_t fir_packed_smem(int CG, int R, int W, int D, int KT, bool skew = false)
+{
+  const size_t hs = (size_t)((R / 2) * (32 / CG) * W - 1) * D + KT;
+  return ((size_t)KT * CG + hs + (skew ? hs / D + 2 : 0)) * sizeof(float4);
+}
 
 template <int BLK>
 __global__ void k_dmm_stateless(Geom G, DevBatch W, const float *__restrict__ mmse_g, const float *__restrict__ atan_g);
 template <int BLK>
 __global__ void k_mm_stateless_v2(Geom G, DevBatch W, const float *__restrict__ mmse_g, const float *__restrict__ demT);
 
-static size_t fir_smem(int CG, int R, int W, int D, int KT) { return ((size_t)KT * CG + (size_t)((32 / CG) * R * W - 1) * D + KT) * sizeof(c32); }
+static size_t fir_smem(int CG, int R, int W, int D, int KT, bool skew = false)
+{
+  const size_t span = (size_t)((32 / CG) * R * W - 1) * D + KT;
+  return ((size_t)KT * CG + span + (skew ? span / D + 2 : 0)) * sizeof(c32);
+}
 static int g_max_smem = 48 * 1024;
 
 int fir_setup(int device)
@@ -371,17 +450,17 @@ int fir_setup(int device)
   if (!opt_in((const void *)k_fir_tiled<16, 8, 14>)) return -1;
   if (!opt_in((const void *)k_dmm_stateless<64>)) return -1;
   if (!opt_in((const void *)k_mm_stateless_v2<64>)) return -1;
-  if (!opt_in((const void *)k_fir_packed<8, 16>)) return -1;
-  if (!opt_in((const void *)k_fir_packed<8, 14>)) return -1;
+  if (!opt_in((const void *)k_fir_packed<16, 8, 16>)) return -1;
+  if (!opt_in((const void *)k_fir_packed<16, 8, 14>)) return -1;
   return 0;
 }
 
 // largest tap chunk (multiple of 32, <= N rounded up) whose tile fits in shared memory
-static int pick_kt(int CG, int R, int W, int D, int N, int blocks_per_sm)
+static int pick_kt(int CG, int R, int W, int D, int N, int blocks_per_sm, bool skew = false)
 {
   int kt = (N + 31) & ~31;
   const size_t budget = (size_t)(g_max_smem + 1024) / blocks_per_sm - 2048;   // 1 KB/block reserved + static
-  while (kt > 32 && fir_smem(CG, R, W, D, kt) > budget) kt -= 32;
+  while (kt > 32 && fir_smem(CG, R, W, D, kt, skew) > budget) kt -= 32;
   return kt;
 }
 
@@ -723,11 +802,11 @@ __global__ void k_energy_list(Geom G, DevBatch W, const int4 *__restrict__ list,
   e_off[l] = n / G.n_noise;
 }
 
-static int pick_kt_packed(int R, int W, int D, int N)
+static int pick_kt_packed(int CG, int R, int W, int D, int N, int blocks_per_sm = 1, bool skew = false)
 {
   int kt = (N + 31) & ~31;
-  const size_t budget = (size_t)g_max_smem - 1024;
-  while (kt > 32 && fir_packed_smem(R, W, D, kt) > budget) kt -= 32;
+  const size_t budget = (size_t)(g_max_smem + 1024) / blocks_per_sm - 2048;
+  while (kt > 32 && fir_packed_smem(CG, R, W, D, kt, skew) > budget) kt -= 32;
   return kt;
 }
 
@@ -755,8 +834,8 @@ void launch_chan_fir(const Geom &G, const DevTables &T, const DevBatch &W, int i
     J.KT = pick_kt(16, R, Wp, G.D, G.Nc, 1);
     k_fir_tiled<16, R, Wp><<<grid, Wp * 32, fir_smem(16, R, Wp, G.D, J.KT), s>>>(J);
   } else {
-    J.KT = pick_kt_packed(R, Wp, G.D, G.Nc);
-    k_fir_packed<R, Wp><<<grid, Wp * 32, fir_packed_smem(R, Wp, G.D, J.KT), s>>>(J);
+    J.KT = pick_kt_packed(16, R, Wp, G.D, G.Nc);
+    k_fir_packed<16, R, Wp><<<grid, Wp * 32, fir_packed_smem(16, R, Wp, G.D, J.KT), s>>>(J);
   }
 }
 
@@ -779,8 +858,8 @@ void launch_noise_fir(const Geom &G, const DevTables &T, const DevBatch &W, int 
     J.KT = pick_kt(16, R, Wp, G.D, G.Nn < 512 ? G.Nn : 512, 1);
     k_fir_tiled<16, R, Wp><<<grid, Wp * 32, fir_smem(16, R, Wp, G.D, J.KT), s>>>(J);
   } else {
-    J.KT = pick_kt_packed(R, Wp, G.D, G.Nn < 256 ? G.Nn : 256);
-    k_fir_packed<R, Wp><<<grid, Wp * 32, fir_packed_smem(R, Wp, G.D, J.KT), s>>>(J);
+    J.KT = pick_kt_packed(16, R, Wp, G.D, G.Nn < 256 ? G.Nn : 256);
+    k_fir_packed<16, R, Wp><<<grid, Wp * 32, fir_packed_smem(16, R, Wp, G.D, J.KT), s>>>(J);
   }
 }
 
@@ -840,7 +919,7 @@ void launch_fill_pass(const DevBatch &W, int n, int v, cudaStream_t s)
 
 // Deferred noise FIR over listed (slot, <=cg channels) groups.  Configurations (channels per
 // group, outputs per thread, warps, blocks per SM) are selectable for tuning (BTB200_LAZY_CFG).
-template <int CG, int R, int Wp, int BPS>
+template <int CG, int R, int Wp, int BPS, bool SKEW = false, int KTMAX = 512>
 static void launch_list_cfg(const Geom &G, const DevTables &T, const DevBatch &W, const int *groups, int n_groups,
                             c32 *NzL, cudaStream_t s)
 {
@@ -848,19 +927,42 @@ static void launch_list_cfg(const Geom &G, const DevTables &T, const DevBatch &W
   static bool opted = false;
   if (!opted) {
     cudaFuncAttributes fa{};
-    cudaFuncGetAttributes(&fa, (const void *)k_fir_tiled<CG, R, Wp>);
-    cudaFuncSetAttribute((const void *)k_fir_tiled<CG, R, Wp>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaFuncGetAttributes(&fa, (const void *)k_fir_tiled<CG, R, Wp, SKEW, BPS>);
+    cudaFuncSetAttribute((const void *)k_fir_tiled<CG, R, Wp, SKEW, BPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          g_max_smem - (int)fa.sharedSizeBytes);
     opted = true;
   }
   FirJob J{};
   J.x = W.x; J.n_x = (long)(W.B - 1) * G.S + G.H; J.taps = T.noise_rtaps; J.out = NzL;
   J.N = G.Nn; J.D = G.D; J.nch = G.nch;
-  J.KT = pick_kt(CG, R, Wp, G.D, G.Nn < 512 ? G.Nn : 512, BPS);
+  J.KT = pick_kt(CG, R, Wp, G.D, G.Nn < KTMAX ? G.Nn : KTMAX, BPS, SKEW);
   J.mode = 2; J.S = G.S; J.fns = G.fns; J.n_noise = G.n_noise; J.tiles_per_slot = (G.n_noise + TJ - 1) / TJ;
   J.groups = groups;
   dim3 grid((unsigned)(n_groups * J.tiles_per_slot), 1);
-  k_fir_tiled<CG, R, Wp><<<grid, Wp * 32, fir_smem(CG, R, Wp, G.D, J.KT), s>>>(J);
+  k_fir_tiled<CG, R, Wp, SKEW, BPS><<<grid, Wp * 32, fir_smem(CG, R, Wp, G.D, J.KT, SKEW), s>>>(J);
+}
+
+template <int CG, int R, int Wp, int BPS, bool SKEW, int KTMAX = 512>
+static void launch_list_packed(const Geom &G, const DevTables &T, const DevBatch &W, const int *groups, int n_groups,
+                               c32 *NzL, cudaStream_t s)
+{
+  constexpr int TJ = (32 / CG) * R * Wp;
+  static bool opted = false;
+  if (!opted) {
+    cudaFuncAttributes fa{};
+    cudaFuncGetAttributes(&fa, (const void *)k_fir_packed<CG, R, Wp, SKEW, BPS>);
+    cudaFuncSetAttribute((const void *)k_fir_packed<CG, R, Wp, SKEW, BPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         g_max_smem - (int)fa.sharedSizeBytes);
+    opted = true;
+  }
+  FirJob J{};
+  J.x = W.x; J.n_x = (long)(W.B - 1) * G.S + G.H; J.taps = T.noise_rtaps; J.out = NzL;
+  J.N = G.Nn; J.D = G.D; J.nch = G.nch;
+  J.KT = pick_kt_packed(CG, R, Wp, G.D, G.Nn < KTMAX ? G.Nn : KTMAX, BPS, SKEW);
+  J.mode = 2; J.S = G.S; J.fns = G.fns; J.n_noise = G.n_noise; J.tiles_per_slot = (G.n_noise + TJ - 1) / TJ;
+  J.groups = groups;
+  dim3 grid((unsigned)(n_groups * J.tiles_per_slot), 1);
+  k_fir_packed<CG, R, Wp, SKEW, BPS><<<grid, Wp * 32, fir_packed_smem(CG, R, Wp, G.D, J.KT, SKEW), s>>>(J);
 }
 
 int lazy_group_channels()
@@ -868,8 +970,8 @@ int lazy_group_channels()
   static int cg = -1;
   if (cg < 0) {
     const char *e = getenv("BTB200_LAZY_CFG");
-    const int cfg = e ? atoi(e) : 5;
-    cg = (cfg >= 3) ? 2 : 4;
+    const int cfg = e ? atoi(e) : 11;
+    cg = (cfg == 13 || cfg == 16 || cfg == 19 || cfg < 3) ? 4 : 2;
   }
   return cg;
 }
@@ -878,15 +980,29 @@ void launch_noise_fir_list(const Geom &G, const DevTables &T, const DevBatch &W,
                            c32 *NzL, cudaStream_t s)
 {
   static int cfg = -1;
-  if (cfg < 0) { const char *e = getenv("BTB200_LAZY_CFG"); cfg = e ? atoi(e) : 5; }     // 5 measured fastest on B200
+  if (cfg < 0) { const char *e = getenv("BTB200_LAZY_CFG"); cfg = e ? atoi(e) : 11; }    // measured on B200 (512 slots): 11, 15, 5 within 1 % of each other (21.7 ms), others slower
   switch (cfg) {
     case 0: launch_list_cfg<4, 8, 4, 2>(G, T, W, groups, n_groups, NzL, s); break;   // 256 outputs, 8 warps/SM
     case 1: launch_list_cfg<4, 4, 8, 2>(G, T, W, groups, n_groups, NzL, s); break;   // 256 outputs, 16 warps/SM
     case 2: launch_list_cfg<4, 6, 6, 1>(G, T, W, groups, n_groups, NzL, s); break;   // 288 outputs, 6 warps/SM
     case 3: launch_list_cfg<2, 9, 2, 1>(G, T, W, groups, n_groups, NzL, s); break;   // 288 outputs, 2 warps/SM
     case 4: launch_list_cfg<2, 6, 3, 1>(G, T, W, groups, n_groups, NzL, s); break;   // 288 outputs, 3 warps/SM
-    default:
     case 5: launch_list_cfg<2, 4, 4, 2>(G, T, W, groups, n_groups, NzL, s); break;   // 256 outputs, 8 warps/SM
+    case 6: launch_list_cfg<2, 4, 4, 2, true>(G, T, W, groups, n_groups, NzL, s); break;   // same, skewed layout
+    case 7: launch_list_cfg<2, 3, 3, 3, true>(G, T, W, groups, n_groups, NzL, s); break;   // 144 outputs (850 = 6 tiles, 98 %), 9 warps/SM
+    case 8: launch_list_cfg<2, 3, 6, 1, true>(G, T, W, groups, n_groups, NzL, s); break;   // 288 outputs, 6 warps/SM
+    case 9: launch_list_cfg<2, 2, 8, 2, true>(G, T, W, groups, n_groups, NzL, s); break;   // 256 outputs, 16 warps/SM
+    case 10: launch_list_packed<2, 4, 4, 2, true>(G, T, W, groups, n_groups, NzL, s); break;   // packed, 256 outputs, 2 blocks/SM
+    default:
+    case 11: launch_list_packed<2, 4, 4, 2, false>(G, T, W, groups, n_groups, NzL, s); break;   // packed fp32, 2 ch x 256 outputs, 2 blocks/SM
+    case 12: launch_list_packed<2, 8, 2, 2, true>(G, T, W, groups, n_groups, NzL, s); break;   // packed, R=8
+    case 13: launch_list_packed<4, 8, 4, 2, false>(G, T, W, groups, n_groups, NzL, s); break;  // packed, 4 channels
+    case 14: launch_list_packed<2, 4, 8, 1, true>(G, T, W, groups, n_groups, NzL, s); break;   // packed, 512 outputs, 1 block/SM
+    case 15: launch_list_cfg<2, 2, 8, 1, false, 4096>(G, T, W, groups, n_groups, NzL, s); break;    // big tap chunks, 8 warps/SM
+    case 16: launch_list_cfg<4, 4, 8, 1, false, 2048>(G, T, W, groups, n_groups, NzL, s); break;
+    case 17: launch_list_packed<2, 4, 4, 1, false, 4096>(G, T, W, groups, n_groups, NzL, s); break;
+    case 18: launch_list_cfg<2, 4, 4, 1, false, 4096>(G, T, W, groups, n_groups, NzL, s); break;
+    case 19: launch_list_packed<4, 8, 4, 1, false, 2048>(G, T, W, groups, n_groups, NzL, s); break;
   }
 }
 

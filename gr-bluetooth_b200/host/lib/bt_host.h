@@ -1,0 +1,141 @@
+// bt_host.h -- host-side Bluetooth packet layer of the B200 blocks.
+//
+// What happens to a packet AFTER the GPU path has found it: header / payload decoding of
+// basic-rate packets (whitening, FEC 1/3 and 2/3, HEC, CRC), UAP and CLK1-6 discovery per
+// piconet, FHS parsing, and the BLE header printout.  Behavioural restatement of the
+// reference's lib/packet_impl.cc:367-1275,1529-1665 and lib/piconet_impl.cc:33-60,370-547
+// (each function cites its lines), written so that the blocks print exactly what the
+// reference's ac()/aa() call chains print.  Runs on a handful of packets per second: plain C++.
+#pragma once
+#include <stdint.h>
+#include <deque>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+namespace btb200_host {
+
+// one period of the x^7+x^4+1 whitening sequence (packet::WHITENING_DATA, packet_impl.cc:84-90)
+const uint8_t *whitening_sequence();
+// position in that sequence for CLK1-6 (classic_packet::INDICES, packet_impl.cc:185-189)
+int classic_whitening_index(int clk6);
+// position for a BLE channel index (le_packet::INDICES, packet_impl.cc:1446-1450)
+int le_whitening_index(int channel_index);
+// le_packet::freq2index, packet_impl.cc:1285-1314
+int le_freq_to_index(double freq);
+
+inline uint32_t air_to_host(const char *air, int bits)          // packet_impl.cc:104-136
+{
+  uint32_t v = 0;
+  for (int i = 0; i < bits; i++) v |= (uint32_t)(air[i] & 1) << i;
+  return v;
+}
+
+class ClassicPacket {
+ public:
+  static const int MAX_SYMBOLS = 3125;                          // include/gr_bluetooth/packet.h:59
+  ClassicPacket(const char *stream, int length, uint32_t clkn, double freq);   // packet_impl.cc:40-58,210-245
+  uint32_t clkn;
+  int channel;
+  uint32_t lap() const { return d_lap; }
+  bool header_present() const;                                  // :1205-1242
+  uint8_t try_clock(int clock);                                 // :1045-1063
+  int crc_check(int clock);                                     // :609-668
+  void set_clock(uint32_t clock, bool have27);                  // :578-590
+  void set_uap(uint8_t uap) { d_uap = uap; }
+  void decode();                                                // :173-179 (decode_header + decode_payload)
+  bool got_payload() const { return d_have_payload; }
+  int type() const { return d_type; }
+  void print() const;                                           // :1161-1173
+  // FHS fields (:1243-1275)
+  uint32_t lap_from_fhs() const { return air_to_host(&d_payload[34], 24); }
+  uint8_t uap_from_fhs() const { return (uint8_t)air_to_host(&d_payload[64], 8); }
+  uint16_t nap_from_fhs() const { return (uint16_t)(uint8_t)air_to_host(&d_payload[72], 16); }   // air_to_host8(...,16) in the reference
+  uint32_t clock_from_fhs() const { return air_to_host(&d_payload[115], 26); }
+
+  static bool unfec13(const char *in, char *out, int length);   // :367-384
+  static bool unfec23(const char *in, int length, std::vector<char> &out);   // :387-468
+  static uint16_t crcgen(const char *payload, int length, int uap);          // :529-548
+  static int uap_from_hec(uint16_t data, uint8_t hec);          // :593-606
+
+ private:
+  std::vector<char> d_sym;      // MAX_SYMBOLS entries, zero beyond d_length
+  int d_length;
+  uint32_t d_lap;
+  uint8_t d_uap = 0;
+  uint32_t d_clock = 0;
+  bool d_have_clk6 = false, d_have_payload = false;
+  int d_type = 0;
+  int d_payload_length = 0, d_payload_header_length = 0, d_llid = 0, d_flow = 0;
+  char d_packet_header[18];
+  char d_payload_header[16];
+  std::vector<char> d_payload;  // 2744 bits worth of chars in the reference (one bit per char)
+
+  void unwhiten(const char *in, char *out, int clock, int length, int skip) const;   // :513-526
+  bool payload_crc() const;                                     // :671-680
+  bool decode_header();                                         // :1066-1090
+  void decode_payload();                                        // :1092-1158
+  bool decode_payload_header(const char *stream, int clock, int header_bytes, int size, bool fec);   // :726-770
+  int fhs(int clock);
+  int DM(int clock);
+  int DH(int clock);
+  int EV3(int clock);
+  int EV4(int clock);
+  int EV5(int clock);
+  int HV(int clock);
+};
+
+// UAP / CLK1-6 discovery state of one piconet (basic_rate_piconet_impl, piconet_impl.cc:63-80,370-547)
+class Piconet {
+ public:
+  explicit Piconet(uint32_t lap) : d_lap(lap) {}
+  void enqueue(std::shared_ptr<ClassicPacket> p) { d_queue.push_back(p); }
+  std::shared_ptr<ClassicPacket> dequeue();
+  bool uap_from_header(ClassicPacket &pkt);
+  void reset();
+  bool have_uap() const { return d_have_uap; }
+  bool have_nap() const { return d_have_nap; }
+  bool have_clk6() const { return d_have_clk6; }
+  bool have_clk27() const { return d_have_clk27; }
+  uint8_t uap() const { return d_uap; }
+  uint16_t nap() const { return d_nap; }
+  uint32_t offset() const { return d_clk_offset; }
+  void set_uap(uint8_t u) { d_uap = u; d_have_uap = true; }
+  void set_nap(uint16_t n) { d_nap = n; d_have_nap = true; }
+  void set_offset(uint32_t o) { d_clk_offset = o; d_have_clk6 = true; d_have_clk27 = true; }
+
+ private:
+  static const int MAX_PATTERN_LENGTH = 1000;                   // lib/piconet_impl.h:45
+  uint32_t d_lap;
+  std::deque<std::shared_ptr<ClassicPacket>> d_queue;
+  bool d_got_first_packet = false, d_have_uap = false, d_have_nap = false, d_have_clk6 = false, d_have_clk27 = false;
+  int d_packets_observed = 0, d_total_packets_observed = 0;
+  uint32_t d_first_pkt_time = 0, d_clk_offset = 0;
+  uint8_t d_uap = 0;
+  uint16_t d_nap = 0;
+  int d_clock6_candidates[64];
+};
+
+// le_packet_impl: constructor + print (packet_impl.cc:1529-1646)
+void le_print(const char *stream, int available, double freq);
+
+// The per-packet call chain of the sniffer block: multi_sniffer_impl::ac / aa / id / decode /
+// discover / recall / fhs, lib/multi_sniffer_impl.cc:169-365.  Independent of the GPU path so
+// that it can be driven from any hit source (the CPU test tier drives it from the oracle).
+class SnifferHost {
+ public:
+  void ac(const char *symbols, int len, uint32_t clkn, double freq, double snr);
+  void aa(const char *symbols, int len, uint32_t clkn, double freq, double snr);
+
+ private:
+  static const uint32_t GIAC = 0x9E8B33, LIAC = 0x9E8B00;      // lib/multi_sniffer_impl.h:41-42
+  std::map<int, std::shared_ptr<Piconet>> d_piconets;
+  void id(uint32_t lap);
+  void decode(std::shared_ptr<ClassicPacket> pkt, std::shared_ptr<Piconet> pn, bool first_run);
+  void discover(std::shared_ptr<ClassicPacket> pkt, std::shared_ptr<Piconet> pn);
+  void recall(std::shared_ptr<Piconet> pn);
+  void fhs(std::shared_ptr<ClassicPacket> pkt);
+};
+
+}  // namespace btb200_host

@@ -1,6 +1,9 @@
 #ifndef INCLUDED_GR_BLUETOOTH_B200_MULTI_SNIFFER_IMPL_H
 #define INCLUDED_GR_BLUETOOTH_B200_MULTI_SNIFFER_IMPL_H
 #include "gr_bluetooth/multi_sniffer.h"
+#include "bt_host.h"
+#include <map>
+#include <memory>
 
 namespace gr {
 namespace bluetooth {
@@ -8,9 +11,7 @@ namespace bluetooth {
 class multi_sniffer_impl : virtual public multi_sniffer {
  private:
   bool d_tun;
-  // handle AC / AA: what the reference's ac()/aa() print first (lib/multi_sniffer_impl.cc:169-214)
-  void ac(const char *symbols, int len, int sym_avail, double freq, double snr, uint32_t lap);
-  void aa(const char *symbols, int len, int sym_avail, double freq, double snr);
+  btb200_host::SnifferHost d_host;       // the reference's ac()/aa() call chain (lib/multi_sniffer_impl.cc:169-365)
   void handle_hit(const btb200_hit &hit, const char *symbols, int n_symbols, double freq);
 
  public:

@@ -247,29 +247,43 @@ def test_work_call_surface():
     blk.close()
 
 
-def test_cpp_blocks_btrx_b200(tmp_path):
-    """The C++ adapter blocks (gr::bluetooth::multi_sniffer::make + work(), same signatures as the
-    reference) driven by btrx_b200 the way the GNU Radio scheduler drives them: every BR line the
-    reference prints -- time, snr, channel, LAP and the ID / has-header classification -- matches."""
+def _btrx(tmp_path, iq, fs, fc, env=None):
     import subprocess
     from conftest import ROOT
     exe = os.path.join(ROOT, "gr-bluetooth_b200", "host", "btrx_b200")
     if not os.path.exists(exe):
         pytest.skip("btrx_b200 not built")
-    ex = load_excerpt("headset1", "chained")
     path = tmp_path / "x.cfile"
-    ex["iq"].tofile(path)
-    out = subprocess.run([exe, "-f", "%.1f" % ex["fc"], "-r", "%.0f" % ex["fs"], "-i", str(path), "-S"],
-                         capture_output=True, text=True, timeout=300)
+    iq.tofile(path)
+    e = dict(os.environ)
+    e.update(env or {})
+    out = subprocess.run([exe, "-f", repr(fc), "-r", repr(fs), "-i", str(path), "-S"], capture_output=True, text=True,
+                         timeout=600, env=e)
     assert out.returncode == 0, out.stderr
-    ref_lines = [l for l in ex["stdout"].splitlines() if ", channel" in l and "LAP" in l and l.startswith("time")]
-    got_lines = [l for l in out.stdout.splitlines() if ", channel" in l and "LAP" in l]
-    # the excerpt's last slot window may be cut differently: compare calls the excerpt fully contains
-    def key(l):
-        head = l.split(" LAP ")[0] + " LAP " + l.split(" LAP ")[1][:6]
-        return head, l.rstrip().endswith("ID")
-    assert [key(l) for l in got_lines] == [key(l) for l in ref_lines] and len(ref_lines) >= 4
-    assert out.stdout.splitlines()[0] == ex["stdout"].splitlines()[0]       # "history set to ..." line
+    return out.stdout
+
+
+@pytest.mark.parametrize("name", list(FILES))
+def test_cpp_blocks_btrx_b200_excerpt_stdout(name, tmp_path):
+    """The C++ blocks (gr::bluetooth::multi_sniffer::make + work(), the reference's signatures) driven by
+    btrx_b200 the way the GNU Radio scheduler drives them, CUDA front end + NATIVE host packet layer:
+    the complete stdout (UAP/CLK discovery, payload decodes, BLE lines) equals the reference's."""
+    ex = load_excerpt(name, "chained")
+    assert _btrx(tmp_path, ex["iq"], ex["fs"], ex["fc"]) == ex["stdout"]
+    # a different batching of the same stream must not change a byte
+    assert _btrx(tmp_path, ex["iq"], ex["fs"], ex["fc"], {"BTB200_BATCH_SLOTS": "5"}) == ex["stdout"]
+
+
+@pytest.mark.parametrize("name", list(FILES))
+def test_cpp_blocks_btrx_b200_full_capture_digest(name, kats, tmp_path):
+    """BASELINE config 1: btrx_b200 on the whole bundled capture == the reference's stdout digest."""
+    import hashlib
+    iq = full_capture(name)
+    if iq is None:
+        pytest.skip("full capture not staged")
+    fs, fc = FILES[name]
+    out = _btrx(tmp_path, iq, fs, fc)
+    assert hashlib.md5(out.encode()).hexdigest() == kats["stdout_md5"][name]
 
 
 # ---------------------------------------------------------------------------------------------

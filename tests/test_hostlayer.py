@@ -1,0 +1,63 @@
+"""CPU tier: the product's native host packet layer (gr-bluetooth_b200/host/lib/bt_host.cc: header
+and payload decode, UAP/CLK1-6 discovery, FHS, BLE printout = the reference's ac()/aa() call chains,
+SURVEY.md 8f-1/2) driven by the ORACLE's hit list must print the reference's stdout, byte for byte."""
+import hashlib
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, FILES, REF_SAMPLES, load_excerpt
+from oracle import oracle as O
+
+HDIR = os.path.join(ROOT, "tests", "hostlayer")
+
+
+@pytest.fixture(scope="module")
+def harness():
+    exe = os.path.join(HDIR, "_build", "hostlayer")
+    srcs = [os.path.join(HDIR, "hostlayer_main.cc"), os.path.join(ROOT, "gr-bluetooth_b200", "host", "lib", "bt_host.cc")]
+    deps = srcs + [os.path.join(ROOT, "gr-bluetooth_b200", "host", "lib", "bt_host.h")]
+    if not os.path.exists(exe) or os.path.getmtime(exe) < max(os.path.getmtime(d) for d in deps):
+        os.makedirs(os.path.dirname(exe), exist_ok=True)
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", *srcs, "-o", exe])
+    return exe
+
+
+def host_stdout(harness, P, iq, tmp_path, num_calls=None):
+    o = P.run(iq, num_calls=num_calls, stateless=False, want_bits=True, n_total=None if num_calls is None else len(iq) + P.S)
+    path = tmp_path / "hits.bin"
+    first_call = 0
+    with open(path, "wb") as f:
+        for h in o["hits"]:
+            call, chi = int(h["slot"]) - first_call, int(h["channel"]) - P.ch_lo
+            n = int(o["nsym"][call, chi])
+            # len symbols from the hit's offset; the BR search may have consumed part of the window (h['len'])
+            sym = o["bits"][call, chi, int(h["offset"]):n]
+            ln = min(int(h["len"]), 3125, len(sym))
+            f.write(struct.pack("<Iiddi", int(h["slot"]), int(h["kind"]), 2402e6 + 1e6 * int(h["channel"]), float(h["snr"]), ln))
+            f.write(sym[:ln].astype(np.uint8).tobytes())
+    out = subprocess.run([harness, str(path)], capture_output=True, timeout=120)
+    assert out.returncode == 0
+    chist = P.Nc + P.D * 8
+    banner = "history set to %d samples: channel=%d, noise=%d\n" % (P.S + max(chist, P.Nn), chist, P.Nn)
+    return banner + out.stdout.decode()
+
+
+@pytest.mark.parametrize("name", list(FILES))
+def test_excerpt_stdout_identical(harness, name, tmp_path):
+    ex = load_excerpt(name, "chained")
+    P = O.Plan(ex["fs"], ex["fc"])
+    got = host_stdout(harness, P, ex["iq"], tmp_path, num_calls=ex["nslots"])
+    assert got == ex["stdout"]
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_SAMPLES), reason="needs the bundled captures")
+@pytest.mark.parametrize("name", list(FILES))
+def test_full_capture_stdout_digest(harness, name, kats, tmp_path):
+    fs, fc = FILES[name]
+    iq = np.fromfile(os.path.join(REF_SAMPLES, name + ".cfile"), dtype=np.complex64)
+    got = host_stdout(harness, O.Plan(fs, fc), iq, tmp_path)
+    assert hashlib.md5(got.encode()).hexdigest() == kats["stdout_md5"][name]

@@ -233,20 +233,19 @@ __global__ void __launch_bounds__(W * 32, MINB) k_fir_tiled(FirJob J)
     const c32 *tp = ts + cg;
     if (SKEW) {
       const int D1 = J.D + 1;
-      const c32 *xp = xs + jj0 * D1;
+      const c32 *xq = xs + jj0 * D1;
       const int rs = NH * W * D1;
-      for (int kq = 0, k = 0; k < kt; kq++) {
-        const int kn = (kt - k) < J.D ? (kt - k) : J.D;
-        const c32 *xq = xp + kq * D1;
-#pragma unroll 5
-        for (int kp = 0; kp < kn; kp++, k++) {
-          const c32 t = tp[k * CG];
+      int kp = 0;
+#pragma unroll 2
+      for (int k = 0; k < kt; k++) {
+        const c32 t = tp[k * CG];
 #pragma unroll
-          for (int r = 0; r < R; r++) {
-            const c32 v = xq[r * rs + kp];
-            cmac(ar[r], ai[r], v.re, v.im, t.re, t.im);
-          }
+        for (int r = 0; r < R; r++) {
+          const c32 v = xq[r * rs];
+          cmac(ar[r], ai[r], v.re, v.im, t.re, t.im);
         }
+        xq++;
+        if (++kp == J.D) { kp = 0; xq++; }
       }
     } else {
       const c32 *xp = xs + jj0 * J.D;
@@ -370,25 +369,26 @@ __global__ void __launch_bounds__(W * 32, MINB) k_fir_packed(FirJob J)
     __syncthreads();
     const float4 *tp = ts + cg;
     if (SKEW) {
+      // slot of sample (jj*D + k) is jj*(D+1) + k + k/D: walk k with a running slot pointer that skips
+      // one pad slot every D taps (warp-uniform test)
       const int D1 = J.D + 1;
-      const float4 *xp = xs + jj0 * D1;
+      const float4 *xq = xs + jj0 * D1;
       const int rs = NH * W * D1;
-      for (int kq = 0, k = 0; k < kt; kq++) {
-        const int kn = (kt - k) < J.D ? (kt - k) : J.D;
-        const float4 *xq = xp + kq * D1;
-#pragma unroll 5
-        for (int kp = 0; kp < kn; kp++, k++) {
-          const ulonglong2 T = *reinterpret_cast<const ulonglong2 *>(tp + k * CG);
-          const u64 ncc = pk_neg(T.x);
+      int kp = 0;
+#pragma unroll 2
+      for (int k = 0; k < kt; k++) {
+        const ulonglong2 T = *reinterpret_cast<const ulonglong2 *>(tp + k * CG);
+        const u64 ncc = pk_neg(T.x);
 #pragma unroll
-          for (int r = 0; r < RP; r++) {
-            const ulonglong2 V = *reinterpret_cast<const ulonglong2 *>(xq + r * rs + kp);
-            const u64 pr = pk_xsubp(pk_mul(V.x, T.x), pk_mul(V.y, T.y));
-            const u64 pi = pk_xsubp(pk_mul(V.x, T.y), pk_mul(V.y, ncc));
-            are[r] = pk_add(are[r], pr);
-            aim[r] = pk_add(aim[r], pi);
-          }
+        for (int r = 0; r < RP; r++) {
+          const ulonglong2 V = *reinterpret_cast<const ulonglong2 *>(xq + r * rs);
+          const u64 pr = pk_xsubp(pk_mul(V.x, T.x), pk_mul(V.y, T.y));
+          const u64 pi = pk_xsubp(pk_mul(V.x, T.y), pk_mul(V.y, ncc));
+          are[r] = pk_add(are[r], pr);
+          aim[r] = pk_add(aim[r], pi);
         }
+        xq++;
+        if (++kp == J.D) { kp = 0; xq++; }
       }
     } else {
       const float4 *xp = xs + jj0 * J.D;

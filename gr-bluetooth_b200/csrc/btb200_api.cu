@@ -50,6 +50,7 @@ struct btb200_ctx {
   double *h_eon = nullptr, *h_eoff = nullptr;
   size_t list_cap = 0, group_cap = 0;
   DevBatch pendW{};
+  int *d_res4 = nullptr;
   // fast guarded snr
   bool fast_snr = false;
   FastNoisePlan F{};
@@ -728,6 +729,91 @@ int btb200_process_device(btb200_ctx *ctx, const float *d_iq, size_t n_samples, 
   int rc = btb200_submit(ctx, d_iq, 1, n_samples, first_slot, n_slots);
   if (rc) return rc;
   return btb200_collect(ctx, out);
+}
+
+int btb200_process_channels(btb200_ctx *ctx, const float *iq, size_t n_samples, uint64_t slot, int32_t first_channel,
+                            int32_t n_channels, uint32_t stop_lap, btb200_chan_result *res, uint8_t *symbols,
+                            size_t symbols_cap)
+{
+  (void)slot;
+  if (!ctx || !iq || !res || n_channels < 0) return BTB200_ERR_ARG;
+  const Plan &P = ctx->plan;
+  const Geom &G = ctx->G;
+  if (G.stateless || ctx->pending) return BTB200_ERR_ARG;
+  const int first = first_channel - P.ch_lo;
+  if (n_channels > 0 && (first < 0 || first + n_channels > P.nch)) return BTB200_ERR_ARG;
+  if (n_samples < (size_t)P.H) return BTB200_ERR_SHORT_INPUT;
+  if (n_channels == 0) return BTB200_OK;
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  DevBatch W = ctx->W;
+  W.B = 1;
+  const size_t nch = (size_t)P.nch;
+  // rotators advance only for channels whose DDC objects the reference actually calls: keep a copy
+  std::vector<Rotator> save_c = ctx->rot_c, save_n = ctx->rot_n;
+  CK(cudaMemcpyAsync(ctx->d_x, iq, (size_t)P.H * sizeof(c32), cudaMemcpyHostToDevice, s));
+  W.x = ctx->d_x;
+  cf32 *hp = reinterpret_cast<cf32 *>(ctx->h_ph);
+  for (int c = 0; c < P.nch; c++) ctx->rot_c[c].generate(hp + c, P.n_ddc, P.nch);
+  CK(cudaMemcpyAsync(ctx->d_phc, hp, (size_t)P.n_ddc * nch * sizeof(c32), cudaMemcpyHostToDevice, s));
+  CK(cudaStreamSynchronize(s));
+  for (int c = 0; c < P.nch; c++) ctx->rot_n[c].generate(hp + c, P.n_noise, P.nch);
+  CK(cudaMemcpyAsync(ctx->d_phn, hp, (size_t)P.n_noise * nch * sizeof(c32), cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(W.mm_state, &ctx->mm, sizeof(MmState), cudaMemcpyHostToDevice, s));
+  launch_chan_fir(G, ctx->T, W, ctx->impl, s);
+  launch_noise_fir(G, ctx->T, W, ctx->impl, s);
+  launch_energy(G, ctx->T, W, 0, s);
+  ctx->launches += 3;
+  CK(cudaMemcpyAsync(ctx->h_energy, W.energy, nch * sizeof(double), cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(ctx->h_noise, W.noise, nch * sizeof(double), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  std::vector<double> snr(nch);
+  for (size_t i = 0; i < nch; i++) {
+    snr[i] = 10.0 * std::log10(ctx->h_energy[i] / ctx->h_noise[i]);
+    const bool listed = (int)i >= first && (int)i < first + n_channels;
+    ctx->h_pass[i] = (listed && snr[i] >= P.squelch_db) ? 1 : 0;
+  }
+  CK(cudaMemcpyAsync(W.pass, ctx->h_pass, nch * sizeof(int), cudaMemcpyHostToDevice, s));
+  launch_demod(G, ctx->T, W, s);
+  int *d_res = ctx->d_list ? ctx->d_list : nullptr;
+  if (!ctx->d_res4) { int rc = dev_alloc(ctx, &ctx->d_res4, 4 * 128); if (rc) return rc; }
+  d_res = ctx->d_res4;
+  launch_mm_chained_list(G, ctx->T, W, first, n_channels, stop_lap, d_res, s);
+  ctx->launches += 2;
+  std::vector<int> r4(4 * nch);
+  std::vector<uint32_t> rows(nch * (size_t)G.bw);
+  CK(cudaMemcpyAsync(r4.data(), d_res, 4 * nch * sizeof(int), cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(rows.data(), W.bits, rows.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(&ctx->mm, W.mm_state, sizeof(MmState), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  ctx->last_slots = 1;
+  size_t used = 0;
+  for (int c = 0; c < P.nch; c++) {
+    const bool listed = c >= first && c < first + n_channels;
+    const bool processed = listed && r4[4 * c] != 0;
+    if (!processed) { ctx->rot_c[c] = save_c[c]; ctx->rot_n[c] = save_n[c]; }    // DDC objects never called
+    if (!listed) continue;
+    btb200_chan_result &o = res[c - first];
+    o.channel = P.ch_lo + c;
+    o.processed = processed ? 1 : 0;
+    o.pass = processed ? ctx->h_pass[c] : 0;
+    o.n_symbols = r4[4 * c + 1];
+    o.ac_index = processed ? r4[4 * c + 2] : -1;
+    o.lap = (uint32_t)r4[4 * c + 3];
+    o.snr = snr[c];
+    o.sym_offset = 0; o.sym_count = 0; o.reserved = 0;
+    if (o.ac_index >= 0 && symbols) {
+      int cnt = o.n_symbols - o.ac_index;
+      if (cnt > 3125) cnt = 3125;
+      if (used + (size_t)cnt <= symbols_cap) {
+        const uint32_t *row = &rows[(size_t)c * G.bw];
+        for (int i = 0; i < cnt; i++) { const int b = o.ac_index + i; symbols[used + i] = (row[b >> 5] >> (b & 31)) & 1; }
+        o.sym_offset = used; o.sym_count = (uint32_t)cnt;
+        used += (size_t)cnt;
+      }
+    }
+  }
+  return BTB200_OK;
 }
 
 int btb200_last_timing(const btb200_ctx *ctx, float ms[8])

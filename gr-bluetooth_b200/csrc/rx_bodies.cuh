@@ -117,6 +117,27 @@ BTB_HD void bits_window(const uint32_t *__restrict__ row, int lag, uint64_t *lo,
   *hi = (uint32_t)(b >> s) & 0xff;
 }
 
+BTB_HD int row_bit(const uint32_t *__restrict__ row, int i) { return (row[i >> 5] >> (i & 31)) & 1; }
+
+// classic_packet_impl::header_present (lib/packet_impl.cc:1205-1242) on a packed symbol row:
+// the packet starts at symbol `start` and has `length` symbols
+BTB_HD int header_present_bits(const uint32_t *__restrict__ row, int start, int length)
+{
+  if (length < 126) return 0;
+  const int s = start + 67;
+  int be = 0;
+  const int msb = row_bit(row, s);
+  be += row_bit(row, s + 1) ^ !msb;
+  be += row_bit(row, s + 2) ^ msb;
+  be += row_bit(row, s + 3) ^ !msb;
+  be += row_bit(row, s + 4) ^ msb;
+  for (int a = 0; a < 54; a += 3) {
+    const int x = row_bit(row, s + 5 + a), y = row_bit(row, s + 6 + a), z = row_bit(row, s + 7 + a);
+    be += ((x ^ y) | (y ^ z) | (z ^ x));
+  }
+  return be < 5;
+}
+
 struct DevHit {
   int32_t  b;           // slot in batch
   int16_t  chi;         // channel index

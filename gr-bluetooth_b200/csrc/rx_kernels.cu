@@ -87,6 +87,45 @@ __global__ void k_mm_chained(Geom G, DevBatch W, const float *__restrict__ mmse)
   *W.mm_state = st;
 }
 
+// multi_hopper channel loop (lib/multi_hopper_impl.cc:93-137, 152-209) on the shared chained state:
+// channels first..first+n-1 of slot 0 in order; per channel ONE sniff_ac over min(nsym-68, 625) lags;
+// the loop ends after the first channel whose packet has LAP == stop_lap and a header.
+// res[c] = {processed, nsym, ac_index, lap}
+__global__ void k_mm_chained_list(Geom G, DevBatch W, const float *__restrict__ mmse, const uint64_t *__restrict__ ac_lut,
+                                  int first, int n, uint32_t stop_lap, int4 *__restrict__ res)
+{
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  MmState st = *W.mm_state;
+  bool stopped = false;
+  for (int c = 0; c < G.nch; c++) {
+    int4 r = make_int4(0, 0, -1, 0);
+    if (c >= first && c < first + n && !stopped) {
+      r.x = 1;
+      if (W.pass[c]) {
+        uint32_t *row = W.bits + (long)c * G.bw;
+        const int nsym = window_mm(G, mmse, W.dem + (long)c * G.n_dem_pad, st, row,
+                                   W.soft ? W.soft + (long)c * G.n_dem_pad : nullptr);
+        r.y = nsym;
+        if (nsym >= 68) {
+          const int latest = (nsym - 68 < 625) ? nsym - 68 : 625;
+          for (int lag = 0; lag < latest; lag++) {
+            uint64_t lo; uint32_t hi, lap;
+            bits_window(row, lag, &lo, &hi);
+            if (br_lag_test(ac_lut, lo, hi, &lap)) { r.z = lag; r.w = (int)lap; break; }
+          }
+          if (r.z >= 0 && (uint32_t)r.w == stop_lap) {
+            const int len = (nsym - r.z) < 3125 ? (nsym - r.z) : 3125;
+            if (header_present_bits(row, r.z, len)) stopped = true;
+          }
+        }
+      }
+    }
+    W.nsym[c] = r.y;
+    res[c] = r;
+  }
+  *W.mm_state = st;
+}
+
 struct HitEmitter {
   const Geom &G; const DevBatch &W; int b, c, nsym;
   __device__ void operator()(int kind, int offset, int n_symbols, uint32_t lap) const
@@ -879,6 +918,12 @@ void launch_mm(const Geom &G, const DevTables &T, const DevBatch &W, cudaStream_
 {
   if (G.stateless) k_mm_stateless<<<cdiv((long)W.B * G.nch, 32), 32, 0, s>>>(G, W, T.mmse);
   else             k_mm_chained<<<1, 32, 0, s>>>(G, W, T.mmse);
+}
+
+void launch_mm_chained_list(const Geom &G, const DevTables &T, const DevBatch &W, int first, int n, unsigned stop_lap,
+                            int *res4, cudaStream_t s)
+{
+  k_mm_chained_list<<<1, 32, 0, s>>>(G, W, T.mmse, T.ac_lut, first, n, stop_lap, reinterpret_cast<int4 *>(res4));
 }
 
 void launch_search(const Geom &G, const DevTables &T, const DevBatch &W, cudaStream_t s)

@@ -48,6 +48,8 @@ void launch_noise_fir(const Geom &G, const DevTables &T, const DevBatch &W, int 
 void launch_energy(const Geom &G, const DevTables &T, const DevBatch &W, int device_gate, cudaStream_t s);
 void launch_demod(const Geom &G, const DevTables &T, const DevBatch &W, cudaStream_t s);
 void launch_mm(const Geom &G, const DevTables &T, const DevBatch &W, cudaStream_t s);
+void launch_mm_chained_list(const Geom &G, const DevTables &T, const DevBatch &W, int first, int n, unsigned stop_lap,
+                            int *res4, cudaStream_t s);
 void launch_search(const Geom &G, const DevTables &T, const DevBatch &W, cudaStream_t s);
 void launch_gather(const Geom &G, const DevBatch &W, cudaStream_t s);
 void launch_demod_mm_v2(const Geom &G, const DevTables &T, const DevBatch &W, float *demT, cudaStream_t s);

@@ -3,9 +3,10 @@
 // role of the GNU Radio scheduler for one block -- zero history in front of the stream, then
 // work() until the file is consumed.
 //   -f/--freq Hz   -r/--rate sps   -i/--input-file FILE   -S (all-piconet sniffer, default)
-//   -L (LAP printer)   -s/--snr dB   -N/--nsamples n   -2/--input-shorts
+//   -L (LAP printer)   -l HEXLAP [-p] (follow one piconet: multi_hopper)   -s/--snr dB   -N/--nsamples n   -2/--input-shorts
 #include "gr_bluetooth/multi_sniffer.h"
 #include "gr_bluetooth/multi_LAP.h"
+#include "gr_bluetooth/multi_hopper.h"
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -27,7 +28,8 @@ int main(int argc, char **argv)
   double freq = 2476e6, rate = 2e6, snr = 10;
   std::string in;
   long nsamples = -1;
-  bool shorts = false, lap_mode = false;
+  bool shorts = false, lap_mode = false, hop_mode = false;
+  int target_lap = 0;
   for (int i = 1; i < argc; i++) {
     std::string a = argv[i];
     auto next = [&]() -> const char * { return i + 1 < argc ? argv[++i] : ""; };
@@ -38,7 +40,9 @@ int main(int argc, char **argv)
     else if (a == "-N" || a == "--nsamples") nsamples = (long)parse_eng(next());
     else if (a == "-2" || a == "--input-shorts") shorts = true;
     else if (a == "-S" || a == "--sniff-all") lap_mode = false;
-    else if (a == "-L" || a == "--lap") lap_mode = true;
+    else if (a == "-L" || a == "--lap-printer") lap_mode = true;
+    else if (a == "-l" || a == "--lap") { target_lap = (int)std::strtol(next(), nullptr, 16); hop_mode = true; }      // apps/btrx:-l LAP
+    else if (a == "-p" || a == "--hop") hop_mode = true;
     else { std::fprintf(stderr, "unknown option %s\n", a.c_str()); return 2; }
   }
   if (in.empty()) { std::fprintf(stderr, "usage: btrx_b200 -f FREQ -r RATE -i FILE [-S|-L] [-s SNR] [-N n] [-2]\n"); return 2; }
@@ -51,7 +55,8 @@ int main(int argc, char **argv)
 
   boost::shared_ptr<gr::bluetooth::multi_block> blk;
   try {
-    if (lap_mode) blk = gr::bluetooth::multi_LAP::make(rate, freq, snr);
+    if (hop_mode) blk = gr::bluetooth::multi_hopper::make(rate, freq, snr, target_lap, false, false);
+    else if (lap_mode) blk = gr::bluetooth::multi_LAP::make(rate, freq, snr);
     else blk = gr::bluetooth::multi_sniffer::make(rate, freq, snr, false);
   } catch (const std::exception &e) {
     std::fprintf(stderr, "btrx_b200: %s\n", e.what());

@@ -26,7 +26,7 @@ class GR_BLUETOOTH_API multi_block : virtual public gr::sync_block {
   multi_block() {}   // to allow for pure virtual
   // extra_symbols: 3125 for sniffer/hopper, 68 for multi_LAP (set_symbol_history in the reference)
   multi_block(double sample_rate, double center_freq, double squelch_threshold, int extra_symbols,
-              int search_mask);
+              int search_mask, bool force_chained = false);
 
   static const int SYMBOLS_PER_BASIC_RATE_SLOT = 625;
 

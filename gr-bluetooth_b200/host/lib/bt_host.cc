@@ -475,6 +475,8 @@ bool Piconet::uap_from_header(ClassicPacket &pkt)
     reset();
     return false;
   }
+  d_pattern_indices[d_packets_observed] = (int)(clkn - d_first_pkt_time);
+  d_pattern_channels[d_packets_observed] = (uint8_t)pkt.channel;
   d_packets_observed++;
   d_total_packets_observed++;
   for (int count = 0; count < 64; count++) {
@@ -523,11 +525,134 @@ bool Piconet::uap_from_header(ClassicPacket &pkt)
 void Piconet::reset()
 {
   std::printf("no candidates remaining! starting over . . .\n");
+  if (d_hop_reversal_inited) { d_clock_candidates.clear(); d_sequence.clear(); d_sequence.shrink_to_fit(); }
   d_got_first_packet = false;
   d_packets_observed = 0;
+  d_hop_reversal_inited = false;
   d_have_uap = false;
   d_have_clk6 = false;
   d_have_clk27 = false;
+  /* two packets in a row on one channel hint at adaptive frequency hopping: try AFH next time */
+  d_afh = d_looks_like_afh;
+  d_looks_like_afh = false;
+}
+
+// 5-bit butterfly permutation of the hop selection kernel (Core spec vol 2 part B 2.6; piconet_impl.cc:165-199)
+static int perm5(int z, int p_high, int p_low)
+{
+  static const int index1[14] = {0, 2, 1, 3, 0, 1, 0, 3, 1, 0, 2, 1, 0, 1};
+  static const int index2[14] = {1, 3, 2, 4, 4, 3, 2, 4, 4, 3, 4, 3, 3, 2};
+  int zb[5], p[14];
+  for (int i = 0; i < 9; i++) p[i] = (p_low >> i) & 1;
+  for (int i = 0; i < 5; i++) p[i + 9] = (p_high >> i) & 1;
+  for (int i = 0; i < 5; i++) zb[i] = (z >> i) & 1;
+  for (int i = 13; i >= 0; i--)
+    if (p[i]) { const int t = zb[index1[i]]; zb[index1[i]] = zb[index2[i]]; zb[index2[i]] = t; }
+  int out = 0;
+  for (int i = 0; i < 5; i++) out += zb[i] << i;
+  return out;
+}
+
+// the complete hopping sequence, index = CLK1-27 (piconet_impl.cc:131-159, 214-255)
+void Piconet::gen_hops()
+{
+  const int address = (int)((((uint32_t)d_uap << 24) | d_lap) & 0xfffffff);
+  int bank[CHANNELS];
+  for (int i = 0; i < CHANNELS; i++) bank[i] = (i * 2) % CHANNELS;
+  const int a1 = (address >> 23) & 0x1f, bb = (address >> 19) & 0x0f;
+  const int c1 = ((address >> 4) & 0x10) + ((address >> 3) & 0x08) + ((address >> 2) & 0x04) + ((address >> 1) & 0x02) + (address & 0x01);
+  const int d1 = (address >> 10) & 0x1ff;
+  const int e = ((address >> 7) & 0x40) + ((address >> 6) & 0x20) + ((address >> 5) & 0x10) + ((address >> 4) & 0x08) +
+                ((address >> 3) & 0x04) + ((address >> 2) & 0x02) + ((address >> 1) & 0x01);
+  // permutation table for the two control words used per (c, d): [z][c][d]
+  std::vector<char> perm((size_t)32 * 32 * 512);
+  for (int z = 0; z < 32; z++)
+    for (int ph = 0; ph < 32; ph++)
+      for (int pl = 0; pl < 512; pl++) perm[((size_t)z * 32 + ph) * 512 + pl] = (char)perm5(z, ph, pl);
+  d_sequence.assign((size_t)SEQUENCE_LENGTH, 0);
+  size_t index = 0;
+  int f = 0;
+  for (int h = 0; h < 4; h++)
+    for (int i = 0; i < 32; i++) {
+      const int a = a1 ^ i;
+      for (int j = 0; j < 32; j++) {
+        const int cc = c1 ^ j, cf = cc ^ 0x1f;
+        for (int k = 0; k < 512; k++) {
+          const int d = d1 ^ k;
+          for (int x = 0; x < 32; x++) {
+            const int pin = ((x + a) % 32) ^ bb;
+            int pout = perm[((size_t)pin * 32 + cc) * 512 + d];
+            d_sequence[index] = (char)bank[(pout + e + f) % CHANNELS];
+            if (d_afh) {
+              d_sequence[index + 1] = d_sequence[index];
+            } else {
+              pout = perm[((size_t)pin * 32 + cf) * 512 + d];
+              d_sequence[index + 1] = (char)bank[(pout + e + f + 32) % CHANNELS];
+            }
+            index += 2;
+          }
+          f += 16;
+        }
+      }
+    }
+}
+
+int Piconet::init_hop_reversal(bool aliased)
+{
+  std::printf("\nCalculating complete hopping sequence.\n");
+  gen_hops();
+  d_aliased = aliased;
+  const uint32_t clock = (d_clk_offset + d_first_pkt_time) & 0x3f;
+  // candidates: clock values with the known low bits whose hop lands on the first observed channel
+  d_clock_candidates.clear();
+  const char first_channel = (char)d_pattern_channels[0];
+  for (uint32_t i = clock; i < (uint32_t)SEQUENCE_LENGTH; i += 0x40) {
+    const char obs = d_aliased ? aliased_channel(d_sequence[i]) : d_sequence[i];
+    if (obs == first_channel) d_clock_candidates.push_back(i);
+  }
+  d_num_candidates = (int)d_clock_candidates.size();
+  d_winnowed = 0;
+  d_hop_reversal_inited = true;
+  d_have_clk27 = false;
+  std::printf("%d initial CLK1-27 candidates\n", d_num_candidates);
+  return d_num_candidates;
+}
+
+int Piconet::winnow(int offset, char channel)
+{
+  int n = 0;
+  for (int i = 0; i < d_num_candidates; i++) {
+    const char s = d_sequence[(size_t)((d_clock_candidates[(size_t)i] + (uint32_t)offset) % (uint32_t)SEQUENCE_LENGTH)];
+    const char obs = d_aliased ? aliased_channel(s) : s;
+    if (obs == channel) d_clock_candidates[(size_t)n++] = d_clock_candidates[(size_t)i];
+  }
+  d_num_candidates = n;
+  if (n == 1) {
+    d_clk_offset = (d_clock_candidates[0] - d_first_pkt_time) & 0x7ffffff;
+    d_have_clk27 = true;
+    std::printf("\nAcquired CLK1-27 offset = 0x%07x\n", d_clk_offset);
+  } else if (n == 0) {
+    reset();
+  } else {
+    std::printf("%d CLK1-27 candidates remaining\n", n);
+  }
+  return n;
+}
+
+int Piconet::winnow()
+{
+  int n = d_num_candidates;
+  for (; d_winnowed < d_packets_observed; d_winnowed++) {
+    const int index = d_pattern_indices[d_winnowed];
+    const uint8_t channel = d_pattern_channels[d_winnowed];
+    n = winnow(index, (char)channel);
+    if (d_packets_observed > 0 && d_winnowed > 0) {
+      const int last_index = d_pattern_indices[d_winnowed - 1];
+      const uint8_t last_channel = d_pattern_channels[d_winnowed - 1];
+      if (!d_looks_like_afh && (index == last_index + 1) && (channel == last_channel)) d_looks_like_afh = true;
+    }
+  }
+  return n;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -682,5 +807,61 @@ void SnifferHost::fhs(std::shared_ptr<ClassicPacket> pkt)
   slot->set_offset(offset);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+HopperHost::SlotPlan HopperHost::plan(uint32_t clkn) const
+{
+  SlotPlan p;
+  if (d_piconet.have_clk27()) {
+    /* follow along on the predicted channel, multi_hopper_impl.cc:152-166 */
+    p.hopalong = true;
+    p.clock27 = (clkn + d_piconet.offset()) & 0x7ffffff;
+    const int hopch = d_piconet.hop((int)p.clock27);
+    p.obs_channel = d_aliased ? Piconet::aliased_channel((char)hopch) : hopch;
+    if (p.obs_channel >= d_ch_lo && p.obs_channel <= d_ch_hi) { p.first_channel = hopch; p.n_channels = 1; }
+  } else {
+    p.first_channel = d_ch_lo;
+    p.n_channels = d_ch_hi - d_ch_lo + 1;
+    p.stop_lap = d_lap;
+  }
+  return p;
+}
+
+/* multi_hopper_impl.cc:107-135 */
+bool HopperHost::scan_packet(uint32_t clkn, int channel, const char *symbols, int len)
+{
+  ClassicPacket pkt(symbols, len, clkn, 2402000000.0 + 1e6 * channel);
+  if (!(pkt.lap() == d_lap && pkt.header_present())) return false;
+  if (!d_piconet.have_clk6()) {
+    /* working on CLK1-6/UAP discovery */
+    d_piconet.uap_from_header(pkt);
+    if (d_piconet.have_clk6()) {
+      /* got CLK1-6/UAP, start working on CLK1-27 with the packets seen so far */
+      d_piconet.init_hop_reversal(d_aliased);
+      d_piconet.winnow();
+    }
+  } else {
+    /* continue working on CLK1-27: timing of an additional packet */
+    d_piconet.uap_from_header(pkt);
+    if (d_piconet.have_clk6()) d_piconet.winnow();
+  }
+  return true;
+}
+
+/* multi_hopper_impl.cc:176-205 */
+void HopperHost::hop_packet(const SlotPlan &p, const char *symbols, int len)
+{
+  ClassicPacket pkt(symbols, len, 0, 2402000000.0 + 1e6 * p.obs_channel);
+  if (pkt.lap() != d_lap) return;
+  std::printf("clock 0x%07x, channel %2d: ", p.clock27, pkt.channel);
+  if (pkt.header_present()) {
+    pkt.set_uap(d_piconet.uap());
+    pkt.set_clock(p.clock27, true);
+    pkt.decode();
+    if (pkt.got_payload()) pkt.print();
+  } else {
+    std::printf("ID\n");
+  }
+}
 
 }  // namespace btb200_host

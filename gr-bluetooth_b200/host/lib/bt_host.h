@@ -105,8 +105,26 @@ class Piconet {
   void set_nap(uint16_t n) { d_nap = n; d_have_nap = true; }
   void set_offset(uint32_t o) { d_clk_offset = o; d_have_clk6 = true; d_have_clk27 = true; }
 
+  // CLK1-27 discovery by hop reversal (piconet_impl.cc:96-368): the complete 2^27-entry hopping
+  // sequence of (UAP, LAP) is generated, candidates = clock values whose hop matches the first
+  // observed channel, then winnowed with every later observation.
+  int init_hop_reversal(bool aliased);                          // :96-129
+  int winnow();                                                 // :345-368
+  char hop(int clock) const { return d_sequence[(size_t)clock]; }   // :279-282
+  static char aliased_channel(char channel) { return (char)(((channel + 24) % 25) + 26); }   // :520-523
+
  private:
   static const int MAX_PATTERN_LENGTH = 1000;                   // lib/piconet_impl.h:45
+  static const int SEQUENCE_LENGTH = 134217728;                 // include/gr_bluetooth/piconet.h:83
+  static const int CHANNELS = 79, ALIASED_CHANNELS = 25;
+  int d_pattern_indices[MAX_PATTERN_LENGTH];
+  uint8_t d_pattern_channels[MAX_PATTERN_LENGTH];
+  std::vector<char> d_sequence;
+  std::vector<uint32_t> d_clock_candidates;
+  int d_num_candidates = 0, d_winnowed = 0;
+  bool d_hop_reversal_inited = false, d_aliased = false, d_afh = false, d_looks_like_afh = false;
+  int winnow(int offset, char channel);                         // :303-343
+  void gen_hops();                                              // :214-255
   uint32_t d_lap;
   std::deque<std::shared_ptr<ClassicPacket>> d_queue;
   bool d_got_first_packet = false, d_have_uap = false, d_have_nap = false, d_have_clk6 = false, d_have_clk27 = false;
@@ -136,6 +154,33 @@ class SnifferHost {
   void discover(std::shared_ptr<ClassicPacket> pkt, std::shared_ptr<Piconet> pn);
   void recall(std::shared_ptr<Piconet> pn);
   void fhs(std::shared_ptr<ClassicPacket> pkt);
+};
+
+// The per-slot logic of the hopper block: multi_hopper_impl::work / hopalong,
+// lib/multi_hopper_impl.cc:76-209 -- scan every channel until CLK1-27 is known (UAP/CLK1-6 from
+// packet headers, then hop reversal), afterwards follow the piconet on its predicted channel.
+class HopperHost {
+ public:
+  HopperHost(uint32_t lap, bool aliased, int ch_lo, int ch_hi)
+      : d_lap(lap), d_aliased(aliased), d_ch_lo(ch_lo), d_ch_hi(ch_hi), d_piconet(lap) {}
+  struct SlotPlan {
+    bool hopalong = false;
+    uint32_t clock27 = 0;
+    int first_channel = 0, n_channels = 0;     // classic channels to process, in ascending order
+    int obs_channel = -1;                      // hopalong: channel the packet is reported on
+    uint32_t stop_lap = 0xffffffffu;           // scan: a packet with this LAP and a header ends the channel loop
+  };
+  SlotPlan plan(uint32_t clkn) const;
+  // scan phase: the first access code found on `channel`; returns true when the reference breaks out of the loop
+  bool scan_packet(uint32_t clkn, int channel, const char *symbols, int len);
+  // hopalong phase: the first access code found on the predicted channel
+  void hop_packet(const SlotPlan &p, const char *symbols, int len);
+
+ private:
+  uint32_t d_lap;
+  bool d_aliased;
+  int d_ch_lo, d_ch_hi;
+  Piconet d_piconet;
 };
 
 }  // namespace btb200_host

@@ -11,7 +11,7 @@ namespace gr {
 namespace bluetooth {
 
 multi_block::multi_block(double sample_rate, double center_freq, double squelch_threshold,
-                         int extra_symbols, int search_mask)
+                         int extra_symbols, int search_mask, bool force_chained)
     : gr::sync_block("bluetooth multi block", gr::io_signature::make(1, 1, sizeof(gr_complex)),
                      gr::io_signature::make(0, 0, 0))
 {
@@ -28,7 +28,7 @@ multi_block::multi_block(double sample_rate, double center_freq, double squelch_
   cfg.search = search_mask;
   // reference semantics by default: one clock-recovery state shared by all channel-windows
   const char *mm = std::getenv("BTB200_MM_MODE");
-  cfg.mm_mode = (mm && std::string(mm) == "stateless") ? BTB200_MM_STATELESS : BTB200_MM_CHAINED;
+  cfg.mm_mode = (!force_chained && mm && std::string(mm) == "stateless") ? BTB200_MM_STATELESS : BTB200_MM_CHAINED;
   const char *bs = std::getenv("BTB200_BATCH_SLOTS");
   d_batch_slots = bs ? (unsigned)std::atoi(bs) : 16u;
   if (d_batch_slots < 1) d_batch_slots = 1;

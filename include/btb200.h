@@ -190,6 +190,33 @@ BTB200_API int  btb200_process(btb200_ctx *ctx, const float *iq, size_t n_sample
 BTB200_API int  btb200_process_device(btb200_ctx *ctx, const float *d_iq, size_t n_samples,
                            uint64_t first_slot, uint32_t n_slots, btb200_hits *out);
 
+/*
+ * One multi_hopper work() call (lib/multi_hopper_impl.cc:76-209), BTB200_MM_CHAINED only: process the
+ * classic channels first_channel .. first_channel+n_channels-1 of ONE window in ascending order on the
+ * shared clock-recovery state -- channel_samples, check_snr, channel_symbols and a single sniff_ac over
+ * min(n_symbols-68, 625) lags per channel -- and stop after the first channel whose packet carries
+ * stop_lap and has a packet header (the reference's `break`, multi_hopper_impl.cc:109-133; pass
+ * 0xffffffff for "never", as hopalong() does with its single channel).  Channels that are not reached keep
+ * their rotator and clock-recovery state untouched.  res[i] describes channel first_channel+i; symbols
+ * receives, per channel with an access code, the symbols from the access code on (what the reference
+ * hands to classic_packet::make).
+ */
+typedef struct btb200_chan_result {
+  int32_t  channel;              /* classic channel number */
+  int32_t  processed;            /* 0: not reached (after the break) */
+  int32_t  pass;                 /* squelch decision */
+  int32_t  n_symbols;            /* symbols produced by clock recovery */
+  int32_t  ac_index;             /* first access code, -1 if none */
+  uint32_t lap;
+  double   snr;
+  uint64_t sym_offset;           /* into the symbols arena */
+  uint32_t sym_count;            /* min(n_symbols - ac_index, 3125) */
+  uint32_t reserved;
+} btb200_chan_result;
+BTB200_API int btb200_process_channels(btb200_ctx *ctx, const float *iq, size_t n_samples, uint64_t slot,
+                                       int32_t first_channel, int32_t n_channels, uint32_t stop_lap,
+                                       btb200_chan_result *res, uint8_t *symbols, size_t symbols_cap);
+
 /* split form for overlap / benchmarking: enqueue everything on the ctx stream,
  * then wait and collect.  btb200_process == submit + collect. */
 BTB200_API int  btb200_submit(btb200_ctx *ctx, const float *iq, int iq_on_device, size_t n_samples,

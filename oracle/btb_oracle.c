@@ -533,6 +533,82 @@ done:
   return rc;
 }
 
+/* classic_packet_impl::header_present, lib/packet_impl.cc:1205-1242 */
+int btbo_header_present(const uint8_t *sym, int length)
+{
+  if (length < 126) return 0;
+  const uint8_t *s = sym + 67;
+  int be = 0;
+  const uint8_t msb = s[0];
+  be += s[1] ^ !msb;
+  be += s[2] ^ msb;
+  be += s[3] ^ !msb;
+  be += s[4] ^ msb;
+  s += 5;
+  for (int a = 0; a < 54; a += 3)
+    be += ((s[a] ^ s[a + 1]) | (s[a + 1] ^ s[a + 2]) | (s[a + 2] ^ s[a]));
+  return be < 5;
+}
+
+/* the channel loop of multi_hopper_impl::work / hopalong, lib/multi_hopper_impl.cc:93-137, 152-209 */
+int btbo_window_list(const btbo_plan *p, btbo_state *st, const float *window, const int32_t *chis, int n,
+                     uint32_t stop_lap, btbo_chan_result *res, uint8_t *symbols_out)
+{
+  const btbo_info *I = &p->info;
+  const gra_c32 *in = (const gra_c32 *)window;
+  gra_c32 *ddc_out = (gra_c32 *)malloc(sizeof(gra_c32) * (size_t)(I->n_ddc + 1));
+  gra_c32 *nz_out = (gra_c32 *)malloc(sizeof(gra_c32) * (size_t)(I->n_noise + 1));
+  float *demod_out = (float *)malloc(sizeof(float) * (size_t)(I->n_ddc + 1));
+  float *cr_out = (float *)malloc(sizeof(float) * (size_t)(I->n_ddc + 1));
+  int stopped = 0;
+  for (int q = 0; q < n; q++) {
+    btbo_chan_result *r = &res[q];
+    const int chi = chis[q];
+    uint8_t *symbols = symbols_out + (size_t)q * I->H;
+    memset(r, 0, sizeof *r);
+    r->chi = chi; r->ac_index = -1;
+    if (stopped) continue;
+    r->processed = 1;
+    gra_fxlat cf = p->chan_ddc[chi];
+    cf.phase = st->chan_phase[chi]; cf.counter = st->chan_counter[chi];
+    gra_fxlat_work(&cf, I->n_ddc, in + I->fcs, ddc_out);
+    st->chan_phase[chi] = cf.phase; st->chan_counter[chi] = cf.counter;
+    double energy = 0.0;
+    for (int i = 0; i < I->n_ddc; i++) energy += gra_mag2(ddc_out[i]);
+    energy /= I->n_ddc;
+    gra_fxlat nf = p->noise_ddc[chi];
+    nf.phase = st->noise_phase[chi]; nf.counter = st->noise_counter[chi];
+    gra_fxlat_work(&nf, I->n_noise, in + I->fns, nz_out);
+    st->noise_phase[chi] = nf.phase; st->noise_counter[chi] = nf.counter;
+    double off = 0.0;
+    for (int i = 0; i < I->n_noise; i++) off += gra_mag2(nz_out[i]);
+    off /= I->n_noise;
+    r->snr = 10.0 * log10(energy / off);
+    r->pass = (r->snr >= I->snr_db);
+    if (!r->pass) continue;
+    const int n_demod = I->n_ddc - 1;
+    btbo_demod(p, (const float *)ddc_out, demod_out, n_demod);
+    float mm[3];
+    btbo_state_get_mm(st, mm);
+    const int len = btbo_mm_cr(p, mm, demod_out, n_demod, cr_out, n_demod);
+    btbo_state_set_mm(st, mm);
+    memset(symbols, 0, (size_t)I->H);
+    for (int i = 0; i < len; i++) symbols[i] = (cr_out[i] < 0) ? 0 : 1;
+    r->nsym = len;
+    if (len >= AC_SYMBOLS) {
+      const int latest = ((len - AC_SYMBOLS) < SLOT_SYMBOLS) ? (len - AC_SYMBOLS) : SLOT_SYMBOLS;
+      const int ac = btbo_sniff_ac(symbols, latest);
+      r->ac_index = ac;
+      if (ac >= 0) {
+        r->lap = air_to_host(symbols + ac + 38, 24);
+        if (r->lap == stop_lap && btbo_header_present(symbols + ac, (len - ac) < 3125 ? (len - ac) : 3125)) stopped = 1;
+      }
+    }
+  }
+  free(ddc_out); free(nz_out); free(demod_out); free(cr_out);
+  return 0;
+}
+
 typedef struct {
   const btbo_plan *p; const float *iq; long iq_first, iq_n, first_call, num_calls;
   int flags, per_cap; btbo_hit *tmp; int *cnt;

@@ -101,6 +101,26 @@ typedef struct {
 int btbo_window(const btbo_plan *, btbo_state *, const float *window, int slot, int flags,
                 btbo_hit *hits, int hits_cap, int *nhits, const btbo_debug *dbg);
 
+/* ---- one multi_hopper work() call (multi_hopper_impl.cc:76-209) ---------------------------------
+ * Processes the listed channel indices IN ORDER with the chained state (channel_samples, check_snr,
+ * channel_symbols, ONE sniff_ac over min(nsym-68, 625) lags), and stops after the first channel whose
+ * packet carries stop_lap and has a header (the reference's `break`, multi_hopper_impl.cc:109-133);
+ * stop_lap = 0xffffffff never stops (hopalong passes a single channel).  Channels after the stop are
+ * not touched at all (rotators and clock recovery keep their state).  symbols: [n][H] bytes. */
+typedef struct {
+  int32_t chi;          /* channel index */
+  int32_t processed;    /* 0: not reached (after the break) */
+  int32_t pass;         /* squelch */
+  int32_t nsym;
+  int32_t ac_index;     /* first access code, -1 if none */
+  uint32_t lap;
+  double  snr;
+} btbo_chan_result;
+int btbo_window_list(const btbo_plan *, btbo_state *, const float *window, const int32_t *chis, int n,
+                     uint32_t stop_lap, btbo_chan_result *res, uint8_t *symbols);
+/* classic_packet_impl::header_present, packet_impl.cc:1205-1242 */
+int btbo_header_present(const uint8_t *symbols, int length);
+
 /* Scheduler emulation over a sample array: calls
  * first_call .. first_call+num_calls-1 of a stream of n_total samples, of which
  * iq holds samples [iq_first, iq_first+iq_n) (zeros elsewhere).

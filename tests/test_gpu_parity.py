@@ -286,6 +286,26 @@ def test_cpp_blocks_btrx_b200_full_capture_digest(name, kats, tmp_path):
     assert hashlib.md5(out.encode()).hexdigest() == kats["stdout_md5"][name]
 
 
+def test_cpp_multi_hopper_block_digest(tmp_path):
+    """gr::bluetooth::multi_hopper::make(..., LAP, aliased, tun) through btrx_b200 -l 24d952 on headset1:
+    the channel loop with the reference's early `break` runs on the GPU (btb200_process_channels, chained
+    state), UAP/CLK1-6, hop reversal and hop-along decode on the host -> the reference's stdout digest."""
+    import hashlib
+    import subprocess
+    from conftest import ROOT
+    exe = os.path.join(ROOT, "gr-bluetooth_b200", "host", "btrx_b200")
+    iq = full_capture("headset1")
+    if not os.path.exists(exe) or iq is None:
+        pytest.skip("btrx_b200 or full capture not staged")
+    path = tmp_path / "h1.cfile"
+    iq.tofile(path)
+    out = subprocess.run([exe, "-f", "2476.5M", "-r", "8M", "-i", str(path), "-l", "24d952"], capture_output=True,
+                         timeout=600)
+    assert out.returncode == 0, out.stderr.decode()[-1500:]
+    assert b"Acquired CLK1-27 offset = 0x00a3c6f" in out.stdout
+    assert hashlib.md5(out.stdout).hexdigest() == "a5dd1f5176e5c96ef4836ff30035fea3"
+
+
 # ---------------------------------------------------------------------------------------------
 # BTB200_SNR_FAST_GUARDED: polyphase + DFT noise estimate with a guard band and exact fall-back.
 # Tolerances (the only floating-point tolerances in this suite):

@@ -61,3 +61,34 @@ def test_full_capture_stdout_digest(harness, name, kats, tmp_path):
     iq = np.fromfile(os.path.join(REF_SAMPLES, name + ".cfile"), dtype=np.complex64)
     got = host_stdout(harness, O.Plan(fs, fc), iq, tmp_path)
     assert hashlib.md5(got.encode()).hexdigest() == kats["stdout_md5"][name]
+
+
+HOPPER_MD5 = "a5dd1f5176e5c96ef4836ff30035fea3"     # headset1, multi_hopper, LAP 24d952
+
+
+@pytest.fixture(scope="module")
+def hopper_harness():
+    exe = os.path.join(HDIR, "_build", "hopper")
+    obj = os.path.join(HDIR, "_build", "btb_oracle.o")
+    srcs = [os.path.join(HDIR, "hopper_main.cc"), os.path.join(ROOT, "gr-bluetooth_b200", "host", "lib", "bt_host.cc")]
+    deps = srcs + [os.path.join(ROOT, "gr-bluetooth_b200", "host", "lib", "bt_host.h"),
+                   os.path.join(ROOT, "oracle", "btb_oracle.c"), os.path.join(ROOT, "oracle", "btb_oracle.h")]
+    if not os.path.exists(exe) or os.path.getmtime(exe) < max(os.path.getmtime(d) for d in deps):
+        os.makedirs(os.path.dirname(exe), exist_ok=True)
+        subprocess.check_call(["gcc", "-std=gnu11", "-O2", "-ffp-contract=off", "-c",
+                               os.path.join(ROOT, "oracle", "btb_oracle.c"), "-o", obj])
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", *srcs, obj, "-lpthread", "-lm", "-o", exe])
+    return exe
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_SAMPLES), reason="needs the bundled captures")
+def test_hopper_logic_reproduces_reference_digest(hopper_harness):
+    """multi_hopper (BASELINE config 4 logic): native HopperHost + hop reversal over the oracle front end
+    (oracle/btb_oracle.c: btbo_window_list) on headset1 -> UAP 0xaf after 7 packets, 26555 -> 408 -> 49 ->
+    10 -> 2 -> 2 CLK1-27 candidates, offset 0x00a3c6f, then hop-along decodes: the reference's stdout."""
+    out = subprocess.run([hopper_harness, "8e6", "2476.5e6", "24d952", os.path.join(REF_SAMPLES, "headset1.cfile")],
+                         capture_output=True, timeout=300)
+    assert out.returncode == 0
+    text = out.stdout.decode()
+    assert "Acquired CLK1-27 offset = 0x00a3c6f" in text and "26555 initial CLK1-27 candidates" in text
+    assert hashlib.md5(out.stdout).hexdigest() == HOPPER_MD5

@@ -286,6 +286,22 @@ def test_cpp_blocks_btrx_b200_full_capture_digest(name, kats, tmp_path):
     assert hashlib.md5(out.encode()).hexdigest() == kats["stdout_md5"][name]
 
 
+@pytest.mark.parametrize("name", ["headset1", "headset3"])
+def test_multi_lap_geometry_equals_oracle(name):
+    """multi_LAP window geometry (history + 68 symbols, lib/multi_LAP_impl.cc:54): BR hits, energies and
+    bits equal the oracle run with the same geometry (search semantics = sniff_ac; libbtbb's btbb_find_ac
+    is external: parity unpinned)."""
+    ex = load_excerpt(name, "stateless")
+    P = O.Plan(ex["fs"], ex["fc"], extra_symbols=68)
+    o = P.run(ex["iq"], stateless=True, want_bits=True, want_energy=True)
+    blk = g.multi_LAP(ex["fs"], ex["fc"], 10.0, mm_mode=g.MM_STATELESS, max_slots=32, squelch=g.SQUELCH_EAGER)
+    assert blk.history() == P.H
+    hits = blk.run_stream(ex["iq"])
+    want = [h for h in oracle_hit_tuples(o["hits"]) if h[2] == 0]
+    assert gpu_hit_tuples(hits) == want and len(want) >= 2
+    blk.close()
+
+
 def test_cpp_multi_hopper_block_digest(tmp_path):
     """gr::bluetooth::multi_hopper::make(..., LAP, aliased, tun) through btrx_b200 -l 24d952 on headset1:
     the channel loop with the reference's early `break` runs on the GPU (btb200_process_channels, chained

@@ -92,3 +92,16 @@ def test_hopper_logic_reproduces_reference_digest(hopper_harness):
     text = out.stdout.decode()
     assert "Acquired CLK1-27 offset = 0x00a3c6f" in text and "26555 initial CLK1-27 candidates" in text
     assert hashlib.md5(out.stdout).hexdigest() == HOPPER_MD5
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_SAMPLES), reason="needs the bundled captures")
+def test_hopper_logic_keyboard1_equals_reference_build(hopper_harness):
+    """BASELINE config 4 input (keyboard1, LAP 4831dd): same stdout as the verbatim reference build."""
+    from oracle import ref as R
+    if not R.available():
+        pytest.skip("oracle/_ref/btref not built")
+    path = os.path.join(REF_SAMPLES, "keyboard1.cfile")
+    want = R.sniff(path, 8e6, 2476.5e6, hop_lap=0x4831DD)["stdout"]
+    out = subprocess.run([hopper_harness, "8e6", "2476.5e6", "4831dd", path], capture_output=True, timeout=300)
+    assert out.returncode == 0 and out.stdout.decode() == want
+    assert "UAP = 0x61" in want

@@ -197,7 +197,7 @@ struct FirJob {
                         // input span run back to back and the span is read from DRAM once (L2 serves the rest)
 };
 
-template <int CG, int R, int W, bool SKEW = false, int MINB = ((CG == 16) ? 1 : 2)>
+template <int CG, int R, int W, int MINB = ((CG == 16) ? 1 : 2)>
 __global__ void __launch_bounds__(W * 32, MINB) k_fir_tiled(FirJob J)
 {
   constexpr int NH = 32 / CG;                 // output sub-groups per warp
@@ -255,38 +255,13 @@ __global__ void __launch_bounds__(W * 32, MINB) k_fir_tiled(FirJob J)
     }
     const int sp = (TJ - 1) * J.D + kt;
     const long base = s0 + k0;
-    if (SKEW) {
-      // one pad element per D samples: sample i sits at i + i/D, so the NH outputs a warp reads at once
-      // (D samples apart) are D+1 slots apart and fall into distinct banks even when 2D is a multiple of 32
-      for (int i = threadIdx.x; i < sp; i += W * 32) {
-        const long n = base + i;
-        xs[i + i / J.D] = (n < J.n_x) ? J.x[n] : c32{0.0f, 0.0f};
-      }
-    } else {
-      for (int i = threadIdx.x; i < sp; i += W * 32) {
-        const long n = base + i;
-        xs[i] = (n < J.n_x) ? J.x[n] : c32{0.0f, 0.0f};
-      }
+    for (int i = threadIdx.x; i < sp; i += W * 32) {
+      const long n = base + i;
+      xs[i] = (n < J.n_x) ? J.x[n] : c32{0.0f, 0.0f};
     }
     __syncthreads();
     const c32 *tp = ts + cg;
-    if (SKEW) {
-      const int D1 = J.D + 1;
-      const c32 *xq = xs + jj0 * D1;
-      const int rs = NH * W * D1;
-      int kp = 0;
-#pragma unroll 2
-      for (int k = 0; k < kt; k++) {
-        const c32 t = tp[k * CG];
-#pragma unroll
-        for (int r = 0; r < R; r++) {
-          const c32 v = xq[r * rs];
-          cmac(ar[r], ai[r], v.re, v.im, t.re, t.im);
-        }
-        xq++;
-        if (++kp == J.D) { kp = 0; xq++; }
-      }
-    } else {
+    {
       const c32 *xp = xs + jj0 * J.D;
 #pragma unroll 4
       for (int k = 0; k < kt; k++) {
@@ -339,7 +314,7 @@ __device__ __forceinline__ u64 pk_neg(u64 a) { return a ^ 0x8000000080000000ull;
 __device__ __forceinline__ float pk_lo(u64 v) { return __uint_as_float((unsigned)(v & 0xffffffffull)); }
 __device__ __forceinline__ float pk_hi(u64 v) { return __uint_as_float((unsigned)(v >> 32)); }
 
-template <int CG, int R, int W, bool SKEW = false, int MINB = 1>
+template <int CG, int R, int W, int MINB = 1>
 __global__ void __launch_bounds__(W * 32, MINB) k_fir_packed(FirJob J)
 {
   constexpr int NH = 32 / CG, TJ = NH * R * W, RP = R / 2;
@@ -403,33 +378,11 @@ __global__ void __launch_bounds__(W * 32, MINB) k_fir_packed(FirJob J)
       const long n0 = base + i, n1 = n0 + delta;
       const c32 v0 = (n0 < J.n_x) ? J.x[n0] : c32{0.0f, 0.0f};
       const c32 v1 = (n1 < J.n_x) ? J.x[n1] : c32{0.0f, 0.0f};
-      xs[SKEW ? i + i / J.D : i] = make_float4(v0.re, v1.re, v0.im, v1.im);
+      xs[i] = make_float4(v0.re, v1.re, v0.im, v1.im);
     }
     __syncthreads();
     const float4 *tp = ts + cg;
-    if (SKEW) {
-      // slot of sample (jj*D + k) is jj*(D+1) + k + k/D: walk k with a running slot pointer that skips
-      // one pad slot every D taps (warp-uniform test)
-      const int D1 = J.D + 1;
-      const float4 *xq = xs + jj0 * D1;
-      const int rs = NH * W * D1;
-      int kp = 0;
-#pragma unroll 2
-      for (int k = 0; k < kt; k++) {
-        const ulonglong2 T = *reinterpret_cast<const ulonglong2 *>(tp + k * CG);
-        const u64 ncc = pk_neg(T.x);
-#pragma unroll
-        for (int r = 0; r < RP; r++) {
-          const ulonglong2 V = *reinterpret_cast<const ulonglong2 *>(xq + r * rs);
-          const u64 pr = pk_xsubp(pk_mul(V.x, T.x), pk_mul(V.y, T.y));
-          const u64 pi = pk_xsubp(pk_mul(V.x, T.y), pk_mul(V.y, ncc));
-          are[r] = pk_add(are[r], pr);
-          aim[r] = pk_add(aim[r], pi);
-        }
-        xq++;
-        if (++kp == J.D) { kp = 0; xq++; }
-      }
-    } else {
+    {
       const float4 *xp = xs + jj0 * J.D;
 #pragma unroll 4
       for (int k = 0; k < kt; k++) {
@@ -457,10 +410,10 @@ __global__ void __launch_bounds__(W * 32, MINB) k_fir_packed(FirJob J)
   }
 }
 
-static size_t fir_packed_smem(int CG, int R, int W, int D, int KT, bool skew = false)
+static size_t fir_packed_smem(int CG, int R, int W, int D, int KT)
 {
   const size_t hs = (size_t)((R / 2) * (32 / CG) * W - 1) * D + KT;
-  return ((size_t)KT * CG + hs + (skew ? hs / D + 2 : 0)) * sizeof(float4);
+  return ((size_t)KT * CG + hs) * sizeof(float4);
 }
 
 template <int BLK>
@@ -468,10 +421,10 @@ __global__ void k_dmm_stateless(Geom G, DevBatch W, const float *__restrict__ mm
 template <int BLK>
 __global__ void k_mm_stateless_v2(Geom G, DevBatch W, const float *__restrict__ mmse_g, const float *__restrict__ demT);
 
-static size_t fir_smem(int CG, int R, int W, int D, int KT, bool skew = false)
+static size_t fir_smem(int CG, int R, int W, int D, int KT)
 {
   const size_t span = (size_t)((32 / CG) * R * W - 1) * D + KT;
-  return ((size_t)KT * CG + span + (skew ? span / D + 2 : 0)) * sizeof(c32);
+  return ((size_t)KT * CG + span) * sizeof(c32);
 }
 static int g_max_smem = 48 * 1024;
 
@@ -495,11 +448,11 @@ int fir_setup(int device)
 }
 
 // largest tap chunk (multiple of 32, <= N rounded up) whose tile fits in shared memory
-static int pick_kt(int CG, int R, int W, int D, int N, int blocks_per_sm, bool skew = false)
+static int pick_kt(int CG, int R, int W, int D, int N, int blocks_per_sm)
 {
   int kt = (N + 31) & ~31;
   const size_t budget = (size_t)(g_max_smem + 1024) / blocks_per_sm - 2048;   // 1 KB/block reserved + static
-  while (kt > 32 && fir_smem(CG, R, W, D, kt, skew) > budget) kt -= 32;
+  while (kt > 32 && fir_smem(CG, R, W, D, kt) > budget) kt -= 32;
   return kt;
 }
 
@@ -841,11 +794,11 @@ __global__ void k_energy_list(Geom G, DevBatch W, const int4 *__restrict__ list,
   e_off[l] = n / G.n_noise;
 }
 
-static int pick_kt_packed(int CG, int R, int W, int D, int N, int blocks_per_sm = 1, bool skew = false)
+static int pick_kt_packed(int CG, int R, int W, int D, int N, int blocks_per_sm = 1)
 {
   int kt = (N + 31) & ~31;
   const size_t budget = (size_t)(g_max_smem + 1024) / blocks_per_sm - 2048;
-  while (kt > 32 && fir_packed_smem(CG, R, W, D, kt, skew) > budget) kt -= 32;
+  while (kt > 32 && fir_packed_smem(CG, R, W, D, kt) > budget) kt -= 32;
   return kt;
 }
 
@@ -964,30 +917,34 @@ void launch_fill_pass(const DevBatch &W, int n, int v, cudaStream_t s)
 
 // Deferred noise FIR over listed (slot, <=cg channels) groups.  Configurations (channels per
 // group, outputs per thread, warps, blocks per SM) are selectable for tuning (BTB200_LAZY_CFG).
-template <int CG, int R, int Wp, int BPS, bool SKEW = false, int KTMAX = 512>
-static void launch_list_cfg(const Geom &G, const DevTables &T, const DevBatch &W, const int *groups, int n_groups,
-                            c32 *NzL, cudaStream_t s)
+// Deferred exact noise FIR over listed (slot, <= CG channels) groups.  Measured on B200 (512 slots, 2 260 hit
+// windows): packed 2 ch x 256 outputs 21.7 ms (default) | scalar same shape 21.8 | scalar 2 x 256, one block/SM,
+// 4096-tap chunks 21.7 | 4 ch x 256 23.1 | 288-output tiles (98 % tile fill) 26-46 (too few warps per SM) |
+// bank-skewed layouts 25-35 (the pointer walk costs more than the 2-way conflicts it removes).
+template <int CG, int R, int Wp, int BPS, int KTMAX = 512>
+static void launch_list_scalar(const Geom &G, const DevTables &T, const DevBatch &W, const int *groups, int n_groups,
+                               c32 *NzL, cudaStream_t s)
 {
   constexpr int TJ = (32 / CG) * R * Wp;
   static bool opted = false;
   if (!opted) {
     cudaFuncAttributes fa{};
-    cudaFuncGetAttributes(&fa, (const void *)k_fir_tiled<CG, R, Wp, SKEW, BPS>);
-    cudaFuncSetAttribute((const void *)k_fir_tiled<CG, R, Wp, SKEW, BPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaFuncGetAttributes(&fa, (const void *)k_fir_tiled<CG, R, Wp, BPS>);
+    cudaFuncSetAttribute((const void *)k_fir_tiled<CG, R, Wp, BPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          g_max_smem - (int)fa.sharedSizeBytes);
     opted = true;
   }
   FirJob J{};
   J.x = W.x; J.n_x = (long)(W.B - 1) * G.S + G.H; J.taps = T.noise_rtaps; J.out = NzL;
   J.N = G.Nn; J.D = G.D; J.nch = G.nch;
-  J.KT = pick_kt(CG, R, Wp, G.D, G.Nn < KTMAX ? G.Nn : KTMAX, BPS, SKEW);
+  J.KT = pick_kt(CG, R, Wp, G.D, G.Nn < KTMAX ? G.Nn : KTMAX, BPS);
   J.mode = 2; J.S = G.S; J.fns = G.fns; J.n_noise = G.n_noise; J.tiles_per_slot = (G.n_noise + TJ - 1) / TJ;
   J.groups = groups;
   dim3 grid((unsigned)(n_groups * J.tiles_per_slot), 1);
-  k_fir_tiled<CG, R, Wp, SKEW, BPS><<<grid, Wp * 32, fir_smem(CG, R, Wp, G.D, J.KT, SKEW), s>>>(J);
+  k_fir_tiled<CG, R, Wp, BPS><<<grid, Wp * 32, fir_smem(CG, R, Wp, G.D, J.KT), s>>>(J);
 }
 
-template <int CG, int R, int Wp, int BPS, bool SKEW, int KTMAX = 512>
+template <int CG, int R, int Wp, int BPS, int KTMAX = 512>
 static void launch_list_packed(const Geom &G, const DevTables &T, const DevBatch &W, const int *groups, int n_groups,
                                c32 *NzL, cudaStream_t s)
 {
@@ -995,59 +952,39 @@ static void launch_list_packed(const Geom &G, const DevTables &T, const DevBatch
   static bool opted = false;
   if (!opted) {
     cudaFuncAttributes fa{};
-    cudaFuncGetAttributes(&fa, (const void *)k_fir_packed<CG, R, Wp, SKEW, BPS>);
-    cudaFuncSetAttribute((const void *)k_fir_packed<CG, R, Wp, SKEW, BPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaFuncGetAttributes(&fa, (const void *)k_fir_packed<CG, R, Wp, BPS>);
+    cudaFuncSetAttribute((const void *)k_fir_packed<CG, R, Wp, BPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          g_max_smem - (int)fa.sharedSizeBytes);
     opted = true;
   }
   FirJob J{};
   J.x = W.x; J.n_x = (long)(W.B - 1) * G.S + G.H; J.taps = T.noise_rtaps; J.out = NzL;
   J.N = G.Nn; J.D = G.D; J.nch = G.nch;
-  J.KT = pick_kt_packed(CG, R, Wp, G.D, G.Nn < KTMAX ? G.Nn : KTMAX, BPS, SKEW);
+  J.KT = pick_kt_packed(CG, R, Wp, G.D, G.Nn < KTMAX ? G.Nn : KTMAX, BPS);
   J.mode = 2; J.S = G.S; J.fns = G.fns; J.n_noise = G.n_noise; J.tiles_per_slot = (G.n_noise + TJ - 1) / TJ;
   J.groups = groups;
   dim3 grid((unsigned)(n_groups * J.tiles_per_slot), 1);
-  k_fir_packed<CG, R, Wp, SKEW, BPS><<<grid, Wp * 32, fir_packed_smem(CG, R, Wp, G.D, J.KT, SKEW), s>>>(J);
+  k_fir_packed<CG, R, Wp, BPS><<<grid, Wp * 32, fir_packed_smem(CG, R, Wp, G.D, J.KT), s>>>(J);
 }
 
-int lazy_group_channels()
+static int lazy_cfg()
 {
-  static int cg = -1;
-  if (cg < 0) {
-    const char *e = getenv("BTB200_LAZY_CFG");
-    const int cfg = e ? atoi(e) : 11;
-    cg = (cfg == 13 || cfg == 16 || cfg == 19 || cfg < 3) ? 4 : 2;
-  }
-  return cg;
+  static int cfg = -1;
+  if (cfg < 0) { const char *e = getenv("BTB200_LAZY_CFG"); cfg = e ? atoi(e) : 0; }
+  return cfg;
 }
+
+int lazy_group_channels() { return lazy_cfg() == 3 ? 4 : 2; }
 
 void launch_noise_fir_list(const Geom &G, const DevTables &T, const DevBatch &W, const int *groups, int n_groups,
                            c32 *NzL, cudaStream_t s)
 {
-  static int cfg = -1;
-  if (cfg < 0) { const char *e = getenv("BTB200_LAZY_CFG"); cfg = e ? atoi(e) : 11; }    // measured on B200 (512 slots): 11, 15, 5 within 1 % of each other (21.7 ms), others slower
-  switch (cfg) {
-    case 0: launch_list_cfg<4, 8, 4, 2>(G, T, W, groups, n_groups, NzL, s); break;   // 256 outputs, 8 warps/SM
-    case 1: launch_list_cfg<4, 4, 8, 2>(G, T, W, groups, n_groups, NzL, s); break;   // 256 outputs, 16 warps/SM
-    case 2: launch_list_cfg<4, 6, 6, 1>(G, T, W, groups, n_groups, NzL, s); break;   // 288 outputs, 6 warps/SM
-    case 3: launch_list_cfg<2, 9, 2, 1>(G, T, W, groups, n_groups, NzL, s); break;   // 288 outputs, 2 warps/SM
-    case 4: launch_list_cfg<2, 6, 3, 1>(G, T, W, groups, n_groups, NzL, s); break;   // 288 outputs, 3 warps/SM
-    case 5: launch_list_cfg<2, 4, 4, 2>(G, T, W, groups, n_groups, NzL, s); break;   // 256 outputs, 8 warps/SM
-    case 6: launch_list_cfg<2, 4, 4, 2, true>(G, T, W, groups, n_groups, NzL, s); break;   // same, skewed layout
-    case 7: launch_list_cfg<2, 3, 3, 3, true>(G, T, W, groups, n_groups, NzL, s); break;   // 144 outputs (850 = 6 tiles, 98 %), 9 warps/SM
-    case 8: launch_list_cfg<2, 3, 6, 1, true>(G, T, W, groups, n_groups, NzL, s); break;   // 288 outputs, 6 warps/SM
-    case 9: launch_list_cfg<2, 2, 8, 2, true>(G, T, W, groups, n_groups, NzL, s); break;   // 256 outputs, 16 warps/SM
-    case 10: launch_list_packed<2, 4, 4, 2, true>(G, T, W, groups, n_groups, NzL, s); break;   // packed, 256 outputs, 2 blocks/SM
+  switch (lazy_cfg()) {
     default:
-    case 11: launch_list_packed<2, 4, 4, 2, false>(G, T, W, groups, n_groups, NzL, s); break;   // packed fp32, 2 ch x 256 outputs, 2 blocks/SM
-    case 12: launch_list_packed<2, 8, 2, 2, true>(G, T, W, groups, n_groups, NzL, s); break;   // packed, R=8
-    case 13: launch_list_packed<4, 8, 4, 2, false>(G, T, W, groups, n_groups, NzL, s); break;  // packed, 4 channels
-    case 14: launch_list_packed<2, 4, 8, 1, true>(G, T, W, groups, n_groups, NzL, s); break;   // packed, 512 outputs, 1 block/SM
-    case 15: launch_list_cfg<2, 2, 8, 1, false, 4096>(G, T, W, groups, n_groups, NzL, s); break;    // big tap chunks, 8 warps/SM
-    case 16: launch_list_cfg<4, 4, 8, 1, false, 2048>(G, T, W, groups, n_groups, NzL, s); break;
-    case 17: launch_list_packed<2, 4, 4, 1, false, 4096>(G, T, W, groups, n_groups, NzL, s); break;
-    case 18: launch_list_cfg<2, 4, 4, 1, false, 4096>(G, T, W, groups, n_groups, NzL, s); break;
-    case 19: launch_list_packed<4, 8, 4, 1, false, 2048>(G, T, W, groups, n_groups, NzL, s); break;
+    case 0: launch_list_packed<2, 4, 4, 2>(G, T, W, groups, n_groups, NzL, s); break;          // packed fp32 (default)
+    case 1: launch_list_scalar<2, 4, 4, 2>(G, T, W, groups, n_groups, NzL, s); break;          // scalar, same shape
+    case 2: launch_list_scalar<2, 2, 8, 1, 4096>(G, T, W, groups, n_groups, NzL, s); break;    // one block/SM, big tap chunks
+    case 3: launch_list_scalar<4, 4, 8, 2>(G, T, W, groups, n_groups, NzL, s); break;          // 4 channels per group
   }
 }
 

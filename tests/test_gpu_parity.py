@@ -302,6 +302,33 @@ def test_multi_lap_geometry_equals_oracle(name):
     blk.close()
 
 
+@pytest.mark.parametrize("world", [2, 3])
+def test_time_shards_equal_single_run(world):
+    """a capture split into `world` contiguous slot ranges, each processed by its own context
+    from its own guard-overlapped span (H-1 samples), gives -- concatenated in rank order -- exactly the hit
+    list of one context over the whole capture (stateless mode).  On the 8-GPU box the ranks of bench.py do
+    the same with one context per GPU; tests/test_sharding.py covers the torch.distributed merge."""
+    from gr_bluetooth_b200 import sharding, synth
+    fs, fc, nslots = 100e6, 2441e6, 24
+    iq, _ = synth.generate(fs, fc, nslots, seed=77, laps=[0x9E8B33, 0x24D952, 0x4831DD], occupancy=0.08, snr_db=20.0)
+    whole = g.multi_sniffer(fs, fc, 10.0, mm_mode=g.MM_STATELESS, max_slots=8)
+    S, H = whole.samples_per_slot, whole.history()
+    single = whole.run_stream(iq)
+    whole.close()
+    parts = []
+    for rank in range(world):
+        blk = g.multi_sniffer(fs, fc, 10.0, mm_mode=g.MM_STATELESS, max_slots=5)
+        def process(span, first, n, blk=blk):
+            hits, _, ovf = blk.process(span, first, n)
+            assert ovf == 0
+            return hits
+        parts.append(sharding.run_sharded(iq, process, S, H, world, rank, dist=None, batch=5))
+        blk.close()
+    merged = np.concatenate([p for p in parts if p is not None])
+    assert len(single) > 10
+    assert gpu_hit_tuples(merged) == gpu_hit_tuples(single)
+
+
 def test_cpp_multi_hopper_block_digest(tmp_path):
     """gr::bluetooth::multi_hopper::make(..., LAP, aliased, tun) through btrx_b200 -l 24d952 on headset1:
     the channel loop with the reference's early `break` runs on the GPU (btb200_process_channels, chained

@@ -314,7 +314,11 @@ __device__ __forceinline__ u64 pk_neg(u64 a) { return a ^ 0x8000000080000000ull;
 __device__ __forceinline__ float pk_lo(u64 v) { return __uint_as_float((unsigned)(v & 0xffffffffull)); }
 __device__ __forceinline__ float pk_hi(u64 v) { return __uint_as_float((unsigned)(v >> 32)); }
 
-template <int CG, int R, int W, int MINB = 1>
+// DT > 0: the decimation is the compile-time constant DT and the staged span is SKEWED -- one pad slot per DT
+// samples (sample i sits at i + i/DT) -- so that the NH outputs a warp reads at once, DT samples apart, are
+// DT+1 slots apart: with DT = 50 the 16 addresses of a 2-channel group then spread over all eight 16-byte bank
+// groups (2 wavefronts per load instead of 4; the kernel is shared-memory bound otherwise: ncu in profiles/).
+template <int CG, int R, int W, int MINB = 1, int DT = 0>
 __global__ void __launch_bounds__(W * 32, MINB) k_fir_packed(FirJob J)
 {
   constexpr int NH = 32 / CG, TJ = NH * R * W, RP = R / 2;
@@ -378,11 +382,43 @@ __global__ void __launch_bounds__(W * 32, MINB) k_fir_packed(FirJob J)
       const long n0 = base + i, n1 = n0 + delta;
       const c32 v0 = (n0 < J.n_x) ? J.x[n0] : c32{0.0f, 0.0f};
       const c32 v1 = (n1 < J.n_x) ? J.x[n1] : c32{0.0f, 0.0f};
-      xs[i] = make_float4(v0.re, v1.re, v0.im, v1.im);
+      xs[DT > 0 ? i + i / (DT > 0 ? DT : 1) : i] = make_float4(v0.re, v1.re, v0.im, v1.im);
     }
     __syncthreads();
     const float4 *tp = ts + cg;
-    {
+    if (DT > 0) {
+      constexpr int D1 = DT + 1;
+      const float4 *xq = xs + jj0 * D1;
+      const int rs = NH * W * D1;
+      int k = 0;
+      for (; k + DT <= kt; k += DT, xq += D1) {            // whole segments: constant trip count
+#pragma unroll 5
+        for (int kp = 0; kp < DT; kp++) {
+          const ulonglong2 T = *reinterpret_cast<const ulonglong2 *>(tp + (k + kp) * CG);
+          const u64 ncc = pk_neg(T.x);
+#pragma unroll
+          for (int r = 0; r < RP; r++) {
+            const ulonglong2 V = *reinterpret_cast<const ulonglong2 *>(xq + r * rs + kp);
+            const u64 pr = pk_xsubp(pk_mul(V.x, T.x), pk_mul(V.y, T.y));
+            const u64 pi = pk_xsubp(pk_mul(V.x, T.y), pk_mul(V.y, ncc));
+            are[r] = pk_add(are[r], pr);
+            aim[r] = pk_add(aim[r], pi);
+          }
+        }
+      }
+      for (int kp = 0; k < kt; k++, kp++) {                 // tail of the last chunk
+        const ulonglong2 T = *reinterpret_cast<const ulonglong2 *>(tp + k * CG);
+        const u64 ncc = pk_neg(T.x);
+#pragma unroll
+        for (int r = 0; r < RP; r++) {
+          const ulonglong2 V = *reinterpret_cast<const ulonglong2 *>(xq + r * rs + kp);
+          const u64 pr = pk_xsubp(pk_mul(V.x, T.x), pk_mul(V.y, T.y));
+          const u64 pi = pk_xsubp(pk_mul(V.x, T.y), pk_mul(V.y, ncc));
+          are[r] = pk_add(are[r], pr);
+          aim[r] = pk_add(aim[r], pi);
+        }
+      }
+    } else {
       const float4 *xp = xs + jj0 * J.D;
 #pragma unroll 4
       for (int k = 0; k < kt; k++) {
@@ -410,10 +446,10 @@ __global__ void __launch_bounds__(W * 32, MINB) k_fir_packed(FirJob J)
   }
 }
 
-static size_t fir_packed_smem(int CG, int R, int W, int D, int KT)
+static size_t fir_packed_smem(int CG, int R, int W, int D, int KT, bool skew = false)
 {
   const size_t hs = (size_t)((R / 2) * (32 / CG) * W - 1) * D + KT;
-  return ((size_t)KT * CG + hs) * sizeof(float4);
+  return ((size_t)KT * CG + hs + (skew ? hs / D + 2 : 0)) * sizeof(float4);
 }
 
 template <int BLK>
@@ -794,9 +830,15 @@ __global__ void k_energy_list(Geom G, DevBatch W, const int4 *__restrict__ list,
   e_off[l] = n / G.n_noise;
 }
 
-static int pick_kt_packed(int CG, int R, int W, int D, int N, int blocks_per_sm = 1)
+static int pick_kt_packed(int CG, int R, int W, int D, int N, int blocks_per_sm = 1, bool skew = false)
 {
   int kt = (N + 31) & ~31;
+  if (skew) {                     // whole multiples of D per chunk
+    const size_t budget = (size_t)(g_max_smem + 1024) / blocks_per_sm - 2048;
+    kt = (N / D) * D; if (kt < D) kt = D;
+    while (kt > D && fir_packed_smem(CG, R, W, D, kt, true) > budget) kt -= D;
+    return kt;
+  }
   const size_t budget = (size_t)(g_max_smem + 1024) / blocks_per_sm - 2048;
   while (kt > 32 && fir_packed_smem(CG, R, W, D, kt) > budget) kt -= 32;
   return kt;
@@ -917,10 +959,8 @@ void launch_fill_pass(const DevBatch &W, int n, int v, cudaStream_t s)
 
 // Deferred noise FIR over listed (slot, <=cg channels) groups.  Configurations (channels per
 // group, outputs per thread, warps, blocks per SM) are selectable for tuning (BTB200_LAZY_CFG).
-// Deferred exact noise FIR over listed (slot, <= CG channels) groups.  Measured on B200 (512 slots, 2 260 hit
-// windows): packed 2 ch x 256 outputs 21.7 ms (default) | scalar same shape 21.8 | scalar 2 x 256, one block/SM,
-// 4096-tap chunks 21.7 | 4 ch x 256 23.1 | 288-output tiles (98 % tile fill) 26-46 (too few warps per SM) |
-// bank-skewed layouts 25-35 (the pointer walk costs more than the 2-way conflicts it removes).
+// Deferred exact noise FIR over listed (slot, <= CG channels) groups (lazy squelch); configurations and their
+// measured times are listed at launch_noise_fir_list().
 template <int CG, int R, int Wp, int BPS, int KTMAX = 512>
 static void launch_list_scalar(const Geom &G, const DevTables &T, const DevBatch &W, const int *groups, int n_groups,
                                c32 *NzL, cudaStream_t s)
@@ -944,7 +984,7 @@ static void launch_list_scalar(const Geom &G, const DevTables &T, const DevBatch
   k_fir_tiled<CG, R, Wp, BPS><<<grid, Wp * 32, fir_smem(CG, R, Wp, G.D, J.KT), s>>>(J);
 }
 
-template <int CG, int R, int Wp, int BPS, int KTMAX = 512>
+template <int CG, int R, int Wp, int BPS, int KTMAX = 512, int DT = 0>
 static void launch_list_packed(const Geom &G, const DevTables &T, const DevBatch &W, const int *groups, int n_groups,
                                c32 *NzL, cudaStream_t s)
 {
@@ -952,19 +992,19 @@ static void launch_list_packed(const Geom &G, const DevTables &T, const DevBatch
   static bool opted = false;
   if (!opted) {
     cudaFuncAttributes fa{};
-    cudaFuncGetAttributes(&fa, (const void *)k_fir_packed<CG, R, Wp, BPS>);
-    cudaFuncSetAttribute((const void *)k_fir_packed<CG, R, Wp, BPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaFuncGetAttributes(&fa, (const void *)k_fir_packed<CG, R, Wp, BPS, DT>);
+    cudaFuncSetAttribute((const void *)k_fir_packed<CG, R, Wp, BPS, DT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          g_max_smem - (int)fa.sharedSizeBytes);
     opted = true;
   }
   FirJob J{};
   J.x = W.x; J.n_x = (long)(W.B - 1) * G.S + G.H; J.taps = T.noise_rtaps; J.out = NzL;
   J.N = G.Nn; J.D = G.D; J.nch = G.nch;
-  J.KT = pick_kt_packed(CG, R, Wp, G.D, G.Nn < KTMAX ? G.Nn : KTMAX, BPS);
+  J.KT = pick_kt_packed(CG, R, Wp, G.D, G.Nn < KTMAX ? G.Nn : KTMAX, BPS, DT > 0);
   J.mode = 2; J.S = G.S; J.fns = G.fns; J.n_noise = G.n_noise; J.tiles_per_slot = (G.n_noise + TJ - 1) / TJ;
   J.groups = groups;
   dim3 grid((unsigned)(n_groups * J.tiles_per_slot), 1);
-  k_fir_packed<CG, R, Wp, BPS><<<grid, Wp * 32, fir_packed_smem(CG, R, Wp, G.D, J.KT), s>>>(J);
+  k_fir_packed<CG, R, Wp, BPS, DT><<<grid, Wp * 32, fir_packed_smem(CG, R, Wp, G.D, J.KT, DT > 0), s>>>(J);
 }
 
 static int lazy_cfg()
@@ -974,17 +1014,29 @@ static int lazy_cfg()
   return cfg;
 }
 
-int lazy_group_channels() { return lazy_cfg() == 3 ? 4 : 2; }
+int lazy_group_channels() { return lazy_cfg() == 4 ? 4 : 2; }
 
+// Measured on B200 (512 slots, 2 260 hit windows x 17 M complex MAC), ms per launch:
+//   0  packed, skewed, 2 ch x 448 outputs (850 = 2 tiles, 95 %), 14 warps, one block/SM ....... 17.0  (default, D = 50)
+//   1  same shape, no skew ................................................................... 18.9
+//   2  packed, skewed, 2 ch x 288 outputs (3 tiles, 98 %), 9 warps ............................ 19.0
+//   3  packed 2 ch x 256 outputs, 2 blocks/SM (default for D != 50) ........................... 21.7
+//   4  scalar 4 ch x 256 outputs .............................................................. 23.1
+//   5  scalar 2 ch x 256 outputs .............................................................. 21.8
+// (also tried: 144-output tiles 22.3, 320-output tiles with R = 4 24.8, run-time-D skew 25-35.)
 void launch_noise_fir_list(const Geom &G, const DevTables &T, const DevBatch &W, const int *groups, int n_groups,
                            c32 *NzL, cudaStream_t s)
 {
-  switch (lazy_cfg()) {
+  int cfg = lazy_cfg();
+  if (G.D != 50 && cfg <= 2) cfg = 3;      // the skewed variants are instantiated for D = 50 (100 Msps)
+  switch (cfg) {
     default:
-    case 0: launch_list_packed<2, 4, 4, 2>(G, T, W, groups, n_groups, NzL, s); break;          // packed fp32 (default)
-    case 1: launch_list_scalar<2, 4, 4, 2>(G, T, W, groups, n_groups, NzL, s); break;          // scalar, same shape
-    case 2: launch_list_scalar<2, 2, 8, 1, 4096>(G, T, W, groups, n_groups, NzL, s); break;    // one block/SM, big tap chunks
-    case 3: launch_list_scalar<4, 4, 8, 2>(G, T, W, groups, n_groups, NzL, s); break;          // 4 channels per group
+    case 0: launch_list_packed<2, 2, 14, 1, 1000, 50>(G, T, W, groups, n_groups, NzL, s); break;
+    case 1: launch_list_packed<2, 2, 14, 1, 1024, 0>(G, T, W, groups, n_groups, NzL, s); break;
+    case 2: launch_list_packed<2, 2, 9, 1, 2000, 50>(G, T, W, groups, n_groups, NzL, s); break;
+    case 3: launch_list_packed<2, 4, 4, 2>(G, T, W, groups, n_groups, NzL, s); break;
+    case 4: launch_list_scalar<4, 4, 8, 2>(G, T, W, groups, n_groups, NzL, s); break;
+    case 5: launch_list_scalar<2, 4, 4, 2>(G, T, W, groups, n_groups, NzL, s); break;
   }
 }
 

@@ -112,8 +112,10 @@ void launch_noise_fast(const FastNoisePlan &F, const c32 *x, int B, int S, int f
   k_noise_poly<<<g1, 128, 0, s>>>(F, x, S, fns, D, n_noise);
   const int nthreads = F.nchp * (DF_JT / DF_JR);
   const size_t smem = sizeof(c32) * ((size_t)F.M * F.nchp + (size_t)DF_JT * F.M);
-  static bool opted = false;
-  if (!opted) { cudaFuncSetAttribute(k_noise_dft, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); opted = true; }
+  static bool opted[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!opted[dev & 63]) { cudaFuncSetAttribute(k_noise_dft, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); opted[dev & 63] = true; }
   dim3 g2((unsigned)((n_noise + DF_JT - 1) / DF_JT), (unsigned)B);
   k_noise_dft<<<g2, nthreads, smem, s>>>(F, n_noise, nch);
 }

@@ -464,6 +464,20 @@ static size_t fir_smem(int CG, int R, int W, int D, int KT)
 }
 static int g_max_smem = 48 * 1024;
 
+// function attributes are per device: remember which devices a kernel has been opted in on
+struct OptIn {
+  bool done[64] = {};
+  bool need()
+  {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 63;
+    if (done[dev]) return false;
+    done[dev] = true;
+    return true;
+  }
+};
+
 int fir_setup(int device)
 {
   int v = 0;
@@ -966,13 +980,12 @@ static void launch_list_scalar(const Geom &G, const DevTables &T, const DevBatch
                                c32 *NzL, cudaStream_t s)
 {
   constexpr int TJ = (32 / CG) * R * Wp;
-  static bool opted = false;
-  if (!opted) {
+  static OptIn opt;
+  if (opt.need()) {
     cudaFuncAttributes fa{};
     cudaFuncGetAttributes(&fa, (const void *)k_fir_tiled<CG, R, Wp, BPS>);
     cudaFuncSetAttribute((const void *)k_fir_tiled<CG, R, Wp, BPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          g_max_smem - (int)fa.sharedSizeBytes);
-    opted = true;
   }
   FirJob J{};
   J.x = W.x; J.n_x = (long)(W.B - 1) * G.S + G.H; J.taps = T.noise_rtaps; J.out = NzL;
@@ -989,13 +1002,12 @@ static void launch_list_packed(const Geom &G, const DevTables &T, const DevBatch
                                c32 *NzL, cudaStream_t s)
 {
   constexpr int TJ = (32 / CG) * R * Wp;
-  static bool opted = false;
-  if (!opted) {
+  static OptIn opt;
+  if (opt.need()) {
     cudaFuncAttributes fa{};
     cudaFuncGetAttributes(&fa, (const void *)k_fir_packed<CG, R, Wp, BPS, DT>);
     cudaFuncSetAttribute((const void *)k_fir_packed<CG, R, Wp, BPS, DT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          g_max_smem - (int)fa.sharedSizeBytes);
-    opted = true;
   }
   FirJob J{};
   J.x = W.x; J.n_x = (long)(W.B - 1) * G.S + G.H; J.taps = T.noise_rtaps; J.out = NzL;

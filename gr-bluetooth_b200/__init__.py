@@ -54,12 +54,18 @@ HIT_DTYPE = np.dtype([("slot", "<u4"), ("channel", "<u2"), ("kind", "<u2"), ("of
                       ("sym_offset", "<u8"), ("sym_count", "<u4"), ("reserved", "<u4")], align=True)
 
 
+class ChanResult(C.Structure):
+    _fields_ = [("channel", C.c_int32), ("processed", C.c_int32), ("pass_", C.c_int32), ("n_symbols", C.c_int32),
+                ("ac_index", C.c_int32), ("lap", C.c_uint32), ("snr", C.c_double), ("sym_offset", C.c_uint64),
+                ("sym_count", C.c_uint32), ("reserved", C.c_uint32)]
+
+
 class Hits(C.Structure):
     _fields_ = [("hits", C.c_void_p), ("cap", C.c_uint32), ("count", C.c_uint32), ("overflow", C.c_uint32),
                 ("symbols", C.c_void_p), ("symbols_cap", C.c_uint64), ("symbols_used", C.c_uint64)]
 
 
-EXPORTS = ["btb200_create", "btb200_destroy", "btb200_get_info", "btb200_process", "btb200_process_device",
+EXPORTS = ["btb200_process_channels", "btb200_create", "btb200_destroy", "btb200_get_info", "btb200_process", "btb200_process_device",
            "btb200_submit", "btb200_collect", "btb200_host_alloc", "btb200_host_free",
            "btb200_get_mm_state", "btb200_set_mm_state", "btb200_reset", "btb200_get_stage",
            "btb200_last_timing", "btb200_launch_count", "btb200_strerror", "btb200_last_error",
@@ -101,6 +107,8 @@ def lib():
         L.btb200_last_error.restype = C.c_char_p
         L.btb200_version.restype = C.c_char_p
         L.btb200_set_impl.argtypes = [C.c_void_p, C.c_int]
+        L.btb200_process_channels.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint64, C.c_int32, C.c_int32,
+                                              C.c_uint32, C.c_void_p, C.c_void_p, C.c_size_t]
         _lib = L
     return _lib
 
@@ -202,6 +210,16 @@ class multi_block:
         self._check(self._L.btb200_process_device(self._ctx, C.c_void_p(dptr), n_samples, first_slot, n_slots,
                                                   C.byref(h)))
         return self._take(h, want_symbols)
+
+    def process_channels(self, window, slot, first_channel, n_channels, stop_lap=0xFFFFFFFF):
+        """One multi_hopper work() call (chained mode): channels first_channel.. in order, ends after the first
+        channel whose packet carries stop_lap and a header.  -> (list of ChanResult, symbols uint8 array)"""
+        x = np.ascontiguousarray(window, dtype=np.complex64)
+        res = (ChanResult * max(n_channels, 1))()
+        syms = np.zeros(max(n_channels, 1) * 3125, np.uint8)
+        self._check(self._L.btb200_process_channels(self._ctx, x.ctypes.data, len(x), slot, first_channel, n_channels,
+                                                    stop_lap, C.byref(res), syms.ctypes.data, len(syms)))
+        return list(res)[:n_channels], syms
 
     def submit(self, ptr, on_device, n_samples, first_slot, n_slots):
         self._check(self._L.btb200_submit(self._ctx, C.c_void_p(ptr), int(on_device), n_samples, first_slot, n_slots))

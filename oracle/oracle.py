@@ -31,6 +31,11 @@ HIT_DTYPE = np.dtype([("slot", "<i4"), ("channel", "<i2"), ("kind", "<i2"), ("of
                       ("len", "<i4"), ("lap", "<u4"), ("snr", "<f8")], align=True)
 
 
+class ChanResult(C.Structure):
+    _fields_ = [("chi", C.c_int32), ("processed", C.c_int32), ("pass_", C.c_int32), ("nsym", C.c_int32),
+                ("ac_index", C.c_int32), ("lap", C.c_uint32), ("snr", C.c_double)]
+
+
 class Debug(C.Structure):
     _fields_ = [("energy", C.c_void_p), ("noise", C.c_void_p), ("snr", C.c_void_p),
                 ("pass_", C.c_void_p), ("nsym", C.c_void_p), ("bits", C.c_void_p),
@@ -84,6 +89,9 @@ def lib():
                                C.c_long, C.c_long, C.c_int, C.c_int,
                                C.c_void_p, C.c_int, C.POINTER(C.c_int),
                                C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.btbo_window_list.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_uint32,
+                                       C.c_void_p, C.c_void_p]
+        L.btbo_header_present.argtypes = [C.c_void_p, C.c_int]
         _lib = L
     return _lib
 
@@ -169,6 +177,18 @@ class Plan:
                                 _ptr(hits), len(hits), C.byref(nh), C.byref(dbg) if debug else None)
         assert rc == 0
         return hits[:nh.value].copy(), d
+
+    def window_list(self, win, state, chis, stop_lap=0xFFFFFFFF):
+        """One multi_hopper work() call (multi_hopper_impl.cc:76-209) on the chained state.
+        -> (list of ChanResult, symbols [n][H])"""
+        w = np.ascontiguousarray(win, dtype=np.complex64)
+        assert len(w) == self.H
+        ch = np.ascontiguousarray(chis, dtype=np.int32)
+        res = (ChanResult * len(ch))()
+        sym = np.zeros((len(ch), self.H), np.uint8)
+        rc = self.L.btbo_window_list(self.h, state.h, _ptr(w), _ptr(ch), len(ch), stop_lap, C.byref(res), _ptr(sym))
+        assert rc == 0
+        return list(res), sym
 
     def run(self, iq, first_call=0, num_calls=None, stateless=True, threads=1, state=None,
             iq_first=0, n_total=None, want_bits=False, want_energy=False, hits_cap=1 << 16):

@@ -329,6 +329,46 @@ def test_time_shards_equal_single_run(world):
     assert gpu_hit_tuples(merged) == gpu_hit_tuples(single)
 
 
+@pytest.mark.parametrize("name,stop_lap", [("headset1", 0x24D952), ("keyboard1", 0x4831DD), ("headset1", 0xFFFFFFFF)])
+def test_process_channels_equals_oracle(name, stop_lap):
+    """btb200_process_channels (the multi_hopper channel loop on the chained state, with the reference's early
+    break) against the oracle's btbo_window_list, call by call: which channels were reached, squelch, symbol
+    counts, first access code, LAP, f64 snr and the symbols handed to classic_packet::make."""
+    ex = load_excerpt(name, "chained")
+    P = O.Plan(ex["fs"], ex["fc"])
+    st = O.State(P)
+    blk = g.multi_sniffer(ex["fs"], ex["fc"], 10.0, mm_mode=g.MM_CHAINED, max_slots=4, search=g.SEARCH_BR)
+    S, H = P.S, P.H
+    x = np.concatenate([np.zeros(H - 1, np.complex64), ex["iq"]])
+    breaks = 0
+    for k in range(min(ex["nslots"], 30)):
+        win = x[k * S:k * S + H]
+        # alternate between the scan (all channels) and a hop-along style single channel
+        if k % 5 == 4:
+            first, n = P.ch_lo + (k % P.nch), 1
+        else:
+            first, n = P.ch_lo, P.nch
+        want, wsym = P.window_list(win, st, list(range(first - P.ch_lo, first - P.ch_lo + n)), stop_lap)
+        got, gsym = blk.process_channels(win, k, first, n, stop_lap)
+        for q in range(n):
+            w, r = want[q], got[q]
+            assert (r.processed, r.channel) == (w.processed, P.ch_lo + w.chi)
+            if not w.processed:
+                breaks += 1
+                continue
+            assert (r.pass_, r.n_symbols, r.ac_index) == (w.pass_, w.nsym, w.ac_index)
+            assert (r.snr == w.snr) or (np.isnan(r.snr) and np.isnan(w.snr))
+            if w.ac_index >= 0:
+                assert r.lap == w.lap
+                cnt = min(w.nsym - w.ac_index, 3125)
+                assert r.sym_count == cnt
+                assert np.array_equal(gsym[r.sym_offset:r.sym_offset + cnt], wsym[q, w.ac_index:w.ac_index + cnt])
+        assert np.array_equal(blk.get_mm_state(), st.mm)
+    if stop_lap != 0xFFFFFFFF:
+        assert breaks > 0          # the early break was exercised
+    blk.close()
+
+
 def test_cpp_multi_hopper_block_digest(tmp_path):
     """gr::bluetooth::multi_hopper::make(..., LAP, aliased, tun) through btrx_b200 -l 24d952 on headset1:
     the channel loop with the reference's early `break` runs on the GPU (btb200_process_channels, chained

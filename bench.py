@@ -185,7 +185,8 @@ def run_ours(args):
 
     def measure(snr_mode, steps, warmup):
         mk = lambda: g.multi_sniffer.make(FS, FC, SNR_DB, False, mm_mode=g.MM_STATELESS, device=local, max_slots=B,
-                                          snr_mode=g.SNR_FAST_GUARDED if snr_mode == "fast" else g.SNR_EXACT)
+                                          snr_mode=g.SNR_FAST_GUARDED if snr_mode == "fast" else g.SNR_EXACT,
+                                          tail=g.TAIL_FULL if args.tail == "full" else g.TAIL_LAZY)
         blks = [mk(), mk()]                       # two contexts: the e2e loop overlaps H2D of batch k+1 with batch k
         blk = blks[0]
         H = blk.history()
@@ -198,7 +199,7 @@ def run_ours(args):
 
         # ---- device-resident throughput (`value`) ----
         for _ in range(warmup):
-            hits, _, _ = blk.process_device(d_iq.data_ptr(), n_in, lead, B)
+            hits, _, _ = blk.process_device(d_iq.data_ptr(), n_in, lead, B, want_symbols=True)
         stage_ms = {}
         barrier()
         l0 = blk.launch_count()
@@ -206,7 +207,7 @@ def run_ours(args):
             dev_ms = 0.0
             for _ in range(steps):
                 flush.zero_()                                   # L2 flush between timed iterations
-                hits, _, _ = blk.process_device(d_iq.data_ptr(), n_in, lead, B)
+                hits, _, _ = blk.process_device(d_iq.data_ptr(), n_in, lead, B, want_symbols=True)
                 tm = blk.last_timing()
                 dev_ms += tm["total"]
                 for k, v in tm.items():
@@ -318,6 +319,8 @@ def main():
     ap.add_argument("--slots", type=int, default=512, help="slots (625 us each) per step per GPU")
     ap.add_argument("--no-alt", action="store_true", help="skip the second measurement in the other snr mode")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--tail", default="lazy", choices=["lazy", "full"],
+                    help="lazy (default): clock recovery past the searchable prefix only for windows with hits")
     ap.add_argument("--snr-mode", default="exact", choices=["exact", "fast"],
                     help="exact: reference arithmetic for every printed snr; fast: guarded polyphase estimate")
     args = ap.parse_args()

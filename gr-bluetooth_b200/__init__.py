@@ -19,6 +19,7 @@ MM_CHAINED, MM_STATELESS = 0, 1
 SEARCH_BR, SEARCH_LE = 1, 2
 SQUELCH_DEFAULT, SQUELCH_EAGER, SQUELCH_LAZY = 0, 1, 2
 SNR_EXACT, SNR_FAST_GUARDED = 0, 1
+TAIL_LAZY, TAIL_FULL = 0, 1
 
 STAGE = dict(noise_fast=10, energy=1, noise=2, snr=3, pass_=4, nsym=5, bits=6, ddc=7, demod=8, soft=9,
              chan_taps=20, noise_taps=21, mmse_table=22, atan_table=23, ac_lut=24)
@@ -36,7 +37,8 @@ class Config(C.Structure):
                 ("squelch_threshold", C.c_double), ("extra_history_symbols", C.c_uint32),
                 ("mm_mode", C.c_int32), ("search", C.c_int32), ("device", C.c_int32),
                 ("max_slots_per_call", C.c_uint32), ("keep_stages", C.c_uint32),
-                ("squelch_mode", C.c_uint32), ("snr_mode", C.c_uint32), ("reserved", C.c_uint32 * 3)]
+                ("squelch_mode", C.c_uint32), ("snr_mode", C.c_uint32), ("tail_mode", C.c_uint32),
+                ("reserved", C.c_uint32 * 2)]
 
 
 class Info(C.Structure):
@@ -142,12 +144,12 @@ class multi_block:
 
     def __init__(self, sample_rate, center_freq, squelch_threshold, *, mm_mode=MM_CHAINED,
                  search=SEARCH_BR | SEARCH_LE, device=0, max_slots=64, keep_stages=False,
-                 squelch=SQUELCH_DEFAULT, snr_mode=SNR_EXACT):
+                 squelch=SQUELCH_DEFAULT, snr_mode=SNR_EXACT, tail=TAIL_LAZY):
         self._L = lib()
         cfg = Config(abi_version=ABI_VERSION, sample_rate=sample_rate, center_freq=center_freq,
                      squelch_threshold=squelch_threshold, extra_history_symbols=self.EXTRA_SYMBOLS,
                      mm_mode=mm_mode, search=search, device=device, max_slots_per_call=max_slots,
-                     keep_stages=int(keep_stages), squelch_mode=squelch, snr_mode=snr_mode)
+                     keep_stages=int(keep_stages), squelch_mode=squelch, snr_mode=snr_mode, tail_mode=tail)
         self._ctx = C.c_void_p()
         rc = self._L.btb200_create(C.byref(cfg), C.byref(self._ctx))
         if rc:

@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <chrono>
 #include <cstring>
 #include <new>
 #include <string>
@@ -33,6 +34,7 @@ struct btb200_ctx {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[kNumEvents + 1]{};
   cudaEvent_t evl[3]{};      // lazy squelch: noise FIR / energies
+  cudaEvent_t ev_tail = nullptr;
   bool lazy_timed = false;
   // device allocations
   std::vector<void *> allocs;
@@ -50,6 +52,11 @@ struct btb200_ctx {
   double *h_eon = nullptr, *h_eoff = nullptr;
   size_t list_cap = 0, group_cap = 0;
   DevBatch pendW{};
+  // lazy tail: clock recovery stops after the searchable prefix; hit windows are resumed in collect()
+  bool early = false, pend_early = false;
+  Geom pendG{};
+  cudaStream_t stream2 = nullptr;
+  int *d_list2 = nullptr, *h_list2 = nullptr, *h_nsym = nullptr;
   int *d_res4 = nullptr;
   // fast guarded snr
   bool fast_snr = false;
@@ -81,6 +88,17 @@ struct btb200_ctx {
 namespace {
 
 thread_local std::string g_create_error;
+
+struct Trace {
+  bool on = std::getenv("BTB200_TRACE") != nullptr;
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  void mark(const char *what)
+  {
+    if (!on) return;
+    const double us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
+    std::fprintf(stderr, "[btb200 trace] %8.1f us  %s\n", us, what);
+  }
+};
 
 #define CK(call)                                                                          \
   do {                                                                                    \
@@ -202,10 +220,12 @@ int setup(btb200_ctx *ctx)
   G.squelch_db = P.squelch_db;
   G.search = ctx->cfg.search;
   G.stateless = ctx->cfg.mm_mode == BTB200_MM_STATELESS;
+  G.early = 0; G.ne_dem = P.n_dem; G.sym_target = P.n_dem;
 
   CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   for (auto &e : ctx->ev) CK(cudaEventCreate(&e));
   for (auto &e : ctx->evl) CK(cudaEventCreate(&e));
+  CK(cudaEventCreateWithFlags(&ctx->ev_tail, cudaEventDisableTiming));
 
   int rc;
   if ((rc = upload_raw<c32>(ctx, &ctx->T.chan_rtaps, P.chan_rtaps.data(), P.chan_rtaps.size()))) return rc;
@@ -259,6 +279,42 @@ int setup(btb200_ctx *ctx)
     if ((rc = dev_alloc(ctx, &ctx->d_list, ctx->list_cap * 4))) return rc;
     if ((rc = dev_alloc(ctx, &ctx->d_eon, ctx->list_cap))) return rc;
     if ((rc = dev_alloc(ctx, &ctx->d_eoff, ctx->list_cap))) return rc;
+  }
+  ctx->early = false;
+  if (ctx->lazy && ctx->cfg.tail_mode == BTB200_TAIL_LAZY && !ctx->cfg.keep_stages) {
+    // Lazy tail.  The access-code search only looks at lags < 625 (72-symbol windows), i.e. at the first 697
+    // symbols of a window; everything after that is payload for ac()/aa() and only matters for windows with a
+    // hit.  Bound the loop's input advance per symbol rigorously: |out| <= max_imu sum|taps| * gain*pi,
+    // |mm_val| <= 2|out|, advance <= floor(1 + omega_max + gain_mu*|mm_val|).
+    double tsum = 0;
+    for (int i = 0; i < 129; i++) {
+      double a = 0;
+      for (int k = 0; k < 8; k++) a += std::fabs((double)P.mmse[(size_t)i * 8 + k]);
+      tsum = std::max(tsum, a);
+    }
+    const double outmax = 1.001 * tsum * std::fabs((double)P.demod_gain) * 3.1415927;
+    const double adv = 1.0 + (double)P.omega_mid + (double)P.omega_lim + std::fabs((double)P.gain_mu) * 2.0 * outmax;
+    const int max_adv = (int)std::floor(adv * 1.0001);      // mu < 1 is the "1.0 +" above
+    const int sym_target = 704;                       // 625 + 72 rounded up to whole words
+    const long ne = (long)sym_target * max_adv + 16;
+    const long nsym_lb = std::min<long>(P.n_dem, (P.n_dem - 8) / max_adv);
+    // both search limits must be 625 whatever the (unknown) symbol count: nsym >= 625 + 68 + 692
+    if (ne + 64 < P.n_dem && nsym_lb >= 1400 && G.bw >= 32) {
+      ctx->early = true;
+      G.ne_dem = (int)ne; G.sym_target = sym_target;
+    }
+  }
+  if (ctx->early) {
+    void *sv = nullptr;
+    if ((rc = dev_alloc(ctx, reinterpret_cast<char **>(&sv), B * nch * 24))) return rc;
+    W.mm_save = sv;
+    if ((rc = dev_alloc(ctx, &ctx->d_list2, ctx->list_cap * 4))) return rc;
+    CK(cudaMallocHost(&ctx->h_list2, ctx->list_cap * 4 * sizeof(int)));
+    CK(cudaMallocHost(&ctx->h_nsym, B * nch * sizeof(int)));
+    // high priority: its few blocks take the first SMs the deferred noise FIR frees, and finish under it
+    int pr_lo = 0, pr_hi = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&pr_lo, &pr_hi));
+    CK(cudaStreamCreateWithPriority(&ctx->stream2, cudaStreamNonBlocking, pr_hi));
   }
   const size_t bp = G.stateless ? 1 : B;
   if ((rc = dev_alloc(ctx, &ctx->d_phc, bp * P.n_ddc * nch))) return rc;
@@ -324,10 +380,13 @@ void teardown(btb200_ctx *ctx)
   for (void *p : ctx->allocs) cudaFree(p);
   for (void *p : {(void *)ctx->h_energy, (void *)ctx->h_noise, (void *)ctx->h_pass, (void *)ctx->h_counts,
                   (void *)ctx->h_hits, (void *)ctx->h_arena, (void *)ctx->h_ph, (void *)ctx->h_groups,
-                  (void *)ctx->h_list, (void *)ctx->h_eon, (void *)ctx->h_eoff, (void *)ctx->h_esum})
+                  (void *)ctx->h_list, (void *)ctx->h_eon, (void *)ctx->h_eoff, (void *)ctx->h_esum,
+                  (void *)ctx->h_list2, (void *)ctx->h_nsym})
     if (p) cudaFreeHost(p);
   for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
   for (auto &e : ctx->evl) if (e) cudaEventDestroy(e);
+  if (ctx->ev_tail) cudaEventDestroy(ctx->ev_tail);
+  if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
 }
 
@@ -452,7 +511,8 @@ int btb200_submit(btb200_ctx *ctx, const float *iq, int iq_on_device, size_t n_s
   if (ctx->pending) return BTB200_ERR_ARG;
   if (n_slots > ctx->max_slots) return BTB200_ERR_TOO_MANY;
   const Plan &P = ctx->plan;
-  const Geom &G = ctx->G;
+  Geom G = ctx->G;
+  G.early = (ctx->early && ctx->impl == IMPL_TUNED) ? 1 : 0;
   const size_t need = (size_t)(n_slots - 1) * P.S + P.H;
   if (n_samples < need) return BTB200_ERR_SHORT_INPUT;
   CK(cudaSetDevice(ctx->device));
@@ -526,8 +586,8 @@ int btb200_submit(btb200_ctx *ctx, const float *iq, int iq_on_device, size_t n_s
   CK(cudaEventRecord(ctx->ev[5], s));
   if (ctx->impl == IMPL_BASELINE) launch_search(G, ctx->T, W, s);
   else launch_search_warp(G, ctx->T, W, s);
-  launch_gather(G, W, s);
-  ctx->launches += 2;
+  if (!G.early) launch_gather(G, W, s);         // lazy tail: symbols are gathered in collect(), after the resume
+  ctx->launches += G.early ? 1 : 2;
   CK(cudaEventRecord(ctx->ev[6], s));
   CK(cudaMemcpyAsync(ctx->h_counts, W.hit_count, 4 * sizeof(unsigned), cudaMemcpyDeviceToHost, s));
   if (!G.stateless) CK(cudaMemcpyAsync(&ctx->mm, W.mm_state, sizeof(MmState), cudaMemcpyDeviceToHost, s));
@@ -537,6 +597,8 @@ int btb200_submit(btb200_ctx *ctx, const float *iq, int iq_on_device, size_t n_s
   ctx->pend_slots = n_slots;
   ctx->pend_first_slot = first_slot;
   ctx->pendW = W;
+  ctx->pendG = G;
+  ctx->pend_early = G.early != 0;
   return BTB200_OK;
 }
 
@@ -549,14 +611,45 @@ int btb200_collect(btb200_ctx *ctx, btb200_hits *out)
   ctx->pending = false;
   CK(cudaStreamSynchronize(s));
   unsigned nh = ctx->h_counts[0];
+  Trace tr; tr.mark("batch done");
   unsigned long long used;
   std::memcpy(&used, ctx->h_counts + 2, sizeof used);
   unsigned dropped = 0;
   if (nh > kHitCap) { dropped = nh - kHitCap; nh = kHitCap; }
   if (used > kArenaCap) used = kArenaCap;
   if (nh) CK(cudaMemcpyAsync(ctx->h_hits, ctx->W.hits, (size_t)nh * sizeof(DevHit), cudaMemcpyDeviceToHost, s));
+  if (ctx->pend_early) used = 0;
   if (used && out && out->symbols) CK(cudaMemcpyAsync(ctx->h_arena, ctx->W.arena, used, cudaMemcpyDeviceToHost, s));
   ctx->lazy_timed = false;
+  // lazy tail, second half (host side): runs while the deferred noise FIR is still busy on the main stream
+  bool tail_done = false;
+  auto finish_tail = [&]() -> int {
+      if (!ctx->pend_early || !nh || tail_done) return 0;
+      tail_done = true;
+      // the symbol counts are known now: complete the hit records, lay the arena out, gather the symbols
+      CK(cudaStreamSynchronize(ctx->stream2));
+      unsigned long long off = 0;
+      tr.mark("resume done (host)");
+      for (unsigned i = 0; i < nh; i++) {
+        DevHit &h = ctx->h_hits[i];
+        h.n_symbols += ctx->h_nsym[(size_t)h.b * P.nch + h.chi];
+        int cnt = h.n_symbols < 3125 ? h.n_symbols : 3125;
+        if (cnt < 0) cnt = 0;
+        h.sym_offset = off;
+        h.sym_count = (off + (unsigned)cnt <= kArenaCap) ? (uint32_t)cnt : 0u;
+        off += (unsigned)cnt;
+      }
+      used = off > kArenaCap ? kArenaCap : off;
+      if (out && out->symbols && used) {
+        cudaStream_t s2 = ctx->stream2;
+        CK(cudaMemcpyAsync(ctx->W.hits, ctx->h_hits, (size_t)nh * sizeof(DevHit), cudaMemcpyHostToDevice, s2));
+        launch_gather(ctx->pendG, ctx->pendW, s2); ctx->launches++;
+        CK(cudaMemcpyAsync(ctx->h_arena, ctx->W.arena, used, cudaMemcpyDeviceToHost, s2));
+      }
+      CK(cudaEventRecord(ctx->ev_tail, ctx->stream2));
+      CK(cudaStreamWaitEvent(s, ctx->ev_tail, 0));     // the batch (and its timing) ends when the tail has
+    return 0;
+  };
   std::vector<uint8_t> est_flag;       // per listed window: 1 = snr from the fast estimate
   if (ctx->lazy) {
     const size_t nbc = (size_t)ctx->pend_slots * P.nch;
@@ -573,6 +666,19 @@ int btb200_collect(btb200_ctx *ctx, btb200_hits *out)
       std::sort(keys.begin(), keys.end());
       keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
       const int nl_all = (int)keys.size();
+      if (ctx->pend_early) {
+        // lazy tail: finish demod + clock recovery of the hit windows on the second stream, under the noise FIR
+        for (int l = 0; l < nl_all; l++) {
+          int *q = ctx->h_list2 + (size_t)l * 4;
+          q[0] = (int)(keys[l] / P.nch); q[1] = (int)(keys[l] % P.nch); q[2] = 0; q[3] = 0;
+        }
+        cudaStream_t s2 = ctx->stream2;
+        CK(cudaMemcpyAsync(ctx->d_list2, ctx->h_list2, (size_t)nl_all * 4 * sizeof(int), cudaMemcpyHostToDevice, s2));
+        launch_mm_resume_list(ctx->pendG, ctx->T, ctx->pendW, ctx->d_dem, ctx->d_list2, nl_all, s2);
+        ctx->launches += 2;
+        CK(cudaMemcpyAsync(ctx->h_nsym, ctx->pendW.nsym, nbc * sizeof(int), cudaMemcpyDeviceToHost, s2));
+        tr.mark("resume launched");
+      }
       // pass 1 (fast mode): exact on-channel energy of every hit window, off-channel from the estimate
       std::vector<uint32_t> need_exact;
       if (ctx->fast_snr) {
@@ -589,6 +695,7 @@ int btb200_collect(btb200_ctx *ctx, btb200_hits *out)
         ctx->lazy_timed = true;
         CK(cudaMemcpyAsync(ctx->h_eon, ctx->d_eon, (size_t)nl_all * sizeof(double), cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
+        tr.mark("pass-1 energies back");
         const double guard = 5e-3;
         for (int l = 0; l < nl_all; l++) {
           const size_t bc = keys[l];
@@ -632,7 +739,9 @@ int btb200_collect(btb200_ctx *ctx, btb200_hits *out)
         ctx->launches += 2;
         CK(cudaMemcpyAsync(ctx->h_eon, ctx->d_eon, (size_t)nl * sizeof(double), cudaMemcpyDeviceToHost, s));
         CK(cudaMemcpyAsync(ctx->h_eoff, ctx->d_eoff, (size_t)nl * sizeof(double), cudaMemcpyDeviceToHost, s));
+        if (int rc = finish_tail()) return rc;
         CK(cudaStreamSynchronize(s));
+        tr.mark("exact energies back");
         for (int l = 0; l < nl; l++) {
           const size_t bc = (size_t)ctx->h_list[(size_t)l * 4] * P.nch + ctx->h_list[(size_t)l * 4 + 1];
           ctx->h_energy[bc] = ctx->h_eon[l];
@@ -645,8 +754,10 @@ int btb200_collect(btb200_ctx *ctx, btb200_hits *out)
       }
     }
   }
+  if (int rc = finish_tail()) return rc;
   CK(cudaEventRecord(ctx->ev[8], s));
   CK(cudaStreamSynchronize(s));
+  tr.mark("all done");
   ctx->last_slots = ctx->pend_slots;
   for (int i = 0; i < 7; i++) {
     float ms = 0;

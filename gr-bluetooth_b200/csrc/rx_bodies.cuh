@@ -33,6 +33,8 @@ struct Geom {
   double squelch_db;
   int search;         // BTB200_SEARCH_* mask
   int stateless;
+  int early;          // lazy tail: clock recovery stops at sym_target symbols, demod computed for i < ne_dem
+  int ne_dem, sym_target;
 };
 
 // ---- channel FIR: Y[g][c] = sum_k x[fcs + g*D + k] * rt[c][k]  (k ascending)

@@ -128,12 +128,13 @@ __global__ void k_mm_chained_list(Geom G, DevBatch W, const float *__restrict__ 
 
 struct HitEmitter {
   const Geom &G; const DevBatch &W; int b, c, nsym;
+  bool relative = false;      // lazy tail: n_symbols is relative to the (not yet known) symbol count; no symbols yet
   __device__ void operator()(int kind, int offset, int n_symbols, uint32_t lap) const
   {
     const unsigned slot = atomicAdd(W.hit_count, 1u);
     if (slot >= W.hit_cap) return;
     int cnt = n_symbols < 3125 ? n_symbols : 3125;
-    if (cnt < 0) cnt = 0;
+    if (cnt < 0 || relative) cnt = 0;
     const unsigned long long so = atomicAdd(W.arena_used, (unsigned long long)cnt);
     DevHit h;
     h.b = b; h.chi = (int16_t)c; h.kind = (int16_t)kind; h.offset = offset; h.n_symbols = n_symbols;
@@ -454,8 +455,10 @@ static size_t fir_packed_smem(int CG, int R, int W, int D, int KT, bool skew = f
 
 template <int BLK>
 __global__ void k_dmm_stateless(Geom G, DevBatch W, const float *__restrict__ mmse_g, const float *__restrict__ atan_g);
+struct MmSave;
 template <int BLK>
-__global__ void k_mm_stateless_v2(Geom G, DevBatch W, const float *__restrict__ mmse_g, const float *__restrict__ demT);
+__global__ void k_mm_stateless_v2(Geom G, DevBatch W, const float *__restrict__ mmse_g, const float *__restrict__ demT,
+                                  int mode, MmSave *__restrict__ save, const int4 *__restrict__ list, int n_list);
 
 static size_t fir_smem(int CG, int R, int W, int D, int KT)
 {
@@ -611,7 +614,7 @@ __global__ void __launch_bounds__(BLK) k_dmm_stateless(Geom G, DevBatch W, const
 // rotated sample, so each DDC output is rotated once and all loads/stores are channel-contiguous.
 constexpr int DM_WARPS = 8, DM_RUN = 16, DM_TI = DM_WARPS * DM_RUN;
 __global__ void __launch_bounds__(DM_WARPS * 32) k_demod_all(Geom G, DevBatch W, const float *__restrict__ atan_g,
-                                                             float *__restrict__ demT)
+                                                             float *__restrict__ demT, int i_end)
 {
   __shared__ float s_atan[257];
   for (int i = threadIdx.x; i < 257; i += blockDim.x) s_atan[i] = atan_g[i];
@@ -622,8 +625,8 @@ __global__ void __launch_bounds__(DM_WARPS * 32) k_demod_all(Geom G, DevBatch W,
   if (c >= G.nch) return;
   if (!W.pass[b * G.nch + c]) return;
   const int i0 = blockIdx.x * DM_TI + w * DM_RUN;
-  if (i0 >= G.n_dem) return;
-  const int i1 = (i0 + DM_RUN < G.n_dem) ? i0 + DM_RUN : G.n_dem;
+  if (i0 >= i_end) return;
+  const int i1 = (i0 + DM_RUN < i_end) ? i0 + DM_RUN : i_end;
   const c32 *y = W.Y + ((long)b * G.gps) * G.nch + c;
   const c32 *p = W.phc + (long)(b * W.bp_stride) * G.n_ddc * G.nch + c;
   float *d = demT + ((long)b * G.n_dem_pad) * G.nch + c;
@@ -639,17 +642,50 @@ __global__ void __launch_bounds__(DM_WARPS * 32) k_demod_all(Geom G, DevBatch W,
   }
 }
 
+// demod tail [i_begin, n_dem) of LISTED windows (lazy tail): one thread per output
+__global__ void k_demod_list(Geom G, DevBatch W, const float *__restrict__ atan_g, float *__restrict__ demT,
+                             const int4 *__restrict__ list, int i_begin)
+{
+  __shared__ float s_atan[257];
+  for (int i = threadIdx.x; i < 257; i += blockDim.x) s_atan[i] = atan_g[i];
+  __syncthreads();
+  const int4 it = list[blockIdx.y];
+  const int b = it.x, c = it.y;
+  const int i = i_begin + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= G.n_dem) return;
+  const c32 *y = W.Y + ((long)b * G.gps) * G.nch + c;
+  const c32 *p = W.phc + c;                                   // stateless: one phase table
+  float val = 0.0f;
+  if (i > 0) {
+    const c32 cur = crot(y[(long)i * G.nch], p[(long)i * G.nch]);
+    const c32 prev = crot(y[(long)(i - 1) * G.nch], p[(long)(i - 1) * G.nch]);
+    val = demod_point(s_atan, G.demod_gain, cur, prev);
+  }
+  demT[((long)b * G.n_dem_pad + i) * G.nch + c] = val;
+}
+
 __device__ __forceinline__ void cp_async4(void *smem_dst, const void *gsrc)
 {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(gsrc));
 }
 
+struct MmSave { float mu, omega, last; unsigned ii; int oo; uint32_t word; };
+// ring depth of the clock-recovery kernel: a refill reaches ii+96 and the reader is at most 40 samples further
+// when the next one is issued, so 128 slots never overwrite a live sample; 36 KB per 64 windows keeps six
+// blocks per SM resident = the whole 512-slot batch in ONE wave (the loop is latency-bound, not issue-bound)
+constexpr int MM_RD = 128;
+
+// mode 0: every window from the constructor state to the end (reference loop).
+// mode 1 (lazy tail, first pass): every window, stop at G.sym_target symbols, demod floats exist for i < G.ne_dem
+//         (enough for sym_target symbols at the loop's maximum advance); the loop state is saved.
+// mode 2 (lazy tail, resume): LISTED windows continue from the saved state to the end.
 template <int BLK>
 __global__ void __launch_bounds__(BLK) k_mm_stateless_v2(Geom G, DevBatch W, const float *__restrict__ mmse_g,
-                                                         const float *__restrict__ demT)
+                                                         const float *__restrict__ demT, int mode,
+                                                         MmSave *__restrict__ save, const int4 *__restrict__ list, int n_list)
 {
-  constexpr int RD = 256;          // ring depth (demod samples per window)
+  constexpr int RD = MM_RD;        // ring depth (demod samples per window)
   constexpr int AHEAD = 88;        // refill target: ii + 8 + AHEAD
   constexpr int PERIOD = 8;        // refill every PERIOD steps (warp-uniform: all lanes share the step counter)
   // The loop advances ii by at most 5 samples per step (|demod| <= gain*pi bounds mm_val), so a refill
@@ -659,9 +695,15 @@ __global__ void __launch_bounds__(BLK) k_mm_stateless_v2(Geom G, DevBatch W, con
   float (*s_mmse)[132] = reinterpret_cast<float (*)[132]>(mm_smem + sizeof(float) * RD * BLK);   // [8][132]
   for (int i = threadIdx.x; i < 129 * 8; i += BLK) s_mmse[7 - (i & 7)][i >> 3] = mmse_g[i];   // [k][imu] = taps[imu][7-k]
   __syncthreads();
-  const int idx = blockIdx.x * BLK + threadIdx.x;
-  if (idx >= W.B * G.nch) return;
-  if (!W.pass[idx]) { W.nsym[idx] = 0; return; }
+  int idx = blockIdx.x * BLK + threadIdx.x;
+  if (mode == 2) {
+    if (idx >= n_list) return;
+    const int4 it = list[idx];
+    idx = it.x * G.nch + it.y;
+  } else {
+    if (idx >= W.B * G.nch) return;
+    if (!W.pass[idx]) { W.nsym[idx] = 0; return; }
+  }
   const int b = idx / G.nch, c = idx - b * G.nch;
   const float *gp = demT + ((long)b * G.n_dem_pad) * G.nch + c;    // next sample to prefetch
   uint32_t *__restrict__ bits_row = W.bits + (long)idx * G.bw;
@@ -669,27 +711,37 @@ __global__ void __launch_bounds__(BLK) k_mm_stateless_v2(Geom G, DevBatch W, con
   MmState st{G.mu0, G.mm.omega_mid, 0.0f};
   unsigned ii = 0;
   int oo = 0;
-  const unsigned ni = (unsigned)(G.n_dem - 8);
-  int pf = 0;                      // samples [pf-RD, pf) are in (or on their way to) the ring
-  int ready = 0;                   // samples below `ready` have landed
   uint32_t word = 0;
+  if (mode == 2) {
+    const MmSave sv = save[idx];
+    st = MmState{sv.mu, sv.omega, sv.last};
+    ii = sv.ii; oo = sv.oo; word = sv.word;
+  }
+  const int avail = (mode == 1) ? G.ne_dem : G.n_dem;            // demod floats that exist
+  const int oo_end = (mode == 1) ? G.sym_target : G.n_dem;
+  const unsigned ni = (unsigned)((mode == 1 ? G.ne_dem : G.n_dem) - 8);
+  int pf = (int)ii;                // samples [pf-RD, pf) are in (or on their way to) the ring
+  int ready = 0;                   // samples below `ready` have landed
   const int tid = threadIdx.x;
   const int nch = G.nch;
+  gp += (long)pf * nch;
   {
-    int want = 8 + AHEAD; if (want > G.n_dem) want = G.n_dem;
+    int want = (int)ii + 8 + AHEAD; if (want > avail) want = avail;
     for (; pf < want; pf++, gp += nch) cp_async4(&ring[pf & (RD - 1)][tid], gp);
     cp_async_commit();
     cp_async_wait<0>();
     ready = pf;
   }
-  while (oo < G.n_dem && ii < ni) {
-    if ((oo & (PERIOD - 1)) == 0 && oo) {
+  int step = 0;
+  while (oo < oo_end && ii < ni) {
+    if ((step & (PERIOD - 1)) == 0 && step) {
       cp_async_wait<0>();          // the previous refill (issued PERIOD steps ago) has long landed
       ready = pf;
-      int want = (int)ii + 8 + AHEAD; if (want > G.n_dem) want = G.n_dem;
+      int want = (int)ii + 8 + AHEAD; if (want > avail) want = avail;
       for (; pf < want; pf++, gp += nch) cp_async4(&ring[pf & (RD - 1)][tid], gp);
       cp_async_commit();
     }
+    step++;
     if ((int)ii + 8 > ready) { cp_async_wait<0>(); ready = pf; }     // never taken for bounded inputs
     int imu = __float2int_rn(st.mu * 128.0f);
     imu = imu < 0 ? 0 : (imu > 128 ? 128 : imu);
@@ -703,6 +755,7 @@ __global__ void __launch_bounds__(BLK) k_mm_stateless_v2(Geom G, DevBatch W, con
     oo++;
   }
   cp_async_wait<0>();
+  if (mode == 1) save[idx] = MmSave{st.mu, st.omega, st.last, ii, oo, word};
   if (oo & 31) bits_row[oo >> 5] = word;
   for (int w = (oo + 31) >> 5; w < G.bw; w++) bits_row[w] = 0;
   W.nsym[idx] = oo;
@@ -740,8 +793,11 @@ __global__ void k_search_warp(Geom G, DevTables T, DevBatch W)
     if (lane == q) { br_mask = mb; le_mask = ml; }
   }
   // replay of the search loops (warp-uniform control flow; lane 0 emits)
-  HitEmitter em{G, W, b, c, nsym};
-  int len = nsym;
+  // lazy tail: the rows hold the first G.sym_target symbols; the true count is >= 1386 for this geometry,
+  // so both limits are 625, and symbol counts are emitted RELATIVE to it (the host adds the true count)
+  const int nsym_eff = G.early ? 0 : nsym;
+  HitEmitter em{G, W, b, c, nsym, G.early != 0};
+  int len = G.early ? (1 << 20) : nsym;
   if (G.search & 1) {
     const int limit0 = (len - 68 < 625) ? len - 68 : 625;
     int start = 0;
@@ -756,15 +812,15 @@ __global__ void k_search_warp(Geom G, DevTables T, DevBatch W)
       if (lane == 0) {
         uint64_t lo; uint32_t hi;
         bits_window(row, found, &lo, &hi);
-        em(0, found, nsym - found, (uint32_t)(lo >> 38) & 0xffffff);
+        em(0, found, nsym_eff - found, (uint32_t)(lo >> 38) & 0xffffff);
       }
       start = found + 68;
     }
-    len = nsym - start;
+    len = (G.early ? (1 << 20) : nsym) - start;
   }
   if ((G.search & 2) && le_idx >= 0) {
     const int limit0 = (len - 68 < 625) ? len - 68 : 625;
-    const int len_le = len;
+    const int len_le = G.early ? len - (1 << 20) : len;          // relative to the true symbol count in lazy-tail mode
     int start = 0;
     while (limit0 - start >= 0) {
       int found = -1;
@@ -947,11 +1003,29 @@ void launch_gather(const Geom &G, const DevBatch &W, cudaStream_t s)
 
 void launch_demod_mm_v2(const Geom &G, const DevTables &T, const DevBatch &W, float *demT, cudaStream_t s)
 {
-  dim3 grid(cdiv(G.n_dem, DM_TI), (unsigned)W.B, (unsigned)((G.nch + 31) / 32));
-  k_demod_all<<<grid, DM_WARPS * 32, 0, s>>>(G, W, T.atan_tab, demT);
+  const int i_end = G.early ? G.ne_dem : G.n_dem;
+  dim3 grid(cdiv(i_end, DM_TI), (unsigned)W.B, (unsigned)((G.nch + 31) / 32));
+  k_demod_all<<<grid, DM_WARPS * 32, 0, s>>>(G, W, T.atan_tab, demT, i_end);
   constexpr int BLK = 64;
-  const size_t smem = sizeof(float) * 256 * BLK + sizeof(float) * 8 * 132;
-  k_mm_stateless_v2<BLK><<<cdiv((long)W.B * G.nch, BLK), BLK, smem, s>>>(G, W, T.mmse, demT);
+  const size_t smem = sizeof(float) * MM_RD * BLK + sizeof(float) * 8 * 132;
+  k_mm_stateless_v2<BLK><<<cdiv((long)W.B * G.nch, BLK), BLK, smem, s>>>(G, W, T.mmse, demT, G.early ? 1 : 0,
+                                                                            reinterpret_cast<MmSave *>(W.mm_save), nullptr, 0);
+}
+
+// lazy tail, second pass: demod tail + clock-recovery resume of the LISTED windows (list4[l] = {b, chi, ., .})
+void launch_mm_resume_list(const Geom &G, const DevTables &T, const DevBatch &W, float *demT, const int *list4,
+                           int n_list, cudaStream_t s)
+{
+  if (n_list <= 0) return;
+  const int tail = G.n_dem - G.ne_dem;
+  if (tail > 0) {
+    dim3 grid(cdiv(tail, 128), (unsigned)n_list);
+    k_demod_list<<<grid, 128, 0, s>>>(G, W, T.atan_tab, demT, reinterpret_cast<const int4 *>(list4), G.ne_dem);
+  }
+  constexpr int BLK = 64;
+  const size_t smem = sizeof(float) * MM_RD * BLK + sizeof(float) * 8 * 132;
+  k_mm_stateless_v2<BLK><<<cdiv(n_list, BLK), BLK, smem, s>>>(G, W, T.mmse, demT, 2, reinterpret_cast<MmSave *>(W.mm_save),
+                                                               reinterpret_cast<const int4 *>(list4), n_list);
 }
 
 void launch_search_warp(const Geom &G, const DevTables &T, const DevBatch &W, cudaStream_t s)

@@ -31,6 +31,7 @@ struct DevBatch {
   uint32_t *bits;            // [B][nch][bw]
   int *nsym;                 // [B][nch]
   MmState *mm_state;         // [1] chained-mode state in/out
+  void *mm_save;             // [B][nch] saved clock-recovery loop state (lazy tail)
   DevHit *hits;              // [hit_cap]
   unsigned *hit_count;       // [1]
   unsigned long long *arena_used;   // [1]
@@ -53,6 +54,8 @@ void launch_mm_chained_list(const Geom &G, const DevTables &T, const DevBatch &W
 void launch_search(const Geom &G, const DevTables &T, const DevBatch &W, cudaStream_t s);
 void launch_gather(const Geom &G, const DevBatch &W, cudaStream_t s);
 void launch_demod_mm_v2(const Geom &G, const DevTables &T, const DevBatch &W, float *demT, cudaStream_t s);
+void launch_mm_resume_list(const Geom &G, const DevTables &T, const DevBatch &W, float *demT, const int *list4,
+                           int n_list, cudaStream_t s);
 void launch_search_warp(const Geom &G, const DevTables &T, const DevBatch &W, cudaStream_t s);
 void launch_dmm_stateless(const Geom &G, const DevTables &T, const DevBatch &W, cudaStream_t s);
 void launch_fill_pass(const DevBatch &W, int n, int v, cudaStream_t s);

@@ -102,6 +102,17 @@ enum {
   BTB200_SNR_FAST_GUARDED = 1
 };
 
+/* how much of a window's symbol stream is produced before the access-code search (lazy squelch) */
+enum {
+  /* lazy tail (default where the geometry allows it): only lags 0..624 are ever searched, i.e. 697 of the
+   * ~3742 symbols of a window, and the clock-recovery loop advances at most 5 samples per step, so every
+   * window is demodulated up to symbol 704 only; windows with a hit are resumed from the saved loop state
+   * to produce the rest (bit-identical: same loop, same state).  Symbol counts / bit streams of windows
+   * without a hit then stop at 704 (btb200_get_stage). */
+  BTB200_TAIL_LAZY = 0,
+  BTB200_TAIL_FULL = 1           /* every window to the end */
+};
+
 enum {
   BTB200_SEARCH_BR = 1,          /* classic_packet::sniff_ac */
   BTB200_SEARCH_LE = 2           /* le_packet::sniff_aa */
@@ -126,7 +137,8 @@ typedef struct btb200_config {
   uint32_t keep_stages;          /* 1: keep demod/soft-symbol buffers for btb200_get_stage */
   uint32_t squelch_mode;         /* BTB200_SQUELCH_* (stateless mode only; chained is always eager) */
   uint32_t snr_mode;             /* BTB200_SNR_* (lazy squelch only) */
-  uint32_t reserved[3];
+  uint32_t tail_mode;            /* BTB200_TAIL_* (lazy squelch only) */
+  uint32_t reserved[2];
 } btb200_config;
 
 /* derived constants (lib/multi_block.cc:56-119, 299-342) */

@@ -53,25 +53,32 @@ def test_uploaded_tables_equal_oracle(fs, fc, extra):
 
 
 @pytest.mark.parametrize("name", list(FILES))
-@pytest.mark.parametrize("mode", ["chained", "stateless", "stateless-lazy"])
+@pytest.mark.parametrize("mode", ["chained", "stateless", "stateless-lazy", "stateless-lazytail"])
 @pytest.mark.parametrize("impl", [0, 1, 2])
 def test_excerpt_bit_exact(name, mode, impl):
     """Committed excerpts of the bundled captures: energies (f64), every sliced symbol of every
     channel-window, and the ac()/aa() call list, identical to the reference's own code.
     `stateless-lazy` = lazy squelch: windows the reference squelches are demodulated too (and
-    their hits dropped afterwards); exact energies exist only for windows with hits."""
-    lazy = mode.endswith("lazy")
+    their hits dropped afterwards); exact energies exist only for windows with hits.
+    `stateless-lazytail` = lazy squelch + lazy tail (the default): clock recovery of a window stops
+    after the 704 symbols the access-code search can look at and is resumed, from the saved loop
+    state, only for windows with hits -- those have every symbol, the others the exact prefix."""
+    lazy = "lazy" in mode
+    tail = mode.endswith("tail")
+    if tail and impl != 1:
+        pytest.skip("lazy tail exists in the tuned kernels only")
     ex = load_excerpt(name, mode.split("-")[0])
     stateless = mode != "chained"
     blk = g.multi_sniffer(ex["fs"], ex["fc"], 10.0, mm_mode=g.MM_STATELESS if stateless else g.MM_CHAINED,
-                          max_slots=32, squelch=g.SQUELCH_LAZY if lazy else g.SQUELCH_EAGER)
+                          max_slots=32, squelch=g.SQUELCH_LAZY if lazy else g.SQUELCH_EAGER,
+                          tail=g.TAIL_LAZY if tail else g.TAIL_FULL)
     blk.set_impl(impl)
     P = O.Plan(ex["fs"], ex["fc"])
     S, H, n = P.S, P.H, ex["nslots"]
     x = np.concatenate([np.zeros(H - 1, np.complex64), ex["iq"]])
     all_hits = []
     k = 0
-    n_energy_checked = 0
+    n_energy_checked = n_full = n_prefix = 0
     while k < n:
         b = min(32 if k else 7, n - k)        # uneven batches on purpose
         hits, _, ovf = blk.process(x[k * S:(k + b - 1) * S + H], k, b)
@@ -87,12 +94,21 @@ def test_excerpt_bit_exact(name, mode, impl):
                     assert (e == we) or (np.isnan(e) and np.isnan(we))
                     assert (z == wz) or (np.isnan(z) and np.isnan(wz))
                     n_energy_checked += 1
+                hit_window = bool(((hits["slot"] == k + j) & (hits["channel"] == P.ch_lo + chi)).any())
+                if tail and not hit_window:
+                    if ex["nsym"][k + j, chi]:
+                        got_bits = blk.stage("bits", j, chi)
+                        assert len(got_bits) == 704 == blk.stage("nsym", j, chi)[0]
+                        assert np.array_equal(got_bits, golden_bits(ex, k + j, chi)[:704])
+                        n_prefix += 1
+                    continue
                 if ex["nsym"][k + j, chi] or not lazy:
                     assert blk.stage("nsym", j, chi)[0] == ex["nsym"][k + j, chi]
                 if ex["nsym"][k + j, chi]:
                     assert np.array_equal(blk.stage("bits", j, chi), golden_bits(ex, k + j, chi))
+                    n_full += 1
         k += b
-    assert n_energy_checked > 0
+    assert n_energy_checked > 0 and n_full > 0 and (n_prefix > 0 or not tail)
     got = np.concatenate(all_hits)
     want = R.parse_stdout_hits(ex["stdout"])
     assert len(got) == len(want) > 0
@@ -143,7 +159,7 @@ def _stage_check(blk, ex):
 
 
 @pytest.mark.parametrize("name", list(FILES))
-@pytest.mark.parametrize("mode", ["chained", "stateless", "stateless-lazy"])
+@pytest.mark.parametrize("mode", ["chained", "stateless", "stateless-lazy", "stateless-lazytail"])
 def test_full_capture_equals_oracle(name, mode):
     """Whole bundled capture (when staged on this box): hit list incl. offsets and f64 snr, and the
     M&M state at the end, identical to the oracle run on this box's CPU."""
@@ -154,9 +170,11 @@ def test_full_capture_equals_oracle(name, mode):
     stateless = mode != "chained"
     P = O.Plan(fs, fc)
     st = O.State(P)
-    o = P.run(iq, stateless=stateless, state=None if stateless else st, threads=8 if stateless else 1)
+    o = P.run(iq, stateless=stateless, state=None if stateless else st, threads=8 if stateless else 1,
+              want_bits=stateless)
     blk = g.multi_sniffer(fs, fc, 10.0, mm_mode=g.MM_STATELESS if stateless else g.MM_CHAINED, max_slots=64,
-                          squelch=g.SQUELCH_LAZY if mode.endswith("lazy") else g.SQUELCH_EAGER)
+                          squelch=g.SQUELCH_LAZY if "lazy" in mode else g.SQUELCH_EAGER,
+                          tail=g.TAIL_LAZY if mode.endswith("tail") else g.TAIL_FULL)
     hits, syms = blk.run_stream(iq, want_symbols=True)
     assert gpu_hit_tuples(hits) == oracle_hit_tuples(o["hits"])
     assert len(hits) > 20
@@ -167,6 +185,13 @@ def test_full_capture_equals_oracle(name, mode):
         s = syms[int(h["sym_offset"]):int(h["sym_offset"]) + int(h["sym_count"])]
         assert h["sym_count"] == min(h["n_symbols"], 3125)
         assert int((s[:68] != O.acgen_bits(int(h["lap"]))[:68]).sum()) < 7
+    if stateless:
+        # every symbol handed to ac()/aa() equals the oracle's sliced stream of that window
+        for h in hits:
+            b, chi, off, cnt = int(h["slot"]), int(h["channel"]) - P.ch_lo, int(h["offset"]), int(h["sym_count"])
+            s = syms[int(h["sym_offset"]):int(h["sym_offset"]) + cnt]
+            assert cnt == max(0, min(int(h["n_symbols"]), 3125))
+            assert np.array_equal(s, o["bits"][b, chi, off:off + cnt])
     blk.close()
 
 
@@ -177,7 +202,7 @@ def synth_small(fs, fc, nslots, seed, laps, snr_db=20.0):
 
 
 @pytest.mark.parametrize("fs,fc,nslots", [(100e6, 2441e6, 11), (30e6, 2414e6, 11)])
-@pytest.mark.parametrize("squelch", ["eager", "lazy"])
+@pytest.mark.parametrize("squelch", ["eager", "lazy", "lazytail"])
 def test_synthetic_wideband_equals_oracle(fs, fc, nslots, squelch):
     """BASELINE configs 2/3/5 geometry at a size the oracle finishes in seconds: 79 (27)
     channels, stateless mode, GPU hit list == oracle hit list, bits of sampled windows equal."""
@@ -186,13 +211,21 @@ def test_synthetic_wideband_equals_oracle(fs, fc, nslots, squelch):
     first = 7                                  # (H-1)/S = 6.32 slots of history
     B = nslots - first
     o = P.run(iq, first_call=first, num_calls=B, stateless=True, threads=8, want_bits=True, want_energy=True)
-    lazy = squelch == "lazy"
+    lazy = squelch != "eager"
+    tail = squelch == "lazytail"
     blk = g.multi_sniffer(fs, fc, 10.0, mm_mode=g.MM_STATELESS, max_slots=B,
-                          squelch=g.SQUELCH_LAZY if lazy else g.SQUELCH_EAGER)
+                          squelch=g.SQUELCH_LAZY if lazy else g.SQUELCH_EAGER,
+                          tail=g.TAIL_LAZY if tail else g.TAIL_FULL)
     S, H = P.S, P.H
     w0 = first * S - (H - 1)
-    hits, _, _ = blk.process(iq[w0:w0 + (B - 1) * S + H], first, B)
+    hits, syms, _ = blk.process(iq[w0:w0 + (B - 1) * S + H], first, B, want_symbols=True)
     assert gpu_hit_tuples(hits) == oracle_hit_tuples(o["hits"])
+    hit_windows = set()
+    for h in hits:
+        b, chi, off, cnt = int(h["slot"]) - first, int(h["channel"]) - P.ch_lo, int(h["offset"]), int(h["sym_count"])
+        hit_windows.add((b, chi))
+        assert cnt == max(0, min(int(h["n_symbols"]), 3125))
+        assert np.array_equal(syms[int(h["sym_offset"]):int(h["sym_offset"]) + cnt], o["bits"][b, chi, off:off + cnt])
     found = {(int(h["channel"]), int(h["lap"])) for h in hits if h["kind"] == 0}
     expect = {(t["channel"], t["lap"]) for t in truth if 1 <= t["slot"] <= nslots - 8}
     # detection recall vs ground truth (adjacent-channel collisions may legitimately be missed)
@@ -204,6 +237,11 @@ def test_synthetic_wideband_equals_oracle(fs, fc, nslots, squelch):
             assert blk.stage("energy", b, chi)[0] == o["energy"][b, chi]
             assert blk.stage("noise", b, chi)[0] == o["noise"][b, chi]
         n = o["nsym"][b, chi]
+        if tail and (b, chi) not in hit_windows:
+            assert blk.stage("nsym", b, chi)[0] == 704
+            if n:
+                assert np.array_equal(blk.stage("bits", b, chi), o["bits"][b, chi, :704])
+            continue
         if n or not lazy:
             assert blk.stage("nsym", b, chi)[0] == n
         if n:

@@ -250,6 +250,17 @@ int setup(btb200_ctx *ctx)
         tg[((size_t)(c / 16) * P.Nn + k) * 16 + (c % 16)] = c32{t.re, t.im};
       }
     if ((rc = upload(ctx, &ctx->T.noise_tg, tg))) return rc;
+    if (ctx->cfg.mm_mode == BTB200_MM_STATELESS && ctx->cfg.squelch_mode != BTB200_SQUELCH_EAGER && P.D == 50) {
+      // delay-line noise FIR (rx_firdl.cu): rotated taps with both parts duplicated, (c, c, d, d)
+      std::vector<float> t4((size_t)P.nch * P.Nn * 4);
+      for (size_t i = 0; i < (size_t)P.nch * P.Nn; i++) {
+        const cf32 t = P.noise_rtaps[i];
+        t4[4 * i] = t4[4 * i + 1] = t.re; t4[4 * i + 2] = t4[4 * i + 3] = t.im;
+      }
+      const float *d4 = nullptr;
+      if ((rc = upload(ctx, &d4, t4))) return rc;
+      ctx->T.noise_taps4 = d4;
+    }
     if (fir_setup(ctx->device) != 0) { ctx->last_error = "cannot opt in to large dynamic shared memory"; return BTB200_ERR_CUDA; }
   }
   std::vector<uint8_t> hdr(4 * 256);
@@ -713,21 +724,28 @@ int btb200_collect(btb200_ctx *ctx, btb200_hits *out)
         need_exact = keys;
       }
       if (!need_exact.empty()) {
-        int ng = 0, nl = 0;
-        const int CGR = lazy_group_channels();
-        int cur_b = -1, fill = CGR;
+        // groups of up to CGR hit channels of one slot (they share the input span); groups with more
+        // channels first: their blocks run longest
+        const int CGR = lazy_group_channels(ctx->G);
+        struct Grp { int b, n, c[LAZY_CG]; };
+        std::vector<Grp> grp;
         for (uint32_t k : need_exact) {
           const int b = (int)(k / P.nch), c = (int)(k % P.nch);
-          if (b != cur_b || fill == CGR) {
-            int *g = ctx->h_groups + (size_t)ng * (1 + CGR);
-            g[0] = b;
-            for (int i = 0; i < CGR; i++) g[1 + i] = -1;
-            ng++; fill = 0; cur_b = b;
+          if (grp.empty() || grp.back().b != b || grp.back().n == CGR) grp.push_back(Grp{b, 0, {-1, -1, -1, -1}});
+          grp.back().c[grp.back().n++] = c;
+        }
+        std::stable_sort(grp.begin(), grp.end(), [](const Grp &x, const Grp &y) { return x.n > y.n; });
+        const int ng = (int)grp.size();
+        int nl = 0;
+        for (int gi = 0; gi < ng; gi++) {
+          int *g = ctx->h_groups + (size_t)gi * (1 + CGR);
+          g[0] = grp[gi].b;
+          for (int i = 0; i < CGR; i++) g[1 + i] = grp[gi].c[i];
+          for (int i = 0; i < grp[gi].n; i++) {
+            int *l = ctx->h_list + (size_t)nl * 4;
+            l[0] = grp[gi].b; l[1] = grp[gi].c[i]; l[2] = gi; l[3] = i;
+            nl++;
           }
-          ctx->h_groups[(size_t)(ng - 1) * (1 + CGR) + 1 + fill] = c;
-          int *l = ctx->h_list + (size_t)nl * 4;
-          l[0] = b; l[1] = c; l[2] = ng - 1; l[3] = fill;
-          nl++; fill++;
         }
         CK(cudaMemcpyAsync(ctx->d_groups, ctx->h_groups, (size_t)ng * (1 + CGR) * sizeof(int), cudaMemcpyHostToDevice, s));
         CK(cudaMemcpyAsync(ctx->d_list, ctx->h_list, (size_t)nl * 4 * sizeof(int), cudaMemcpyHostToDevice, s));

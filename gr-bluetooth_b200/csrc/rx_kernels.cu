@@ -4,6 +4,8 @@
 #include <cstdio>
 #include <cstdlib>
 
+#include "rx_packed.cuh"
+
 namespace btb200 {
 
 // ===========================================================================
@@ -299,22 +301,7 @@ __global__ void __launch_bounds__(W * 32, MINB) k_fir_tiled(FirJob J)
 //   RE pair: (a*c) - (b*d)   IM pair: (a*d) + (b*c)   then acc += ...   = 8 packed
 // instructions per 2 complex MACs (scalar: 16).
 // ===========================================================================
-typedef unsigned long long u64;
-// NOTE on ptxas 12.9: it contracts mul.rn.f32x2 feeding add/sub.rn.f32x2 into one FFMA2 even
-// though the operations carry an explicit .rn (it does not do that for scalar mul.rn/add.rn).
-// That would change the rounding.  A product must therefore never be the direct operand of a
-// packed add/sub: "x - p" is written fma(p, -1, x) (exact: p*(-1) is exact, one rounding),
-// which ptxas keeps as FFMA2 with an immediate and cannot merge with the FMUL2 that made p.
-// The SASS is checked for this in tests/test_build.py.
-__device__ __forceinline__ u64 pk_mul(u64 a, u64 b) { u64 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
-__device__ __forceinline__ u64 pk_add(u64 a, u64 b) { u64 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
-// x - p, p a product
-__device__ __forceinline__ u64 pk_xsubp(u64 x, u64 p)
-{ u64 d; asm("{.reg .b64 m1; mov.b64 m1, 0xbf800000bf800000; fma.rn.f32x2 %0, %2, m1, %1;}" : "=l"(d) : "l"(x), "l"(p)); return d; }
-__device__ __forceinline__ u64 pk_neg(u64 a) { return a ^ 0x8000000080000000ull; }
-__device__ __forceinline__ float pk_lo(u64 v) { return __uint_as_float((unsigned)(v & 0xffffffffull)); }
-__device__ __forceinline__ float pk_hi(u64 v) { return __uint_as_float((unsigned)(v >> 32)); }
-
+// (pk_mul / pk_add / pk_xsubp / pk_neg: rx_packed.cuh, with the note on ptxas contraction)
 // DT > 0: the decimation is the compile-time constant DT and the staged span is SKEWED -- one pad slot per DT
 // samples (sample i sits at i + i/DT) -- so that the NH outputs a warp reads at once, DT samples apart, are
 // DT+1 slots apart: with DT = 50 the 16 addresses of a 2-channel group then spread over all eight 16-byte bank
@@ -1096,14 +1083,20 @@ static void launch_list_packed(const Geom &G, const DevTables &T, const DevBatch
 static int lazy_cfg()
 {
   static int cfg = -1;
-  if (cfg < 0) { const char *e = getenv("BTB200_LAZY_CFG"); cfg = e ? atoi(e) : 0; }
+  if (cfg < 0) { const char *e = getenv("BTB200_LAZY_CFG"); cfg = e ? atoi(e) : 6; }
   return cfg;
 }
 
-int lazy_group_channels() { return lazy_cfg() == 4 ? 4 : 2; }
+int lazy_group_channels(const Geom &G)
+{
+  const int c = lazy_cfg();
+  if (c >= 6) return noise_fir_dl_supported(G) ? 4 : 2;
+  return c == 4 ? 4 : 2;
+}
 
 // Measured on B200 (512 slots, 2 260 hit windows x 17 M complex MAC), ms per launch:
-//   0  packed, skewed, 2 ch x 448 outputs (850 = 2 tiles, 95 %), 14 warps, one block/SM ....... 17.0  (default, D = 50)
+//   6  delay line + cp.async ring (rx_firdl.cu), <= 4 ch x 448 outputs, 7 warps ............... 13.4  (default, D = 50)
+//   0  packed, skewed, 2 ch x 448 outputs (850 = 2 tiles, 95 %), 14 warps, one block/SM ....... 17.0
 //   1  same shape, no skew ................................................................... 18.9
 //   2  packed, skewed, 2 ch x 288 outputs (3 tiles, 98 %), 9 warps ............................ 19.0
 //   3  packed 2 ch x 256 outputs, 2 blocks/SM (default for D != 50) ........................... 21.7
@@ -1114,6 +1107,11 @@ void launch_noise_fir_list(const Geom &G, const DevTables &T, const DevBatch &W,
                            c32 *NzL, cudaStream_t s)
 {
   int cfg = lazy_cfg();
+  if (cfg >= 6) {
+    // delay-line kernel (rx_firdl.cu), D = 50 only -- other rates use the 2-channel packed tiled kernel
+    if (noise_fir_dl_supported(G) && T.noise_taps4) { launch_noise_fir_dl(G, T, W, groups, n_groups, NzL, s); return; }
+    cfg = 3;
+  }
   if (G.D != 50 && cfg <= 2) cfg = 3;      // the skewed variants are instantiated for D = 50 (100 Msps)
   switch (cfg) {
     default:
@@ -1129,7 +1127,7 @@ void launch_noise_fir_list(const Geom &G, const DevTables &T, const DevBatch &W,
 void launch_energy_list(const Geom &G, const DevBatch &W, const int *list4, int n_list, const c32 *NzL,
                         double *e_on, double *e_off, cudaStream_t s)
 {
-  k_energy_list_warp<<<cdiv((long)n_list * 32, 128), 128, 0, s>>>(G, W, reinterpret_cast<const int4 *>(list4), n_list, NzL, lazy_group_channels(), e_on, e_off);
+  k_energy_list_warp<<<cdiv((long)n_list * 32, 128), 128, 0, s>>>(G, W, reinterpret_cast<const int4 *>(list4), n_list, NzL, lazy_group_channels(G), e_on, e_off);
 }
 
 }  // namespace btb200

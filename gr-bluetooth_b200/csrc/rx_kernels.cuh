@@ -10,6 +10,7 @@ struct DevTables {
   const c32 *noise_rtaps;    // [nch][Nn]
   const c32 *chan_tg;        // [ngroups][Nc][16]  channel-group-interleaved taps for the tiled FIR
   const c32 *noise_tg;       // [ngroups][Nn][16]
+  const void *noise_taps4;   // [nch][Nn] float4 (c, c, d, d) for the delay-line noise FIR (D = 50), else null
   const float *mmse;         // [129*8]
   const float *atan_tab;     // [257]
   const uint64_t *ac_lut;    // [769]
@@ -61,11 +62,15 @@ void launch_dmm_stateless(const Geom &G, const DevTables &T, const DevBatch &W, 
 void launch_fill_pass(const DevBatch &W, int n, int v, cudaStream_t s);
 // lazy squelch: noise FIR for listed (slot, <=LAZY_CG channels) groups, then exact energies of listed windows
 constexpr int LAZY_CG = 4;            // upper bound of channels per group (buffer sizing)
-int lazy_group_channels();           // channels per group of the selected configuration   // 4 channels x (8 x 8 x 4 = 256) outputs per block, 2 blocks per SM
+int lazy_group_channels(const Geom &G);   // channels per group of the selected configuration
 void launch_noise_fir_list(const Geom &G, const DevTables &T, const DevBatch &W, const int *groups, int n_groups,
                            c32 *NzL, cudaStream_t s);
 void launch_energy_list(const Geom &G, const DevBatch &W, const int *list4, int n_list, const c32 *NzL,
                         double *e_on, double *e_off, cudaStream_t s);
+// delay-line variant (rx_firdl.cu), D = 50 only; groups of up to LAZY_CG channels, live channels first
+bool noise_fir_dl_supported(const Geom &G);
+int launch_noise_fir_dl(const Geom &G, const DevTables &T, const DevBatch &W, const int *groups, int n_groups,
+                        c32 *NzL, cudaStream_t s);
 int  fir_setup(int device);   // opt in to large dynamic shared memory
 
 }  // namespace btb200

@@ -187,12 +187,13 @@ def run_ours(args):
         mk = lambda: g.multi_sniffer.make(FS, FC, SNR_DB, False, mm_mode=g.MM_STATELESS, device=local, max_slots=B,
                                           snr_mode=g.SNR_FAST_GUARDED if snr_mode == "fast" else g.SNR_EXACT,
                                           tail=g.TAIL_FULL if args.tail == "full" else g.TAIL_LAZY)
-        blks = [mk(), mk()]                       # two contexts: the e2e loop overlaps H2D of batch k+1 with batch k
+        NCTX = args.e2e_contexts                  # the e2e loop keeps NCTX - 1 batches in flight behind the one collected
+        blks = [mk() for _ in range(NCTX)]
         blk = blks[0]
         H = blk.history()
         w0 = lead * S - (H - 1)
         n_in = (B - 1) * S + H
-        pinned = [g.PinnedBuffer(n_in), g.PinnedBuffer(n_in)]
+        pinned = [g.PinnedBuffer(n_in) for _ in range(NCTX)]
         for p in pinned:
             p.array[:] = iq[w0:w0 + n_in]
         d_iq = torch.from_numpy(pinned[0].array.view(np.float32).copy()).to(dev)     # resident copy for `value`
@@ -221,12 +222,19 @@ def run_ours(args):
         # ---- end to end through the public calls with HOST buffers: btb200_submit (H2D copy + kernels)
         #      / btb200_collect (hits + symbols D2H), double-buffered over two contexts ----
         def e2e_loop(n):
-            blks[0].submit(pinned[0].ptr.value, False, n_in, lead, B)
-            for i in range(1, n):
-                blks[i & 1].submit(pinned[i & 1].ptr.value, False, n_in, lead, B)
-                blks[(i - 1) & 1].collect(want_symbols=True)
-            return blks[(n - 1) & 1].collect(want_symbols=True)
-        e2e_loop(2)
+            # batch i lives in context i % NCTX.  Per step: enqueue the deferred work of the oldest batch, submit a
+            # new batch behind it (its input copy overlaps the queued kernels), then wait for the oldest batch.
+            res = None
+            for i in range(min(NCTX - 1, n)):
+                blks[i % NCTX].submit(pinned[i % NCTX].ptr.value, False, n_in, lead, B)
+            for j in range(n):
+                blks[j % NCTX].collect_begin()
+                i = j + NCTX - 1
+                if i < n:
+                    blks[i % NCTX].submit(pinned[i % NCTX].ptr.value, False, n_in, lead, B)
+                res = blks[j % NCTX].collect(want_symbols=True)
+            return res
+        e2e_loop(NCTX)
         barrier()
         t0 = time.perf_counter()
         ehits, esyms, _ = e2e_loop(steps)
@@ -293,7 +301,7 @@ def run_ours(args):
                            "sharding": "time shards, no collective"},
                 "e2e": {"value": main["e2e"], "unit": UNIT, "h2d_bytes_per_step": main["h2d"], "d2h_bytes_per_step": main["d2h"],
                         "ms_per_step": main["e2e_ms_per_step"],
-                        "api": "btb200_submit/btb200_collect with pinned host buffers, two contexts double-buffered"},
+                        "api": "btb200_submit/btb200_collect with pinned host buffers, %d contexts in flight on the shared compute stream" % args.e2e_contexts},
                 "gpu_launches": main["launches"],
                 "clocks": main["clocks"],
                 "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -319,6 +327,8 @@ def main():
     ap.add_argument("--slots", type=int, default=512, help="slots (625 us each) per step per GPU")
     ap.add_argument("--no-alt", action="store_true", help="skip the second measurement in the other snr mode")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--e2e-contexts", type=int, default=3,
+                    help="contexts the end-to-end loop cycles through (batches in flight = contexts)")
     ap.add_argument("--tail", default="lazy", choices=["lazy", "full"],
                     help="lazy (default): clock recovery past the searchable prefix only for windows with hits")
     ap.add_argument("--snr-mode", default="exact", choices=["exact", "fast"],

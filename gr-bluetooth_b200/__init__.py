@@ -68,7 +68,7 @@ class Hits(C.Structure):
 
 
 EXPORTS = ["btb200_process_channels", "btb200_create", "btb200_destroy", "btb200_get_info", "btb200_process", "btb200_process_device",
-           "btb200_submit", "btb200_collect", "btb200_host_alloc", "btb200_host_free",
+           "btb200_submit", "btb200_collect_begin", "btb200_collect", "btb200_host_alloc", "btb200_host_free",
            "btb200_get_mm_state", "btb200_set_mm_state", "btb200_reset", "btb200_get_stage",
            "btb200_last_timing", "btb200_launch_count", "btb200_strerror", "btb200_last_error",
            "btb200_version"]
@@ -91,6 +91,7 @@ def lib():
         L.btb200_process.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint64, C.c_uint32, C.POINTER(Hits)]
         L.btb200_process_device.argtypes = L.btb200_process.argtypes
         L.btb200_submit.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t, C.c_uint64, C.c_uint32]
+        L.btb200_collect_begin.argtypes = [C.c_void_p]
         L.btb200_collect.argtypes = [C.c_void_p, C.POINTER(Hits)]
         L.btb200_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
         L.btb200_host_free.argtypes = [C.c_void_p]
@@ -225,6 +226,10 @@ class multi_block:
 
     def submit(self, ptr, on_device, n_samples, first_slot, n_slots):
         self._check(self._L.btb200_submit(self._ctx, C.c_void_p(ptr), int(on_device), n_samples, first_slot, n_slots))
+
+    def collect_begin(self):
+        """Optional first half of collect(): enqueue the deferred work of the pending batch without waiting."""
+        self._check(self._L.btb200_collect_begin(self._ctx))
 
     def collect(self, want_symbols=False):
         h = self._hits_struct(want_symbols)

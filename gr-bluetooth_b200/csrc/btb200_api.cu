@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <chrono>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
@@ -23,6 +24,20 @@ constexpr unsigned kHitCap = 1u << 18;
 constexpr unsigned long long kArenaCap = 256ull << 20;
 }
 
+namespace {
+// BTB200_TRACE=1: host-side timeline of collect() on stderr
+struct Trace {
+  bool on = std::getenv("BTB200_TRACE") != nullptr;
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  void mark(const char *what)
+  {
+    if (!on) return;
+    const double us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
+    std::fprintf(stderr, "[btb200 trace] %8.1f us  %s\n", us, what);
+  }
+};
+}  // namespace
+
 struct btb200_ctx {
   btb200_config cfg{};
   Plan plan;
@@ -31,7 +46,10 @@ struct btb200_ctx {
   DevBatch W{};
   int device = 0, sm_count = 0;
   uint32_t max_slots = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;       // compute stream: shared by all contexts of a device (see device_stream())
+  bool owns_stream = false;
+  cudaStream_t copy_stream = nullptr;  // host->device input copies, overlapping whatever the compute stream runs
+  cudaEvent_t ev_sync = nullptr, ev_h2d = nullptr;
   cudaEvent_t ev[kNumEvents + 1]{};
   cudaEvent_t evl[3]{};      // lazy squelch: noise FIR / energies
   cudaEvent_t ev_tail = nullptr;
@@ -52,6 +70,16 @@ struct btb200_ctx {
   double *h_eon = nullptr, *h_eoff = nullptr;
   size_t list_cap = 0, group_cap = 0;
   DevBatch pendW{};
+  struct CollectState {
+    bool begun = false;
+    unsigned nh = 0, dropped = 0;
+    unsigned long long used = 0;
+    std::vector<uint32_t> keys, need_exact;
+    std::vector<uint8_t> est_flag;      // per channel-window: 1 = snr from the fast estimate
+    int nl = 0;                         // listed windows whose exact energies are on their way
+  } cb;
+  cudaEvent_t ev_up = nullptr;
+  Trace trace;
   // lazy tail: clock recovery stops after the searchable prefix; hit windows are resumed in collect()
   bool early = false, pend_early = false;
   Geom pendG{};
@@ -89,16 +117,6 @@ namespace {
 
 thread_local std::string g_create_error;
 
-struct Trace {
-  bool on = std::getenv("BTB200_TRACE") != nullptr;
-  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
-  void mark(const char *what)
-  {
-    if (!on) return;
-    const double us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
-    std::fprintf(stderr, "[btb200 trace] %8.1f us  %s\n", us, what);
-  }
-};
 
 #define CK(call)                                                                          \
   do {                                                                                    \
@@ -205,6 +223,34 @@ int setup_fast(btb200_ctx *ctx)
   return 0;
 }
 
+// One compute stream per device, shared by every context: the kernels of this path are sized to fill the
+// GPU (one block per SM), so batches of different contexts gain nothing from running concurrently -- measured:
+// two contexts on private streams 29.6 ms per batch pair step against 24.5 ms serialised -- while issue order on
+// one stream gives the pipeline of the double-buffered submit()/collect() loop for free:
+// K(k), K(k+1), deferred-noise(k), K(k+2), deferred-noise(k+1), ...   BTB200_PRIVATE_STREAM=1 restores private streams.
+cudaStream_t device_stream(int device)
+{
+  static std::mutex mu;
+  static cudaStream_t streams[64] = {};
+  std::lock_guard<std::mutex> lock(mu);
+  cudaStream_t &s = streams[device & 63];
+  if (!s && cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) s = nullptr;
+  return s;
+}
+
+// wait for everything this context has enqueued so far (not for what other contexts enqueue later)
+int sync_here(btb200_ctx *ctx)
+{
+  cudaError_t e = cudaEventRecord(ctx->ev_sync, ctx->stream);
+  if (e == cudaSuccess) e = cudaEventSynchronize(ctx->ev_sync);
+  if (e != cudaSuccess) {
+    ctx->last_error = std::string("sync: ") + cudaGetErrorString(e);
+    return BTB200_ERR_CUDA;
+  }
+  return 0;
+}
+#define SYNC_HERE() do { if (int rc_ = sync_here(ctx)) return rc_; } while (0)
+
 int setup(btb200_ctx *ctx)
 {
   const Plan &P = ctx->plan;
@@ -222,7 +268,17 @@ int setup(btb200_ctx *ctx)
   G.stateless = ctx->cfg.mm_mode == BTB200_MM_STATELESS;
   G.early = 0; G.ne_dem = P.n_dem; G.sym_target = P.n_dem;
 
-  CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  if (std::getenv("BTB200_PRIVATE_STREAM")) {
+    CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    ctx->owns_stream = true;
+  } else {
+    ctx->stream = device_stream(ctx->device);
+    if (!ctx->stream) { ctx->last_error = "cannot create the device compute stream"; return BTB200_ERR_CUDA; }
+  }
+  CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&ctx->ev_sync, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&ctx->ev_h2d, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&ctx->ev_up, cudaEventDisableTiming));
   for (auto &e : ctx->ev) CK(cudaEventCreate(&e));
   for (auto &e : ctx->evl) CK(cudaEventCreate(&e));
   CK(cudaEventCreateWithFlags(&ctx->ev_tail, cudaEventDisableTiming));
@@ -387,7 +443,12 @@ int setup(btb200_ctx *ctx)
 
 void teardown(btb200_ctx *ctx)
 {
-  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  if (ctx->stream && ctx->ev_sync) sync_here(ctx);
+  if (ctx->stream2) cudaStreamSynchronize(ctx->stream2);
+  if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
+  if (ctx->ev_sync) cudaEventDestroy(ctx->ev_sync);
+  if (ctx->ev_h2d) cudaEventDestroy(ctx->ev_h2d);
+  if (ctx->ev_up) cudaEventDestroy(ctx->ev_up);
   for (void *p : ctx->allocs) cudaFree(p);
   for (void *p : {(void *)ctx->h_energy, (void *)ctx->h_noise, (void *)ctx->h_pass, (void *)ctx->h_counts,
                   (void *)ctx->h_hits, (void *)ctx->h_arena, (void *)ctx->h_ph, (void *)ctx->h_groups,
@@ -398,7 +459,7 @@ void teardown(btb200_ctx *ctx)
   for (auto &e : ctx->evl) if (e) cudaEventDestroy(e);
   if (ctx->ev_tail) cudaEventDestroy(ctx->ev_tail);
   if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
-  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->stream && ctx->owns_stream) cudaStreamDestroy(ctx->stream);
 }
 
 }  // namespace
@@ -532,11 +593,15 @@ int btb200_submit(btb200_ctx *ctx, const float *iq, int iq_on_device, size_t n_s
   W.B = (int)n_slots;
   const size_t nbc = (size_t)n_slots * P.nch;
 
-  CK(cudaEventRecord(ctx->ev[0], s));
   if (iq_on_device) {
+    CK(cudaEventRecord(ctx->ev[0], s));
     W.x = reinterpret_cast<const c32 *>(iq);
   } else {
-    CK(cudaMemcpyAsync(ctx->d_x, iq, need * sizeof(c32), cudaMemcpyHostToDevice, s));
+    // the copy runs on its own stream (it overlaps the compute stream's current work); compute waits for it
+    CK(cudaEventRecord(ctx->ev[0], ctx->copy_stream));
+    CK(cudaMemcpyAsync(ctx->d_x, iq, need * sizeof(c32), cudaMemcpyHostToDevice, ctx->copy_stream));
+    CK(cudaEventRecord(ctx->ev_h2d, ctx->copy_stream));
+    CK(cudaStreamWaitEvent(s, ctx->ev_h2d, 0));
     W.x = ctx->d_x;
   }
   if (!G.stateless) {
@@ -547,7 +612,7 @@ int btb200_submit(btb200_ctx *ctx, const float *iq, int iq_on_device, size_t n_s
       for (int c = 0; c < P.nch; c++)
         ctx->rot_c[c].generate(hp + ((size_t)b * P.n_ddc) * P.nch + c, P.n_ddc, P.nch);
     CK(cudaMemcpyAsync(ctx->d_phc, hp, (size_t)n_slots * P.n_ddc * P.nch * sizeof(c32), cudaMemcpyHostToDevice, s));
-    CK(cudaStreamSynchronize(s));
+    SYNC_HERE();
     for (uint32_t b = 0; b < n_slots; b++)
       for (int c = 0; c < P.nch; c++)
         ctx->rot_n[c].generate(hp + ((size_t)b * P.n_noise) * P.nch + c, P.n_noise, P.nch);
@@ -576,7 +641,7 @@ int btb200_submit(btb200_ctx *ctx, const float *iq, int iq_on_device, size_t n_s
     if (!G.stateless) {
       // chained mode: the squelch decides which windows advance the shared M&M
       // state, so it is settled with the reference's own libm arithmetic first
-      CK(cudaStreamSynchronize(s));
+      SYNC_HERE();
       for (size_t i = 0; i < nbc; i++) {
         const double snr = 10.0 * std::log10(ctx->h_energy[i] / ctx->h_noise[i]);
         ctx->h_pass[i] = (snr >= P.squelch_db) ? 1 : 0;
@@ -613,169 +678,189 @@ int btb200_submit(btb200_ctx *ctx, const float *iq, int iq_on_device, size_t n_s
   return BTB200_OK;
 }
 
+// First half of collect(): waits for the batch's search, fetches the hit list and ENQUEUES the deferred work
+// (lazy tail resume on the second stream; deferred noise FIR + exact energies on the compute stream) without
+// waiting for it.  A caller that keeps several batches in flight calls this, then submits the next batch
+// (so that its kernels queue up behind the deferred work and its input copy overlaps it), then btb200_collect().
+int btb200_collect_begin(btb200_ctx *ctx)
+{
+  if (!ctx || !ctx->pending || ctx->cb.begun) return BTB200_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream, cs = ctx->copy_stream;
+  const Plan &P = ctx->plan;
+  auto &cb = ctx->cb;
+  cb = btb200_ctx::CollectState{};
+  cb.begun = true;
+  CK(cudaEventSynchronize(ctx->ev[7]));        // end of this batch's submit()
+  Trace &tr = ctx->trace; tr = Trace{}; tr.mark("batch done");
+  cb.nh = ctx->h_counts[0];
+  std::memcpy(&cb.used, ctx->h_counts + 2, sizeof cb.used);
+  if (cb.nh > kHitCap) { cb.dropped = cb.nh - kHitCap; cb.nh = kHitCap; }
+  if (cb.used > kArenaCap) cb.used = kArenaCap;
+  if (ctx->pend_early) cb.used = 0;
+  const unsigned nh = cb.nh;
+  // small transfers go through the copy stream: on the compute stream they would queue behind other batches
+  if (nh) CK(cudaMemcpyAsync(ctx->h_hits, ctx->W.hits, (size_t)nh * sizeof(DevHit), cudaMemcpyDeviceToHost, cs));
+  ctx->lazy_timed = false;
+  if (!ctx->lazy) { if (nh) CK(cudaStreamSynchronize(cs)); return BTB200_OK; }
+
+  const size_t nbc = (size_t)ctx->pend_slots * P.nch;
+  for (size_t i = 0; i < nbc; i++) ctx->h_energy[i] = ctx->h_noise[i] = std::nan("");
+  if (ctx->fast_snr) {
+    ctx->fast_off.resize(nbc);
+    for (size_t i = 0; i < nbc; i++) ctx->fast_off[i] = ctx->h_esum[i] / P.n_noise;
+  }
+  if (!nh) return BTB200_OK;
+  CK(cudaStreamSynchronize(cs));
+  // unique hit windows, in (slot, channel) order
+  std::vector<uint32_t> &keys = cb.keys;
+  keys.resize(nh);
+  for (unsigned i = 0; i < nh; i++) keys[i] = (uint32_t)ctx->h_hits[i].b * (uint32_t)P.nch + (uint32_t)ctx->h_hits[i].chi;
+  std::sort(keys.begin(), keys.end());
+  keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
+  const int nl_all = (int)keys.size();
+  if (ctx->pend_early) {
+    // lazy tail: finish demod + clock recovery of the hit windows on the second stream, under the noise FIR
+    for (int l = 0; l < nl_all; l++) {
+      int *q = ctx->h_list2 + (size_t)l * 4;
+      q[0] = (int)(keys[l] / P.nch); q[1] = (int)(keys[l] % P.nch); q[2] = 0; q[3] = 0;
+    }
+    cudaStream_t s2 = ctx->stream2;
+    CK(cudaMemcpyAsync(ctx->d_list2, ctx->h_list2, (size_t)nl_all * 4 * sizeof(int), cudaMemcpyHostToDevice, s2));
+    launch_mm_resume_list(ctx->pendG, ctx->T, ctx->pendW, ctx->d_dem, ctx->d_list2, nl_all, s2);
+    ctx->launches += 2;
+    CK(cudaMemcpyAsync(ctx->h_nsym, ctx->pendW.nsym, nbc * sizeof(int), cudaMemcpyDeviceToHost, s2));
+    tr.mark("resume launched");
+  }
+  // pass 1 (fast mode): exact on-channel energy of every hit window, off-channel from the estimate
+  std::vector<uint32_t> &need_exact = cb.need_exact;
+  if (ctx->fast_snr) {
+    for (int l = 0; l < nl_all; l++) {
+      int *q = ctx->h_list + (size_t)l * 4;
+      q[0] = (int)(keys[l] / P.nch); q[1] = (int)(keys[l] % P.nch); q[2] = 0; q[3] = 0;
+    }
+    CK(cudaMemcpyAsync(ctx->d_list, ctx->h_list, (size_t)nl_all * 4 * sizeof(int), cudaMemcpyHostToDevice, cs));
+    CK(cudaEventRecord(ctx->ev_up, cs));
+    CK(cudaStreamWaitEvent(s, ctx->ev_up, 0));
+    CK(cudaEventRecord(ctx->evl[0], s));
+    CK(cudaEventRecord(ctx->evl[1], s));
+    launch_energy_list(ctx->G, ctx->pendW, ctx->d_list, nl_all, nullptr, ctx->d_eon, ctx->d_eoff, s);
+    ctx->launches++;
+    CK(cudaEventRecord(ctx->evl[2], s));
+    ctx->lazy_timed = true;
+    CK(cudaMemcpyAsync(ctx->h_eon, ctx->d_eon, (size_t)nl_all * sizeof(double), cudaMemcpyDeviceToHost, s));
+    SYNC_HERE();
+    tr.mark("pass-1 energies back");
+    const double guard = 5e-3;
+    for (int l = 0; l < nl_all; l++) {
+      const size_t bc = keys[l];
+      const double on = ctx->h_eon[l], off = ctx->fast_off[bc];
+      const double snr = 10.0 * std::log10(on / off);
+      bool sure = std::isfinite(snr) && std::fabs(snr - P.squelch_db) > guard;
+      if (sure) {
+        const double d = snr * 10.0, t = d - std::floor(d);        // %.1f rounds at x.x5
+        if (std::fabs(t - 0.5) <= 10.0 * guard) sure = false;
+      }
+      if (sure) { ctx->h_energy[bc] = on; ctx->h_noise[bc] = off; }
+      else need_exact.push_back(keys[l]);
+    }
+    cb.est_flag.assign(nbc, 1);
+    for (uint32_t k : need_exact) cb.est_flag[k] = 0;
+  } else {
+    need_exact = keys;
+  }
+  if (!need_exact.empty()) {
+    // groups of up to CGR hit channels of one slot (they share the input span); groups with more
+    // channels first: their blocks run longest
+    const int CGR = lazy_group_channels(ctx->G);
+    struct Grp { int b, n, c[LAZY_CG]; };
+    std::vector<Grp> grp;
+    for (uint32_t k : need_exact) {
+      const int b = (int)(k / P.nch), c = (int)(k % P.nch);
+      if (grp.empty() || grp.back().b != b || grp.back().n == CGR) grp.push_back(Grp{b, 0, {-1, -1, -1, -1}});
+      grp.back().c[grp.back().n++] = c;
+    }
+    std::stable_sort(grp.begin(), grp.end(), [](const Grp &x, const Grp &y) { return x.n > y.n; });
+    const int ng = (int)grp.size();
+    int nl = 0;
+    for (int gi = 0; gi < ng; gi++) {
+      int *g = ctx->h_groups + (size_t)gi * (1 + CGR);
+      g[0] = grp[gi].b;
+      for (int i = 0; i < CGR; i++) g[1 + i] = grp[gi].c[i];
+      for (int i = 0; i < grp[gi].n; i++) {
+        int *l = ctx->h_list + (size_t)nl * 4;
+        l[0] = grp[gi].b; l[1] = grp[gi].c[i]; l[2] = gi; l[3] = i;
+        nl++;
+      }
+    }
+    cb.nl = nl;
+    CK(cudaMemcpyAsync(ctx->d_groups, ctx->h_groups, (size_t)ng * (1 + CGR) * sizeof(int), cudaMemcpyHostToDevice, cs));
+    CK(cudaMemcpyAsync(ctx->d_list, ctx->h_list, (size_t)nl * 4 * sizeof(int), cudaMemcpyHostToDevice, cs));
+    CK(cudaEventRecord(ctx->ev_up, cs));
+    CK(cudaStreamWaitEvent(s, ctx->ev_up, 0));
+    if (!ctx->fast_snr) CK(cudaEventRecord(ctx->evl[0], s));
+    launch_noise_fir_list(ctx->G, ctx->T, ctx->pendW, ctx->d_groups, ng, ctx->d_NzL, s);
+    if (!ctx->fast_snr) CK(cudaEventRecord(ctx->evl[1], s));
+    launch_energy_list(ctx->G, ctx->pendW, ctx->d_list, nl, ctx->d_NzL, ctx->d_eon, ctx->d_eoff, s);
+    if (!ctx->fast_snr) { CK(cudaEventRecord(ctx->evl[2], s)); ctx->lazy_timed = true; }
+    ctx->launches += 2;
+    CK(cudaMemcpyAsync(ctx->h_eon, ctx->d_eon, (size_t)nl * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(ctx->h_eoff, ctx->d_eoff, (size_t)nl * sizeof(double), cudaMemcpyDeviceToHost, s));
+    tr.mark("deferred noise FIR enqueued");
+  }
+  CK(cudaGetLastError());
+  return BTB200_OK;
+}
+
 int btb200_collect(btb200_ctx *ctx, btb200_hits *out)
 {
   if (!ctx || !ctx->pending) return BTB200_ERR_ARG;
+  if (!ctx->cb.begun) { if (int rc = btb200_collect_begin(ctx)) return rc; }
   CK(cudaSetDevice(ctx->device));
   cudaStream_t s = ctx->stream;
   const Plan &P = ctx->plan;
+  auto &cb = ctx->cb;
+  Trace &tr = ctx->trace;
   ctx->pending = false;
-  CK(cudaStreamSynchronize(s));
-  unsigned nh = ctx->h_counts[0];
-  Trace tr; tr.mark("batch done");
-  unsigned long long used;
-  std::memcpy(&used, ctx->h_counts + 2, sizeof used);
-  unsigned dropped = 0;
-  if (nh > kHitCap) { dropped = nh - kHitCap; nh = kHitCap; }
-  if (used > kArenaCap) used = kArenaCap;
-  if (nh) CK(cudaMemcpyAsync(ctx->h_hits, ctx->W.hits, (size_t)nh * sizeof(DevHit), cudaMemcpyDeviceToHost, s));
-  if (ctx->pend_early) used = 0;
-  if (used && out && out->symbols) CK(cudaMemcpyAsync(ctx->h_arena, ctx->W.arena, used, cudaMemcpyDeviceToHost, s));
-  ctx->lazy_timed = false;
-  // lazy tail, second half (host side): runs while the deferred noise FIR is still busy on the main stream
-  bool tail_done = false;
-  auto finish_tail = [&]() -> int {
-      if (!ctx->pend_early || !nh || tail_done) return 0;
-      tail_done = true;
-      // the symbol counts are known now: complete the hit records, lay the arena out, gather the symbols
-      CK(cudaStreamSynchronize(ctx->stream2));
-      unsigned long long off = 0;
-      tr.mark("resume done (host)");
-      for (unsigned i = 0; i < nh; i++) {
-        DevHit &h = ctx->h_hits[i];
-        h.n_symbols += ctx->h_nsym[(size_t)h.b * P.nch + h.chi];
-        int cnt = h.n_symbols < 3125 ? h.n_symbols : 3125;
-        if (cnt < 0) cnt = 0;
-        h.sym_offset = off;
-        h.sym_count = (off + (unsigned)cnt <= kArenaCap) ? (uint32_t)cnt : 0u;
-        off += (unsigned)cnt;
-      }
-      used = off > kArenaCap ? kArenaCap : off;
-      if (out && out->symbols && used) {
-        cudaStream_t s2 = ctx->stream2;
-        CK(cudaMemcpyAsync(ctx->W.hits, ctx->h_hits, (size_t)nh * sizeof(DevHit), cudaMemcpyHostToDevice, s2));
-        launch_gather(ctx->pendG, ctx->pendW, s2); ctx->launches++;
-        CK(cudaMemcpyAsync(ctx->h_arena, ctx->W.arena, used, cudaMemcpyDeviceToHost, s2));
-      }
-      CK(cudaEventRecord(ctx->ev_tail, ctx->stream2));
-      CK(cudaStreamWaitEvent(s, ctx->ev_tail, 0));     // the batch (and its timing) ends when the tail has
-    return 0;
-  };
-  std::vector<uint8_t> est_flag;       // per listed window: 1 = snr from the fast estimate
-  if (ctx->lazy) {
-    const size_t nbc = (size_t)ctx->pend_slots * P.nch;
-    for (size_t i = 0; i < nbc; i++) ctx->h_energy[i] = ctx->h_noise[i] = std::nan("");
-    if (ctx->fast_snr) {
-      ctx->fast_off.resize(nbc);
-      for (size_t i = 0; i < nbc; i++) ctx->fast_off[i] = ctx->h_esum[i] / P.n_noise;
+  cb.begun = false;
+  const unsigned nh = cb.nh, dropped = cb.dropped;
+  unsigned long long used = cb.used;
+  const std::vector<uint8_t> &est_flag = cb.est_flag;
+  if (ctx->pend_early && nh) {
+    // lazy tail, second half: the symbol counts are known once the resume has finished (it runs under the
+    // deferred noise FIR): complete the hit records, lay the arena out, gather the symbols
+    cudaStream_t s2 = ctx->stream2;
+    CK(cudaStreamSynchronize(s2));
+    tr.mark("resume done (host)");
+    unsigned long long off = 0;
+    for (unsigned i = 0; i < nh; i++) {
+      DevHit &h = ctx->h_hits[i];
+      h.n_symbols += ctx->h_nsym[(size_t)h.b * P.nch + h.chi];
+      int cnt = h.n_symbols < 3125 ? h.n_symbols : 3125;
+      if (cnt < 0) cnt = 0;
+      h.sym_offset = off;
+      h.sym_count = (off + (unsigned)cnt <= kArenaCap) ? (uint32_t)cnt : 0u;
+      off += (unsigned)cnt;
     }
-    if (nh) {
-      CK(cudaStreamSynchronize(s));
-      // unique hit windows, in (slot, channel) order
-      std::vector<uint32_t> keys(nh);
-      for (unsigned i = 0; i < nh; i++) keys[i] = (uint32_t)ctx->h_hits[i].b * (uint32_t)P.nch + (uint32_t)ctx->h_hits[i].chi;
-      std::sort(keys.begin(), keys.end());
-      keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
-      const int nl_all = (int)keys.size();
-      if (ctx->pend_early) {
-        // lazy tail: finish demod + clock recovery of the hit windows on the second stream, under the noise FIR
-        for (int l = 0; l < nl_all; l++) {
-          int *q = ctx->h_list2 + (size_t)l * 4;
-          q[0] = (int)(keys[l] / P.nch); q[1] = (int)(keys[l] % P.nch); q[2] = 0; q[3] = 0;
-        }
-        cudaStream_t s2 = ctx->stream2;
-        CK(cudaMemcpyAsync(ctx->d_list2, ctx->h_list2, (size_t)nl_all * 4 * sizeof(int), cudaMemcpyHostToDevice, s2));
-        launch_mm_resume_list(ctx->pendG, ctx->T, ctx->pendW, ctx->d_dem, ctx->d_list2, nl_all, s2);
-        ctx->launches += 2;
-        CK(cudaMemcpyAsync(ctx->h_nsym, ctx->pendW.nsym, nbc * sizeof(int), cudaMemcpyDeviceToHost, s2));
-        tr.mark("resume launched");
-      }
-      // pass 1 (fast mode): exact on-channel energy of every hit window, off-channel from the estimate
-      std::vector<uint32_t> need_exact;
-      if (ctx->fast_snr) {
-        for (int l = 0; l < nl_all; l++) {
-          int *q = ctx->h_list + (size_t)l * 4;
-          q[0] = (int)(keys[l] / P.nch); q[1] = (int)(keys[l] % P.nch); q[2] = 0; q[3] = 0;
-        }
-        CK(cudaMemcpyAsync(ctx->d_list, ctx->h_list, (size_t)nl_all * 4 * sizeof(int), cudaMemcpyHostToDevice, s));
-        CK(cudaEventRecord(ctx->evl[0], s));
-        CK(cudaEventRecord(ctx->evl[1], s));
-        launch_energy_list(ctx->G, ctx->pendW, ctx->d_list, nl_all, nullptr, ctx->d_eon, ctx->d_eoff, s);
-        ctx->launches++;
-        CK(cudaEventRecord(ctx->evl[2], s));
-        ctx->lazy_timed = true;
-        CK(cudaMemcpyAsync(ctx->h_eon, ctx->d_eon, (size_t)nl_all * sizeof(double), cudaMemcpyDeviceToHost, s));
-        CK(cudaStreamSynchronize(s));
-        tr.mark("pass-1 energies back");
-        const double guard = 5e-3;
-        for (int l = 0; l < nl_all; l++) {
-          const size_t bc = keys[l];
-          const double on = ctx->h_eon[l], off = ctx->fast_off[bc];
-          const double snr = 10.0 * std::log10(on / off);
-          bool sure = std::isfinite(snr) && std::fabs(snr - P.squelch_db) > guard;
-          if (sure) {
-            const double d = snr * 10.0, t = d - std::floor(d);        // %.1f rounds at x.x5
-            if (std::fabs(t - 0.5) <= 10.0 * guard) sure = false;
-          }
-          if (sure) { ctx->h_energy[bc] = on; ctx->h_noise[bc] = off; }
-          else need_exact.push_back(keys[l]);
-        }
-      } else {
-        need_exact = keys;
-      }
-      if (!need_exact.empty()) {
-        // groups of up to CGR hit channels of one slot (they share the input span); groups with more
-        // channels first: their blocks run longest
-        const int CGR = lazy_group_channels(ctx->G);
-        struct Grp { int b, n, c[LAZY_CG]; };
-        std::vector<Grp> grp;
-        for (uint32_t k : need_exact) {
-          const int b = (int)(k / P.nch), c = (int)(k % P.nch);
-          if (grp.empty() || grp.back().b != b || grp.back().n == CGR) grp.push_back(Grp{b, 0, {-1, -1, -1, -1}});
-          grp.back().c[grp.back().n++] = c;
-        }
-        std::stable_sort(grp.begin(), grp.end(), [](const Grp &x, const Grp &y) { return x.n > y.n; });
-        const int ng = (int)grp.size();
-        int nl = 0;
-        for (int gi = 0; gi < ng; gi++) {
-          int *g = ctx->h_groups + (size_t)gi * (1 + CGR);
-          g[0] = grp[gi].b;
-          for (int i = 0; i < CGR; i++) g[1 + i] = grp[gi].c[i];
-          for (int i = 0; i < grp[gi].n; i++) {
-            int *l = ctx->h_list + (size_t)nl * 4;
-            l[0] = grp[gi].b; l[1] = grp[gi].c[i]; l[2] = gi; l[3] = i;
-            nl++;
-          }
-        }
-        CK(cudaMemcpyAsync(ctx->d_groups, ctx->h_groups, (size_t)ng * (1 + CGR) * sizeof(int), cudaMemcpyHostToDevice, s));
-        CK(cudaMemcpyAsync(ctx->d_list, ctx->h_list, (size_t)nl * 4 * sizeof(int), cudaMemcpyHostToDevice, s));
-        if (!ctx->fast_snr) CK(cudaEventRecord(ctx->evl[0], s));
-        launch_noise_fir_list(ctx->G, ctx->T, ctx->pendW, ctx->d_groups, ng, ctx->d_NzL, s);
-        if (!ctx->fast_snr) CK(cudaEventRecord(ctx->evl[1], s));
-        launch_energy_list(ctx->G, ctx->pendW, ctx->d_list, nl, ctx->d_NzL, ctx->d_eon, ctx->d_eoff, s);
-        if (!ctx->fast_snr) { CK(cudaEventRecord(ctx->evl[2], s)); ctx->lazy_timed = true; }
-        ctx->launches += 2;
-        CK(cudaMemcpyAsync(ctx->h_eon, ctx->d_eon, (size_t)nl * sizeof(double), cudaMemcpyDeviceToHost, s));
-        CK(cudaMemcpyAsync(ctx->h_eoff, ctx->d_eoff, (size_t)nl * sizeof(double), cudaMemcpyDeviceToHost, s));
-        if (int rc = finish_tail()) return rc;
-        CK(cudaStreamSynchronize(s));
-        tr.mark("exact energies back");
-        for (int l = 0; l < nl; l++) {
-          const size_t bc = (size_t)ctx->h_list[(size_t)l * 4] * P.nch + ctx->h_list[(size_t)l * 4 + 1];
-          ctx->h_energy[bc] = ctx->h_eon[l];
-          ctx->h_noise[bc] = ctx->h_eoff[l];
-        }
-      }
-      if (ctx->fast_snr) {
-        est_flag.assign(nbc, 1);
-        for (uint32_t k : need_exact) est_flag[k] = 0;
-      }
+    used = off > kArenaCap ? kArenaCap : off;
+    if (out && out->symbols && used) {
+      CK(cudaMemcpyAsync(ctx->W.hits, ctx->h_hits, (size_t)nh * sizeof(DevHit), cudaMemcpyHostToDevice, s2));
+      launch_gather(ctx->pendG, ctx->pendW, s2); ctx->launches++;
+      CK(cudaMemcpyAsync(ctx->h_arena, ctx->W.arena, used, cudaMemcpyDeviceToHost, s2));
     }
+    CK(cudaEventRecord(ctx->ev_tail, s2));
+    CK(cudaStreamWaitEvent(s, ctx->ev_tail, 0));     // the batch (and its timing) ends when the tail has
+  } else if (used && out && out->symbols) {
+    CK(cudaMemcpyAsync(ctx->h_arena, ctx->W.arena, used, cudaMemcpyDeviceToHost, s));
   }
-  if (int rc = finish_tail()) return rc;
   CK(cudaEventRecord(ctx->ev[8], s));
-  CK(cudaStreamSynchronize(s));
+  SYNC_HERE();
   tr.mark("all done");
+  for (int l = 0; l < cb.nl; l++) {
+    const size_t bc = (size_t)ctx->h_list[(size_t)l * 4] * P.nch + ctx->h_list[(size_t)l * 4 + 1];
+    ctx->h_energy[bc] = ctx->h_eon[l];
+    ctx->h_noise[bc] = ctx->h_eoff[l];
+  }
   ctx->last_slots = ctx->pend_slots;
   for (int i = 0; i < 7; i++) {
     float ms = 0;
@@ -885,7 +970,7 @@ int btb200_process_channels(btb200_ctx *ctx, const float *iq, size_t n_samples, 
   cf32 *hp = reinterpret_cast<cf32 *>(ctx->h_ph);
   for (int c = 0; c < P.nch; c++) ctx->rot_c[c].generate(hp + c, P.n_ddc, P.nch);
   CK(cudaMemcpyAsync(ctx->d_phc, hp, (size_t)P.n_ddc * nch * sizeof(c32), cudaMemcpyHostToDevice, s));
-  CK(cudaStreamSynchronize(s));
+  SYNC_HERE();
   for (int c = 0; c < P.nch; c++) ctx->rot_n[c].generate(hp + c, P.n_noise, P.nch);
   CK(cudaMemcpyAsync(ctx->d_phn, hp, (size_t)P.n_noise * nch * sizeof(c32), cudaMemcpyHostToDevice, s));
   CK(cudaMemcpyAsync(W.mm_state, &ctx->mm, sizeof(MmState), cudaMemcpyHostToDevice, s));
@@ -895,7 +980,7 @@ int btb200_process_channels(btb200_ctx *ctx, const float *iq, size_t n_samples, 
   ctx->launches += 3;
   CK(cudaMemcpyAsync(ctx->h_energy, W.energy, nch * sizeof(double), cudaMemcpyDeviceToHost, s));
   CK(cudaMemcpyAsync(ctx->h_noise, W.noise, nch * sizeof(double), cudaMemcpyDeviceToHost, s));
-  CK(cudaStreamSynchronize(s));
+  SYNC_HERE();
   std::vector<double> snr(nch);
   for (size_t i = 0; i < nch; i++) {
     snr[i] = 10.0 * std::log10(ctx->h_energy[i] / ctx->h_noise[i]);
@@ -914,7 +999,7 @@ int btb200_process_channels(btb200_ctx *ctx, const float *iq, size_t n_samples, 
   CK(cudaMemcpyAsync(r4.data(), d_res, 4 * nch * sizeof(int), cudaMemcpyDeviceToHost, s));
   CK(cudaMemcpyAsync(rows.data(), W.bits, rows.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
   CK(cudaMemcpyAsync(&ctx->mm, W.mm_state, sizeof(MmState), cudaMemcpyDeviceToHost, s));
-  CK(cudaStreamSynchronize(s));
+  SYNC_HERE();
   ctx->last_slots = 1;
   size_t used = 0;
   for (int c = 0; c < P.nch; c++) {

@@ -229,10 +229,18 @@ BTB200_API int btb200_process_channels(btb200_ctx *ctx, const float *iq, size_t 
                                        int32_t first_channel, int32_t n_channels, uint32_t stop_lap,
                                        btb200_chan_result *res, uint8_t *symbols, size_t symbols_cap);
 
-/* split form for overlap / benchmarking: enqueue everything on the ctx stream,
- * then wait and collect.  btb200_process == submit + collect. */
+/* split form for overlap / benchmarking.  btb200_process == submit + collect.
+ *   submit         copies the input (own copy stream) and enqueues the batch's kernels on the device's compute
+ *                  stream, which all contexts of a device share: batches execute in the order they were enqueued;
+ *   collect_begin  (optional) waits for the batch's access-code search, fetches the hit list and enqueues the
+ *                  deferred work (exact noise FIR + energies of the hit windows) WITHOUT waiting for it;
+ *   collect        = collect_begin if it was not called, then waits and writes the hits.
+ * A streaming caller with contexts A, B keeps the device busy and every copy hidden with
+ *   submit(A,0) submit(B,1) | begin(A) submit(A',2) collect(A) | begin(B) submit(B',3) collect(B) | ...
+ * (A' = a third context, or A again after collect(A) -- bench.py's end-to-end loop). */
 BTB200_API int  btb200_submit(btb200_ctx *ctx, const float *iq, int iq_on_device, size_t n_samples,
                    uint64_t first_slot, uint32_t n_slots);
+BTB200_API int  btb200_collect_begin(btb200_ctx *ctx);
 BTB200_API int  btb200_collect(btb200_ctx *ctx, btb200_hits *out);
 
 /* pinned host buffers for the H2D path */

@@ -45,7 +45,7 @@ for rep in sys.argv[2:]:
             i = H.index(k)
             return float(r[i]) * UNIT.get(U[i], 1)
         t = int(b("dram__bytes_read.sum") + b("dram__bytes_write.sum"))
-        for key, tag in (("k_fir_packed<16", "chan_fir"), ("k_fir_packed<2", "noise_fir"), ("k_fir_tiled<2", "noise_fir"),
+        for key, tag in (("k_fir_packed<16", "chan_fir"), ("k_fir_packed<2", "noise_fir"), ("k_fir_tiled<2", "noise_fir"), ("k_fir_dl", "noise_fir"),
                          ("k_mm_stateless", "demod_mm")):
             if key in name.replace("(int)", ""):
                 traffic[tag] = t

@@ -28,7 +28,7 @@ int main(int argc, char **argv)
   double freq = 2476e6, rate = 2e6, snr = 10;
   std::string in;
   long nsamples = -1;
-  bool shorts = false, lap_mode = false, hop_mode = false;
+  bool shorts = false, lap_mode = false, hop_mode = false, tun = false;
   int target_lap = 0;
   for (int i = 1; i < argc; i++) {
     std::string a = argv[i];
@@ -43,6 +43,7 @@ int main(int argc, char **argv)
     else if (a == "-L" || a == "--lap-printer") lap_mode = true;
     else if (a == "-l" || a == "--lap") { target_lap = (int)std::strtol(next(), nullptr, 16); hop_mode = true; }      // apps/btrx:-l LAP
     else if (a == "-p" || a == "--hop") hop_mode = true;
+    else if (a == "-w" || a == "--wireshark") tun = true;           // apps/btrx:57-58; BTB200_TUN_FILE redirects the frames to a file
     else { std::fprintf(stderr, "unknown option %s\n", a.c_str()); return 2; }
   }
   if (in.empty()) { std::fprintf(stderr, "usage: btrx_b200 -f FREQ -r RATE -i FILE [-S|-L] [-s SNR] [-N n] [-2]\n"); return 2; }
@@ -55,9 +56,9 @@ int main(int argc, char **argv)
 
   boost::shared_ptr<gr::bluetooth::multi_block> blk;
   try {
-    if (hop_mode) blk = gr::bluetooth::multi_hopper::make(rate, freq, snr, target_lap, false, false);
+    if (hop_mode) blk = gr::bluetooth::multi_hopper::make(rate, freq, snr, target_lap, false, tun);
     else if (lap_mode) blk = gr::bluetooth::multi_LAP::make(rate, freq, snr);
-    else blk = gr::bluetooth::multi_sniffer::make(rate, freq, snr, false);
+    else blk = gr::bluetooth::multi_sniffer::make(rate, freq, snr, tun);
   } catch (const std::exception &e) {
     std::fprintf(stderr, "btrx_b200: %s\n", e.what());
     return 1;

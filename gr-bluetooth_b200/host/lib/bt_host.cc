@@ -1,7 +1,13 @@
 // bt_host.cc -- see bt_host.h.
+#include <fcntl.h>
+#include <linux/if.h>
+#include <linux/if_tun.h>
+#include <sys/ioctl.h>
+#include <unistd.h>
 #include "bt_host.h"
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 namespace btb200_host {
@@ -197,6 +203,20 @@ void ClassicPacket::set_clock(uint32_t clock, bool have27)
 {
   d_clock = have27 ? (clock & 0x7ffffff) : (clock & 0x3f);
   d_have_clk6 = true;
+  d_have_clk27 = have27;
+}
+
+std::vector<uint8_t> ClassicPacket::tun_format() const
+{
+  std::vector<uint8_t> out((size_t)9 + (size_t)d_payload_length);
+  for (int i = 0; i < 4; i++) out[(size_t)i] = (uint8_t)(d_clock >> (8 * i));
+  out[4] = (uint8_t)channel;
+  out[5] = (uint8_t)((d_have_clk27 ? 1 : 0) | ((d_have_nap ? 1 : 0) << 1));
+  out[6] = (uint8_t)air_to_host(&d_packet_header[0], 7);      /* LT_ADDR and type */
+  out[7] = (uint8_t)air_to_host(&d_packet_header[7], 3);      /* flags */
+  out[8] = (uint8_t)air_to_host(&d_packet_header[10], 8);     /* HEC */
+  for (int i = 0; i < d_payload_length; i++) out[(size_t)9 + (size_t)i] = (uint8_t)air_to_host(&d_payload[(size_t)i * 8], 8);
+  return out;
 }
 
 bool ClassicPacket::payload_crc() const
@@ -744,7 +764,11 @@ void SnifferHost::aa(const char *symbols, int len, uint32_t clkn, double freq, d
 }
 
 /* ID packet (no header), :229-236 */
-void SnifferHost::id(uint32_t) { std::printf("ID\n"); }
+void SnifferHost::id(uint32_t lap)
+{
+  std::printf("ID\n");
+  write_frame(d_tunfd, nullptr, 0, 0, lap, TUN_ETHER_TYPE);
+}
 
 /* decode packets with headers, :238-281 */
 void SnifferHost::decode(std::shared_ptr<ClassicPacket> pkt, std::shared_ptr<Piconet> pn, bool first_run)
@@ -755,6 +779,16 @@ void SnifferHost::decode(std::shared_ptr<ClassicPacket> pkt, std::shared_ptr<Pic
   pkt->decode();
   if (pkt->got_payload()) {
     pkt->print();
+    if (d_tunfd >= 0) {
+      /* destination address = NAP:UAP:LAP as far as known (:252-267) */
+      uint64_t addr = ((uint32_t)pkt->uap() << 24) | pkt->lap();
+      if (pn->have_nap()) {
+        addr |= (uint64_t)pn->nap() << 32;
+        pkt->set_nap(pn->nap());
+      }
+      const std::vector<uint8_t> data = pkt->tun_format();
+      write_frame(d_tunfd, data.data(), (unsigned)data.size(), 0, addr, TUN_ETHER_TYPE);
+    }
     if (pkt->type() == 2) fhs(pkt);
   } else if (first_run) {
     std::printf("lost clock!\n");
@@ -858,10 +892,66 @@ void HopperHost::hop_packet(const SlotPlan &p, const char *symbols, int len)
     pkt.set_uap(d_piconet.uap());
     pkt.set_clock(p.clock27, true);
     pkt.decode();
-    if (pkt.got_payload()) pkt.print();
+    if (pkt.got_payload()) {
+      pkt.print();
+      if (d_tunfd >= 0) {
+        /* the reference keeps this address in an int (:190-193): sign-extended when UAP >= 0x80 */
+        const int addr = (int)(((uint32_t)pkt.uap() << 24) | pkt.lap());
+        const std::vector<uint8_t> data = pkt.tun_format();
+        write_frame(d_tunfd, data.data(), (unsigned)data.size(), 0, (uint64_t)(int64_t)addr, TUN_ETHER_TYPE);
+      }
+    }
   } else {
     std::printf("ID\n");
+    if (d_tunfd >= 0) {
+      const int addr = (int)(((uint32_t)d_piconet.uap() << 24) | pkt.lap());
+      write_frame(d_tunfd, nullptr, 0, 0, (uint64_t)(int64_t)addr, TUN_ETHER_TYPE);
+    }
   }
+}
+
+/* ---- Wireshark interface (lib/tun.cc) ---------------------------------------------------- */
+int write_frame(int fd, const uint8_t *data, unsigned data_len, uint64_t src_addr, uint64_t dst_addr,
+                unsigned short ether_type)
+{
+  if (fd < 0) return (int)data_len;
+  const unsigned MTU = 1500, HDR = 14;
+  uint8_t frame[MTU] = {0};
+  for (int i = 0; i < 6; i++) {
+    const int shift = 8 * (5 - i);
+    frame[i] = (uint8_t)(dst_addr >> shift);
+    frame[6 + i] = (uint8_t)(src_addr >> shift);
+  }
+  frame[12] = (uint8_t)(ether_type >> 8);
+  frame[13] = (uint8_t)ether_type;
+  const unsigned room = MTU - HDR, n = data_len < room ? data_len : room;
+  if (n) std::memcpy(frame + HDR, data, n);
+  if (::write(fd, frame, HDR + n) == -1) {
+    std::perror("write");
+    return -1;
+  }
+  return (int)data_len;
+}
+
+int open_tap(const char *name)
+{
+  const int fd = ::open("/dev/net/tun", O_RDWR);
+  if (fd < 0) return -1;
+  struct ifreq ifr;
+  std::memset(&ifr, 0, sizeof ifr);
+  ifr.ifr_flags = IFF_TAP | IFF_NO_PI;
+  std::strncpy(ifr.ifr_name, name, IFNAMSIZ - 1);
+  if (::ioctl(fd, TUNSETIFF, (void *)&ifr) < 0) { ::close(fd); return -1; }
+  return fd;
+}
+
+int open_tun_output()
+{
+  int fd = -1;
+  if (const char *path = std::getenv("BTB200_TUN_FILE")) fd = ::open(path, O_WRONLY | O_CREAT | O_TRUNC, 0644);
+  else fd = open_tap("btbb");                                   /* lib/multi_sniffer_impl.cc:64-66 */
+  if (fd < 0) std::fprintf(stderr, "warning: was not able to open TUN device, disabling Wireshark interface\n");
+  return fd;
 }
 
 }  // namespace btb200_host

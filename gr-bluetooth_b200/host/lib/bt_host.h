@@ -44,6 +44,12 @@ class ClassicPacket {
   int crc_check(int clock);                                     // :609-668
   void set_clock(uint32_t clock, bool have27);                  // :578-590
   void set_uap(uint8_t uap) { d_uap = uap; }
+  uint8_t uap() const { return d_uap; }
+  void set_nap(uint16_t nap) { d_nap = nap; d_have_nap = true; }   // :570-574
+  int payload_length() const { return d_payload_length; }
+  // 9 + payload_length bytes for the Wireshark interface: CLK (4, little endian), channel, flags, the packet
+  // header squeezed into 3 bytes, then the payload bytes (packet_impl.cc:1175-1202)
+  std::vector<uint8_t> tun_format() const;
   void decode();                                                // :173-179 (decode_header + decode_payload)
   bool got_payload() const { return d_have_payload; }
   int type() const { return d_type; }
@@ -66,6 +72,8 @@ class ClassicPacket {
   uint8_t d_uap = 0;
   uint32_t d_clock = 0;
   bool d_have_clk6 = false, d_have_payload = false;
+  bool d_have_clk27 = false, d_have_nap = false;
+  uint16_t d_nap = 0;
   int d_type = 0;
   int d_payload_length = 0, d_payload_header_length = 0, d_llid = 0, d_flow = 0;
   char d_packet_header[18];
@@ -141,13 +149,28 @@ void le_print(const char *stream, int available, double freq);
 // The per-packet call chain of the sniffer block: multi_sniffer_impl::ac / aa / id / decode /
 // discover / recall / fhs, lib/multi_sniffer_impl.cc:169-365.  Independent of the GPU path so
 // that it can be driven from any hit source (the CPU test tier drives it from the oracle).
+// One frame on the TAP interface (lib/tun.cc:91-123): Ethernet header (destination = the six low-order bytes
+// of dst_addr, big endian; source likewise; EtherType) followed by the data.  A negative fd is "no interface":
+// nothing is written.  Returns data_len, or -1 when the write fails.
+static const unsigned short TUN_ETHER_TYPE = 0xFFF0;              // lib/multi_sniffer_impl.h:52, multi_hopper_impl.h:62
+int write_frame(int fd, const uint8_t *data, unsigned data_len, uint64_t src_addr, uint64_t dst_addr,
+                unsigned short ether_type);
+// open the TAP device `name` (lib/tun.cc:41-78: /dev/net/tun, IFF_TAP | IFF_NO_PI); -1 when that is not possible
+int open_tap(const char *name);
+// what the blocks do for tun = true: the file named by BTB200_TUN_FILE if set (frames are appended as written:
+// capture/tests), else the TAP device "btbb" as in the reference; -1 and the reference's warning when neither opens
+int open_tun_output();
+
 class SnifferHost {
  public:
+  // frames go to this descriptor (a TAP device, or any file/pipe for capture and tests); -1 = off
+  void set_tun_fd(int fd) { d_tunfd = fd; }
   void ac(const char *symbols, int len, uint32_t clkn, double freq, double snr);
   void aa(const char *symbols, int len, uint32_t clkn, double freq, double snr);
 
  private:
   static const uint32_t GIAC = 0x9E8B33, LIAC = 0x9E8B00;      // lib/multi_sniffer_impl.h:41-42
+  int d_tunfd = -1;
   std::map<int, std::shared_ptr<Piconet>> d_piconets;
   void id(uint32_t lap);
   void decode(std::shared_ptr<ClassicPacket> pkt, std::shared_ptr<Piconet> pn, bool first_run);
@@ -175,12 +198,14 @@ class HopperHost {
   bool scan_packet(uint32_t clkn, int channel, const char *symbols, int len);
   // hopalong phase: the first access code found on the predicted channel
   void hop_packet(const SlotPlan &p, const char *symbols, int len);
+  void set_tun_fd(int fd) { d_tunfd = fd; }
 
  private:
   uint32_t d_lap;
   bool d_aliased;
   int d_ch_lo, d_ch_hi;
   Piconet d_piconet;
+  int d_tunfd = -1;
 };
 
 }  // namespace btb200_host

@@ -27,9 +27,9 @@ multi_hopper_impl::multi_hopper_impl(double sample_rate, double center_freq, dou
       multi_block(sample_rate, center_freq, squelch_threshold, 3125, BTB200_SEARCH_BR, /*force_chained=*/true)
 {
   if (aliased) throw std::runtime_error("multi_hopper: the aliased receiver mode is not supported on the B200 path");
-  if (tun) std::fprintf(stderr, "warning: the TUN/Wireshark interface (lib/tun.cc) is not part of the B200 path, disabling it\n");
   const int lo = (int)((d_low_freq - 2402000000.0) / 1e6), hi = (int)((d_high_freq - 2402000000.0) / 1e6);
   d_host.reset(new btb200_host::HopperHost((uint32_t)LAP, aliased, lo, hi));
+  if (tun) d_host->set_tun_fd(btb200_host::open_tun_output());     /* lib/multi_hopper_impl.cc:56-64 */
   d_res.resize((size_t)(hi - lo + 1));
   d_symbols.resize((size_t)(hi - lo + 1) * 3125);
 }

@@ -25,8 +25,10 @@ multi_sniffer_impl::multi_sniffer_impl(double sample_rate, double center_freq, d
       d_tun(tun)
 {
   if (d_tun) {
-    std::fprintf(stderr, "warning: the TUN/Wireshark interface (lib/tun.cc) is not part of the B200 path, disabling it\n");
-    d_tun = false;
+    /* Tun interface (lib/multi_sniffer_impl.cc:63-72): a failure only warns */
+    const int fd = btb200_host::open_tun_output();
+    if (fd < 0) d_tun = false;
+    d_host.set_tun_fd(fd);
   }
 }
 

@@ -11,14 +11,26 @@
  *
  * Sub-commands:
  *   sniff   --fs F --fc F --snr F --in FILE [--i16] [--first-call K] [--num-calls N]
- *           [--stateless] [--dump FILE] [--heavy A:B] [--quiet]
+ *           [--stateless] [--dump FILE] [--heavy A:B] [--quiet] [--tun-out FILE]
  *   hop     same + --lap HEX [--aliased]
  *   acgen   HEXLAP...                 print the 9 access-code bytes (packet_impl.cc:309)
  *   sniffdem FILE                     loop sniff_ac over a 1-bit-per-byte symbol file
  *   tables                            print the reference's detection LUTs
  */
+/* --tun-out needs the blocks' private TAP descriptor; the reference headers stay untouched, the keyword is
+ * redefined around their inclusion only (standard and shim headers first, so nothing else is affected) */
+#include <map>
+#include <string>
+#include <vector>
+#include <iostream>
+#include <memory>
+#include <gnuradio/sync_block.h>
+#include <gnuradio/io_signature.h>
+#include <fcntl.h>
+#define private protected
 #include "multi_sniffer_impl.h"
 #include "multi_hopper_impl.h"
+#undef private
 #include "btref_hooks.h"
 #include <string>
 #include <vector>
@@ -34,6 +46,7 @@ struct probe_sniffer : public multi_sniffer_impl {
     : multi_block(fs, fc, snr), gr::sync_block("probe", sig(), sig()),
       multi_sniffer_impl(fs, fc, snr, false) {}
   void reset_mm() { d_mu = 0.32; d_omega = d_omega_mid; d_last_sample = 0; }   /* multi_block.cc:91-98 */
+  void tun_to(int fd) { d_tun = true; d_tunfd = fd; }      /* frames of the Wireshark interface -> fd */
   int S() const { return (int)d_samples_per_slot; }
   void info() const {
     fprintf(stderr, "btref: S=%d D=%d Nc=%zu Nn=%zu fcs=%d fns=%d low=%.0f high=%.0f gain=%.9g\n",
@@ -50,6 +63,7 @@ struct probe_hopper : public multi_hopper_impl {
     : multi_block(fs, fc, snr), gr::sync_block("probe", sig(), sig()),
       multi_hopper_impl(fs, fc, snr, lap, aliased, false) {}
   void reset_mm() { d_mu = 0.32; d_omega = d_omega_mid; d_last_sample = 0; }
+  void tun_to(int fd) { d_tun = true; d_tunfd = fd; }
   int S() const { return (int)d_samples_per_slot; }
 };
 
@@ -58,7 +72,7 @@ static void hook_hopper(void *u) { ((probe_hopper *)u)->reset_mm(); }
 
 struct args {
   double fs = 2e6, fc = 2476e6, snr = 10;
-  std::string in, dump;
+  std::string in, dump, tun_out;
   bool i16 = false, stateless = false, aliased = false, timing = false;
   long first_call = 0, num_calls = -1;
   int heavy_a = 0, heavy_b = 0;
@@ -162,6 +176,7 @@ int main(int argc, char **argv)
     else if (s == "--snr") a.snr = atof(next());
     else if (s == "--in") a.in = next();
     else if (s == "--dump") a.dump = next();
+    else if (s == "--tun-out") a.tun_out = next();
     else if (s == "--i16") a.i16 = true;
     else if (s == "--stateless") a.stateless = true;
     else if (s == "--aliased") a.aliased = true;
@@ -177,11 +192,13 @@ int main(int argc, char **argv)
     probe_sniffer blk(a.fs, a.fc, a.snr);
     blk.info();
     if (a.stateless) { g_btref.on_channel_ddc = hook_sniffer; g_btref.user = &blk; }
+    if (!a.tun_out.empty()) blk.tun_to(open(a.tun_out.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644));
     return run_block(blk, a);
   }
   if (cmd == "hop") {
     probe_hopper blk(a.fs, a.fc, a.snr, a.lap, a.aliased);
     if (a.stateless) { g_btref.on_channel_ddc = hook_hopper; g_btref.user = &blk; }
+    if (!a.tun_out.empty()) blk.tun_to(open(a.tun_out.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644));
     return run_block(blk, a);
   }
   if (cmd == "design") {

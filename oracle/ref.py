@@ -77,7 +77,7 @@ def parse_stdout_hits(text):
 
 
 def sniff(path, fs, fc, snr=10.0, i16=False, stateless=False, first_call=0, num_calls=None,
-          dump=False, heavy=None, hop_lap=None):
+          dump=False, heavy=None, hop_lap=None, tun_out=None):
     """Run the reference multi_sniffer (or multi_hopper) over a file.
     -> dict(stdout, stderr, records (if dump))."""
     args = ["--fs", fs, "--fc", fc, "--snr", snr, "--in", path, "--first-call", first_call]
@@ -94,6 +94,8 @@ def sniff(path, fs, fc, snr=10.0, i16=False, stateless=False, first_call=0, num_
         args += ["--dump", tmp.name]
         if heavy:
             args += ["--heavy", "%d:%d" % heavy]
+    if tun_out:
+        args += ["--tun-out", tun_out]        # the Wireshark-interface frames (lib/tun.cc) go to this file
     cmd = "sniff"
     if hop_lap is not None:
         cmd = "hop"

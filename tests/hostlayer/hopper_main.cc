@@ -8,11 +8,12 @@ extern "C" {
 }
 #include <cstdio>
 #include <cstdlib>
+#include <fcntl.h>
 #include <vector>
 
 int main(int argc, char **argv)
 {
-  if (argc < 5) { std::fprintf(stderr, "usage: hopper FS FC LAPHEX FILE.cfile\n"); return 2; }
+  if (argc < 5) { std::fprintf(stderr, "usage: hopper FS FC LAPHEX FILE.cfile [TUNFRAMES.out]\n"); return 2; }
   const double fs = std::atof(argv[1]), fc = std::atof(argv[2]);
   const uint32_t lap = (uint32_t)std::strtoul(argv[3], nullptr, 16);
   btbo_plan *P = btbo_plan_create(fs, fc, 10.0, 3125);
@@ -30,6 +31,7 @@ int main(int argc, char **argv)
   const int chist = I.Nc + I.D * 8;
   std::printf("history set to %d samples: channel=%d, noise=%d\n", I.S + (chist > I.Nn ? chist : I.Nn), chist, I.Nn);
   btb200_host::HopperHost host(lap, false, I.ch_lo, I.ch_hi);
+  if (argc > 5) host.set_tun_fd(open(argv[5], O_WRONLY | O_CREAT | O_TRUNC, 0644));
   std::vector<btbo_chan_result> res((size_t)I.nch);
   std::vector<uint8_t> sym((size_t)I.nch * I.H);
   std::vector<int32_t> chis((size_t)I.nch);

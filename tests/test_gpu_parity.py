@@ -547,3 +547,31 @@ def test_ble_advertising_channels_30msps():
     want = [t for t in truth if t["kind"] == 1 and 1 <= t["slot"] <= nslots - 8]
     assert want and len(adv) >= 0.7 * len(want)
     assert {int(h["channel"]) for h in adv} <= {0, 24}
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["sniffer", "hopper"])
+def test_cpp_blocks_wireshark_frames(mode, tmp_path):
+    """tun = true on the C++ blocks (btrx_b200 -w, frames redirected with BTB200_TUN_FILE): GPU front end +
+    native host layer write the reference's TAP frames (lib/tun.cc + classic_packet::tun_format) byte for byte;
+    the expected bytes come from the verbatim reference build running on this box's CPU."""
+    import subprocess
+    from conftest import ROOT
+    from oracle import ref as REF
+    exe = os.path.join(ROOT, "gr-bluetooth_b200", "host", "btrx_b200")
+    iq = full_capture("headset1")
+    if not os.path.exists(exe) or iq is None or not REF.available():
+        pytest.skip("btrx_b200, the full capture or oracle/_ref/btref missing")
+    path = tmp_path / "h1.cfile"
+    iq.tofile(path)
+    want_file, got_file = tmp_path / "ref.frames", tmp_path / "got.frames"
+    hop = 0x24D952 if mode == "hopper" else None
+    want_txt = REF.sniff(str(path), 8e6, 2476.5e6, hop_lap=hop, tun_out=str(want_file))["stdout"]
+    e = dict(os.environ)
+    e["BTB200_TUN_FILE"] = str(got_file)
+    args = [exe, "-f", "2476.5M", "-r", "8M", "-i", str(path), "-w"] + (["-l", "24d952"] if hop else ["-S"])
+    out = subprocess.run(args, capture_output=True, timeout=900, env=e)
+    assert out.returncode == 0, out.stderr.decode()[-1500:]
+    assert out.stdout.decode() == want_txt
+    want = want_file.read_bytes()
+    assert got_file.read_bytes() == want and len(want) > 14

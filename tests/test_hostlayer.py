@@ -26,7 +26,7 @@ def harness():
     return exe
 
 
-def host_stdout(harness, P, iq, tmp_path, num_calls=None):
+def host_stdout(harness, P, iq, tmp_path, num_calls=None, tun_out=None):
     o = P.run(iq, num_calls=num_calls, stateless=False, want_bits=True, n_total=None if num_calls is None else len(iq) + P.S)
     path = tmp_path / "hits.bin"
     first_call = 0
@@ -39,7 +39,7 @@ def host_stdout(harness, P, iq, tmp_path, num_calls=None):
             ln = min(int(h["len"]), 3125, len(sym))
             f.write(struct.pack("<Iiddi", int(h["slot"]), int(h["kind"]), 2402e6 + 1e6 * int(h["channel"]), float(h["snr"]), ln))
             f.write(sym[:ln].astype(np.uint8).tobytes())
-    out = subprocess.run([harness, str(path)], capture_output=True, timeout=120)
+    out = subprocess.run([harness, str(path)] + ([str(tun_out)] if tun_out else []), capture_output=True, timeout=120)
     assert out.returncode == 0
     chist = P.Nc + P.D * 8
     banner = "history set to %d samples: channel=%d, noise=%d\n" % (P.S + max(chist, P.Nn), chist, P.Nn)
@@ -105,3 +105,41 @@ def test_hopper_logic_keyboard1_equals_reference_build(hopper_harness):
     out = subprocess.run([hopper_harness, "8e6", "2476.5e6", "4831dd", path], capture_output=True, timeout=300)
     assert out.returncode == 0 and out.stdout.decode() == want
     assert "UAP = 0x61" in want
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_SAMPLES), reason="needs the bundled captures")
+@pytest.mark.parametrize("name", list(FILES))
+def test_wireshark_frames_equal_reference_sniffer(harness, name, tmp_path):
+    """SURVEY 8f-4: the TAP frames (lib/tun.cc:91-123 around classic_packet::tun_format,
+    packet_impl.cc:1175-1202) the native host layer writes for tun = true are the reference's, byte for byte.
+    The verbatim reference build writes them to a file through its own write_interface()."""
+    from oracle import ref as R
+    if not R.available():
+        pytest.skip("oracle/_ref/btref not built")
+    fs, fc = FILES[name]
+    path = os.path.join(REF_SAMPLES, name + ".cfile")
+    want_file, got_file = tmp_path / "ref.frames", tmp_path / "got.frames"
+    want_txt = R.sniff(path, fs, fc, tun_out=str(want_file))["stdout"]
+    iq = np.fromfile(path, dtype=np.complex64)
+    got_txt = host_stdout(harness, O.Plan(fs, fc), iq, tmp_path, tun_out=got_file)
+    assert got_txt == want_txt
+    want, got = want_file.read_bytes(), got_file.read_bytes()
+    assert got == want
+    assert len(want) >= 14 and want[12:14] == b"\xff\xf0"          # EtherType 0xFFF0, big endian
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_SAMPLES), reason="needs the bundled captures")
+def test_wireshark_frames_equal_reference_hopper(hopper_harness, tmp_path):
+    """multi_hopper hop-along frames on headset1 (UAP 0xaf: the reference keeps the address in an int, so the
+    two NAP bytes of the destination MAC come out as ff:ff -- reproduced)."""
+    from oracle import ref as R
+    if not R.available():
+        pytest.skip("oracle/_ref/btref not built")
+    path = os.path.join(REF_SAMPLES, "headset1.cfile")
+    want_file, got_file = tmp_path / "ref.frames", tmp_path / "got.frames"
+    want_txt = R.sniff(path, 8e6, 2476.5e6, hop_lap=0x24D952, tun_out=str(want_file))["stdout"]
+    out = subprocess.run([hopper_harness, "8e6", "2476.5e6", "24d952", path, str(got_file)], capture_output=True, timeout=300)
+    assert out.returncode == 0 and out.stdout.decode() == want_txt
+    want, got = want_file.read_bytes(), got_file.read_bytes()
+    assert got == want and len(want) > 14
+    assert want[:6] == bytes([0xFF, 0xFF, 0xAF, 0x24, 0xD9, 0x52])

@@ -21,6 +21,7 @@ namespace {
 constexpr int kNumEvents = 8;
 constexpr uint32_t kDefaultMaxSlots = 64;
 constexpr unsigned kHitCap = 1u << 18;
+constexpr int kCopyParts = 4;
 constexpr unsigned long long kArenaCap = 256ull << 20;
 }
 
@@ -50,6 +51,7 @@ struct btb200_ctx {
   bool owns_stream = false;
   cudaStream_t copy_stream = nullptr;  // host->device input copies, overlapping whatever the compute stream runs
   cudaEvent_t ev_sync = nullptr, ev_h2d = nullptr;
+  cudaEvent_t ev_part[4] = {};
   cudaEvent_t ev[kNumEvents + 1]{};
   cudaEvent_t evl[3]{};      // lazy squelch: noise FIR / energies
   cudaEvent_t ev_tail = nullptr;
@@ -279,6 +281,7 @@ int setup(btb200_ctx *ctx)
   CK(cudaEventCreateWithFlags(&ctx->ev_sync, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&ctx->ev_h2d, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&ctx->ev_up, cudaEventDisableTiming));
+  for (auto &e : ctx->ev_part) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   for (auto &e : ctx->ev) CK(cudaEventCreate(&e));
   for (auto &e : ctx->evl) CK(cudaEventCreate(&e));
   CK(cudaEventCreateWithFlags(&ctx->ev_tail, cudaEventDisableTiming));
@@ -449,6 +452,7 @@ void teardown(btb200_ctx *ctx)
   if (ctx->ev_sync) cudaEventDestroy(ctx->ev_sync);
   if (ctx->ev_h2d) cudaEventDestroy(ctx->ev_h2d);
   if (ctx->ev_up) cudaEventDestroy(ctx->ev_up);
+  for (auto &e : ctx->ev_part) if (e) cudaEventDestroy(e);
   for (void *p : ctx->allocs) cudaFree(p);
   for (void *p : {(void *)ctx->h_energy, (void *)ctx->h_noise, (void *)ctx->h_pass, (void *)ctx->h_counts,
                   (void *)ctx->h_hits, (void *)ctx->h_arena, (void *)ctx->h_ph, (void *)ctx->h_groups,
@@ -593,15 +597,33 @@ int btb200_submit(btb200_ctx *ctx, const float *iq, int iq_on_device, size_t n_s
   W.B = (int)n_slots;
   const size_t nbc = (size_t)n_slots * P.nch;
 
+  bool chan_fir_done = false;
   if (iq_on_device) {
     CK(cudaEventRecord(ctx->ev[0], s));
     W.x = reinterpret_cast<const c32 *>(iq);
   } else {
-    // the copy runs on its own stream (it overlaps the compute stream's current work); compute waits for it
+    // the copy runs on its own stream (it overlaps the compute stream's current work); compute waits for it.
+    // With the tuned kernels it is cut in kCopyParts pieces and the channel FIR follows piece by piece, so only
+    // the first piece of a batch is exposed when nothing else is queued (blocking btb200_process callers).
     CK(cudaEventRecord(ctx->ev[0], ctx->copy_stream));
-    CK(cudaMemcpyAsync(ctx->d_x, iq, need * sizeof(c32), cudaMemcpyHostToDevice, ctx->copy_stream));
+    W.x = ctx->d_x;
+    const long ntile = chan_fir_tiles(G, W);
+    const int parts = (ctx->impl != IMPL_BASELINE && G.stateless && ntile >= 64) ? kCopyParts : 1;
+    size_t copied = 0;
+    for (int c = 0; c < parts; c++) {
+      const long t0 = ntile * c / parts, t1 = ntile * (c + 1) / parts;
+      size_t upto = (c == parts - 1) ? need : std::min<size_t>(need, (size_t)chan_fir_samples(G, t1));
+      if (upto > copied) {
+        CK(cudaMemcpyAsync(ctx->d_x + copied, reinterpret_cast<const c32 *>(iq) + copied, (upto - copied) * sizeof(c32),
+                           cudaMemcpyHostToDevice, ctx->copy_stream));
+        copied = upto;
+      }
+      CK(cudaEventRecord(ctx->ev_part[c], ctx->copy_stream));
+      CK(cudaStreamWaitEvent(s, ctx->ev_part[c], 0));
+      if (parts > 1) { launch_chan_fir_range(G, ctx->T, W, ctx->impl, t0, t1, s); ctx->launches++; }
+    }
+    chan_fir_done = parts > 1;
     CK(cudaEventRecord(ctx->ev_h2d, ctx->copy_stream));
-    CK(cudaStreamWaitEvent(s, ctx->ev_h2d, 0));
     W.x = ctx->d_x;
   }
   if (!G.stateless) {
@@ -621,7 +643,7 @@ int btb200_submit(btb200_ctx *ctx, const float *iq, int iq_on_device, size_t n_s
   }
   CK(cudaMemsetAsync(W.hit_count, 0, 4 * sizeof(unsigned), s));
   CK(cudaEventRecord(ctx->ev[1], s));
-  launch_chan_fir(G, ctx->T, W, ctx->impl, s); ctx->launches++;
+  if (!chan_fir_done) { launch_chan_fir(G, ctx->T, W, ctx->impl, s); ctx->launches++; }
   CK(cudaEventRecord(ctx->ev[2], s));
   if (ctx->lazy) {
     // lazy squelch: every window is demodulated and searched; the squelch (and the snr

@@ -840,22 +840,34 @@ __global__ void k_energy_list_warp(Geom G, DevBatch W, const int4 *__restrict__ 
   const int b = it.x, c = it.y;
   const c32 *y = W.Y + ((long)b * G.gps) * G.nch + c;
   const c32 *p = W.phc + c;
+  // the loads of the next 32 samples are issued before the serial fp64 chain of the current 32 (their latency,
+  // rows 632 bytes apart, would otherwise add to every step of a latency-bound kernel)
   double e = 0.0;
-  for (int i0 = 0; i0 < G.n_ddc; i0 += 32) {
-    const int i = i0 + lane;
-    const float m = (i < G.n_ddc) ? mag2(crot(y[(long)i * G.nch], p[(long)i * G.nch])) : 0.0f;
-    const int cnt = (G.n_ddc - i0) < 32 ? (G.n_ddc - i0) : 32;
-    for (int j = 0; j < cnt; j++) e += (double)__shfl_sync(0xffffffffu, m, j);
+  {
+    c32 yv = (lane < G.n_ddc) ? y[(long)lane * G.nch] : c32{0.0f, 0.0f};
+    c32 pv = (lane < G.n_ddc) ? p[(long)lane * G.nch] : c32{0.0f, 0.0f};
+    for (int i0 = 0; i0 < G.n_ddc; i0 += 32) {
+      const float m = (i0 + lane < G.n_ddc) ? mag2(crot(yv, pv)) : 0.0f;
+      const int in = i0 + 32 + lane;
+      if (in < G.n_ddc) { yv = y[(long)in * G.nch]; pv = p[(long)in * G.nch]; }
+      const int cnt = (G.n_ddc - i0) < 32 ? (G.n_ddc - i0) : 32;
+      for (int j = 0; j < cnt; j++) e += (double)__shfl_sync(0xffffffffu, m, j);
+    }
   }
   if (!NzL) { if (lane == 0) { e_on[l] = e / G.n_ddc; e_off[l] = 0.0; } return; }    // on-channel only
   const c32 *z = NzL + ((long)it.z * G.n_noise) * cgw + it.w;
   const c32 *q = W.phn + c;
   double n = 0.0;
-  for (int j0 = 0; j0 < G.n_noise; j0 += 32) {
-    const int j = j0 + lane;
-    const float m = (j < G.n_noise) ? mag2(crot(z[(long)j * cgw], q[(long)j * G.nch])) : 0.0f;
-    const int cnt = (G.n_noise - j0) < 32 ? (G.n_noise - j0) : 32;
-    for (int k = 0; k < cnt; k++) n += (double)__shfl_sync(0xffffffffu, m, k);
+  {
+    c32 zv = (lane < G.n_noise) ? z[(long)lane * cgw] : c32{0.0f, 0.0f};
+    c32 qv = (lane < G.n_noise) ? q[(long)lane * G.nch] : c32{0.0f, 0.0f};
+    for (int j0 = 0; j0 < G.n_noise; j0 += 32) {
+      const float m = (j0 + lane < G.n_noise) ? mag2(crot(zv, qv)) : 0.0f;
+      const int jn = j0 + 32 + lane;
+      if (jn < G.n_noise) { zv = z[(long)jn * cgw]; qv = q[(long)jn * G.nch]; }
+      const int cnt = (G.n_noise - j0) < 32 ? (G.n_noise - j0) : 32;
+      for (int k = 0; k < cnt; k++) n += (double)__shfl_sync(0xffffffffu, m, k);
+    }
   }
   if (lane == 0) { e_on[l] = e / G.n_ddc; e_off[l] = n / G.n_noise; }
 }
@@ -906,19 +918,29 @@ static int pick_kt_packed(int CG, int R, int W, int D, int N, int blocks_per_sm 
 // ===========================================================================
 static inline unsigned cdiv(long a, long b) { return (unsigned)((a + b - 1) / b); }
 
-void launch_chan_fir(const Geom &G, const DevTables &T, const DevBatch &W, int impl, cudaStream_t s)
+constexpr int CHAN_R = 8, CHAN_W = 16, CHAN_TJ = 2 * CHAN_R * CHAN_W;   // 16 channels x 256 outputs per block
+
+long chan_fir_tiles(const Geom &G, const DevBatch &W)
 {
   const long Gtot = (long)(W.B - 1) * G.gps + G.n_ddc;
-  if (impl == IMPL_BASELINE) {
-    k_chan_fir_v1<<<cdiv(Gtot * G.nch, 128), 128, 0, s>>>(G, W.x, T.chan_rtaps, W.Y, Gtot);
-    return;
-  }
-  constexpr int R = 8, Wp = 16, TJ = 2 * R * Wp;   // 16 channels x 256 outputs per block
+  return (Gtot + CHAN_TJ - 1) / CHAN_TJ;
+}
+// input samples (from W.x[0]) the tiles below `tile_end` read
+long chan_fir_samples(const Geom &G, long tile_end) { return (long)G.fcs + (tile_end * CHAN_TJ - 1) * G.D + G.Nc; }
+
+// tiles [tile0, tile1) of the channel FIR (tuned kernels): the job is the whole-batch job with its origin moved
+void launch_chan_fir_range(const Geom &G, const DevTables &T, const DevBatch &W, int impl, long tile0, long tile1,
+                           cudaStream_t s)
+{
+  const long Gtot = (long)(W.B - 1) * G.gps + G.n_ddc;
+  const long g0 = tile0 * CHAN_TJ, g1 = (tile1 * CHAN_TJ < Gtot) ? tile1 * CHAN_TJ : Gtot;
+  if (g1 <= g0) return;
+  constexpr int R = CHAN_R, Wp = CHAN_W, TJ = CHAN_TJ;
   FirJob J{};
-  J.x = W.x; J.n_x = (long)(W.B - 1) * G.S + G.H; J.taps = T.chan_tg; J.out = W.Y;
+  J.x = W.x + g0 * G.D; J.n_x = (long)(W.B - 1) * G.S + G.H - g0 * G.D; J.taps = T.chan_tg; J.out = W.Y + g0 * G.nch;
   J.N = G.Nc; J.D = G.D; J.nch = G.nch;
-  J.mode = 0; J.Gtot = Gtot; J.fcs = G.fcs;
-  const unsigned ntile = cdiv(Gtot, TJ), ngrp = (unsigned)((G.nch + 15) / 16);
+  J.mode = 0; J.Gtot = g1 - g0; J.fcs = G.fcs;
+  const unsigned ntile = cdiv(g1 - g0, TJ), ngrp = (unsigned)((G.nch + 15) / 16);
   J.group_fast = ntile <= 65535u;
   dim3 grid(J.group_fast ? ngrp : ntile, J.group_fast ? ntile : ngrp);
   if (impl == IMPL_TILED_SCALAR) {
@@ -928,6 +950,16 @@ void launch_chan_fir(const Geom &G, const DevTables &T, const DevBatch &W, int i
     J.KT = pick_kt_packed(16, R, Wp, G.D, G.Nc);
     k_fir_packed<16, R, Wp><<<grid, Wp * 32, fir_packed_smem(16, R, Wp, G.D, J.KT), s>>>(J);
   }
+}
+
+void launch_chan_fir(const Geom &G, const DevTables &T, const DevBatch &W, int impl, cudaStream_t s)
+{
+  const long Gtot = (long)(W.B - 1) * G.gps + G.n_ddc;
+  if (impl == IMPL_BASELINE) {
+    k_chan_fir_v1<<<cdiv(Gtot * G.nch, 128), 128, 0, s>>>(G, W.x, T.chan_rtaps, W.Y, Gtot);
+    return;
+  }
+  launch_chan_fir_range(G, T, W, impl, 0, chan_fir_tiles(G, W), s);
 }
 
 void launch_noise_fir(const Geom &G, const DevTables &T, const DevBatch &W, int impl, cudaStream_t s)

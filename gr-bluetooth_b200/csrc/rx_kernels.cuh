@@ -46,6 +46,12 @@ struct DevBatch {
 enum { IMPL_BASELINE = 0, IMPL_TUNED = 1, IMPL_TILED_SCALAR = 2 };
 
 void launch_chan_fir(const Geom &G, const DevTables &T, const DevBatch &W, int impl, cudaStream_t s);
+// the channel FIR in tile ranges (input copy and filtering overlap, btb200_submit): tiles of the tuned kernels,
+// and the number of input samples the tiles below `tile_end` read
+long chan_fir_tiles(const Geom &G, const DevBatch &W);
+long chan_fir_samples(const Geom &G, long tile_end);
+void launch_chan_fir_range(const Geom &G, const DevTables &T, const DevBatch &W, int impl, long tile0, long tile1,
+                           cudaStream_t s);
 void launch_noise_fir(const Geom &G, const DevTables &T, const DevBatch &W, int impl, cudaStream_t s);
 void launch_energy(const Geom &G, const DevTables &T, const DevBatch &W, int device_gate, cudaStream_t s);
 void launch_demod(const Geom &G, const DevTables &T, const DevBatch &W, cudaStream_t s);

@@ -1064,32 +1064,8 @@ void launch_fill_pass(const DevBatch &W, int n, int v, cudaStream_t s)
   k_fill_pass<<<cdiv(n, 256), 256, 0, s>>>(W.pass, n, v);
 }
 
-// Deferred noise FIR over listed (slot, <=cg channels) groups.  Configurations (channels per
-// group, outputs per thread, warps, blocks per SM) are selectable for tuning (BTB200_LAZY_CFG).
-// Deferred exact noise FIR over listed (slot, <= CG channels) groups (lazy squelch); configurations and their
-// measured times are listed at launch_noise_fir_list().
-template <int CG, int R, int Wp, int BPS, int KTMAX = 512>
-static void launch_list_scalar(const Geom &G, const DevTables &T, const DevBatch &W, const int *groups, int n_groups,
-                               c32 *NzL, cudaStream_t s)
-{
-  constexpr int TJ = (32 / CG) * R * Wp;
-  static OptIn opt;
-  if (opt.need()) {
-    cudaFuncAttributes fa{};
-    cudaFuncGetAttributes(&fa, (const void *)k_fir_tiled<CG, R, Wp, BPS>);
-    cudaFuncSetAttribute((const void *)k_fir_tiled<CG, R, Wp, BPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         g_max_smem - (int)fa.sharedSizeBytes);
-  }
-  FirJob J{};
-  J.x = W.x; J.n_x = (long)(W.B - 1) * G.S + G.H; J.taps = T.noise_rtaps; J.out = NzL;
-  J.N = G.Nn; J.D = G.D; J.nch = G.nch;
-  J.KT = pick_kt(CG, R, Wp, G.D, G.Nn < KTMAX ? G.Nn : KTMAX, BPS);
-  J.mode = 2; J.S = G.S; J.fns = G.fns; J.n_noise = G.n_noise; J.tiles_per_slot = (G.n_noise + TJ - 1) / TJ;
-  J.groups = groups;
-  dim3 grid((unsigned)(n_groups * J.tiles_per_slot), 1);
-  k_fir_tiled<CG, R, Wp, BPS><<<grid, Wp * 32, fir_smem(CG, R, Wp, G.D, J.KT), s>>>(J);
-}
-
+// Deferred exact noise FIR over listed (slot, <= CG channels) groups (lazy squelch), tiled packed kernel; the
+// default for D = 50 is the delay-line kernel of rx_firdl.cu -- see launch_noise_fir_list().
 template <int CG, int R, int Wp, int BPS, int KTMAX = 512, int DT = 0>
 static void launch_list_packed(const Geom &G, const DevTables &T, const DevBatch &W, const int *groups, int n_groups,
                                c32 *NzL, cudaStream_t s)
@@ -1121,39 +1097,26 @@ static int lazy_cfg()
 
 int lazy_group_channels(const Geom &G)
 {
-  const int c = lazy_cfg();
-  if (c >= 6) return noise_fir_dl_supported(G) ? 4 : 2;
-  return c == 4 ? 4 : 2;
+  return (lazy_cfg() >= 6 && noise_fir_dl_supported(G)) ? 4 : 2;
 }
 
-// Measured on B200 (512 slots, 2 260 hit windows x 17 M complex MAC), ms per launch:
+// Measured on B200 (512 slots, 2 260 hit windows x 17 M complex MAC), ms per launch (BTB200_LAZY_CFG selects):
 //   6  delay line + cp.async ring (rx_firdl.cu), <= 4 ch x 448 outputs, 7 warps ............... 13.4  (default, D = 50)
-//   0  packed, skewed, 2 ch x 448 outputs (850 = 2 tiles, 95 %), 14 warps, one block/SM ....... 17.0
-//   1  same shape, no skew ................................................................... 18.9
-//   2  packed, skewed, 2 ch x 288 outputs (3 tiles, 98 %), 9 warps ............................ 19.0
+//   0  packed, skewed, 2 ch x 448 outputs (850 = 2 tiles, 95 %), 14 warps, one block/SM ....... 17.0  (kept as cross-check)
 //   3  packed 2 ch x 256 outputs, 2 blocks/SM (default for D != 50) ........................... 21.7
-//   4  scalar 4 ch x 256 outputs .............................................................. 23.1
-//   5  scalar 2 ch x 256 outputs .............................................................. 21.8
-// (also tried: 144-output tiles 22.3, 320-output tiles with R = 4 24.8, run-time-D skew 25-35.)
+// Tried and removed: same shape as 0 without the skew 18.9; skewed 2 ch x 288 outputs (3 tiles, 9 warps) 19.0;
+// scalar 4 ch x 256 outputs 23.1; scalar 2 ch x 256 outputs 21.8; 144-output tiles 22.3; 320-output tiles with
+// R = 4 24.8; run-time-D skew 25-35; scalar delay line (instruction-fetch bound) 19.1.
 void launch_noise_fir_list(const Geom &G, const DevTables &T, const DevBatch &W, const int *groups, int n_groups,
                            c32 *NzL, cudaStream_t s)
 {
-  int cfg = lazy_cfg();
-  if (cfg >= 6) {
-    // delay-line kernel (rx_firdl.cu), D = 50 only -- other rates use the 2-channel packed tiled kernel
-    if (noise_fir_dl_supported(G) && T.noise_taps4) { launch_noise_fir_dl(G, T, W, groups, n_groups, NzL, s); return; }
-    cfg = 3;
+  const int cfg = lazy_cfg();
+  if (cfg >= 6 && noise_fir_dl_supported(G) && T.noise_taps4) {
+    launch_noise_fir_dl(G, T, W, groups, n_groups, NzL, s);
+    return;
   }
-  if (G.D != 50 && cfg <= 2) cfg = 3;      // the skewed variants are instantiated for D = 50 (100 Msps)
-  switch (cfg) {
-    default:
-    case 0: launch_list_packed<2, 2, 14, 1, 1000, 50>(G, T, W, groups, n_groups, NzL, s); break;
-    case 1: launch_list_packed<2, 2, 14, 1, 1024, 0>(G, T, W, groups, n_groups, NzL, s); break;
-    case 2: launch_list_packed<2, 2, 9, 1, 2000, 50>(G, T, W, groups, n_groups, NzL, s); break;
-    case 3: launch_list_packed<2, 4, 4, 2>(G, T, W, groups, n_groups, NzL, s); break;
-    case 4: launch_list_scalar<4, 4, 8, 2>(G, T, W, groups, n_groups, NzL, s); break;
-    case 5: launch_list_scalar<2, 4, 4, 2>(G, T, W, groups, n_groups, NzL, s); break;
-  }
+  if (cfg == 0 && G.D == 50) launch_list_packed<2, 2, 14, 1, 1000, 50>(G, T, W, groups, n_groups, NzL, s);
+  else launch_list_packed<2, 4, 4, 2>(G, T, W, groups, n_groups, NzL, s);
 }
 
 void launch_energy_list(const Geom &G, const DevBatch &W, const int *list4, int n_list, const c32 *NzL,

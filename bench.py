@@ -236,15 +236,17 @@ def run_ours(args):
             return res
         e2e_loop(NCTX)
         barrier()
-        t0 = time.perf_counter()
-        ehits, esyms, _ = e2e_loop(steps)
-        barrier()
-        e2e_s = allmax(time.perf_counter() - t0)
+        with ClockSampler(local) as clk_e2e:
+            t0 = time.perf_counter()
+            ehits, esyms, _ = e2e_loop(steps)
+            barrier()
+            e2e_s = allmax(time.perf_counter() - t0)
         e2e_val = total_samples / e2e_s / 1e6
         d2h = int(len(ehits) * 56 + len(esyms) + 16 + (8 * B * blk.info.n_channels if snr_mode == "fast" else 0))
         nwin = len({(int(h["slot"]), int(h["channel"])) for h in hits})
         res = dict(value=value, ms_per_step=dev_ms / steps, e2e=e2e_val, e2e_ms_per_step=e2e_s / steps * 1e3,
                    stage_ms={k: round(v, 3) for k, v in stage_ms.items()}, launches=int(launches), clocks=clk.summary(),
+                   clocks_e2e=clk_e2e.summary(),
                    h2d=int(n_in * 8), d2h=d2h, hits=hits, n_in=n_in, hit_windows=nwin, info=blk.info)
         for bk in blks:
             bk.close()
@@ -258,7 +260,7 @@ def run_ours(args):
     alt = None
     if not args.no_alt:
         other = "fast" if args.snr_mode == "exact" else "exact"
-        alt = measure(other, max(2, args.steps // 2), 2)
+        alt = measure(other, max(2, args.steps // 2), 3)
     # everything that needs the other ranks is done: release them before rank 0 times the CPU baseline
     if world > 1:
         dist.barrier()
@@ -300,7 +302,7 @@ def run_ours(args):
                            "timing": "value: CUDA events on the ctx stream; e2e: wall clock between barriers; max over ranks",
                            "sharding": "time shards, no collective"},
                 "e2e": {"value": main["e2e"], "unit": UNIT, "h2d_bytes_per_step": main["h2d"], "d2h_bytes_per_step": main["d2h"],
-                        "ms_per_step": main["e2e_ms_per_step"],
+                        "ms_per_step": main["e2e_ms_per_step"], "clocks": main["clocks_e2e"],
                         "api": "btb200_submit/btb200_collect with pinned host buffers, %d contexts in flight on the shared compute stream" % args.e2e_contexts},
                 "gpu_launches": main["launches"],
                 "clocks": main["clocks"],
@@ -321,7 +323,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--slots", type=int, default=512, help="slots (625 us each) per step per GPU")

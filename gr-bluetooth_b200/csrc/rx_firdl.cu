@@ -14,7 +14,10 @@
 //    (FMUL2 / FFMA2(-1) / FADD2, each half rounding like the scalar instruction);
 //  * inputs live in a shared-memory RING of rows of 100 samples (+1 pad slot: lanes are 100 samples
 //    apart, i.e. 101 slots = conflict-free).  A tap chunk needs only KT new samples, fetched with
-//    cp.async together with the next chunk's taps while the current chunk is being computed.
+//    cp.async (LDGSTS: it splits re/im into the two planes) while the current chunk is being computed;
+//  * the next chunk's tap bank -- one contiguous run of (c, c, d, d) entries per channel -- is staged by
+//    the TMA engine: one `cp.async.bulk` per channel issued by a single thread, completion through an
+//    mbarrier (expect_tx / try_wait.parity), double-buffered.
 // Summation order per accumulator is untouched, so results are bit-identical to noise_fir_point().
 #include "rx_kernels.cuh"
 #include "rx_packed.cuh"
@@ -49,12 +52,36 @@ __device__ __forceinline__ void cp_async4z(void *smem_dst, const void *gsrc, boo
   const int n = valid ? 4 : 0;                       // src-size 0: the slot is zero-filled
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(d), "l"(gsrc), "r"(n));
 }
-__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc, bool valid)
+// ---- TMA bulk copy + mbarrier (tap banks) ----
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count)
 {
-  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-  const int n = valid ? 16 : 0;
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gsrc), "r"(n));
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity)
+{
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// global -> shared, `bytes` a multiple of 16, both addresses 16-byte aligned; completes on `bar`
+__device__ __forceinline__ void tma_bulk_g2s(void *smem_dst, const void *gsrc, unsigned bytes, uint64_t *bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+               ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// generic-proxy accesses to shared memory (the LDS of the chunk just finished) before async-proxy writes
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 __device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 __device__ __forceinline__ void cp_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::); }
 
@@ -62,8 +89,8 @@ __device__ __forceinline__ void cp_wait_all() { asm volatile("cp.async.wait_grou
 __device__ __forceinline__ int dl_slot(int n) { return ((n / DL_ROW) % DL_M) * DL_PITCH + (n % DL_ROW); }
 
 template <int NC>
-__device__ __forceinline__ void dl_body(const DlJob &J, float *ra, float *rb, float4 *tbuf, const int *ch, long s0, int nj,
-                                        c32 *outp)
+__device__ __forceinline__ void dl_body(const DlJob &J, float *ra, float *rb, float4 *tbuf, uint64_t *tbar,
+                                        const int *ch, long s0, int nj, c32 *outp)
 {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int pairidx = 32 * w + lane;                     // outputs 2*pairidx, 2*pairidx + 1
@@ -82,14 +109,18 @@ __device__ __forceinline__ void dl_body(const DlJob &J, float *ra, float *rb, fl
       cp_async4z(ra + e, src, ok);
       cp_async4z(rb + e, src + 1, ok);
     }
-    float4 *tb = tbuf + (c & 1) * (DL_KT * DL_CG);
-    const int k0 = c * DL_KT;
-    for (int i = threadIdx.x; i < DL_KT * NC; i += DL_NT) {
-      const int k = i / NC, ci = i - k * NC;
-      const bool ok = k0 + k < J.N;
-      cp_async16(tb + k * NC + ci, J.taps4 + (size_t)ch[ci] * J.N + (ok ? k0 + k : 0), ok);
-    }
     cp_commit();
+    if (threadIdx.x == 0) {
+      // tap bank of chunk c, [channel][KT]: one TMA bulk copy per channel
+      float4 *tb = tbuf + (c & 1) * (DL_KT * DL_CG);
+      const int k0 = c * DL_KT;
+      const unsigned kt = (unsigned)((J.N - k0) < DL_KT ? (J.N - k0) : DL_KT);
+      fence_proxy_async();
+      mbar_expect_tx(&tbar[c & 1], (unsigned)NC * kt * (unsigned)sizeof(float4));
+#pragma unroll
+      for (int ci = 0; ci < NC; ci++)
+        tma_bulk_g2s(tb + ci * DL_KT, J.taps4 + (size_t)ch[ci] * J.N + k0, kt * (unsigned)sizeof(float4), &tbar[c & 1]);
+    }
   };
 
   const int nchunks = (J.N + DL_KT - 1) / DL_KT;
@@ -110,6 +141,7 @@ __device__ __forceinline__ void dl_body(const DlJob &J, float *ra, float *rb, fl
       fetch(f, f + DL_KT, c + 1);
     }
     const float4 *tb = tbuf + (c & 1) * (DL_KT * DL_CG);
+    mbar_wait(&tbar[c & 1], (unsigned)(c >> 1) & 1u);      // the taps of this chunk have landed
     const int nseg = kt / DL_D, rem = kt - nseg * DL_D;
     for (int u = 0; u < nseg; u++) {
       // new samples: output B at taps k0 + 50u + kp -> local sample 100*pairidx + 50 + k0 + 50u + kp
@@ -119,7 +151,7 @@ __device__ __forceinline__ void dl_body(const DlJob &J, float *ra, float *rb, fl
       row = row >= DL_M ? row - DL_M : row;
       const int e = row * DL_PITCH + (q % DL_ROW);
       const float *pa = ra + e, *pb = rb + e;
-      const float4 *tp = tb + (DL_D * u) * NC;
+      const float4 *tp = tb + DL_D * u;
 #pragma unroll
       for (int kp = 0; kp < DL_D; kp++) {
         const float an = pa[kp], bn = pb[kp];
@@ -127,7 +159,7 @@ __device__ __forceinline__ void dl_body(const DlJob &J, float *ra, float *rb, fl
         const u64 Vn = pk_neg(Vb);                                     // (-b) * c = -(b * c) exactly
 #pragma unroll
         for (int ci = 0; ci < NC; ci++) {
-          const ulonglong2 T = *reinterpret_cast<const ulonglong2 *>(tp + kp * NC + ci);   // (c, c), (d, d)
+          const ulonglong2 T = *reinterpret_cast<const ulonglong2 *>(tp + ci * DL_KT + kp);   // (c, c), (d, d)
           const u64 pr = pk_xsubp(pk_mul(Va, T.x), pk_mul(Vb, T.y));   // a*c - b*d
           const u64 pi = pk_xsubp(pk_mul(Va, T.y), pk_mul(Vn, T.x));   // a*d - (-b)*c: the roundings of a*d + b*c
           are[ci] = pk_add(are[ci], pr);
@@ -143,7 +175,7 @@ __device__ __forceinline__ void dl_body(const DlJob &J, float *ra, float *rb, fl
       const u64 Va = pk_pack(ra[eA], ra[eB]), Vb = pk_pack(rb[eA], rb[eB]), Vn = pk_neg(Vb);
 #pragma unroll
       for (int ci = 0; ci < NC; ci++) {
-        const ulonglong2 T = *reinterpret_cast<const ulonglong2 *>(tb + (DL_D * nseg + kp) * NC + ci);
+        const ulonglong2 T = *reinterpret_cast<const ulonglong2 *>(tb + ci * DL_KT + DL_D * nseg + kp);
         const u64 pr = pk_xsubp(pk_mul(Va, T.x), pk_mul(Vb, T.y));
         const u64 pi = pk_xsubp(pk_mul(Va, T.y), pk_mul(Vn, T.x));
         are[ci] = pk_add(are[ci], pr);
@@ -165,6 +197,12 @@ __global__ void __launch_bounds__(DL_NT, 1) k_fir_dl(DlJob J)
 {
   extern __shared__ __align__(16) unsigned char dl_smem[];
   __shared__ int s_ch[DL_CG];
+  __shared__ __align__(8) uint64_t s_tbar[2];          // mbarriers of the two tap buffers
+  if (threadIdx.x == 0) {
+    mbar_init(&s_tbar[0], 1);
+    mbar_init(&s_tbar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
   const int q = blockIdx.x / J.tiles, jt = blockIdx.x - q * J.tiles;
   const int j0 = jt * DL_TJ;
   const int nj = (J.n_noise - j0) < DL_TJ ? (J.n_noise - j0) : DL_TJ;
@@ -175,16 +213,16 @@ __global__ void __launch_bounds__(DL_NT, 1) k_fir_dl(DlJob J)
 #pragma unroll
   for (int i = 0; i < DL_CG; i++) nc += (g[1 + i] >= 0) ? 1 : 0;
   __syncthreads();
-  float4 *tbuf = reinterpret_cast<float4 *>(dl_smem);                      // [2][KT][<=CG]
+  float4 *tbuf = reinterpret_cast<float4 *>(dl_smem);                      // [2][<=CG][KT]
   float *ra = reinterpret_cast<float *>(tbuf + 2 * DL_KT * DL_CG);         // [M][PITCH] re plane
   float *rb = ra + DL_M * DL_PITCH;                                        // [M][PITCH] im plane
   const long s0 = (long)b * J.S + J.fns + (long)j0 * DL_D;
   c32 *outp = J.out + ((long)q * J.n_noise + j0) * DL_CG;
   switch (nc) {
-    case 1: dl_body<1>(J, ra, rb, tbuf, s_ch, s0, nj, outp); break;
-    case 2: dl_body<2>(J, ra, rb, tbuf, s_ch, s0, nj, outp); break;
-    case 3: dl_body<3>(J, ra, rb, tbuf, s_ch, s0, nj, outp); break;
-    case 4: dl_body<4>(J, ra, rb, tbuf, s_ch, s0, nj, outp); break;
+    case 1: dl_body<1>(J, ra, rb, tbuf, s_tbar, s_ch, s0, nj, outp); break;
+    case 2: dl_body<2>(J, ra, rb, tbuf, s_tbar, s_ch, s0, nj, outp); break;
+    case 3: dl_body<3>(J, ra, rb, tbuf, s_tbar, s_ch, s0, nj, outp); break;
+    case 4: dl_body<4>(J, ra, rb, tbuf, s_tbar, s_ch, s0, nj, outp); break;
     default: break;
   }
 }

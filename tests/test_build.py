@@ -62,7 +62,7 @@ def test_packed_fir_keeps_separate_roundings(sass):
 
 def test_delay_line_fir_keeps_separate_roundings(sass):
     """Same rule for the delay-line noise FIR (rx_firdl.cu): FFMA2 only as 'x - p' with the -1
-    immediate, 4 FMUL2 : 2 FFMA2 : 2 FADD2, inputs and taps fetched with cp.async (LDGSTS)."""
+    immediate, 4 FMUL2 : 2 FFMA2 : 2 FADD2; inputs fetched with cp.async (LDGSTS), tap banks with TMA bulk copies."""
     lines = body(sass, "k_fir_dl")
     ffma2 = [l for l in lines if " FFMA2 " in l]
     assert ffma2 and all(", -1, " in l for l in ffma2)
@@ -70,7 +70,9 @@ def test_delay_line_fir_keeps_separate_roundings(sass):
     nadd = sum(" FADD2 " in l for l in lines)
     assert nmul == 2 * len(ffma2) and nadd == len(ffma2)
     assert not any(re.search(r"\bFFMA\b", l) for l in lines)
-    assert any("LDGSTS" in l for l in lines)
+    assert any("LDGSTS" in l for l in lines)                      # cp.async: input ring
+    assert any("UBLKCP" in l for l in lines)                      # cp.async.bulk (TMA): tap banks
+    assert any("SYNCS.ARRIVE.TRANS64" in l for l in lines)        # mbarrier expect_tx
 
 
 def test_no_fmad_flag_in_makefile():

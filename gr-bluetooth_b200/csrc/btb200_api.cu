@@ -302,6 +302,13 @@ int setup(btb200_ctx *ctx)
         tg[((size_t)(c / 16) * P.Nc + k) * 16 + (c % 16)] = c32{t.re, t.im};
       }
     if ((rc = upload(ctx, &ctx->T.chan_tg, tg))) return rc;
+    {
+      std::vector<float> t4(tg.size() * 4);
+      for (size_t i = 0; i < tg.size(); i++) { t4[4 * i] = t4[4 * i + 1] = tg[i].re; t4[4 * i + 2] = t4[4 * i + 3] = tg[i].im; }
+      const float *d4 = nullptr;
+      if ((rc = upload(ctx, &d4, t4))) return rc;
+      ctx->T.chan_tg4 = d4;
+    }
     tg.assign((size_t)ng * P.Nn * 16, c32{0.0f, 0.0f});
     for (int c = 0; c < P.nch; c++)
       for (int k = 0; k < P.Nn; k++) {

@@ -5,6 +5,7 @@
 #include <cstdlib>
 
 #include "rx_packed.cuh"
+#include "rx_tma.cuh"
 
 namespace btb200 {
 
@@ -189,6 +190,7 @@ __global__ void k_gather(Geom G, DevBatch W)
 struct FirJob {
   const c32 *x; long n_x;
   const c32 *taps;      // mode 0/1: [ngroups][N][16] group-interleaved; mode 2: [nch][N] per channel
+  const float4 *taps4;  // packed kernel, modes 0/1, optional: [ngroups][N][16] (c, c, d, d) -- staged by TMA bulk copy
   c32 *out;             // mode 0/1: rows of nch, channel fastest; mode 2: [group][n_noise][CG]
   int N, D, nch, KT;
   int mode;             // 0: channel grid (tile t = outputs t*TJ..), 1: noise, every slot x channel group,
@@ -314,6 +316,13 @@ __global__ void __launch_bounds__(W * 32, MINB) k_fir_packed(FirJob J)
   float4 *ts = reinterpret_cast<float4 *>(smem_raw);     // [KT][CG]  (c, c, d, d)
   float4 *xs = ts + (size_t)J.KT * CG;                   // [HS]      (re[e], re[e+DELTA], im[e], im[e+DELTA])
   __shared__ int s_ch[CG];
+  __shared__ __align__(8) uint64_t s_tbar;               // mbarrier of the TMA tap-bank copies
+  const bool tma_taps = (J.taps4 != nullptr) && (J.mode != 2);
+  unsigned tphase = 0;
+  if (tma_taps && threadIdx.x == 0) {
+    mbar_init(&s_tbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
   long s0;
   int nj, ostride;
   c32 *outp;
@@ -360,6 +369,14 @@ __global__ void __launch_bounds__(W * 32, MINB) k_fir_packed(FirJob J)
         const c32 t = (ch >= 0) ? J.taps[(size_t)ch * J.N + k0 + k] : c32{0.0f, 0.0f};
         ts[k * CG + ci] = make_float4(t.re, t.re, t.im, t.im);
       }
+    } else if (tma_taps) {
+      // the chunk's tap bank is one contiguous run of (c, c, d, d) entries: a single TMA bulk copy, issued before
+      // the input span is staged by the threads and waited for after it
+      if (threadIdx.x == 0) {
+        fence_proxy_async();
+        mbar_expect_tx(&s_tbar, (unsigned)(kt * CG) * (unsigned)sizeof(float4));
+        tma_bulk_g2s(ts, J.taps4 + ((size_t)by * J.N + k0) * CG, (unsigned)(kt * CG) * (unsigned)sizeof(float4), &s_tbar);
+      }
     } else {
       const c32 *tg = J.taps + ((size_t)by * J.N + k0) * CG;
       for (int i = threadIdx.x; i < kt * CG; i += W * 32) { const c32 t = tg[i]; ts[i] = make_float4(t.re, t.re, t.im, t.im); }
@@ -372,6 +389,7 @@ __global__ void __launch_bounds__(W * 32, MINB) k_fir_packed(FirJob J)
       const c32 v1 = (n1 < J.n_x) ? J.x[n1] : c32{0.0f, 0.0f};
       xs[DT > 0 ? i + i / (DT > 0 ? DT : 1) : i] = make_float4(v0.re, v1.re, v0.im, v1.im);
     }
+    if (tma_taps) { mbar_wait(&s_tbar, tphase); tphase ^= 1u; }
     __syncthreads();
     const float4 *tp = ts + cg;
     if (DT > 0) {
@@ -938,6 +956,7 @@ void launch_chan_fir_range(const Geom &G, const DevTables &T, const DevBatch &W,
   constexpr int R = CHAN_R, Wp = CHAN_W, TJ = CHAN_TJ;
   FirJob J{};
   J.x = W.x + g0 * G.D; J.n_x = (long)(W.B - 1) * G.S + G.H - g0 * G.D; J.taps = T.chan_tg; J.out = W.Y + g0 * G.nch;
+  J.taps4 = reinterpret_cast<const float4 *>(T.chan_tg4);
   J.N = G.Nc; J.D = G.D; J.nch = G.nch;
   J.mode = 0; J.Gtot = g1 - g0; J.fcs = G.fcs;
   const unsigned ntile = cdiv(g1 - g0, TJ), ngrp = (unsigned)((G.nch + 15) / 16);

@@ -10,6 +10,7 @@ struct DevTables {
   const c32 *noise_rtaps;    // [nch][Nn]
   const c32 *chan_tg;        // [ngroups][Nc][16]  channel-group-interleaved taps for the tiled FIR
   const c32 *noise_tg;       // [ngroups][Nn][16]
+  const void *chan_tg4;      // [ngroups][Nc][16] float4 (c, c, d, d): the channel tap banks as the TMA copies them
   const void *noise_taps4;   // [nch][Nn] float4 (c, c, d, d) for the delay-line noise FIR (D = 50), else null
   const float *mmse;         // [129*8]
   const float *atan_tab;     // [257]

@@ -58,6 +58,7 @@ def test_packed_fir_keeps_separate_roundings(sass):
     assert nmul == 2 * len(ffma2) and nadd == len(ffma2)
     assert not any(re.search(r"\bFFMA\b", l) for l in lines)
     assert any("LDS.128" in l for l in lines)
+    assert any("UBLKCP" in l for l in lines)          # tap banks arrive by TMA bulk copy (cp.async.bulk + mbarrier)
 
 
 def test_delay_line_fir_keeps_separate_roundings(sass):

@@ -16,7 +16,8 @@ tot = sum(sum(v) for v in d.values())
 md = ["# Round %s profiles (B200, sm_100a)\n" % rnd[1:], "## Launch list\n",
       "Command: `ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file %s_launches.csv python bench.py --steps 2 --warmup 1 --no-alt --no-cpu`" % rnd,
       "(512 slots = 32 M samples per step, exact snr mode, stateless + lazy squelch; cold-cache, serialised: compare SHARES).",
-      "Raw list: `profiles/%s_launches.csv`.\n" % rnd,
+      "Raw list: `profiles/%s_launches.csv`.  The channel FIR (`k_fir_packed<16, ...>`) appears once per batch on the device-"
+      "resident path and in 4 parts (following the 4 parts of the input copy) on the host path, hence its launch count.\n" % rnd,
       "| kernel | launches | mean ms | share of GPU time |", "|---|---|---|---|"]
 for k, v in sorted(d.items(), key=lambda kv: -sum(kv[1])):
     md.append("| `%s` | %d | %.3f | %.1f %% |" % (k[:90], len(v), sum(v) / len(v) / 1e6, 100 * sum(v) / tot))
@@ -28,7 +29,8 @@ keys = ["gpu__time_duration.sum", "sm__throughput.avg.pct_of_peak_sustained_elap
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__cycles_elapsed.avg"]
 traffic = {}
 md += ["\n## `ncu --set full` summaries\n",
-       "Commands: `ncu --set full --clock-control none --import-source on -k regex:<kernels> ... python bench.py --steps 1 --no-alt --no-cpu [--snr-mode fast]` (512 slots per launch).\n"]
+       "Commands: `ncu --set full --clock-control none --import-source on -k regex:\"k_fir_packed|k_fir_dl\" -s 4 -c 2 python tools/trace_collect.py exact` "
+       "(whole-batch launches, 512 slots) and `... -k regex:\"k_demod|k_mm_|k_search|k_energy|k_gather\" -s 7 -c 7 python bench.py --steps 1 --warmup 1 --no-alt --no-cpu`.\n"]
 for rep in sys.argv[2:]:
     out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rr = list(csv.reader(io.StringIO(out)))

@@ -126,15 +126,19 @@ class PinnedBuffer:
             raise Btb200Error(rc)
         buf = (C.c_float * (2 * int(n_samples))).from_address(self.ptr.value)
         self.array = np.frombuffer(buf, dtype=np.complex64)
+        self._free = lib().btb200_host_free          # kept: module globals may be gone at interpreter shutdown
 
     def close(self):
-        if self.ptr:
+        if getattr(self, "ptr", None):
             self.array = None
-            lib().btb200_host_free(self.ptr)
+            self._free(self.ptr)
             self.ptr = None
 
     def __del__(self):
-        self.close()
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class multi_block:

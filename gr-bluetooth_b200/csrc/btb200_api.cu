@@ -582,8 +582,11 @@ int btb200_set_mm_state(btb200_ctx *ctx, const float mm[3])
 int btb200_reset(btb200_ctx *ctx)
 {
   if (!ctx) return BTB200_ERR_ARG;
+  // a batch still in flight (submitted, perhaps begun) is abandoned: let its work drain first
+  if (ctx->pending) { sync_here(ctx); if (ctx->stream2) cudaStreamSynchronize(ctx->stream2); }
   reset_stream_state(ctx);
   ctx->pending = false;
+  ctx->cb.begun = false;
   return BTB200_OK;
 }
 

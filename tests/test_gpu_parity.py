@@ -575,3 +575,47 @@ def test_cpp_blocks_wireshark_frames(mode, tmp_path):
     assert out.stdout.decode() == want_txt
     want = want_file.read_bytes()
     assert got_file.read_bytes() == want and len(want) > 14
+
+
+@pytest.mark.gpu
+def test_pipelined_submit_collect_equals_blocking_process():
+    """btb200_submit / btb200_collect_begin / btb200_collect over three contexts sharing the device's compute
+    stream (bench.py's end-to-end loop) return, batch for batch, what the blocking btb200_process returns;
+    collect_begin is refused when nothing is pending or when it was already called."""
+    fs, fc, nslots = 100e6, 2441e6, 13
+    iq, _ = synth_small(fs, fc, nslots, 5, [0x9E8B33, 0x24D952])
+    first, B = 7, 2
+    blks = [g.multi_sniffer(fs, fc, 10.0, mm_mode=g.MM_STATELESS, max_slots=B) for _ in range(3)]
+    S, H = blks[0].samples_per_slot, blks[0].history()
+    batches = []
+    for k in range(3):
+        f0 = first + k * B
+        w0 = f0 * S - (H - 1)
+        batches.append((f0, np.ascontiguousarray(iq[w0:w0 + (B - 1) * S + H])))
+    want = [blks[0].process(x, f0, B, want_symbols=True) for f0, x in batches]
+    pins = []
+    for f0, x in batches:
+        p = g.PinnedBuffer(len(x)); p.array[:] = x; pins.append(p)
+    with pytest.raises(g.Btb200Error):
+        blks[0].collect_begin()                       # nothing pending
+    n = len(batches)
+    for i in range(2):
+        blks[i].submit(pins[i].ptr.value, False, len(batches[i][1]), batches[i][0], B)
+    got = []
+    for j in range(n):
+        blks[j].collect_begin()
+        with pytest.raises(g.Btb200Error):
+            blks[j].collect_begin()                   # already begun
+        i = j + 2
+        if i < n:
+            blks[i].submit(pins[i].ptr.value, False, len(batches[i][1]), batches[i][0], B)
+        got.append(blks[j].collect(want_symbols=True))
+    assert sum(len(h) for h, _, _ in want) > 0
+    for (wh, ws, wo), (gh, gs, go) in zip(want, got):
+        assert gpu_hit_tuples(gh) == gpu_hit_tuples(wh) and wo == go == 0
+        assert np.array_equal(gs, ws)
+        assert np.array_equal(gh["snr"], wh["snr"]) and np.array_equal(gh["n_symbols"], wh["n_symbols"])
+    for p in pins:
+        p.close()
+    for b in blks:
+        b.close()

@@ -7,6 +7,7 @@
 #include "gr_bluetooth/multi_sniffer.h"
 #include "gr_bluetooth/multi_LAP.h"
 #include "gr_bluetooth/multi_hopper.h"
+#include "gr_bluetooth/multi_UAP.h"
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -28,7 +29,7 @@ int main(int argc, char **argv)
   double freq = 2476e6, rate = 2e6, snr = 10;
   std::string in;
   long nsamples = -1;
-  bool shorts = false, lap_mode = false, hop_mode = false, tun = false;
+  bool shorts = false, hop_mode = false, tun = false, have_lap = false, sniff = false;
   int target_lap = 0;
   for (int i = 1; i < argc; i++) {
     std::string a = argv[i];
@@ -39,14 +40,14 @@ int main(int argc, char **argv)
     else if (a == "-s" || a == "--snr") snr = std::atof(next());
     else if (a == "-N" || a == "--nsamples") nsamples = (long)parse_eng(next());
     else if (a == "-2" || a == "--input-shorts") shorts = true;
-    else if (a == "-S" || a == "--sniff-all") lap_mode = false;
-    else if (a == "-L" || a == "--lap-printer") lap_mode = true;
-    else if (a == "-l" || a == "--lap") { target_lap = (int)std::strtol(next(), nullptr, 16); hop_mode = true; }      // apps/btrx:-l LAP
+    else if (a == "-S" || a == "--sniff-all") sniff = true;
+    else if (a == "-L" || a == "--lap-printer") sniff = false;
+    else if (a == "-l" || a == "--lap") { target_lap = (int)std::strtol(next(), nullptr, 16); have_lap = true; }     // apps/btrx:45
     else if (a == "-p" || a == "--hop") hop_mode = true;
     else if (a == "-w" || a == "--wireshark") tun = true;           // apps/btrx:57-58; BTB200_TUN_FILE redirects the frames to a file
     else { std::fprintf(stderr, "unknown option %s\n", a.c_str()); return 2; }
   }
-  if (in.empty()) { std::fprintf(stderr, "usage: btrx_b200 -f FREQ -r RATE -i FILE [-S|-L] [-s SNR] [-N n] [-2]\n"); return 2; }
+  if (in.empty()) { std::fprintf(stderr, "usage: btrx_b200 -f FREQ -r RATE -i FILE [-S | -L | -l LAP [-p]] [-w] [-s SNR] [-N n] [-2]\n"); return 2; }
   FILE *f = std::fopen(in.c_str(), "rb");
   if (!f) { std::perror(in.c_str()); return 2; }
   std::fseek(f, 0, SEEK_END);
@@ -56,9 +57,11 @@ int main(int argc, char **argv)
 
   boost::shared_ptr<gr::bluetooth::multi_block> blk;
   try {
-    if (hop_mode) blk = gr::bluetooth::multi_hopper::make(rate, freq, snr, target_lap, false, tun);
-    else if (lap_mode) blk = gr::bluetooth::multi_LAP::make(rate, freq, snr);
-    else blk = gr::bluetooth::multi_sniffer::make(rate, freq, snr, tun);
+    // mode selection of apps/btrx:140-159: -S sniffer; no LAP: LAP printer; LAP + -p: hopper; LAP alone: UAP discovery
+    if (sniff) blk = gr::bluetooth::multi_sniffer::make(rate, freq, snr, tun);
+    else if (have_lap && hop_mode) blk = gr::bluetooth::multi_hopper::make(rate, freq, snr, target_lap, false, tun);
+    else if (have_lap) blk = gr::bluetooth::multi_UAP::make(rate, freq, snr, target_lap);
+    else blk = gr::bluetooth::multi_LAP::make(rate, freq, snr);      // print the LAP of every frame detected (also -L)
   } catch (const std::exception &e) {
     std::fprintf(stderr, "btrx_b200: %s\n", e.what());
     return 1;
@@ -83,6 +86,7 @@ int main(int argc, char **argv)
     if (k + n > ncalls) n = ncalls - k;
     inv[0] = &buf[(size_t)consumed];
     const int got = blk->work((int)((n - 1) * S + 1), inv, outv);
+    if (got < 0) break;                 // WORK_DONE (multi_UAP: the UAP has been determined)
     consumed += got;
     k += got / S;
   }

@@ -910,6 +910,15 @@ void HopperHost::hop_packet(const SlotPlan &p, const char *symbols, int len)
   }
 }
 
+/* multi_UAP_impl.cc:100-113 */
+bool UapHost::packet(uint32_t clkn, int channel, const char *symbols, int len)
+{
+  ClassicPacket pkt(symbols, len, clkn, 2402000000.0 + 1e6 * channel);
+  if (!(pkt.lap() == d_lap && pkt.header_present())) return false;
+  if (d_piconet.uap_from_header(pkt)) d_done = true;           /* the reference exits the process here */
+  return true;
+}
+
 /* ---- Wireshark interface (lib/tun.cc) ---------------------------------------------------- */
 int write_frame(int fd, const uint8_t *data, unsigned data_len, uint64_t src_addr, uint64_t dst_addr,
                 unsigned short ether_type)

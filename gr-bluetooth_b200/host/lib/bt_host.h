@@ -208,4 +208,24 @@ class HopperHost {
   int d_tunfd = -1;
 };
 
+// The per-slot logic of the UAP block (multi_UAP_impl::work, lib/multi_UAP_impl.cc:67-124): packets of the target
+// piconet that carry a header feed the UAP/CLK1-6 discovery until the UAP is known.
+class UapHost {
+ public:
+  UapHost(uint32_t lap, int ch_lo, int ch_hi) : d_lap(lap), d_ch_lo(ch_lo), d_ch_hi(ch_hi), d_piconet(lap) {}
+  // the first access code found on `channel`; true when the reference leaves the channel loop (target packet with a header)
+  bool packet(uint32_t clkn, int channel, const char *symbols, int len);
+  bool done() const { return d_done; }
+  uint8_t uap() const { return d_piconet.uap(); }
+  uint32_t lap() const { return d_lap; }
+  int ch_lo() const { return d_ch_lo; }
+  int ch_hi() const { return d_ch_hi; }
+
+ private:
+  uint32_t d_lap;
+  int d_ch_lo, d_ch_hi;
+  Piconet d_piconet;
+  bool d_done = false;
+};
+
 }  // namespace btb200_host

@@ -9,11 +9,12 @@ extern "C" {
 #include <cstdio>
 #include <cstdlib>
 #include <fcntl.h>
+#include <string>
 #include <vector>
 
 int main(int argc, char **argv)
 {
-  if (argc < 5) { std::fprintf(stderr, "usage: hopper FS FC LAPHEX FILE.cfile [TUNFRAMES.out]\n"); return 2; }
+  if (argc < 5) { std::fprintf(stderr, "usage: hopper FS FC LAPHEX FILE.cfile [TUNFRAMES.out | uap]\n"); return 2; }
   const double fs = std::atof(argv[1]), fc = std::atof(argv[2]);
   const uint32_t lap = (uint32_t)std::strtoul(argv[3], nullptr, 16);
   btbo_plan *P = btbo_plan_create(fs, fc, 10.0, 3125);
@@ -31,11 +32,27 @@ int main(int argc, char **argv)
   const int chist = I.Nc + I.D * 8;
   std::printf("history set to %d samples: channel=%d, noise=%d\n", I.S + (chist > I.Nn ? chist : I.Nn), chist, I.Nn);
   btb200_host::HopperHost host(lap, false, I.ch_lo, I.ch_hi);
-  if (argc > 5) host.set_tun_fd(open(argv[5], O_WRONLY | O_CREAT | O_TRUNC, 0644));
+  if (argc > 5 && std::string(argv[5]) != "uap") host.set_tun_fd(open(argv[5], O_WRONLY | O_CREAT | O_TRUNC, 0644));
   std::vector<btbo_chan_result> res((size_t)I.nch);
   std::vector<uint8_t> sym((size_t)I.nch * I.H);
   std::vector<int32_t> chis((size_t)I.nch);
   const long ncalls = (total + I.S - 1) / I.S;
+  if (argc > 5 && std::string(argv[5]) == "uap") {
+    // multi_UAP: the same channel loop, packets of the target piconet feed the UAP discovery until it is known
+    btb200_host::UapHost uh(lap, I.ch_lo, I.ch_hi);
+    for (long k = 0; k < ncalls && !uh.done(); k++) {
+      for (int q = 0; q < I.nch; q++) chis[(size_t)q] = q;
+      btbo_window_list(P, st, &buf[(size_t)k * I.S * 2], chis.data(), I.nch, lap, res.data(), sym.data());
+      for (int q = 0; q < I.nch; q++) {
+        const btbo_chan_result &r = res[(size_t)q];
+        if (!r.processed) break;
+        if (r.ac_index < 0) continue;
+        if (uh.packet((uint32_t)k, I.ch_lo + q, reinterpret_cast<const char *>(&sym[(size_t)q * I.H + r.ac_index]), r.nsym - r.ac_index)) break;
+      }
+    }
+    std::printf("multi_UAP %s: UAP 0x%02x\n", uh.done() ? "done" : "not found", uh.uap());
+    return 0;
+  }
   for (long k = 0; k < ncalls; k++) {
     const auto pl = host.plan((uint32_t)k);
     if (pl.n_channels == 0) continue;

@@ -408,7 +408,7 @@ def test_process_channels_equals_oracle(name, stop_lap):
 
 
 def test_cpp_multi_hopper_block_digest(tmp_path):
-    """gr::bluetooth::multi_hopper::make(..., LAP, aliased, tun) through btrx_b200 -l 24d952 on headset1:
+    """gr::bluetooth::multi_hopper::make(..., LAP, aliased, tun) through btrx_b200 -l 24d952 -p on headset1:
     the channel loop with the reference's early `break` runs on the GPU (btb200_process_channels, chained
     state), UAP/CLK1-6, hop reversal and hop-along decode on the host -> the reference's stdout digest."""
     import hashlib
@@ -420,7 +420,7 @@ def test_cpp_multi_hopper_block_digest(tmp_path):
         pytest.skip("btrx_b200 or full capture not staged")
     path = tmp_path / "h1.cfile"
     iq.tofile(path)
-    out = subprocess.run([exe, "-f", "2476.5M", "-r", "8M", "-i", str(path), "-l", "24d952"], capture_output=True,
+    out = subprocess.run([exe, "-f", "2476.5M", "-r", "8M", "-i", str(path), "-l", "24d952", "-p"], capture_output=True,
                          timeout=600)
     assert out.returncode == 0, out.stderr.decode()[-1500:]
     assert b"Acquired CLK1-27 offset = 0x00a3c6f" in out.stdout
@@ -569,7 +569,7 @@ def test_cpp_blocks_wireshark_frames(mode, tmp_path):
     want_txt = REF.sniff(str(path), 8e6, 2476.5e6, hop_lap=hop, tun_out=str(want_file))["stdout"]
     e = dict(os.environ)
     e["BTB200_TUN_FILE"] = str(got_file)
-    args = [exe, "-f", "2476.5M", "-r", "8M", "-i", str(path), "-w"] + (["-l", "24d952"] if hop else ["-S"])
+    args = [exe, "-f", "2476.5M", "-r", "8M", "-i", str(path), "-w"] + (["-l", "24d952", "-p"] if hop else ["-S"])
     out = subprocess.run(args, capture_output=True, timeout=900, env=e)
     assert out.returncode == 0, out.stderr.decode()[-1500:]
     assert out.stdout.decode() == want_txt
@@ -619,3 +619,25 @@ def test_pipelined_submit_collect_equals_blocking_process():
         p.close()
     for b in blks:
         b.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,lap,uap", [("headset1", "24d952", 0xAF), ("keyboard1", "4831dd", 0x61)])
+def test_cpp_multi_uap_block(name, lap, uap, tmp_path):
+    """gr::bluetooth::multi_UAP::make(sample_rate, center_freq, squelch_threshold, LAP) through btrx_b200 -l LAP:
+    the channel loop runs on the GPU (btb200_process_channels), UAP/CLK1-6 discovery from the packet headers in
+    the native piconet code; it finds the UAP the reference's hopper and sniffer find for the same piconet
+    (doc/README.first: headset UAP 0xaf, keyboard 0x61) and then stops (WORK_DONE where the reference exits)."""
+    import subprocess
+    from conftest import ROOT
+    exe = os.path.join(ROOT, "gr-bluetooth_b200", "host", "btrx_b200")
+    iq = full_capture(name)
+    if not os.path.exists(exe) or iq is None:
+        pytest.skip("btrx_b200 or full capture not staged")
+    path = tmp_path / "x.cfile"
+    iq.tofile(path)
+    out = subprocess.run([exe, "-f", "2476.5M", "-r", "8M", "-i", str(path), "-l", lap], capture_output=True, timeout=600)
+    assert out.returncode == 0, out.stderr.decode()[-1500:]
+    text = out.stdout.decode()
+    assert ("UAP = 0x%x found after" % uap) in text
+    assert text.rstrip().splitlines()[-1].startswith("Correct CRC! UAP = 0x%x" % uap)      # nothing after the UAP is known

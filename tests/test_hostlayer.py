@@ -143,3 +143,16 @@ def test_wireshark_frames_equal_reference_hopper(hopper_harness, tmp_path):
     want, got = want_file.read_bytes(), got_file.read_bytes()
     assert got == want and len(want) > 14
     assert want[:6] == bytes([0xFF, 0xFF, 0xAF, 0x24, 0xD9, 0x52])
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_SAMPLES), reason="needs the bundled captures")
+@pytest.mark.parametrize("name,lap,uap", [("headset1", "24d952", 0xAF), ("keyboard1", "4831dd", 0x61)])
+def test_multi_uap_logic_finds_documented_uap(hopper_harness, name, lap, uap):
+    """multi_UAP (UapHost over the oracle front end): the UAP the reference documents for the bundled captures
+    (doc/README.first:45-67) and that its hopper/sniffer derive; stops as soon as it is known."""
+    out = subprocess.run([hopper_harness, "8e6", "2476.5e6", lap, os.path.join(REF_SAMPLES, name + ".cfile"), "uap"],
+                         capture_output=True, timeout=300)
+    assert out.returncode == 0
+    text = out.stdout.decode()
+    assert ("UAP = 0x%x found after" % uap) in text
+    assert text.rstrip().splitlines()[-1] == "multi_UAP done: UAP 0x%02x" % uap

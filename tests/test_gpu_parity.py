@@ -640,4 +640,4 @@ def test_cpp_multi_uap_block(name, lap, uap, tmp_path):
     assert out.returncode == 0, out.stderr.decode()[-1500:]
     text = out.stdout.decode()
     assert ("UAP = 0x%x found after" % uap) in text
-    assert text.rstrip().splitlines()[-1].startswith("Correct CRC! UAP = 0x%x" % uap)      # nothing after the UAP is known
+    assert ("UAP = 0x%x found after" % uap) in text.rstrip().splitlines()[-1]      # nothing after the UAP is known

@@ -132,11 +132,11 @@ _CPU_PLAN = {}
 
 def cpu_plan(max_threads):
     """How the reference uses this box best: the direct-form 20001-tap FIRs are cache/memory bound, so more threads
-    than the memory system feeds do not help.  Probe all, half and a quarter of the host threads (one slot per
-    thread each) and keep the fastest; size the timed sample to ~15 s of wall time.  -> (threads, slots)"""
+    than the memory system feeds do not help.  Probe all, a half, a quarter and an eighth of the host threads (one slot
+    per thread each) and keep the fastest; size the timed sample to ~15 s of wall time.  -> (threads, slots)"""
     if "plan" not in _CPU_PLAN:
         best = None
-        for t in sorted({max_threads, max(max_threads // 2, 1), max(max_threads // 4, 1)}, reverse=True):
+        for t in sorted({max_threads, max(max_threads // 2, 1), max(max_threads // 4, 1), max(max_threads // 8, 1)}, reverse=True):
             r = cpu_baseline(t, t)
             wall = t * int(625 * FS / 1e6) / (r["value"] * 1e6)
             if best is None or r["value"] > best[0]:

@@ -134,3 +134,20 @@ def test_mmse_table_check_values():
     assert np.array_equal(t[0], np.eye(8, dtype=np.float32)[4]) and np.array_equal(t[128], np.eye(8, dtype=np.float32)[3])
     assert np.array_equal(t[64][:4], np.array([-6.77751e-03, 3.94578e-02, -1.42658e-01, 6.09836e-01], np.float32))
     assert np.array_equal(t[64], t[64][::-1])
+
+
+@pytest.mark.parametrize("name", list(FILES))
+def test_lazy_tail_assumptions_hold_in_reference_streams(name):
+    """The product's lazy tail rests on two facts about the clock-recovery loop, proven
+    from the loop constants at create(): the input advance per symbol is at most 5, so (i) 704 symbols never need
+    more than 704*5+16 demod outputs and (ii) a window yields at least (n_dem-8)/5 >= 1400 symbols, which keeps
+    both search limits at 625.  Cross-check on the reference's own streams: the symbol counts of every window of
+    the committed excerpts lie far above the bound and close to n_dem/2."""
+    ex = load_excerpt(name, "stateless")
+    P = O.Plan(ex["fs"], ex["fc"])
+    n_dem = P.n_ddc - 1                      # demod outputs per window (multi_block.cc:158-168)
+    nsym = ex["nsym"][ex["nsym"] > 0]
+    assert len(nsym) > 0
+    assert nsym.min() >= (n_dem - 8) // 5 >= 1400
+    assert abs(float(nsym.mean()) - n_dem / 2) < 32
+    assert 704 * 5 + 16 < n_dem

@@ -20,6 +20,7 @@ SEARCH_BR, SEARCH_LE = 1, 2
 SQUELCH_DEFAULT, SQUELCH_EAGER, SQUELCH_LAZY = 0, 1, 2
 SNR_EXACT, SNR_FAST_GUARDED = 0, 1
 TAIL_LAZY, TAIL_FULL = 0, 1
+DDC_EXACT, DDC_POLYPHASE = 0, 1
 
 STAGE = dict(noise_fast=10, energy=1, noise=2, snr=3, pass_=4, nsym=5, bits=6, ddc=7, demod=8, soft=9,
              chan_taps=20, noise_taps=21, mmse_table=22, atan_table=23, ac_lut=24)
@@ -38,7 +39,7 @@ class Config(C.Structure):
                 ("mm_mode", C.c_int32), ("search", C.c_int32), ("device", C.c_int32),
                 ("max_slots_per_call", C.c_uint32), ("keep_stages", C.c_uint32),
                 ("squelch_mode", C.c_uint32), ("snr_mode", C.c_uint32), ("tail_mode", C.c_uint32),
-                ("reserved", C.c_uint32 * 2)]
+                ("ddc_mode", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 class Info(C.Structure):
@@ -68,7 +69,7 @@ class Hits(C.Structure):
 
 
 EXPORTS = ["btb200_process_channels", "btb200_create", "btb200_destroy", "btb200_get_info", "btb200_process", "btb200_process_device",
-           "btb200_submit", "btb200_collect_begin", "btb200_collect", "btb200_host_alloc", "btb200_host_free",
+           "btb200_submit", "btb200_submit_i16", "btb200_process_i16", "btb200_collect_begin", "btb200_collect", "btb200_host_alloc", "btb200_host_free",
            "btb200_get_mm_state", "btb200_set_mm_state", "btb200_reset", "btb200_get_stage",
            "btb200_last_timing", "btb200_launch_count", "btb200_strerror", "btb200_last_error",
            "btb200_version"]
@@ -91,6 +92,8 @@ def lib():
         L.btb200_process.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint64, C.c_uint32, C.POINTER(Hits)]
         L.btb200_process_device.argtypes = L.btb200_process.argtypes
         L.btb200_submit.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t, C.c_uint64, C.c_uint32]
+        L.btb200_submit_i16.argtypes = L.btb200_submit.argtypes
+        L.btb200_process_i16.argtypes = L.btb200_process.argtypes
         L.btb200_collect_begin.argtypes = [C.c_void_p]
         L.btb200_collect.argtypes = [C.c_void_p, C.POINTER(Hits)]
         L.btb200_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
@@ -117,15 +120,20 @@ def lib():
 
 
 class PinnedBuffer:
-    """Page-locked host memory (cudaMallocHost) viewed as a complex64 array."""
+    """Page-locked host memory (cudaMallocHost) viewed as a complex64 array, or (i16=True) as an int16 array of
+    interleaved (re, im) pairs."""
 
-    def __init__(self, n_samples):
+    def __init__(self, n_samples, i16=False):
         self.ptr = C.c_void_p()
-        rc = lib().btb200_host_alloc(C.byref(self.ptr), int(n_samples) * 8)
+        rc = lib().btb200_host_alloc(C.byref(self.ptr), int(n_samples) * (4 if i16 else 8))
         if rc:
             raise Btb200Error(rc)
-        buf = (C.c_float * (2 * int(n_samples))).from_address(self.ptr.value)
-        self.array = np.frombuffer(buf, dtype=np.complex64)
+        if i16:
+            buf = (C.c_int16 * (2 * int(n_samples))).from_address(self.ptr.value)
+            self.array = np.frombuffer(buf, dtype=np.int16)
+        else:
+            buf = (C.c_float * (2 * int(n_samples))).from_address(self.ptr.value)
+            self.array = np.frombuffer(buf, dtype=np.complex64)
         self._free = lib().btb200_host_free          # kept: module globals may be gone at interpreter shutdown
 
     def close(self):
@@ -149,12 +157,13 @@ class multi_block:
 
     def __init__(self, sample_rate, center_freq, squelch_threshold, *, mm_mode=MM_CHAINED,
                  search=SEARCH_BR | SEARCH_LE, device=0, max_slots=64, keep_stages=False,
-                 squelch=SQUELCH_DEFAULT, snr_mode=SNR_EXACT, tail=TAIL_LAZY):
+                 squelch=SQUELCH_DEFAULT, snr_mode=SNR_EXACT, tail=TAIL_LAZY, ddc=DDC_EXACT):
         self._L = lib()
         cfg = Config(abi_version=ABI_VERSION, sample_rate=sample_rate, center_freq=center_freq,
                      squelch_threshold=squelch_threshold, extra_history_symbols=self.EXTRA_SYMBOLS,
                      mm_mode=mm_mode, search=search, device=device, max_slots_per_call=max_slots,
-                     keep_stages=int(keep_stages), squelch_mode=squelch, snr_mode=snr_mode, tail_mode=tail)
+                     keep_stages=int(keep_stages), squelch_mode=squelch, snr_mode=snr_mode, tail_mode=tail,
+                     ddc_mode=ddc)
         self._ctx = C.c_void_p()
         rc = self._L.btb200_create(C.byref(cfg), C.byref(self._ctx))
         if rc:
@@ -211,6 +220,16 @@ class multi_block:
         h = self._hits_struct(want_symbols)
         self._check(self._L.btb200_process(self._ctx, x.ctypes.data, len(x), first_slot, n_slots, C.byref(h)))
         return self._take(h, want_symbols)
+
+    def process_i16(self, iq16, first_slot, n_slots, want_symbols=False):
+        """Same with int16 input: interleaved (re, im) pairs, 2 * n_samples values."""
+        x = np.ascontiguousarray(iq16, dtype=np.int16)
+        h = self._hits_struct(want_symbols)
+        self._check(self._L.btb200_process_i16(self._ctx, x.ctypes.data, len(x) // 2, first_slot, n_slots, C.byref(h)))
+        return self._take(h, want_symbols)
+
+    def submit_i16(self, ptr, on_device, n_samples, first_slot, n_slots):
+        self._check(self._L.btb200_submit_i16(self._ctx, C.c_void_p(ptr), int(on_device), n_samples, first_slot, n_slots))
 
     def process_device(self, dptr, n_samples, first_slot, n_slots, want_symbols=False):
         h = self._hits_struct(want_symbols)

@@ -5,6 +5,7 @@
 #include "plan.hpp"
 #include "rx_kernels.cuh"
 #include "rx_fast.cuh"
+#include "rx_pfb.cuh"
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -94,6 +95,12 @@ struct btb200_ctx {
   double *h_esum = nullptr;
   double phi = 0;                    // common fractional MHz offset of the noise DDCs
   std::vector<double> fast_off;      // [B][nch] fast off-channel energy of the last batch
+  // polyphase (throughput) mode: rx_pfb.cu
+  bool poly = false;
+  PfbDesign pfd;
+  PfbPlan PF{};
+  double *d_eon_all = nullptr, *h_eon_all = nullptr;   // [B][nch] on-channel window energies from the channelizer
+  int16_t *d_x16 = nullptr;          // staging of int16 input (btb200_submit_i16)
   // pinned host
   double *h_energy = nullptr, *h_noise = nullptr;
   int *h_pass = nullptr;
@@ -225,6 +232,39 @@ int setup_fast(btb200_ctx *ctx)
   return 0;
 }
 
+// Tables and buffers of the polyphase channelizer (rx_pfb.cu)
+int setup_pfb(btb200_ctx *ctx)
+{
+  const Plan &P = ctx->plan;
+  PfbDesign &F = ctx->pfd;
+  if (F.design(P, PFB_T, PFB_TT, PFB_NCOL) != 0) {
+    ctx->last_error = "polyphase mode needs an even integer number of samples per MHz and <= 8 taps per branch";
+    return BTB200_ERR_ARG;
+  }
+  PfbPlan &K = ctx->PF;
+  K.M = F.M; K.D = F.D; K.Q = F.Q; K.N1 = F.N1; K.N2 = F.N2;
+  K.gps = P.grid_per_slot; K.n_ddc = P.n_ddc; K.nfull = F.nfull; K.rem = F.rem;
+  K.fcs = P.fcs; K.nch = P.nch; K.tps = F.tps; K.CPC = F.CPC; K.ncol = F.ncol; K.span = F.span;
+  K.gain = P.demod_gain;
+  K.phi_step = (float)(-2.0 * F.phi / F.M);
+  int rc;
+  if ((rc = upload(ctx, &K.hq, F.hq))) return rc;
+  if ((rc = upload(ctx, &K.n2_of_rho, F.n2_of_rho))) return rc;
+  if ((rc = upload_raw<c32>(ctx, &K.WB, F.WB.data(), F.WB.size()))) return rc;
+  if ((rc = upload(ctx, &K.col_chan, F.col_chan))) return rc;
+  if ((rc = upload(ctx, &K.chan_col, F.chan_col))) return rc;
+  if ((rc = upload_raw<c32>(ctx, &K.kappa, F.kappa.data(), F.kappa.size()))) return rc;
+  K.atan_tab = ctx->T.atan_tab;
+  const size_t B = ctx->max_slots;
+  const size_t Gtot = (B - 1) * (size_t)P.grid_per_slot + P.n_ddc;
+  if ((rc = dev_alloc(ctx, &K.dem, Gtot * P.nch))) return rc;
+  if ((rc = dev_alloc(ctx, &K.E, (size_t)pfb_tiles(K, (int)B) * K.ncol * 2))) return rc;
+  if ((rc = dev_alloc(ctx, &ctx->d_eon_all, B * P.nch))) return rc;
+  CK(cudaMallocHost(&ctx->h_eon_all, B * P.nch * sizeof(double)));
+  if (pfb_setup(K) != 0) { ctx->last_error = "polyphase channelizer: configuration outside the kernel's limits"; return BTB200_ERR_ARG; }
+  return 0;
+}
+
 // One compute stream per device, shared by every context: the kernels of this path are sized to fill the
 // GPU (one block per SM), so batches of different contexts gain nothing from running concurrently -- measured:
 // two contexts on private streams 29.6 ms per batch pair step against 24.5 ms serialised -- while issue order on
@@ -269,6 +309,13 @@ int setup(btb200_ctx *ctx)
   G.search = ctx->cfg.search;
   G.stateless = ctx->cfg.mm_mode == BTB200_MM_STATELESS;
   G.early = 0; G.ne_dem = P.n_dem; G.sym_target = P.n_dem;
+  G.dem_grid = 0; G.dem_rows = G.n_dem_pad;
+  ctx->poly = ctx->cfg.ddc_mode == BTB200_DDC_POLYPHASE;
+  if (ctx->poly && (!G.stateless || ctx->cfg.squelch_mode == BTB200_SQUELCH_EAGER)) {
+    ctx->last_error = "BTB200_DDC_POLYPHASE needs BTB200_MM_STATELESS and the lazy squelch";
+    return BTB200_ERR_ARG;
+  }
+  if (ctx->poly) { G.dem_grid = 1; G.dem_rows = P.grid_per_slot; }
 
   if (std::getenv("BTB200_PRIVATE_STREAM")) {
     CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
@@ -346,7 +393,7 @@ int setup(btb200_ctx *ctx)
   ctx->x_cap = (B - 1) * (size_t)P.S + P.H;
   if ((rc = dev_alloc(ctx, &ctx->d_x, ctx->x_cap))) return rc;
   DevBatch &W = ctx->W;
-  if ((rc = dev_alloc(ctx, &W.Y, ((B - 1) * P.grid_per_slot + P.n_ddc) * nch))) return rc;
+  if (!ctx->poly) { if ((rc = dev_alloc(ctx, &W.Y, ((B - 1) * P.grid_per_slot + P.n_ddc) * nch))) return rc; }
   if (!ctx->lazy) { if ((rc = dev_alloc(ctx, &W.Nz, B * P.n_noise * nch))) return rc; }
   else {
     ctx->group_cap = B * ((nch + 1) / 2);
@@ -401,7 +448,10 @@ int setup(btb200_ctx *ctx)
   if ((rc = dev_alloc(ctx, &W.pass, B * nch))) return rc;
   // demod floats only travel through HBM in chained mode (separate demod kernel) or for debug taps
   // demod floats: [b][c][i] rows in chained mode (separate kernels), transposed [b][i][c] in stateless mode
-  if ((rc = dev_alloc(ctx, &ctx->d_dem, B * nch * G.n_dem_pad))) return rc;
+  if (ctx->poly) {
+    if ((rc = setup_pfb(ctx))) return rc;
+    ctx->d_dem = ctx->PF.dem;
+  } else if ((rc = dev_alloc(ctx, &ctx->d_dem, B * nch * G.n_dem_pad))) return rc;
   W.dem = G.stateless ? nullptr : ctx->d_dem;
   if (ctx->cfg.keep_stages) { if ((rc = dev_alloc(ctx, &ctx->d_soft, B * nch * G.n_dem_pad))) return rc; }
   if ((rc = dev_alloc(ctx, &W.bits, B * nch * G.bw))) return rc;
@@ -435,9 +485,13 @@ int setup(btb200_ctx *ctx)
   ctx->h_ph_cap = bp * (size_t)P.n_ddc * nch;
   CK(cudaMallocHost(&ctx->h_ph, ctx->h_ph_cap * sizeof(c32)));
 
-  if (ctx->lazy && ctx->cfg.snr_mode == BTB200_SNR_FAST_GUARDED) {
+  if (ctx->lazy && (ctx->cfg.snr_mode == BTB200_SNR_FAST_GUARDED || ctx->poly)) {
     int rcf = setup_fast(ctx);
     if (rcf) return rcf;
+    if (ctx->poly && !ctx->fast_snr) {
+      ctx->last_error = "polyphase mode: the noise estimator does not fit this configuration";
+      return BTB200_ERR_ARG;
+    }
   }
   reset_stream_state(ctx);
   if (G.stateless) {
@@ -464,7 +518,7 @@ void teardown(btb200_ctx *ctx)
   for (void *p : {(void *)ctx->h_energy, (void *)ctx->h_noise, (void *)ctx->h_pass, (void *)ctx->h_counts,
                   (void *)ctx->h_hits, (void *)ctx->h_arena, (void *)ctx->h_ph, (void *)ctx->h_groups,
                   (void *)ctx->h_list, (void *)ctx->h_eon, (void *)ctx->h_eoff, (void *)ctx->h_esum,
-                  (void *)ctx->h_list2, (void *)ctx->h_nsym})
+                  (void *)ctx->h_list2, (void *)ctx->h_nsym, (void *)ctx->h_eon_all})
     if (p) cudaFreeHost(p);
   for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
   for (auto &e : ctx->evl) if (e) cudaEventDestroy(e);
@@ -489,8 +543,7 @@ const char *btb200_strerror(int err)
     case BTB200_ERR_NOMEM: return "out of device memory";
     case BTB200_ERR_SHORT_INPUT: return "input shorter than (n_slots-1)*S + H samples";
     case BTB200_ERR_TOO_MANY: return "n_slots exceeds max_slots_per_call";
-    case BTB200_ERR_BAD_STEP: return "bad step";
-    case BTB200_ERR_MM_RANGE: return "interpolator index out of range";
+    case BTB200_ERR_OVERFLOW: return "hit or symbol buffer too small";
     default: return "unknown error";
   }
 }
@@ -590,8 +643,11 @@ int btb200_reset(btb200_ctx *ctx)
   return BTB200_OK;
 }
 
-int btb200_submit(btb200_ctx *ctx, const float *iq, int iq_on_device, size_t n_samples,
-                  uint64_t first_slot, uint32_t n_slots)
+namespace {
+enum InKind { IN_HOST_C32 = 0, IN_DEV_C32 = 1, IN_HOST_I16 = 2, IN_DEV_I16 = 3 };
+}
+
+static int submit_impl(btb200_ctx *ctx, const void *iq, int kind, size_t n_samples, uint64_t first_slot, uint32_t n_slots)
 {
   if (!ctx || !iq || n_slots == 0) return BTB200_ERR_ARG;
   if (ctx->pending) return BTB200_ERR_ARG;
@@ -606,36 +662,94 @@ int btb200_submit(btb200_ctx *ctx, const float *iq, int iq_on_device, size_t n_s
   DevBatch W = ctx->W;
   W.B = (int)n_slots;
   const size_t nbc = (size_t)n_slots * P.nch;
+  const bool host = kind == IN_HOST_C32 || kind == IN_HOST_I16, i16 = kind == IN_HOST_I16 || kind == IN_DEV_I16;
+  if (kind == IN_HOST_I16 && !ctx->d_x16) {
+    int rc = dev_alloc(ctx, &ctx->d_x16, 2 * ctx->x_cap);
+    if (rc) return rc;
+  }
 
-  bool chan_fir_done = false;
-  if (iq_on_device) {
+  // The front end (channel FIR of the exact mode / polyphase channelizer) runs in tile ranges so that it can follow
+  // the input copy piece by piece.
+  bool front_done = false;
+  const long ntile = ctx->poly ? pfb_tiles(ctx->PF, (int)n_slots) : chan_fir_tiles(G, W);
+  auto front_range = [&](long t0, long t1) {
+    if (ctx->poly) launch_pfb(ctx->PF, W.x, (long)need, (int)n_slots, t0, t1, s);
+    else launch_chan_fir_range(G, ctx->T, W, ctx->impl, t0, t1, s);
+    ctx->launches++;
+  };
+  auto front_samples = [&](long t1) { return ctx->poly ? pfb_samples(ctx->PF, t1) : chan_fir_samples(G, t1); };
+  if (kind == IN_DEV_C32) {
     CK(cudaEventRecord(ctx->ev[0], s));
     W.x = reinterpret_cast<const c32 *>(iq);
   } else {
-    // the copy runs on its own stream (it overlaps the compute stream's current work); compute waits for it.
-    // With the tuned kernels it is cut in kCopyParts pieces and the channel FIR follows piece by piece, so only
+    // host input: the copy runs on its own stream (it overlaps the compute stream's current work); compute waits for
+    // it.  With the tuned kernels it is cut in kCopyParts pieces and the front end follows piece by piece, so only
     // the first piece of a batch is exposed when nothing else is queued (blocking btb200_process callers).
-    CK(cudaEventRecord(ctx->ev[0], ctx->copy_stream));
+    // int16 input is converted to complex64 on the device (exact), piece by piece as well.
+    CK(cudaEventRecord(ctx->ev[0], host ? ctx->copy_stream : s));
     W.x = ctx->d_x;
-    const long ntile = chan_fir_tiles(G, W);
-    const int parts = (ctx->impl != IMPL_BASELINE && G.stateless && ntile >= 64) ? kCopyParts : 1;
+    const int parts = (host && ctx->impl != IMPL_BASELINE && G.stateless && ntile >= 64) ? kCopyParts : 1;
     size_t copied = 0;
     for (int c = 0; c < parts; c++) {
       const long t0 = ntile * c / parts, t1 = ntile * (c + 1) / parts;
-      size_t upto = (c == parts - 1) ? need : std::min<size_t>(need, (size_t)chan_fir_samples(G, t1));
+      size_t upto = need;
+      if (c != parts - 1) { upto = std::min<size_t>(need, ((size_t)front_samples(t1) + 3) & ~(size_t)3); }
       if (upto > copied) {
-        CK(cudaMemcpyAsync(ctx->d_x + copied, reinterpret_cast<const c32 *>(iq) + copied, (upto - copied) * sizeof(c32),
-                           cudaMemcpyHostToDevice, ctx->copy_stream));
-        copied = upto;
+        const size_t n = upto - copied;
+        if (kind == IN_HOST_C32)
+          CK(cudaMemcpyAsync(ctx->d_x + copied, reinterpret_cast<const c32 *>(iq) + copied, n * sizeof(c32),
+                             cudaMemcpyHostToDevice, ctx->copy_stream));
+        else if (kind == IN_HOST_I16)
+          CK(cudaMemcpyAsync(ctx->d_x16 + 2 * copied, reinterpret_cast<const int16_t *>(iq) + 2 * copied, n * 4,
+                             cudaMemcpyHostToDevice, ctx->copy_stream));
       }
-      CK(cudaEventRecord(ctx->ev_part[c], ctx->copy_stream));
-      CK(cudaStreamWaitEvent(s, ctx->ev_part[c], 0));
-      if (parts > 1) { launch_chan_fir_range(G, ctx->T, W, ctx->impl, t0, t1, s); ctx->launches++; }
+      if (host) {
+        CK(cudaEventRecord(ctx->ev_part[c], ctx->copy_stream));
+        CK(cudaStreamWaitEvent(s, ctx->ev_part[c], 0));
+      }
+      if (upto > copied && i16) {
+        const int16_t *src = (kind == IN_HOST_I16 ? ctx->d_x16 : reinterpret_cast<const int16_t *>(iq)) + 2 * copied;
+        launch_i16_to_c32(src, ctx->d_x + copied, (long)(upto - copied), s);
+        ctx->launches++;
+      }
+      if (upto > copied) copied = upto;
+      if (parts > 1) front_range(t0, t1);
     }
-    chan_fir_done = parts > 1;
-    CK(cudaEventRecord(ctx->ev_h2d, ctx->copy_stream));
-    W.x = ctx->d_x;
+    front_done = parts > 1;
+    if (host) CK(cudaEventRecord(ctx->ev_h2d, ctx->copy_stream));
   }
+  if (ctx->poly) {
+    // throughput mode: polyphase channelizer with fused demod + energy, noise estimate for every window, then the
+    // same clock recovery / search as the exact mode, reading the demod floats from the global grid
+    CK(cudaMemsetAsync(W.hit_count, 0, 4 * sizeof(unsigned), s));
+    CK(cudaEventRecord(ctx->ev[1], s));
+    if (!front_done) front_range(0, ntile);
+    launch_pfb_energy(ctx->PF, (int)n_slots, ctx->d_eon_all, s); ctx->launches++;
+    CK(cudaMemcpyAsync(ctx->h_eon_all, ctx->d_eon_all, nbc * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CK(cudaEventRecord(ctx->ev[2], s));
+    launch_noise_fast(ctx->F, W.x, W.B, G.S, G.fns, G.D, G.n_noise, G.nch, s); ctx->launches += 2;
+    CK(cudaMemcpyAsync(ctx->h_esum, ctx->F.esum, nbc * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CK(cudaEventRecord(ctx->ev[3], s));
+    launch_fill_pass(W, (int)nbc, 1, s); ctx->launches++;
+    CK(cudaEventRecord(ctx->ev[4], s));
+    launch_demod_mm_v2(G, ctx->T, W, ctx->d_dem, s); ctx->launches++;
+    CK(cudaEventRecord(ctx->ev[5], s));
+    launch_search_warp(G, ctx->T, W, s);
+    if (!G.early) launch_gather(G, W, s);
+    ctx->launches += G.early ? 1 : 2;
+    CK(cudaEventRecord(ctx->ev[6], s));
+    CK(cudaMemcpyAsync(ctx->h_counts, W.hit_count, 4 * sizeof(unsigned), cudaMemcpyDeviceToHost, s));
+    CK(cudaEventRecord(ctx->ev[7], s));
+    CK(cudaGetLastError());
+    ctx->pending = true;
+    ctx->pend_slots = n_slots;
+    ctx->pend_first_slot = first_slot;
+    ctx->pendW = W;
+    ctx->pendG = G;
+    ctx->pend_early = G.early != 0;
+    return BTB200_OK;
+  }
+  const bool chan_fir_done = front_done;
   if (!G.stateless) {
     // free-running rotators: the phases of this batch's windows, generated with
     // the same libm calls as the reference's rotator (hypotf renormalisation)
@@ -710,6 +824,18 @@ int btb200_submit(btb200_ctx *ctx, const float *iq, int iq_on_device, size_t n_s
   return BTB200_OK;
 }
 
+int btb200_submit(btb200_ctx *ctx, const float *iq, int iq_on_device, size_t n_samples,
+                  uint64_t first_slot, uint32_t n_slots)
+{
+  return submit_impl(ctx, iq, iq_on_device ? IN_DEV_C32 : IN_HOST_C32, n_samples, first_slot, n_slots);
+}
+
+int btb200_submit_i16(btb200_ctx *ctx, const int16_t *iq, int iq_on_device, size_t n_samples,
+                      uint64_t first_slot, uint32_t n_slots)
+{
+  return submit_impl(ctx, iq, iq_on_device ? IN_DEV_I16 : IN_HOST_I16, n_samples, first_slot, n_slots);
+}
+
 // First half of collect(): waits for the batch's search, fetches the hit list and ENQUEUES the deferred work
 // (lazy tail resume on the second stream; deferred noise FIR + exact energies on the compute stream) without
 // waiting for it.  A caller that keeps several batches in flight calls this, then submits the next batch
@@ -737,7 +863,12 @@ int btb200_collect_begin(btb200_ctx *ctx)
   if (!ctx->lazy) { if (nh) CK(cudaStreamSynchronize(cs)); return BTB200_OK; }
 
   const size_t nbc = (size_t)ctx->pend_slots * P.nch;
-  for (size_t i = 0; i < nbc; i++) ctx->h_energy[i] = ctx->h_noise[i] = std::nan("");
+  if (ctx->poly) {
+    // throughput mode: both energies of EVERY window are estimates that arrived with the batch
+    for (size_t i = 0; i < nbc; i++) { ctx->h_energy[i] = ctx->h_eon_all[i]; ctx->h_noise[i] = ctx->h_esum[i] / P.n_noise; }
+    cb.est_flag.assign(nbc, 1);
+  } else
+    for (size_t i = 0; i < nbc; i++) ctx->h_energy[i] = ctx->h_noise[i] = std::nan("");
   if (ctx->fast_snr) {
     ctx->fast_off.resize(nbc);
     for (size_t i = 0; i < nbc; i++) ctx->fast_off[i] = ctx->h_esum[i] / P.n_noise;
@@ -764,6 +895,7 @@ int btb200_collect_begin(btb200_ctx *ctx)
     CK(cudaMemcpyAsync(ctx->h_nsym, ctx->pendW.nsym, nbc * sizeof(int), cudaMemcpyDeviceToHost, s2));
     tr.mark("resume launched");
   }
+  if (ctx->poly) { CK(cudaGetLastError()); return BTB200_OK; }      // no exact fallback: the mode is hit-rate proof
   // pass 1 (fast mode): exact on-channel energy of every hit window, off-channel from the estimate
   std::vector<uint32_t> &need_exact = cb.need_exact;
   if (ctx->fast_snr) {
@@ -946,6 +1078,7 @@ int btb200_collect(btb200_ctx *ctx, btb200_hits *out)
     o.lap = h.lap;
     o.flags = (std::fabs(snr - P.squelch_db) <= 1e-6) ? 1u : 0u;
     if (!est_flag.empty() && est_flag[bc]) o.flags |= 2u;
+    if (ctx->poly) o.flags |= 4u;
     o.snr = snr;
     o.sym_offset = 0;
     o.sym_count = 0;
@@ -965,6 +1098,14 @@ int btb200_process(btb200_ctx *ctx, const float *iq, size_t n_samples, uint64_t 
                    uint32_t n_slots, btb200_hits *out)
 {
   int rc = btb200_submit(ctx, iq, 0, n_samples, first_slot, n_slots);
+  if (rc) return rc;
+  return btb200_collect(ctx, out);
+}
+
+int btb200_process_i16(btb200_ctx *ctx, const int16_t *iq, size_t n_samples, uint64_t first_slot,
+                       uint32_t n_slots, btb200_hits *out)
+{
+  int rc = btb200_submit_i16(ctx, iq, 0, n_samples, first_slot, n_slots);
   if (rc) return rc;
   return btb200_collect(ctx, out);
 }
@@ -1124,6 +1265,7 @@ int64_t btb200_get_stage(btb200_ctx *ctx, int stage, uint32_t b, uint32_t chi, v
       return nsym;
     }
     case BTB200_STAGE_DDC: {
+      if (ctx->poly) return BTB200_ERR_ARG;      // the polyphase front end never materialises the DDC outputs
       // rotated DDC output of the window = Y[b*gps + i][chi] * phase[i] (same fp32 ops as the kernels)
       if ((size_t)P.n_ddc * 8 > cap) return BTB200_ERR_ARG;
       std::vector<c32> y(P.n_ddc), ph(P.n_ddc);
@@ -1139,10 +1281,11 @@ int64_t btb200_get_stage(btb200_ctx *ctx, int stage, uint32_t b, uint32_t chi, v
     }
     case BTB200_STAGE_DEMOD:
       if (!ctx->d_dem || ctx->impl == IMPL_TILED_SCALAR) return BTB200_ERR_ARG;
-      if (G.stateless) {          // transposed [b][i][c]
+      if (G.stateless) {          // transposed [b][i][c]; polyphase mode: window b is a view of the global grid
         if ((size_t)P.n_dem * 4 > cap) return BTB200_ERR_ARG;
-        if (cudaMemcpy2D(dst, 4, ctx->d_dem + ((size_t)b * G.n_dem_pad) * P.nch + chi, (size_t)P.nch * 4, 4, P.n_dem,
+        if (cudaMemcpy2D(dst, 4, ctx->d_dem + ((size_t)b * G.dem_rows) * P.nch + chi, (size_t)P.nch * 4, 4, P.n_dem,
                          cudaMemcpyDeviceToHost) != cudaSuccess) return BTB200_ERR_CUDA;
+        if (G.dem_grid) *(float *)dst = 0.0f;
         return (int64_t)P.n_dem * 4;
       }
       return dev_copy(ctx->d_dem + bc * G.n_dem_pad, (size_t)P.n_dem * 4);

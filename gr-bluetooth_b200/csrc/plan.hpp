@@ -46,6 +46,24 @@ struct Plan {
   int design(double fs, double fc, double squelch_db, int extra_symbols);   // 0 or negative error
 };
 
+// Host tables of the polyphase channelizer (throughput mode, rx_pfb.cu): the per-channel DDCs of
+// lib/multi_block.cc:329-341 as one real-tap bank of M = fs / 1 MHz branches + a Good-Thomas DFT (M = N1 * N2)
+// evaluated at the channel bins.  See rx_pfb.cu for the derivation.
+struct PfbDesign {
+  int M = 0, D = 0, Q = 0, N1 = 1, N2 = 1;
+  int nfull = 0, rem = 0, tps = 0, CPC = 0, ncol = 0, span = 0;
+  int a0 = 0;                        // integer MHz offset of the lowest channel
+  double phi = 0;                    // fractional MHz offset common to all channels
+  std::vector<float> hq;             // [Q][M]
+  std::vector<int> n2_of_rho;        // [N2]
+  std::vector<cf32> WB;              // [N2][ncol]
+  std::vector<int> col_chan;         // [ncol] channel index or -1
+  std::vector<int> chan_col;         // [nch]
+  std::vector<cf32> kappa;           // [ncol]
+  // 0, or -1 when the configuration does not fit the model (non-integer or odd samples per MHz, > 8 taps per branch)
+  int design(const Plan &P, int tile_points, int tile_computed, int cols_per_thread);
+};
+
 // Free-running rotator of one DDC object (GNU Radio's gr::blocks::rotator):
 // phase multiplies output i, then advances; renormalised every 512 outputs.
 struct Rotator {

@@ -35,6 +35,10 @@ struct Geom {
   int stateless;
   int early;          // lazy tail: clock recovery stops at sym_target symbols, demod computed for i < ne_dem
   int ne_dem, sym_target;
+  // polyphase mode: the demod floats live on the GLOBAL decimation grid, dem[g][c] with g = b * gps + i (windows are
+  // views, index 0 of a window reads as 0.0f like the reference's never-written demod_out[0]); else [b][n_dem_pad][c]
+  int dem_grid;
+  int dem_rows;       // rows of nch floats between consecutive windows: gps (grid) or n_dem_pad
 };
 
 // ---- channel FIR: Y[g][c] = sum_k x[fcs + g*D + k] * rt[c][k]  (k ascending)

@@ -710,7 +710,7 @@ __global__ void __launch_bounds__(BLK) k_mm_stateless_v2(Geom G, DevBatch W, con
     if (!W.pass[idx]) { W.nsym[idx] = 0; return; }
   }
   const int b = idx / G.nch, c = idx - b * G.nch;
-  const float *gp = demT + ((long)b * G.n_dem_pad) * G.nch + c;    // next sample to prefetch
+  const float *gp = demT + ((long)b * G.dem_rows) * G.nch + c;     // next sample to prefetch
   uint32_t *__restrict__ bits_row = W.bits + (long)idx * G.bw;
   float *soft_row = W.soft ? W.soft + (long)idx * G.n_dem_pad : nullptr;
   MmState st{G.mu0, G.mm.omega_mid, 0.0f};
@@ -736,6 +736,7 @@ __global__ void __launch_bounds__(BLK) k_mm_stateless_v2(Geom G, DevBatch W, con
     cp_async_commit();
     cp_async_wait<0>();
     ready = pf;
+    if (G.dem_grid && ii == 0) ring[0][tid] = 0.0f;      // demod_out[0] of a window is never written by the reference
   }
   int step = 0;
   while (oo < oo_end && ii < ni) {
@@ -1042,8 +1043,10 @@ void launch_gather(const Geom &G, const DevBatch &W, cudaStream_t s)
 void launch_demod_mm_v2(const Geom &G, const DevTables &T, const DevBatch &W, float *demT, cudaStream_t s)
 {
   const int i_end = G.early ? G.ne_dem : G.n_dem;
-  dim3 grid(cdiv(i_end, DM_TI), (unsigned)W.B, (unsigned)((G.nch + 31) / 32));
-  k_demod_all<<<grid, DM_WARPS * 32, 0, s>>>(G, W, T.atan_tab, demT, i_end);
+  if (!G.dem_grid) {               // polyphase mode: the channelizer's epilogue already wrote the demod floats
+    dim3 grid(cdiv(i_end, DM_TI), (unsigned)W.B, (unsigned)((G.nch + 31) / 32));
+    k_demod_all<<<grid, DM_WARPS * 32, 0, s>>>(G, W, T.atan_tab, demT, i_end);
+  }
   constexpr int BLK = 64;
   const size_t smem = sizeof(float) * MM_RD * BLK + sizeof(float) * 8 * 132;
   k_mm_stateless_v2<BLK><<<cdiv((long)W.B * G.nch, BLK), BLK, smem, s>>>(G, W, T.mmse, demT, G.early ? 1 : 0,
@@ -1056,7 +1059,7 @@ void launch_mm_resume_list(const Geom &G, const DevTables &T, const DevBatch &W,
 {
   if (n_list <= 0) return;
   const int tail = G.n_dem - G.ne_dem;
-  if (tail > 0) {
+  if (tail > 0 && !G.dem_grid) {       // polyphase mode: the grid already holds every demod float
     dim3 grid(cdiv(tail, 128), (unsigned)n_list);
     k_demod_list<<<grid, 128, 0, s>>>(G, W, T.atan_tab, demT, reinterpret_cast<const int4 *>(list4), G.ne_dem);
   }

@@ -1,0 +1,49 @@
+// rx_pfb.cuh -- polyphase (weighted overlap-add) channelizer of the throughput mode, see rx_pfb.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include "rx_math.cuh"
+
+namespace btb200 {
+
+constexpr int PFB_T = 63;          // grid points a tile owns
+constexpr int PFB_TT = 64;         // grid points a tile computes (one more in front: the demod needs Z[g-1])
+constexpr int PFB_NCOL = 5;        // channels per thread in the DFT stage
+
+struct PfbPlan {
+  int M = 0, D = 0, Q = 0;         // samples per MHz (= branches), decimation (2 D = M), taps per branch
+  int N1 = 1, N2 = 1;              // M = N1 * N2, coprime (Good-Thomas); N1 in {1, 2, 4}
+  int gps = 0, n_ddc = 0;          // grid points per slot, DDC outputs per window
+  int nfull = 0, rem = 0;          // n_ddc = nfull * gps + rem
+  int fcs = 0, nch = 0;
+  int tps = 0;                     // tiles per slot segment
+  int CPC = 0, ncol = 0;           // columns per residue class (multiple of PFB_NCOL), columns = N1 * CPC
+  int span = 0;                    // samples staged per tile: (TT - 1) * D + Q * M
+  float gain = 0;                  // demod gain (lib/multi_block.cc:88)
+  float phi_step = 0;              // pre-rotation: x'[i] = x[i] e^{j pi phi_step i}, phi_step = -2 phi / M (0: none)
+  // device tables
+  const float *hq = nullptr;       // [Q][M]  h'[r + M q], h'[k] = h[Nc-1-k], zero padded
+  const int *n2_of_rho = nullptr;  // [N2]    n2 with (N1 n2) mod N2 == rho
+  const c32 *WB = nullptr;         // [N2][ncol]  W_N2^{n2 k2(col)}
+  const int *col_chan = nullptr;   // [ncol]  channel index of a column, -1: padding
+  const int *chan_col = nullptr;   // [nch]   column of a channel
+  const c32 *kappa = nullptr;      // [ncol]  e^{-j 2 pi a_c D / M}: constant of the differential product
+  const float *atan_tab = nullptr; // [257]
+  // outputs
+  float *dem = nullptr;            // [Gtot][nch]  demod floats on the global decimation grid
+  float *E = nullptr;              // [segments * tps][ncol][2]  per-tile sums of |Z|^2 (all points / points below rem)
+};
+
+size_t pfb_smem_bytes(const PfbPlan &P);
+int  pfb_setup(const PfbPlan &P);                                 // opt in to the dynamic shared memory; 0 or -1
+long pfb_tiles(const PfbPlan &P, int B);
+// input samples (from x[0]) the tiles below `tile_end` read
+long pfb_samples(const PfbPlan &P, long tile_end);
+// x: batch input (x[0] = first sample of window 0), n_samples valid samples; tiles [tile0, tile1)
+void launch_pfb(const PfbPlan &P, const c32 *x, long n_samples, int B, long tile0, long tile1, cudaStream_t s);
+// e_on[b][c] = mean |Z|^2 over window b (the on-channel energy of lib/multi_block.cc:206-218)
+void launch_pfb_energy(const PfbPlan &P, int B, double *e_on, cudaStream_t s);
+
+// int16 interleaved IQ -> complex64 (the reference's interleaved_short_to_complex in front of the block, apps/btrx:141-159)
+void launch_i16_to_c32(const int16_t *src, c32 *dst, long n_samples, cudaStream_t s);
+
+}  // namespace btb200

@@ -61,8 +61,7 @@ enum {
   BTB200_ERR_NOMEM       = -4,
   BTB200_ERR_SHORT_INPUT = -5,   /* n_samples < (n_slots-1)*S + H */
   BTB200_ERR_TOO_MANY    = -6,   /* n_slots > max_slots_per_call */
-  BTB200_ERR_BAD_STEP    = -7,   /* the reference's "Bad step" abort (multi_sniffer_impl.cc:119) */
-  BTB200_ERR_MM_RANGE    = -8    /* interpolator index out of range (GNU Radio would throw) */
+  BTB200_ERR_OVERFLOW    = -7    /* reserved for callers: a hit or symbol buffer was too small (see btb200_hits.overflow) */
 };
 
 /* how clock-recovery / rotator state is carried from one channel-window to the next */
@@ -113,6 +112,22 @@ enum {
   BTB200_TAIL_FULL = 1           /* every window to the end */
 };
 
+/* how the per-channel DDCs (lib/multi_block.cc:180-228, 329-341) are evaluated */
+enum {
+  /* exact: every channel's band-pass FIR in direct form, one rounding per operation, sums in the reference's order:
+   * DDC outputs, demod floats, soft symbols and bit streams equal the reference's bit for bit (either mm_mode) */
+  BTB200_DDC_EXACT     = 0,
+  /* polyphase (throughput mode, BTB200_MM_STATELESS only): ONE real-tap polyphase bank of fs / 1 MHz branches + DFT at
+   * the channel bins for all channels, FM demod and window energy fused into its epilogue, off-channel energy from the
+   * polyphase noise estimator.  Mathematically the same filters; floats agree with the reference's to a TOLERANCE
+   * (demod floats: median 1e-5, 99.9 % below 5e-3 of the +-4 range at 100 Msps -- the reference's own taps carry fp32
+   * phase errors of that size; snr within 2e-3 dB).  Because the Mueller & Mueller loop random-walks in noise, bit
+   * streams of noise-only stretches and marginal detections differ from the reference's (measured: ~98 % of the hit
+   * list in common, identical set of LAPs, same recall against ground truth); hit.flags bit2 marks such hits.
+   * Needs an even integer number of samples per MHz. */
+  BTB200_DDC_POLYPHASE = 1
+};
+
 enum {
   BTB200_SEARCH_BR = 1,          /* classic_packet::sniff_ac */
   BTB200_SEARCH_LE = 2           /* le_packet::sniff_aa */
@@ -138,7 +153,8 @@ typedef struct btb200_config {
   uint32_t squelch_mode;         /* BTB200_SQUELCH_* (stateless mode only; chained is always eager) */
   uint32_t snr_mode;             /* BTB200_SNR_* (lazy squelch only) */
   uint32_t tail_mode;            /* BTB200_TAIL_* (lazy squelch only) */
-  uint32_t reserved[2];
+  uint32_t ddc_mode;             /* BTB200_DDC_* */
+  uint32_t reserved;
 } btb200_config;
 
 /* derived constants (lib/multi_block.cc:56-119, 299-342) */
@@ -165,10 +181,12 @@ typedef struct btb200_hit {
   int32_t  offset;               /* symbol index in the window where the packet starts */
   int32_t  n_symbols;            /* the "len - i" argument of ac()/aa() */
   uint32_t lap;                  /* BR: LAP (symbols 38..61); LE: AA (symbols 8..39) */
-  uint32_t flags;                /* bit0: snr within 1e-6 dB of the threshold; bit1: snr from the fast noise estimate */
+  uint32_t flags;                /* bit0: snr within 1e-6 dB of the threshold; bit1: snr from the fast noise estimate;
+                                  * bit2: found by the polyphase (tolerance-mode) front end */
   double   snr;                  /* dB, the value ac() prints */
   uint64_t sym_offset;           /* into btb200_hits.symbols */
-  uint32_t sym_count;            /* min(n_symbols, 3125 + 376) symbols copied, one per byte, air order */
+  uint32_t sym_count;            /* min(n_symbols, 3125) symbols copied (what classic_packet::make keeps,
+                                  * lib/packet_impl.cc:52-58), one per byte, air order; 0 when the arena was full */
   uint32_t reserved;
 } btb200_hit;
 
@@ -240,6 +258,14 @@ BTB200_API int btb200_process_channels(btb200_ctx *ctx, const float *iq, size_t 
  * (A' = a third context, or A again after collect(A) -- bench.py's end-to-end loop). */
 BTB200_API int  btb200_submit(btb200_ctx *ctx, const float *iq, int iq_on_device, size_t n_samples,
                    uint64_t first_slot, uint32_t n_slots);
+/* int16 input: interleaved (re, im) int16 pairs, what the reference's flowgraph feeds through
+ * interleaved_short_to_complex in front of the block (apps/btrx:141-159).  Same batches as btb200_submit /
+ * btb200_process with half the host-to-device bytes; the conversion to complex64 is exact, so results are identical
+ * to feeding the converted samples. */
+BTB200_API int  btb200_submit_i16(btb200_ctx *ctx, const int16_t *iq, int iq_on_device, size_t n_samples,
+                       uint64_t first_slot, uint32_t n_slots);
+BTB200_API int  btb200_process_i16(btb200_ctx *ctx, const int16_t *iq, size_t n_samples,
+                        uint64_t first_slot, uint32_t n_slots, btb200_hits *out);
 BTB200_API int  btb200_collect_begin(btb200_ctx *ctx);
 BTB200_API int  btb200_collect(btb200_ctx *ctx, btb200_hits *out);
 

@@ -136,4 +136,63 @@ int emul_run(double fs, double fc, double snr_db, int extra, int stateless, int 
   return 0;
 }
 
+// Polyphase channelizer of the throughput mode, driven by the PRODUCT's host tables (PfbDesign, plan.cpp) in the
+// stage order of the kernel (rx_pfb.cu): branch sums -> N1-point DFTs -> N2-point DFTs at the channel bins.
+// Double precision, plain loops: checks the tables and the index algebra, not the kernel's thread mapping.
+// x: n_x complex samples (x[0] = first sample of window 0, no pre-rotation applied); Z: [n_grid][nch] complex doubles;
+// kappa: [nch] complex floats; dims: M, D, Q, N1, N2, tps, CPC, ncol, span, nfull, rem, a0
+int emul_pfb(double fs, double fc, int extra, const float *xf, long n_x, int n_grid, double *Z, float *kappa, double *phi_out,
+             int32_t dims[12])
+{
+  Plan P;
+  if (P.design(fs, fc, 10.0, extra)) return -1;
+  PfbDesign F;
+  if (F.design(P, 63, 64, 5)) return -2;
+  const int M = F.M, N1 = F.N1, N2 = F.N2;
+  int32_t d[12] = {F.M, F.D, F.Q, F.N1, F.N2, F.tps, F.CPC, F.ncol, F.span, F.nfull, F.rem, F.a0};
+  std::memcpy(dims, d, sizeof d);
+  *phi_out = F.phi;
+  for (int c = 0; c < P.nch; c++) { kappa[2 * c] = F.kappa[F.chan_col[c]].re; kappa[2 * c + 1] = F.kappa[F.chan_col[c]].im; }
+  std::vector<double> ur(M), ui(M), vr((size_t)N1 * N2), vi((size_t)N1 * N2);
+  for (int g = 0; g < n_grid; g++) {
+    const long n0 = (long)P.fcs + (long)g * F.D;
+    for (int r = 0; r < M; r++) {
+      double ar = 0, ai = 0;
+      for (int q = 0; q < F.Q; q++) {
+        const long n = n0 + r + (long)M * q;
+        if (n >= n_x) continue;
+        // x'[n] = x[n] e^{-j 2 pi phi n / M}
+        const double ang = -2.0 * M_PI * F.phi * (double)n / M;
+        const double xr = xf[2 * n], xi = xf[2 * n + 1], cs = std::cos(ang), sn = std::sin(ang);
+        const double h = F.hq[(size_t)q * M + r];
+        ar += (xr * cs - xi * sn) * h; ai += (xr * sn + xi * cs) * h;
+      }
+      ur[r] = ar; ui[r] = ai;
+    }
+    for (int k1 = 0; k1 < N1; k1++)
+      for (int n2 = 0; n2 < N2; n2++) {
+        double ar = 0, ai = 0;
+        for (int n1 = 0; n1 < N1; n1++) {
+          const int r = (N2 * n1 + N1 * n2) % M;
+          const double ang = -2.0 * M_PI * (double)((n1 * k1) % N1) / N1;
+          const double cs = std::cos(ang), sn = std::sin(ang);
+          ar += ur[r] * cs - ui[r] * sn; ai += ur[r] * sn + ui[r] * cs;
+        }
+        vr[(size_t)k1 * N2 + n2] = ar; vi[(size_t)k1 * N2 + n2] = ai;
+      }
+    for (int c = 0; c < P.nch; c++) {
+      const int col = F.chan_col[c], k1 = col / F.CPC;
+      if (F.col_chan[col] != c) return -3;
+      double ar = 0, ai = 0;
+      for (int n2 = 0; n2 < N2; n2++) {
+        const cf32 w = F.WB[(size_t)n2 * F.ncol + col];
+        const double a = vr[(size_t)k1 * N2 + n2], b = vi[(size_t)k1 * N2 + n2];
+        ar += a * w.re - b * w.im; ai += a * w.im + b * w.re;
+      }
+      Z[((size_t)g * P.nch + c) * 2] = ar; Z[((size_t)g * P.nch + c) * 2 + 1] = ai;
+    }
+  }
+  return 0;
+}
+
 }  // extern "C"

@@ -1,0 +1,107 @@
+"""CPU tier: the mathematics of the throughput-mode (polyphase) channelizer against the oracle.
+
+* tests/pfb_model.py (numpy, brute-force DFT) restates the algebra of rx_pfb.cu independently;
+* emul_pfb (tests/emul) drives the PRODUCT's host tables (PfbDesign in plan.cpp: branch taps, Good-Thomas index
+  maps, column order, DFT matrix, kappa) in the kernel's stage order;
+both must reproduce the oracle's direct-form DDC (lib/multi_block.cc:180-228) up to float rounding, on every
+BASELINE geometry.  What is compared: the demod floats (the only thing downstream stages see) and the window energy.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from conftest import FILES, ROOT, load_excerpt
+from oracle import oracle as O
+from pfb_model import PfbModel, fast_atan2f
+
+EMUL = os.path.join(ROOT, "tests", "emul", "libbtb_emul.so")
+
+
+@pytest.fixture(scope="module")
+def emul():
+    if not os.path.exists(EMUL):
+        import __graft_entry__ as ge
+        ge.build()
+    L = C.CDLL(EMUL)
+    L.emul_pfb.argtypes = [C.c_double, C.c_double, C.c_int, C.c_void_p, C.c_long, C.c_int, C.c_void_p, C.c_void_p,
+                           C.POINTER(C.c_double), C.c_void_p]
+    return L
+
+
+def synth_window(fs, fc, seed=3):
+    import gr_bluetooth_b200  # noqa: F401
+    from gr_bluetooth_b200 import synth
+    P = O.Plan(fs, fc)
+    nsl = (P.H + P.S - 1) // P.S + 1
+    iq, _ = synth.generate(fs, fc, nsl, seed=seed, occupancy=0.3)
+    return P, iq[:P.H]
+
+
+def demod_from_Z(P, Z, kappa):
+    prod = Z[1:] * np.conj(Z[:-1]) * kappa[None, :]
+    d = np.zeros(Z.shape, np.float32)
+    d[1:] = np.float32(P.demod_gain) * fast_atan2f(P.atan_table(), prod.imag.astype(np.float32), prod.real.astype(np.float32))
+    return d
+
+
+CASES = [("headset3", None), ("headset2", None), ("headset1", None), ("keyboard1", None),
+         ("synth30", (30e6, 2414e6)), ("synth100", (100e6, 2441e6))]
+
+
+@pytest.mark.parametrize("name,geom", CASES)
+def test_polyphase_equals_direct_form(emul, name, geom):
+    if geom is None:
+        ex = load_excerpt(name, "stateless")
+        fs, fc = FILES[name]
+        P = O.Plan(fs, fc)
+        k = min(ex["nslots"] - 1, 12)
+        x = np.concatenate([np.zeros(P.H - 1, np.complex64), ex["iq"]])
+        win = x[k * P.S:k * P.S + P.H]
+    else:
+        P, win = synth_window(*geom)
+    n_grid = P.n_ddc if P.fs < 50e6 else 1500
+    hits, d = P.window(win, slot=0, stateless=True)
+    ok = np.where(d["pass_"] > 0)[0]
+    assert len(ok) >= 1
+    ref = d["demod"][ok][:, 1:n_grid - 1]
+    wrap = 2 * np.pi * P.demod_gain
+
+    def cmp(dem):
+        dd = np.abs(dem.T[ok][:, 1:n_grid - 1] - ref)
+        return np.minimum(dd, np.abs(dd - wrap))
+
+    # 1. independent numpy model, fp32
+    m = PfbModel(P, np.complex64)
+    Zm = m.channelize(win, n_grid)
+    dm = cmp(m.demod(Zm, P.atan_table()))
+    # 2. the product's tables in the kernel's stage order, fp64
+    Z = np.zeros((n_grid, P.nch, 2))
+    kap = np.zeros((P.nch, 2), np.float32)
+    dims = np.zeros(12, np.int32)
+    phi = C.c_double()
+    w = np.ascontiguousarray(win, np.complex64)
+    rc = emul.emul_pfb(P.fs, P.fc, 3125, w.ctypes.data, len(w), n_grid, Z.ctypes.data, kap.ctypes.data, C.byref(phi),
+                       dims.ctypes.data)
+    assert rc == 0
+    M, D, Q, N1, N2 = [int(v) for v in dims[:5]]
+    assert M == int(round(P.fs / 1e6)) and 2 * D == M and N1 * N2 == M and np.gcd(N1, N2) == 1
+    assert abs(phi.value - m.phi) < 1e-9 and int(dims[11]) == m.a0
+    Zp = Z[..., 0] + 1j * Z[..., 1]
+    kappa = kap[:, 0] + 1j * kap[:, 1]
+    assert np.allclose(kappa, m.kappa, atol=1e-6)
+    dp = cmp(demod_from_Z(P, Zp, kappa))
+    # energies (whole window) from the model
+    if n_grid == P.n_ddc:
+        e = (np.abs(Zm.astype(np.complex128)) ** 2).mean(axis=0)
+        assert np.max(np.abs(e[ok] / d["energy"][ok] - 1)) < 2e-5
+    # |Z| of the two formulations agree to fp32 rounding (relative to the rms level: bins between channels are small)
+    scale = np.sqrt(np.mean(np.abs(Zp) ** 2))
+    assert np.max(np.abs(np.abs(Zp) - np.abs(Zm))) < 2e-4 * scale
+    # stated tolerance of the throughput mode's demod floats (range +-4 at 100 Msps): the deviation from the reference's
+    # direct form is dominated by the reference's own fp32 tap phases (i * theta in float, up to 1.6e3 rad at 100 Msps)
+    tol_med, tol_999 = (2e-5, 5e-3) if P.fs >= 30e6 else (3e-6, 5e-4)
+    for dd in (dm, dp):
+        assert np.median(dd) < tol_med, np.median(dd)
+        assert np.quantile(dd, 0.999) < tol_999, np.quantile(dd, 0.999)

@@ -6,6 +6,7 @@
 #include "rx_kernels.cuh"
 #include "rx_fast.cuh"
 #include "rx_pfb.cuh"
+#include "rx_nest.cuh"
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -93,6 +94,9 @@ struct btb200_ctx {
   bool fast_snr = false;
   FastNoisePlan F{};
   double *h_esum = nullptr;
+  bool use_nest = false;             // rx_nest.cu (fused polyphase + DFT) instead of the two kernels of rx_fast.cu
+  PfbDesign nfd;
+  NestPlan NP{};
   double phi = 0;                    // common fractional MHz offset of the noise DDCs
   std::vector<double> fast_off;      // [B][nch] fast off-channel energy of the last batch
   // polyphase (throughput) mode: rx_pfb.cu
@@ -224,12 +228,48 @@ int setup_fast(btb200_ctx *ctx)
   if ((rc = upload(ctx, &F.phasor, ph))) return rc;
   if ((rc = upload(ctx, &F.twid, tw))) return rc;
   const size_t B = ctx->max_slots;
-  if ((rc = dev_alloc(ctx, &F.U, B * P.n_noise * (size_t)M))) return rc;
   if ((rc = dev_alloc(ctx, &F.esum, B * P.nch))) return rc;
+  {
+    // fused estimator (rx_nest.cu) when the configuration fits it; else the two-kernel version of rx_fast.cu
+    PfbDesign &N = ctx->nfd;
+    NestPlan &K = ctx->NP;
+    if (!std::getenv("BTB200_NO_NEST") && N.design_noise(P, NEST_NCOL, 16) == 0 && std::fabs(N.phi - phi) < 1e-9) {
+      K.M = N.M; K.D = N.D; K.Q = N.Q; K.q_rows = N.q_rows; K.N1 = N.N1; K.N2 = N.N2; K.CPC = N.CPC; K.ncol = N.ncol;
+      K.nch = P.nch; K.S = P.S; K.fns = P.fns; K.n_noise = P.n_noise;
+      K.tiles_per_slot = ((P.n_noise + 1) / 2 + NEST_TO - 1) / NEST_TO;
+      K.period = F.period; K.phasor = F.phasor; K.esum = F.esum;
+      // the last tile of a slot reads (tiles * 64 + q_rows + 16 * 5) * M samples past the slot's first noise sample
+      const long reach = (long)P.fns + ((long)K.tiles_per_slot * NEST_TO + K.q_rows + 16 * (NEST_K + 1)) * K.M;
+      if (reach <= P.H && nest_setup(K) == 0) {
+        if ((rc = upload(ctx, &K.hq, N.hq))) return rc;
+        if ((rc = upload(ctx, &K.n2_of_rho, N.n2_of_rho))) return rc;
+        if ((rc = upload_raw<c32>(ctx, &K.WB, N.WB.data(), N.WB.size()))) return rc;
+        if ((rc = upload(ctx, &K.col_chan, N.col_chan))) return rc;
+        if ((rc = upload(ctx, &K.chan_col, N.chan_col))) return rc;
+        if ((rc = dev_alloc(ctx, &K.xr, (B - 1) * (size_t)P.S + P.H))) return rc;
+        if ((rc = dev_alloc(ctx, &K.E2, B * K.tiles_per_slot * (size_t)K.ncol))) return rc;
+        ctx->use_nest = true;
+      }
+    }
+  }
+  if (!ctx->use_nest) { if ((rc = dev_alloc(ctx, &F.U, B * P.n_noise * (size_t)M))) return rc; }
   CK(cudaMallocHost(&ctx->h_esum, B * P.nch * sizeof(double)));
   ctx->phi = phi;
   ctx->fast_snr = true;
   return 0;
+}
+
+// off-channel energy estimate of every window of the batch -> F.esum
+void enqueue_noise_estimate(btb200_ctx *ctx, const Geom &G, const DevBatch &W, long n_samples, cudaStream_t s)
+{
+  if (ctx->use_nest) {
+    launch_nest_prerot(ctx->NP, W.x, n_samples, s);
+    launch_nest(ctx->NP, W.B, s);
+    ctx->launches += 3;
+  } else {
+    launch_noise_fast(ctx->F, W.x, W.B, G.S, G.fns, G.D, G.n_noise, G.nch, s);
+    ctx->launches += 2;
+  }
 }
 
 // Tables and buffers of the polyphase channelizer (rx_pfb.cu)
@@ -727,7 +767,7 @@ static int submit_impl(btb200_ctx *ctx, const void *iq, int kind, size_t n_sampl
     launch_pfb_energy(ctx->PF, (int)n_slots, ctx->d_eon_all, s); ctx->launches++;
     CK(cudaMemcpyAsync(ctx->h_eon_all, ctx->d_eon_all, nbc * sizeof(double), cudaMemcpyDeviceToHost, s));
     CK(cudaEventRecord(ctx->ev[2], s));
-    launch_noise_fast(ctx->F, W.x, W.B, G.S, G.fns, G.D, G.n_noise, G.nch, s); ctx->launches += 2;
+    enqueue_noise_estimate(ctx, G, W, (long)need, s);
     CK(cudaMemcpyAsync(ctx->h_esum, ctx->F.esum, nbc * sizeof(double), cudaMemcpyDeviceToHost, s));
     CK(cudaEventRecord(ctx->ev[3], s));
     launch_fill_pass(W, (int)nbc, 1, s); ctx->launches++;
@@ -773,7 +813,7 @@ static int submit_impl(btb200_ctx *ctx, const void *iq, int kind, size_t n_sampl
     // lazy squelch: every window is demodulated and searched; the squelch (and the snr
     // ac() prints) is settled exactly, afterwards, for the windows that produced hits
     if (ctx->fast_snr) {
-      launch_noise_fast(ctx->F, W.x, W.B, G.S, G.fns, G.D, G.n_noise, G.nch, s); ctx->launches += 2;
+      enqueue_noise_estimate(ctx, G, W, (long)need, s);
       CK(cudaMemcpyAsync(ctx->h_esum, ctx->F.esum, nbc * sizeof(double), cudaMemcpyDeviceToHost, s));
     }
     CK(cudaEventRecord(ctx->ev[3], s));

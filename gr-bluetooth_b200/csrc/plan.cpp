@@ -132,62 +132,84 @@ void Rotator::generate(cf32 *dst, int n, int stride)
   }
 }
 
-int PfbDesign::design(const Plan &P, int tile_points, int tile_computed, int cols_per_thread)
+namespace {
+int igcd(int a, int b) { while (b) { const int t = a % b; a = b; b = t; } return a; }
+
+// common part: factorisation, channel -> column maps, DFT matrix, kappa, for channel offsets f0 + c MHz
+int pfb_common(PfbDesign &F, const Plan &P, double f0, int cols_per_thread)
 {
   const double Md = P.fs / kSymbolRate;
-  M = (int)std::llround(Md);
-  if (std::fabs(Md - M) > 1e-9 || M < 2 || (M & 1)) return -1;
-  D = P.D;
-  if (2 * D != M || P.grid_per_slot <= 0) return -1;
+  F.M = (int)std::llround(Md);
+  if (std::fabs(Md - F.M) > 1e-9 || F.M < 2 || (F.M & 1)) return -1;
+  F.D = P.D;
+  if (2 * F.D != F.M || P.grid_per_slot <= 0) return -1;
+  const int M = F.M;
+  // M = N1 * N2 with gcd(N1, N2) = 1 and N1 in {4, 2, 1}
+  F.N1 = 1;
+  if (M % 4 == 0 && igcd(4, M / 4) == 1) F.N1 = 4;
+  else if (M % 2 == 0 && igcd(2, M / 2) == 1) F.N1 = 2;
+  F.N2 = M / F.N1;
+  const int N1 = F.N1, N2 = F.N2;
+  // channel c sits a_c + phi MHz from the centre frequency
+  F.a0 = (int)std::floor(f0 + 1e-9);
+  F.phi = f0 - F.a0;
+  if (std::fabs(F.phi) < 1e-9) F.phi = 0;
+  F.n2_of_rho.assign(N2, 0);
+  for (int n2 = 0; n2 < N2; n2++) F.n2_of_rho[(N1 * n2) % N2] = n2;
+  // columns: channels grouped by residue class k1 = bin mod N1, every class padded to CPC columns
+  std::vector<std::vector<int>> cls(N1);
+  for (int c = 0; c < P.nch; c++) cls[(((F.a0 + c) % M) + M) % M % N1].push_back(c);
+  size_t mx = 0;
+  for (auto &v : cls) mx = std::max(mx, v.size());
+  F.CPC = (int)((mx + cols_per_thread - 1) / cols_per_thread) * cols_per_thread;
+  if (F.CPC == 0) return -1;
+  F.ncol = N1 * F.CPC;
+  F.col_chan.assign(F.ncol, -1);
+  F.chan_col.assign(P.nch, -1);
+  F.WB.assign((size_t)N2 * F.ncol, cf32{0.0f, 0.0f});
+  F.kappa.assign(F.ncol, cf32{1.0f, 0.0f});
+  for (int k1 = 0; k1 < N1; k1++)
+    for (size_t i = 0; i < cls[k1].size(); i++) {
+      const int c = cls[k1][i], col = k1 * F.CPC + (int)i;
+      F.col_chan[col] = c;
+      F.chan_col[c] = col;
+      const int a = F.a0 + c;
+      const int k = ((a % M) + M) % M, k2 = k % N2;
+      for (int n2 = 0; n2 < N2; n2++) {
+        const double ang = -2.0 * M_PI * (double)((n2 * k2) % N2) / N2;
+        F.WB[(size_t)n2 * F.ncol + col] = cf32{(float)std::cos(ang), (float)std::sin(ang)};
+      }
+      const double ak = -2.0 * M_PI * (double)((((long)a * F.D) % M + M) % M) / M;
+      F.kappa[col] = cf32{(float)std::cos(ak), (float)std::sin(ak)};
+    }
+  return 0;
+}
+}  // namespace
+
+int PfbDesign::design(const Plan &P, int tile_points, int tile_computed, int cols_per_thread)
+{
+  if (pfb_common(*this, P, (kBaseFreq + P.ch_lo * kChanWidth - P.fc) / 1e6, cols_per_thread)) return -1;
   Q = (P.Nc + M - 1) / M;
   if (Q > 8) return -1;
   Q = Q <= 7 ? 7 : 8;                                    // the kernel is instantiated for 7 and 8 taps per branch
-  // M = N1 * N2 with gcd(N1, N2) = 1 and N1 in {4, 2, 1}
-  auto gcd = [](int a, int b) { while (b) { const int t = a % b; a = b; b = t; } return a; };
-  N1 = 1;
-  if (M % 4 == 0 && gcd(4, M / 4) == 1) N1 = 4;
-  else if (M % 2 == 0 && gcd(2, M / 2) == 1) N1 = 2;
-  N2 = M / N1;
+  q_rows = Q;
   nfull = P.n_ddc / P.grid_per_slot;
   rem = P.n_ddc % P.grid_per_slot;
   tps = (P.grid_per_slot + tile_points - 1) / tile_points;
   span = (tile_computed - 1) * D + Q * M;
-  // channel c sits a_c + phi MHz from the centre frequency
-  const double f0 = (kBaseFreq + P.ch_lo * kChanWidth - P.fc) / 1e6;
-  a0 = (int)std::floor(f0 + 1e-9);
-  phi = f0 - a0;
-  if (std::fabs(phi) < 1e-9) phi = 0;
   // h'[k] = h[Nc-1-k] (the reversed taps multiply x[n0 + k]); branch r holds h'[r + M q]
   hq.assign((size_t)Q * M, 0.0f);
   for (int k = 0; k < P.Nc; k++) hq[(size_t)(k / M) * M + (k % M)] = P.chan_proto[P.Nc - 1 - k];
-  n2_of_rho.assign(N2, 0);
-  for (int n2 = 0; n2 < N2; n2++) n2_of_rho[(N1 * n2) % N2] = n2;
-  // columns: channels grouped by residue class k1 = bin mod N1, every class padded to CPC columns
-  std::vector<std::vector<int>> cls(N1);
-  for (int c = 0; c < P.nch; c++) cls[(((a0 + c) % M) + M) % M % N1].push_back(c);
-  size_t mx = 0;
-  for (auto &v : cls) mx = std::max(mx, v.size());
-  CPC = (int)((mx + cols_per_thread - 1) / cols_per_thread) * cols_per_thread;
-  if (CPC == 0) return -1;
-  ncol = N1 * CPC;
-  col_chan.assign(ncol, -1);
-  chan_col.assign(P.nch, -1);
-  WB.assign((size_t)N2 * ncol, cf32{0.0f, 0.0f});
-  kappa.assign(ncol, cf32{1.0f, 0.0f});
-  for (int k1 = 0; k1 < N1; k1++)
-    for (size_t i = 0; i < cls[k1].size(); i++) {
-      const int c = cls[k1][i], col = k1 * CPC + (int)i;
-      col_chan[col] = c;
-      chan_col[c] = col;
-      const int a = a0 + c;
-      const int k = ((a % M) + M) % M, k2 = k % N2;
-      for (int n2 = 0; n2 < N2; n2++) {
-        const double ang = -2.0 * M_PI * (double)((n2 * k2) % N2) / N2;
-        WB[(size_t)n2 * ncol + col] = cf32{(float)std::cos(ang), (float)std::sin(ang)};
-      }
-      const double ak = -2.0 * M_PI * (double)((((long)a * D) % M + M) % M) / M;
-      kappa[col] = cf32{(float)std::cos(ak), (float)std::sin(ak)};
-    }
+  return 0;
+}
+
+int PfbDesign::design_noise(const Plan &P, int cols_per_thread, int row_pad)
+{
+  if (pfb_common(*this, P, (kBaseFreq + P.ch_lo * kChanWidth + 790000.0 - P.fc) / 1e6, cols_per_thread)) return -1;
+  Q = (P.Nn + M - 1) / M;
+  q_rows = ((Q + row_pad - 1) / row_pad + 1) * row_pad;
+  hq.assign((size_t)q_rows * M, 0.0f);
+  for (int k = 0; k < P.Nn; k++) hq[(size_t)(k / M) * M + (k % M)] = P.noise_proto[P.Nn - 1 - k];
   return 0;
 }
 

@@ -62,6 +62,11 @@ struct PfbDesign {
   std::vector<cf32> kappa;           // [ncol]
   // 0, or -1 when the configuration does not fit the model (non-integer or odd samples per MHz, > 8 taps per branch)
   int design(const Plan &P, int tile_points, int tile_computed, int cols_per_thread);
+  // Same structure for the off-channel ("noise") DDCs of check_snr (lib/multi_block.cc:253-296): prototype
+  // noise_proto (Nn taps, Q = ceil(Nn / M) taps per branch, rows padded with zeros to a multiple of `row_pad` plus
+  // `row_pad` more), channel offsets + 790 kHz.  The pre-rotation by phi is applied to the input by a separate pass.
+  int design_noise(const Plan &P, int cols_per_thread, int row_pad);
+  int q_rows = 0;                    // rows of hq (noise variant: padded)
 };
 
 // Free-running rotator of one DDC object (GNU Radio's gr::blocks::rotator):

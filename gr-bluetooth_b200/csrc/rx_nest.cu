@@ -1,0 +1,275 @@
+// rx_nest.cu -- off-channel ("noise") energy of EVERY channel-window in the throughput mode: the reference's
+// 20001-tap noise DDCs (check_snr, lib/multi_block.cc:253-296: one freq_xlating_fir_filter_ccf per channel at
+// f_ch + 790 kHz, 850 outputs of the window's first slot, mean |y|^2) restated as ONE real-tap polyphase bank
+// of M = fs / 1 MHz branches with Q = ceil(Nn / M) = 201 taps each, shared by all channels, followed by the same
+// Good-Thomas DFT at the channel bins as rx_pfb.cu.  fp32 with FMA: a tolerance-level estimate (measured <= 7e-4 dB
+// from the exact energy, tests/test_gpu_parity.py::test_fast_noise_estimate_accuracy); the exact value is
+// rx_firdl.cu's job.
+//
+//   x'[n]   = x[n] e^{-j 2 pi phi n / M}              pre-rotation by the common fractional offset (own pass)
+//   u_j[r]  = sum_{q<Q} x'[n_j + r + M q] h'[r + M q]    n_j = b S + fns + j D,  j < 850
+//   |Y_c[j]| = | sum_r e^{-j 2 pi a_c r / M} u_j[r] |
+//
+// One block = one tile of 2 x 64 outputs (64 per parity of j: outputs two apart are exactly one tap apart, 2 D = M)
+// of one slot.  Thread = (branch r, parity p, run k of 16 outputs): it slides its 16 accumulators through the 201
+// taps -- per step ONE new input sample and ONE new tap feed 16 complex-by-real MACs (the last 16 taps sit in a
+// statically rotated register window) -- so shared-memory traffic is 12 bytes per 32 FMA.  Inputs and taps stream
+// through shared memory in chunks of 16 steps: a ring of 6 x 16 x M samples (both parities read the SAME contiguous
+// sample range) and a double-buffered tap chunk, each filled by one TMA bulk copy (cp.async.bulk + mbarrier) issued
+// a whole chunk of compute ahead.  Then, per tile: N1-point DFTs in place, N2-point DFTs at the channel bins (warp
+// = 32 output groups x 4 channels), |Z|^2 summed over the tile's valid outputs.
+#include "rx_nest.cuh"
+#include "rx_tma.cuh"
+
+namespace btb200 {
+
+namespace {
+
+constexpr int RING_CHUNKS = 6;       // ring capacity in chunks of 16 steps
+constexpr int CH = 16;               // steps per chunk
+
+struct NestSmem { size_t ring, taps, wb, n2r, epart, bar, total; };
+
+__host__ __device__ inline NestSmem nest_layout(const NestPlan &P)
+{
+  NestSmem L{};
+  size_t o = 0;
+  auto take = [&o](size_t bytes, size_t align) { o = (o + align - 1) / align * align; const size_t r = o; o += bytes; return r; };
+  const size_t ring = (size_t)RING_CHUNKS * CH * P.M * sizeof(c32);
+  const size_t u = (size_t)2 * NEST_TO * (P.M + 1) * sizeof(c32);         // U / V tile, row pitch M + 1
+  L.ring = take(ring > u ? ring : u, 128);
+  L.taps = take((size_t)2 * CH * P.M * sizeof(float), 128);
+  L.wb = take((size_t)P.N2 * P.ncol * sizeof(c32), 16);
+  L.n2r = take((size_t)P.N2 * sizeof(int), 16);
+  L.epart = take((size_t)32 * P.ncol * sizeof(float), 16);
+  L.bar = take((RING_CHUNKS + 2) * 8, 8);
+  L.total = o;
+  return L;
+}
+
+__global__ void k_nest_prerot(const c32 *__restrict__ x, c32 *__restrict__ xr, long n, const c32 *__restrict__ ph, int period)
+{
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const c32 v = x[i], p = ph[(int)(i % period)];
+  xr[i] = c32{v.re * p.re - v.im * p.im, v.re * p.im + v.im * p.re};
+}
+
+template <int N1>
+__global__ void __launch_bounds__(800, 1) k_nest(NestPlan P)
+{
+  extern __shared__ __align__(128) unsigned char smem[];
+  const NestSmem L = nest_layout(P);
+  c32 *ring = reinterpret_cast<c32 *>(smem + L.ring);
+  float *taps = reinterpret_cast<float *>(smem + L.taps);
+  c32 *WBs = reinterpret_cast<c32 *>(smem + L.wb);
+  int *n2r = reinterpret_cast<int *>(smem + L.n2r);
+  float *epart = reinterpret_cast<float *>(smem + L.epart);
+  uint64_t *bar = reinterpret_cast<uint64_t *>(smem + L.bar);          // [0..5] ring slots, [6..7] tap buffers
+
+  const int M = P.M, N2 = P.N2, ncol = P.ncol;
+  const int tid = threadIdx.x, nthr = blockDim.x;                      // nthr = 2 * NEST_K * M
+  const int r = tid % M, pk = tid / M, p = pk & 1, k = pk >> 1;
+  const int b = blockIdx.x / P.tiles_per_slot, tile = blockIdx.x - b * P.tiles_per_slot;
+  const int i0 = tile * NEST_TO;                                       // first output index (per parity) of the tile
+  const long n_base = (long)b * P.S + P.fns + (long)M * i0;            // sample of ring step 0, branch 0, parity 0
+  const int n_chunks = P.q_rows / CH;                                  // compute chunks
+  const int n_ring = n_chunks + NEST_K;                                // ring chunks the tile reads (+1 for the parity offset)
+  const unsigned ring_bytes = (unsigned)(CH * M * sizeof(c32)), tap_bytes = (unsigned)(CH * M * sizeof(float));
+
+  if (tid == 0) {
+    for (int i = 0; i < RING_CHUNKS + 2; i++) mbar_init(&bar[i], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
+  auto load_ring = [&](int m) {
+    uint64_t *bb = &bar[m % RING_CHUNKS];
+    mbar_expect_tx(bb, ring_bytes);
+    tma_bulk_g2s(ring + (size_t)(m % RING_CHUNKS) * CH * M, P.xr + n_base + (long)m * CH * M, ring_bytes, bb);
+  };
+  auto load_taps = [&](int c) {
+    uint64_t *bb = &bar[RING_CHUNKS + (c & 1)];
+    mbar_expect_tx(bb, tap_bytes);
+    tma_bulk_g2s(taps + (size_t)(c & 1) * CH * M, P.hq + (size_t)c * CH * M, tap_bytes, bb);
+  };
+  if (tid == 0) {
+    for (int m = 0; m < RING_CHUNKS && m < n_ring; m++) load_ring(m);
+    load_taps(0);
+    if (n_chunks > 1) load_taps(1);
+  }
+  for (int i = tid; i < N2 * ncol; i += nthr) WBs[i] = P.WB[i];
+  for (int i = tid; i < N2; i += nthr) n2r[i] = P.n2_of_rho[i];
+
+  // ---- 1. branch sums: 16 outputs i0 + 16 k + o of parity p, branch r
+  float ar[NEST_R], ai[NEST_R], H[NEST_R];
+#pragma unroll
+  for (int o = 0; o < NEST_R; o++) { ar[o] = 0.0f; ai[o] = 0.0f; H[o] = 0.0f; }
+  const int ring_samples = RING_CHUNKS * CH * M;
+  for (int c = 0; c < n_chunks; c++) {
+    if (c == 0) { for (int m = 0; m < NEST_K && m < n_ring; m++) mbar_wait(&bar[m], 0); }
+    if (c + NEST_K < n_ring) mbar_wait(&bar[(c + NEST_K) % RING_CHUNKS], (unsigned)(((c + NEST_K) / RING_CHUNKS) & 1));
+    mbar_wait(&bar[RING_CHUNKS + (c & 1)], (unsigned)((c >> 1) & 1));
+    int off = (int)(((long)M * (NEST_R * k + CH * c) + (long)P.D * p + r) % ring_samples);
+    const float *tp = taps + (size_t)(c & 1) * CH * M + r;
+#pragma unroll
+    for (int s = 0; s < CH; s++) {
+      const c32 X = ring[off];
+      off += M; if (off >= ring_samples) off -= ring_samples;
+      H[s] = tp[s * M];                               // tap q = 16 c + s; H[i] holds the latest tap with q = i (mod 16)
+#pragma unroll
+      for (int o = 0; o < NEST_R; o++) {
+        const float h = H[(s - o) & (NEST_R - 1)];    // tap q = 16 c + s - o
+        ar[o] = fmaf(X.re, h, ar[o]);
+        ai[o] = fmaf(X.im, h, ai[o]);
+      }
+    }
+    __syncthreads();                                  // ring chunk c and tap chunk c are free
+    if (tid == 0) {
+      fence_proxy_async();
+      if (c + RING_CHUNKS < n_ring) load_ring(c + RING_CHUNKS);
+      if (c + 2 < n_chunks) load_taps(c + 2);
+    }
+  }
+  // ---- the tile's branch sums to shared memory (the ring is dead): U[out][r], out = p * 64 + 16 k + o
+  const int UP = M + 1;
+  c32 *U = ring;
+#pragma unroll
+  for (int o = 0; o < NEST_R; o++) U[(size_t)(p * NEST_TO + NEST_R * k + o) * UP + r] = c32{ar[o], ai[o]};
+  __syncthreads();
+
+  // ---- 2. N1-point DFTs, in place: V[out][k1 * N2 + n2] = sum_n1 U[out][(N2 n1 + N1 n2) mod M] W_N1^{n1 k1}
+  {
+    constexpr int ITEMS = 16 / N1;                    // 2 * NEST_TO * N2 items on 8 * N1 * N2 threads
+    float vr[ITEMS][N1], vi[ITEMS][N1];
+#pragma unroll
+    for (int j = 0; j < ITEMS; j++) {
+      const int it = tid + j * nthr;
+      const int out = it / N2, rho = it - out * N2, n2 = n2r[rho];
+      float ur[N1], ui[N1];
+#pragma unroll
+      for (int n1 = 0; n1 < N1; n1++) { const c32 u = U[(size_t)out * UP + (N2 * n1 + N1 * n2) % M]; ur[n1] = u.re; ui[n1] = u.im; }
+      if constexpr (N1 == 1) { vr[j][0] = ur[0]; vi[j][0] = ui[0]; }
+      else if constexpr (N1 == 2) {
+        vr[j][0] = ur[0] + ur[1]; vi[j][0] = ui[0] + ui[1];
+        vr[j][1] = ur[0] - ur[1]; vi[j][1] = ui[0] - ui[1];
+      } else {
+        const float er = ur[0] + ur[2], ei = ui[0] + ui[2], fr = ur[0] - ur[2], fi = ui[0] - ui[2];
+        const float gr = ur[1] + ur[3], gi = ui[1] + ui[3], hr = ur[1] - ur[3], hi = ui[1] - ui[3];
+        vr[j][0] = er + gr; vi[j][0] = ei + gi;
+        vr[j][1] = fr + hi; vi[j][1] = fi - hr;       // f - j h
+        vr[j][2] = er - gr; vi[j][2] = ei - gi;
+        vr[j][3] = fr - hi; vi[j][3] = fi + hr;       // f + j h
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < ITEMS; j++) {
+      const int it = tid + j * nthr;
+      const int out = it / N2, rho = it - out * N2, n2 = n2r[rho];
+#pragma unroll
+      for (int k1 = 0; k1 < N1; k1++) U[(size_t)out * UP + k1 * N2 + n2] = c32{vr[j][k1], vi[j][k1]};
+    }
+    __syncthreads();
+  }
+
+  // ---- 3. N2-point DFTs at the channel bins + |Z|^2 over the valid outputs.  item = (og, cg): outputs og + 32 i
+  const int n_cg = ncol / NEST_NCOL;
+  const int n_par[2] = {(P.n_noise + 1) / 2, P.n_noise / 2};            // outputs of each parity in a slot
+  for (int item = tid; item < 32 * n_cg; item += nthr) {
+    const int og = item & 31, cg = item >> 5;
+    const int col0 = cg * NEST_NCOL, k1 = col0 / P.CPC;
+    float zr[4][NEST_NCOL], zi[4][NEST_NCOL];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+      for (int j = 0; j < NEST_NCOL; j++) { zr[i][j] = 0.0f; zi[i][j] = 0.0f; }
+    const c32 *vrow = U + (size_t)og * UP + k1 * N2;
+    const c32 *wrow = WBs + col0;
+#pragma unroll 5
+    for (int n2 = 0; n2 < N2; n2++) {
+      c32 v[4], w[NEST_NCOL];
+#pragma unroll
+      for (int i = 0; i < 4; i++) v[i] = vrow[(size_t)32 * i * UP + n2];
+#pragma unroll
+      for (int j = 0; j < NEST_NCOL; j++) w[j] = wrow[n2 * ncol + j];
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < NEST_NCOL; j++) {
+          zr[i][j] = fmaf(v[i].re, w[j].re, zr[i][j]); zr[i][j] = fmaf(-v[i].im, w[j].im, zr[i][j]);
+          zi[i][j] = fmaf(v[i].re, w[j].im, zi[i][j]); zi[i][j] = fmaf(v[i].im, w[j].re, zi[i][j]);
+        }
+    }
+    float e[NEST_NCOL];
+#pragma unroll
+    for (int j = 0; j < NEST_NCOL; j++) e[j] = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int out = og + 32 * i, pp = out / NEST_TO, idx = i0 + (out - pp * NEST_TO);
+      if (idx < n_par[pp]) {
+#pragma unroll
+        for (int j = 0; j < NEST_NCOL; j++) e[j] += zr[i][j] * zr[i][j] + zi[i][j] * zi[i][j];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < NEST_NCOL; j++) epart[og * ncol + col0 + j] = e[j];
+  }
+  __syncthreads();
+  for (int col = tid; col < ncol; col += nthr) {
+    float sum = 0.0f;
+    for (int og = 0; og < 32; og++) sum += epart[og * ncol + col];
+    P.E2[(size_t)blockIdx.x * ncol + col] = sum;
+  }
+}
+
+__global__ void k_nest_reduce(NestPlan P, int B)
+{
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * P.nch) return;
+  const int b = idx / P.nch, c = idx - b * P.nch;
+  const int col = P.chan_col[c];
+  double sum = 0.0;
+  for (int t = 0; t < P.tiles_per_slot; t++) sum += (double)P.E2[((size_t)b * P.tiles_per_slot + t) * P.ncol + col];
+  P.esum[idx] = sum;
+}
+
+}  // namespace
+
+size_t nest_smem_bytes(const NestPlan &P) { return nest_layout(P).total; }
+
+#define NEST_DISPATCH(CALL) do { if (P.N1 == 4) { CALL(4); } else if (P.N1 == 2) { CALL(2); } else { CALL(1); } } while (0)
+
+int nest_setup(const NestPlan &P)
+{
+  if (2 * P.D != P.M || P.N1 * P.N2 != P.M || (P.N1 != 1 && P.N1 != 2 && P.N1 != 4)) return -1;
+  if (2 * NEST_K * P.M > 800 || P.q_rows % CH != 0 || P.q_rows < P.Q + CH || P.ncol % NEST_NCOL != 0) return -1;
+  if (((CH * P.M * sizeof(float)) & 15) != 0) return -1;                    // TMA bulk copies move multiples of 16 bytes
+  if ((((long)P.S * sizeof(c32)) & 15) != 0 || (((long)P.fns * sizeof(c32)) & 15) != 0 || ((NEST_TO * P.M * sizeof(c32)) & 15) != 0)
+    return -1;                                                             // ... from 16-byte aligned addresses
+  if (nest_smem_bytes(P) > 227 * 1024) return -1;
+  cudaError_t e = cudaSuccess;
+#define NEST_OPT(N1_) e = cudaFuncSetAttribute((const void *)k_nest<N1_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nest_smem_bytes(P))
+  NEST_DISPATCH(NEST_OPT);
+#undef NEST_OPT
+  return e == cudaSuccess ? 0 : -1;
+}
+
+void launch_nest_prerot(const NestPlan &P, const c32 *x, long n_samples, cudaStream_t s)
+{
+  if (n_samples <= 0) return;
+  k_nest_prerot<<<(unsigned)((n_samples + 255) / 256), 256, 0, s>>>(x, P.xr, n_samples, P.phasor, P.period);
+}
+
+void launch_nest(const NestPlan &P, int B, cudaStream_t s)
+{
+  const dim3 grid((unsigned)(B * P.tiles_per_slot));
+  const int threads = 2 * NEST_K * P.M;
+  const size_t smem = nest_smem_bytes(P);
+#define NEST_RUN(N1_) k_nest<N1_><<<grid, threads, smem, s>>>(P)
+  NEST_DISPATCH(NEST_RUN);
+#undef NEST_RUN
+  const int n = B * P.nch;
+  k_nest_reduce<<<(n + 127) / 128, 128, 0, s>>>(P, B);
+}
+
+}  // namespace btb200

@@ -1,0 +1,37 @@
+// rx_nest.cuh -- off-channel ("noise") energy estimator of the throughput mode, see rx_nest.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include "rx_math.cuh"
+
+namespace btb200 {
+
+constexpr int NEST_R = 16;           // outputs a thread slides through the taps
+constexpr int NEST_K = 4;            // runs per parity per tile
+constexpr int NEST_TO = NEST_R * NEST_K;   // outputs per parity per tile
+constexpr int NEST_NCOL = 4;         // channels per thread in the DFT stage
+
+struct NestPlan {
+  int M = 0, D = 0, Q = 0, q_rows = 0;   // branches, decimation (2 D = M), taps per branch, rows of hq (multiple of 16)
+  int N1 = 1, N2 = 1, CPC = 0, ncol = 0, nch = 0;
+  int S = 0, fns = 0, n_noise = 0;
+  int tiles_per_slot = 0;
+  int period = 0;
+  const float *hq = nullptr;         // [q_rows][M]  h'[r + M q], zero padded
+  const int *n2_of_rho = nullptr;    // [N2]
+  const c32 *WB = nullptr;           // [N2][ncol]
+  const int *col_chan = nullptr;     // [ncol]
+  const int *chan_col = nullptr;     // [nch]
+  const c32 *phasor = nullptr;       // [period]  e^{-j 2 pi phi n / M}
+  c32 *xr = nullptr;                 // pre-rotated input
+  float *E2 = nullptr;               // [B][tiles_per_slot][ncol]  per-tile sums of |Z|^2
+  double *esum = nullptr;            // [B][nch]  sum over the window's noise outputs
+};
+
+size_t nest_smem_bytes(const NestPlan &P);
+int  nest_setup(const NestPlan &P);      // 0, or -1 when the configuration is outside the kernel's limits
+// xr[n] = x[n] * phasor[(n0 + n) % period] for n < n_samples
+void launch_nest_prerot(const NestPlan &P, const c32 *x, long n_samples, cudaStream_t s);
+// esum[b][c] = sum_j |noise DDC output j of window b, channel c|^2 (lib/multi_block.cc:253-287) from P.xr
+void launch_nest(const NestPlan &P, int B, cudaStream_t s);
+
+}  // namespace btb200

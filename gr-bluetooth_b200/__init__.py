@@ -71,6 +71,7 @@ class Hits(C.Structure):
 EXPORTS = ["btb200_process_channels", "btb200_create", "btb200_destroy", "btb200_get_info", "btb200_process", "btb200_process_device",
            "btb200_submit", "btb200_submit_i16", "btb200_process_i16", "btb200_collect_begin", "btb200_collect", "btb200_host_alloc", "btb200_host_free",
            "btb200_get_mm_state", "btb200_set_mm_state", "btb200_reset", "btb200_get_stage",
+           "btb200_search_bits", "btb200_timer_start", "btb200_timer_stop",
            "btb200_last_timing", "btb200_launch_count", "btb200_strerror", "btb200_last_error",
            "btb200_version"]
 
@@ -104,6 +105,9 @@ def lib():
         L.btb200_reset.argtypes = [C.c_void_p]
         L.btb200_get_stage.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_uint32, C.c_void_p, C.c_size_t]
         L.btb200_get_stage.restype = C.c_int64
+        L.btb200_search_bits.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32, C.POINTER(Hits)]
+        L.btb200_timer_start.argtypes = [C.c_void_p]
+        L.btb200_timer_stop.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
         L.btb200_last_timing.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
         L.btb200_launch_count.argtypes = [C.c_void_p]
         L.btb200_launch_count.restype = C.c_uint64
@@ -205,11 +209,20 @@ class multi_block:
             raise Btb200Error(rc, self._L.btb200_last_error(self._ctx).decode())
 
     def _hits_struct(self, want_symbols):
+        if want_symbols == "borrow":         # zero-copy: symbols stay in the context's pinned arena
+            return Hits(hits=self._hits.ctypes.data, cap=self._hit_cap, count=0, overflow=0, symbols=None,
+                        symbols_cap=0xFFFFFFFFFFFFFFFF, symbols_used=0)
         return Hits(hits=self._hits.ctypes.data, cap=self._hit_cap, count=0, overflow=0,
                     symbols=self._syms.ctypes.data if want_symbols else None,
                     symbols_cap=self._sym_cap, symbols_used=0)
 
     def _take(self, h, want_symbols):
+        if want_symbols == "borrow":
+            # views, valid until the next submit on this block: the hit records in this object's buffer, the symbols
+            # in the library's pinned arena
+            n = int(h.symbols_used)
+            syms = np.frombuffer((C.c_uint8 * n).from_address(h.symbols), dtype=np.uint8) if n else np.zeros(0, np.uint8)
+            return self._hits[:h.count], syms, int(h.overflow)
         hits = self._hits[:h.count].copy()
         syms = self._syms[:h.symbols_used].copy() if want_symbols else None
         return hits, syms, int(h.overflow)
@@ -333,6 +346,25 @@ class multi_block:
         if n < 0:
             raise Btb200Error(int(n), self._L.btb200_last_error(self._ctx).decode())
         return buf[:n].view(dt).copy()
+
+    def search_bits(self, symbols, stride=625):
+        """Known-answer entry: the access-code search kernel on a caller-supplied symbol stream (one symbol per byte),
+        cut into windows every `stride` symbols.  -> list of (absolute symbol offset, LAP)."""
+        sym = np.ascontiguousarray(symbols, dtype=np.uint8)
+        h = self._hits_struct(False)
+        self._check(self._L.btb200_search_bits(self._ctx, sym.ctypes.data, len(sym), stride, C.byref(h)))
+        if h.overflow:
+            raise Btb200Error(-7, "hit buffer too small")
+        hits = self._hits[:h.count]
+        return [(int(x["slot"]) * stride + int(x["offset"]), int(x["lap"])) for x in hits]
+
+    def timer_start(self):
+        self._check(self._L.btb200_timer_start(self._ctx))
+
+    def timer_stop(self):
+        ms = C.c_float()
+        self._check(self._L.btb200_timer_stop(self._ctx, C.byref(ms)))
+        return float(ms.value)
 
     def last_timing(self):
         ms = (C.c_float * 8)()

@@ -57,6 +57,7 @@ struct btb200_ctx {
   cudaEvent_t ev[kNumEvents + 1]{};
   cudaEvent_t evl[3]{};      // lazy squelch: noise FIR / energies
   cudaEvent_t ev_tail = nullptr;
+  cudaEvent_t ev_user[2] = {};
   bool lazy_timed = false;
   // device allocations
   std::vector<void *> allocs;
@@ -241,7 +242,11 @@ int setup_fast(btb200_ctx *ctx)
       // the last tile of a slot reads (tiles * 64 + q_rows + 16 * 5) * M samples past the slot's first noise sample
       const long reach = (long)P.fns + ((long)K.tiles_per_slot * NEST_TO + K.q_rows + 16 * (NEST_K + 1)) * K.M;
       if (reach <= P.H && nest_setup(K) == 0) {
-        if ((rc = upload(ctx, &K.hq, N.hq))) return rc;
+        {
+          std::vector<float2> h2(N.hq.size());
+          for (size_t i = 0; i < h2.size(); i++) h2[i] = make_float2(N.hq[i], N.hq[i]);
+          if ((rc = upload(ctx, &K.hq2, h2))) return rc;
+        }
         if ((rc = upload(ctx, &K.n2_of_rho, N.n2_of_rho))) return rc;
         if ((rc = upload_raw<c32>(ctx, &K.WB, N.WB.data(), N.WB.size()))) return rc;
         if ((rc = upload(ctx, &K.col_chan, N.col_chan))) return rc;
@@ -302,6 +307,15 @@ int setup_pfb(btb200_ctx *ctx)
   if ((rc = dev_alloc(ctx, &ctx->d_eon_all, B * P.nch))) return rc;
   CK(cudaMallocHost(&ctx->h_eon_all, B * P.nch * sizeof(double)));
   if (pfb_setup(K) != 0) { ctx->last_error = "polyphase channelizer: configuration outside the kernel's limits"; return BTB200_ERR_ARG; }
+  // device-driven tail (rx_kernels.cuh, TailBufs)
+  TailBufs &Tb = ctx->W.tail;
+  const size_t nw = B * P.nch;
+  if ((rc = dev_alloc(ctx, &Tb.stage, nw * TAIL_MAXW))) return rc;
+  if ((rc = dev_alloc(ctx, &Tb.cnt, nw))) return rc;
+  if ((rc = dev_alloc(ctx, &Tb.base, nw))) return rc;
+  if ((rc = dev_alloc(ctx, &Tb.list, nw))) return rc;
+  if ((rc = dev_alloc(ctx, &Tb.n_list, 1))) return rc;
+  if ((rc = dev_alloc(ctx, &Tb.sorted, (size_t)kHitCap))) return rc;
   return 0;
 }
 
@@ -372,6 +386,7 @@ int setup(btb200_ctx *ctx)
   for (auto &e : ctx->ev) CK(cudaEventCreate(&e));
   for (auto &e : ctx->evl) CK(cudaEventCreate(&e));
   CK(cudaEventCreateWithFlags(&ctx->ev_tail, cudaEventDisableTiming));
+  for (auto &e : ctx->ev_user) CK(cudaEventCreate(&e));
 
   int rc;
   if ((rc = upload_raw<c32>(ctx, &ctx->T.chan_rtaps, P.chan_rtaps.data(), P.chan_rtaps.size()))) return rc;
@@ -480,6 +495,11 @@ int setup(btb200_ctx *ctx)
     CK(cudaDeviceGetStreamPriorityRange(&pr_lo, &pr_hi));
     CK(cudaStreamCreateWithPriority(&ctx->stream2, cudaStreamNonBlocking, pr_hi));
   }
+  if (ctx->poly && !ctx->stream2) {
+    int pr_lo = 0, pr_hi = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&pr_lo, &pr_hi));
+    CK(cudaStreamCreateWithPriority(&ctx->stream2, cudaStreamNonBlocking, pr_hi));
+  }
   const size_t bp = G.stateless ? 1 : B;
   if ((rc = dev_alloc(ctx, &ctx->d_phc, bp * P.n_ddc * nch))) return rc;
   if ((rc = dev_alloc(ctx, &ctx->d_phn, bp * P.n_noise * nch))) return rc;
@@ -563,6 +583,7 @@ void teardown(btb200_ctx *ctx)
   for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
   for (auto &e : ctx->evl) if (e) cudaEventDestroy(e);
   if (ctx->ev_tail) cudaEventDestroy(ctx->ev_tail);
+  for (auto &e : ctx->ev_user) if (e) cudaEventDestroy(e);
   if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
   if (ctx->stream && ctx->owns_stream) cudaStreamDestroy(ctx->stream);
 }
@@ -607,9 +628,11 @@ int btb200_create(const btb200_config *cfg, btb200_ctx **out)
   if (ctx->cfg.extra_history_symbols == 0) ctx->cfg.extra_history_symbols = 3125;
   ctx->max_slots = cfg->max_slots_per_call ? cfg->max_slots_per_call : kDefaultMaxSlots;
   ctx->device = cfg->device;
-  if (ctx->plan.design(cfg->sample_rate, cfg->center_freq, cfg->squelch_threshold,
-                       (int)ctx->cfg.extra_history_symbols) != 0 ||
-      (cfg->mm_mode != BTB200_MM_CHAINED && cfg->mm_mode != BTB200_MM_STATELESS)) {
+  const int drc = ctx->plan.design(cfg->sample_rate, cfg->center_freq, cfg->squelch_threshold,
+                                   (int)ctx->cfg.extra_history_symbols);
+  if (drc != 0 || (cfg->mm_mode != BTB200_MM_CHAINED && cfg->mm_mode != BTB200_MM_STATELESS) || cfg->device >= 64) {
+    g_create_error = drc == -2 ? "sample rate not supported: 625 * fs / 1 MHz must be a multiple of the decimation (int)(fs / 1 MHz) / 2"
+                               : "bad configuration";
     delete ctx;
     return BTB200_ERR_ARG;
   }
@@ -774,12 +797,23 @@ static int submit_impl(btb200_ctx *ctx, const void *iq, int kind, size_t n_sampl
     CK(cudaEventRecord(ctx->ev[4], s));
     launch_demod_mm_v2(G, ctx->T, W, ctx->d_dem, s); ctx->launches++;
     CK(cudaEventRecord(ctx->ev[5], s));
-    launch_search_warp(G, ctx->T, W, s);
-    if (!G.early) launch_gather(G, W, s);
-    ctx->launches += G.early ? 1 : 2;
+    launch_search_warp(G, ctx->T, W, s); ctx->launches++;
     CK(cudaEventRecord(ctx->ev[6], s));
-    CK(cudaMemcpyAsync(ctx->h_counts, W.hit_count, 4 * sizeof(unsigned), cudaMemcpyDeviceToHost, s));
-    CK(cudaEventRecord(ctx->ev[7], s));
+    // the tail -- resume of the windows with hits, hit list in the reference's order, arena layout, symbol gather --
+    // is laid out on the device and runs on the second (high-priority) stream under the next batches' kernels
+    // The tail is a handful of latency-bound kernels (the resumed clock-recovery chains): run under another batch's
+    // compute-bound kernels they are starved of issue slots and take 5x longer, and that batch's own clock recovery
+    // slows down with them (measured: 4.0 ms per step overlapped on a second stream, 3.7 in order) -- so the tail stays
+    // on the compute stream.  BTB200_TAIL_STREAM2=1 restores the overlapped variant.
+    static const bool tail_inline = std::getenv("BTB200_TAIL_STREAM2") == nullptr;
+    cudaStream_t s2 = tail_inline ? s : ctx->stream2;
+    if (!tail_inline) CK(cudaStreamWaitEvent(s2, ctx->ev[6], 0));
+    launch_tail_scan(G, W, s2);
+    if (G.early) launch_tail_resume(G, ctx->T, W, ctx->d_dem, s2);
+    launch_tail_finish(G, W, s2);
+    ctx->launches += G.early ? 5 : 4;
+    CK(cudaMemcpyAsync(ctx->h_counts, W.hit_count, 4 * sizeof(unsigned), cudaMemcpyDeviceToHost, s2));
+    CK(cudaEventRecord(ctx->ev[7], s2));
     CK(cudaGetLastError());
     ctx->pending = true;
     ctx->pend_slots = n_slots;
@@ -790,6 +824,13 @@ static int submit_impl(btb200_ctx *ctx, const void *iq, int kind, size_t n_sampl
     return BTB200_OK;
   }
   const bool chan_fir_done = front_done;
+  // chained mode advances host-side stream state (rotators) while it builds the batch: keep a copy and put it back
+  // on every failure path, so that a transient CUDA error cannot desynchronise the stream
+  struct Restore {
+    btb200_ctx *c; std::vector<Rotator> rc, rn; MmState mm; bool armed;
+    ~Restore() { if (armed) { c->rot_c = rc; c->rot_n = rn; c->mm = mm; } }
+  } restore{ctx, {}, {}, ctx->mm, false};
+  if (!G.stateless) { restore.rc = ctx->rot_c; restore.rn = ctx->rot_n; restore.armed = true; }
   if (!G.stateless) {
     // free-running rotators: the phases of this batch's windows, generated with
     // the same libm calls as the reference's rotator (hypotf renormalisation)
@@ -855,6 +896,7 @@ static int submit_impl(btb200_ctx *ctx, const void *iq, int kind, size_t n_sampl
   if (!G.stateless) CK(cudaMemcpyAsync(&ctx->mm, W.mm_state, sizeof(MmState), cudaMemcpyDeviceToHost, s));
   CK(cudaEventRecord(ctx->ev[7], s));
   CK(cudaGetLastError());
+  restore.armed = false;
   ctx->pending = true;
   ctx->pend_slots = n_slots;
   ctx->pend_first_slot = first_slot;
@@ -883,6 +925,7 @@ int btb200_submit_i16(btb200_ctx *ctx, const int16_t *iq, int iq_on_device, size
 int btb200_collect_begin(btb200_ctx *ctx)
 {
   if (!ctx || !ctx->pending || ctx->cb.begun) return BTB200_ERR_ARG;
+  if (ctx->poly) { ctx->cb = btb200_ctx::CollectState{}; ctx->cb.begun = true; return BTB200_OK; }   // nothing is deferred to the host
   CK(cudaSetDevice(ctx->device));
   cudaStream_t s = ctx->stream, cs = ctx->copy_stream;
   const Plan &P = ctx->plan;
@@ -1016,9 +1059,81 @@ int btb200_collect_begin(btb200_ctx *ctx)
   return BTB200_OK;
 }
 
+namespace {
+// borrowed symbols: the caller passes symbols == NULL and symbols_cap == UINT64_MAX and gets a pointer into the
+// context's pinned arena (valid until the next submit on this context) instead of a copy
+inline bool borrow_symbols(const btb200_hits *out) { return out && !out->symbols && out->symbols_cap == UINT64_MAX; }
+
+int collect_poly(btb200_ctx *ctx, btb200_hits *out)
+{
+  const Plan &P = ctx->plan;
+  cudaStream_t cs = ctx->copy_stream;
+  ctx->pending = false;
+  ctx->cb.begun = false;
+  CK(cudaEventSynchronize(ctx->ev[7]));              // the batch's tail has finished; counts are on the host
+  unsigned nh = ctx->h_counts[0], dropped = 0;
+  if (nh > kHitCap) { dropped = nh - kHitCap; nh = kHitCap; }
+  unsigned long long used = 0;
+  std::memcpy(&used, ctx->h_counts + 2, sizeof used);
+  if (used > kArenaCap) used = kArenaCap;
+  const bool want_sym = out && (out->symbols || borrow_symbols(out));
+  if (nh) CK(cudaMemcpyAsync(ctx->h_hits, ctx->pendW.tail.sorted, (size_t)nh * sizeof(DevHit), cudaMemcpyDeviceToHost, cs));
+  if (want_sym && used) CK(cudaMemcpyAsync(ctx->h_arena, ctx->W.arena, used, cudaMemcpyDeviceToHost, cs));
+  CK(cudaEventRecord(ctx->ev[8], cs));
+  const size_t nbc = (size_t)ctx->pend_slots * P.nch;
+  for (size_t i = 0; i < nbc; i++) { ctx->h_energy[i] = ctx->h_eon_all[i]; ctx->h_noise[i] = ctx->h_esum[i] / P.n_noise; }
+  ctx->fast_off.assign(ctx->h_noise, ctx->h_noise + nbc);
+  CK(cudaEventSynchronize(ctx->ev[8]));
+  ctx->last_slots = ctx->pend_slots;
+  for (int i = 0; i < 6; i++) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev[i], ctx->ev[i + 1]);
+    ctx->timing[i] = ms;
+  }
+  cudaEventElapsedTime(&ctx->timing[6], ctx->ev[6], ctx->ev[8]);
+  cudaEventElapsedTime(&ctx->timing[7], ctx->ev[0], ctx->ev[8]);
+  if (!out) return BTB200_OK;
+  out->count = 0;
+  out->overflow = dropped;
+  out->symbols_used = 0;
+  const bool borrow = borrow_symbols(out);
+  if (borrow) { out->symbols = ctx->h_arena; out->symbols_used = used; }
+  const DevHit *hh = ctx->h_hits;
+  for (unsigned i = 0; i < nh; i++) {
+    const DevHit &h = hh[i];                      // already in the reference's visiting order
+    const size_t bc = (size_t)h.b * P.nch + h.chi;
+    const double snr = 10.0 * std::log10(ctx->h_energy[bc] / ctx->h_noise[bc]);     // multi_block.cc:293
+    if (!(snr >= P.squelch_db)) continue;
+    if (out->count >= out->cap) { out->overflow++; continue; }
+    btb200_hit &o = out->hits[out->count];
+    o.slot = (uint32_t)(ctx->pend_first_slot + (uint64_t)h.b);
+    o.channel = (uint16_t)(P.ch_lo + h.chi);
+    o.kind = (uint16_t)h.kind;
+    o.offset = h.offset;
+    o.n_symbols = h.n_symbols;
+    o.lap = h.lap;
+    o.flags = ((std::fabs(snr - P.squelch_db) <= 1e-6) ? 1u : 0u) | 2u | 4u;
+    o.snr = snr;
+    o.sym_offset = 0;
+    o.sym_count = 0;
+    o.reserved = 0;
+    if (borrow) { o.sym_offset = h.sym_offset; o.sym_count = h.sym_count; }
+    else if (out->symbols && h.sym_count && out->symbols_used + h.sym_count <= out->symbols_cap) {
+      std::memcpy(out->symbols + out->symbols_used, ctx->h_arena + h.sym_offset, h.sym_count);
+      o.sym_offset = out->symbols_used;
+      o.sym_count = h.sym_count;
+      out->symbols_used += h.sym_count;
+    }
+    out->count++;
+  }
+  return BTB200_OK;
+}
+}  // namespace
+
 int btb200_collect(btb200_ctx *ctx, btb200_hits *out)
 {
   if (!ctx || !ctx->pending) return BTB200_ERR_ARG;
+  if (ctx->poly) { CK(cudaSetDevice(ctx->device)); return collect_poly(ctx, out); }
   if (!ctx->cb.begun) { if (int rc = btb200_collect_begin(ctx)) return rc; }
   CK(cudaSetDevice(ctx->device));
   cudaStream_t s = ctx->stream;
@@ -1047,14 +1162,14 @@ int btb200_collect(btb200_ctx *ctx, btb200_hits *out)
       off += (unsigned)cnt;
     }
     used = off > kArenaCap ? kArenaCap : off;
-    if (out && out->symbols && used) {
+    if (out && (out->symbols || borrow_symbols(out)) && used) {
       CK(cudaMemcpyAsync(ctx->W.hits, ctx->h_hits, (size_t)nh * sizeof(DevHit), cudaMemcpyHostToDevice, s2));
       launch_gather(ctx->pendG, ctx->pendW, s2); ctx->launches++;
       CK(cudaMemcpyAsync(ctx->h_arena, ctx->W.arena, used, cudaMemcpyDeviceToHost, s2));
     }
     CK(cudaEventRecord(ctx->ev_tail, s2));
     CK(cudaStreamWaitEvent(s, ctx->ev_tail, 0));     // the batch (and its timing) ends when the tail has
-  } else if (used && out && out->symbols) {
+  } else if (used && out && (out->symbols || borrow_symbols(out))) {
     CK(cudaMemcpyAsync(ctx->h_arena, ctx->W.arena, used, cudaMemcpyDeviceToHost, s));
   }
   CK(cudaEventRecord(ctx->ev[8], s));
@@ -1102,6 +1217,8 @@ int btb200_collect(btb200_ctx *ctx, btb200_hits *out)
   out->count = 0;
   out->overflow = dropped;
   out->symbols_used = 0;
+  const bool borrow = borrow_symbols(out);
+  if (borrow) { out->symbols = ctx->h_arena; out->symbols_used = used; }
   for (unsigned oi = 0; oi < nh; oi++) {
     const DevHit &h = hh[order[oi]];
     const size_t bc = (size_t)h.b * P.nch + h.chi;
@@ -1123,7 +1240,8 @@ int btb200_collect(btb200_ctx *ctx, btb200_hits *out)
     o.sym_offset = 0;
     o.sym_count = 0;
     o.reserved = 0;
-    if (out->symbols && h.sym_count && out->symbols_used + h.sym_count <= out->symbols_cap) {
+    if (borrow) { o.sym_offset = h.sym_offset; o.sym_count = h.sym_count; }
+    else if (out->symbols && h.sym_count && out->symbols_used + h.sym_count <= out->symbols_cap) {
       std::memcpy(out->symbols + out->symbols_used, ctx->h_arena + h.sym_offset, h.sym_count);
       o.sym_offset = out->symbols_used;
       o.sym_count = h.sym_count;
@@ -1243,6 +1361,86 @@ int btb200_process_channels(btb200_ctx *ctx, const float *iq, size_t n_samples, 
   return BTB200_OK;
 }
 
+int btb200_timer_start(btb200_ctx *ctx)
+{
+  if (!ctx) return BTB200_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaEventRecord(ctx->ev_user[0], ctx->stream));
+  return BTB200_OK;
+}
+
+int btb200_timer_stop(btb200_ctx *ctx, float *ms)
+{
+  if (!ctx || !ms) return BTB200_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaEventRecord(ctx->ev_user[1], ctx->stream));
+  CK(cudaEventSynchronize(ctx->ev_user[1]));
+  CK(cudaEventElapsedTime(ms, ctx->ev_user[0], ctx->ev_user[1]));
+  return BTB200_OK;
+}
+
+int btb200_search_bits(btb200_ctx *ctx, const uint8_t *symbols, size_t n_symbols, uint32_t stride, btb200_hits *out)
+{
+  if (!ctx || !symbols || !out || stride == 0 || stride > 625 || ctx->pending) return BTB200_ERR_ARG;
+  const Plan &P = ctx->plan;
+  Geom G = ctx->G;
+  G.early = 0;
+  G.search = BTB200_SEARCH_BR;
+  const int wlen = (int)stride + 72;
+  if (G.bw < (wlen + 31) / 32 + 4) return BTB200_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  const size_t nwin = (n_symbols + stride - 1) / stride;
+  const size_t per_call = (size_t)ctx->max_slots * P.nch;
+  std::vector<uint32_t> rows(per_call * G.bw);
+  std::vector<int> nsym(per_call);
+  out->count = 0; out->overflow = 0; out->symbols_used = 0;
+  for (size_t w0 = 0; w0 < nwin; w0 += per_call) {
+    const size_t nw = std::min(per_call, nwin - w0);
+    const size_t nb = (nw + P.nch - 1) / P.nch;
+    std::fill(rows.begin(), rows.end(), 0u);
+    std::fill(nsym.begin(), nsym.end(), 0);
+    for (size_t i = 0; i < nw; i++) {
+      const size_t first = (w0 + i) * stride;
+      const int len = (int)std::min<size_t>((size_t)wlen, n_symbols - first);
+      nsym[i] = len;
+      uint32_t *row = &rows[i * G.bw];
+      for (int k = 0; k < len; k++) row[k >> 5] |= (uint32_t)(symbols[first + k] & 1) << (k & 31);
+    }
+    DevBatch W = ctx->W;
+    W.B = (int)nb;
+    CK(cudaMemcpyAsync(W.bits, rows.data(), nb * P.nch * G.bw * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(W.nsym, nsym.data(), nb * P.nch * sizeof(int), cudaMemcpyHostToDevice, s));
+    CK(cudaMemsetAsync(W.hit_count, 0, 4 * sizeof(unsigned), s));
+    launch_search_warp(G, ctx->T, W, s); ctx->launches++;
+    CK(cudaMemcpyAsync(ctx->h_counts, W.hit_count, 4 * sizeof(unsigned), cudaMemcpyDeviceToHost, s));
+    SYNC_HERE();
+    unsigned nh = ctx->h_counts[0];
+    if (nh > kHitCap) { out->overflow += nh - kHitCap; nh = kHitCap; }
+    if (nh) CK(cudaMemcpy(ctx->h_hits, W.hits, (size_t)nh * sizeof(DevHit), cudaMemcpyDeviceToHost));
+    std::vector<unsigned> order(nh);
+    for (unsigned i = 0; i < nh; i++) order[i] = i;
+    const DevHit *hh = ctx->h_hits;
+    std::sort(order.begin(), order.end(), [hh](unsigned a, unsigned b) {
+      const DevHit &x = hh[a], &y = hh[b];
+      if (x.b != y.b) return x.b < y.b;
+      if (x.chi != y.chi) return x.chi < y.chi;
+      return x.offset < y.offset;
+    });
+    for (unsigned oi = 0; oi < nh; oi++) {
+      const DevHit &h = hh[order[oi]];
+      if (h.kind != 0) continue;
+      if (out->count >= out->cap) { out->overflow++; continue; }
+      btb200_hit &o = out->hits[out->count++];
+      o = btb200_hit{};
+      o.slot = (uint32_t)(w0 + (size_t)h.b * P.nch + h.chi);
+      o.offset = h.offset; o.n_symbols = h.n_symbols; o.lap = h.lap;
+    }
+  }
+  ctx->last_slots = 0;
+  return BTB200_OK;
+}
+
 int btb200_last_timing(const btb200_ctx *ctx, float ms[8])
 {
   if (!ctx || !ms) return BTB200_ERR_ARG;
@@ -1337,6 +1535,17 @@ int64_t btb200_get_stage(btb200_ctx *ctx, int stage, uint32_t b, uint32_t chi, v
     }
     default: return BTB200_ERR_ARG;
   }
+}
+
+// debug hook (tools/trace_pipeline.py): when the last batch of `ctx` started its kernels, finished its search, finished
+// its tail and finished its copies, in ms after `base`'s btb200_timer_start()
+BTB200_API int btb200_debug_timeline(btb200_ctx *ctx, btb200_ctx *base, float out[5])
+{
+  if (!ctx || !base || !out) return BTB200_ERR_ARG;
+  const int idx[5] = {0, 1, 6, 7, 8};
+  for (int i = 0; i < 5; i++)
+    if (cudaEventElapsedTime(&out[i], base->ev_user[0], ctx->ev[idx[i]]) != cudaSuccess) out[i] = -1.0f;
+  return BTB200_OK;
 }
 
 // test hook: select baseline (0) or tuned (1) kernels

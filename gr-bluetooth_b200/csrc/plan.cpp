@@ -252,7 +252,10 @@ int Plan::design(double fs_, double fc_, double squelch, int extra)
   D = (int)sps / 2;                                          // :82
   if (D < 1) return -1;
   const double csps = sps / D;                               // :83
-  if (S % D != 0) return -1;   // windows must share one decimation grid (true for every integer Msps rate)
+  // windows must share one decimation grid: S = 625 sps must be a multiple of D = (int)sps / 2.  True for the even
+  // integer Msps rates (every BASELINE configuration); NOT for e.g. 5, 7, 9 or 13 Msps, which the reference's block
+  // accepts -- those rates are rejected here (documented in include/btb200.h, btb200_create)
+  if (S % D != 0) return -2;
   grid_per_slot = S / D;
 
   // set_channels(), :306-342

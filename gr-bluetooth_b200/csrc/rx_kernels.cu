@@ -132,8 +132,19 @@ __global__ void k_mm_chained_list(Geom G, DevBatch W, const float *__restrict__ 
 struct HitEmitter {
   const Geom &G; const DevBatch &W; int b, c, nsym;
   bool relative = false;      // lazy tail: n_symbols is relative to the (not yet known) symbol count; no symbols yet
+  int *staged = nullptr;      // device-driven tail: running count of this window's hits (one emitting thread per window)
   __device__ void operator()(int kind, int offset, int n_symbols, uint32_t lap) const
   {
+    if (staged) {
+      const int i = (*staged)++;
+      if (i < TAIL_MAXW) {
+        DevHit h;
+        h.b = b; h.chi = (int16_t)c; h.kind = (int16_t)kind; h.offset = offset; h.n_symbols = n_symbols;
+        h.lap = lap; h.sym_offset = 0; h.sym_count = 0;
+        W.tail.stage[((long)b * G.nch + c) * TAIL_MAXW + i] = h;
+      }
+      return;
+    }
     const unsigned slot = atomicAdd(W.hit_count, 1u);
     if (slot >= W.hit_cap) return;
     int cnt = n_symbols < 3125 ? n_symbols : 3125;
@@ -692,16 +703,19 @@ __global__ void __launch_bounds__(BLK) k_mm_stateless_v2(Geom G, DevBatch W, con
 {
   constexpr int RD = MM_RD;        // ring depth (demod samples per window)
   constexpr int AHEAD = 88;        // refill target: ii + 8 + AHEAD
-  constexpr int PERIOD = 8;        // refill every PERIOD steps (warp-uniform: all lanes share the step counter)
-  // The loop advances ii by at most 5 samples per step (|demod| <= gain*pi bounds mm_val), so a refill
-  // at step t covers everything consumed before step t+2*PERIOD: the group in flight is never read.
+  constexpr int PERIOD = 8;        // steps between refills
+  // The loop advances ii by at most 5 samples per step (|demod| <= gain*pi bounds mm_val), so the refill issued at
+  // the start of a block of PERIOD steps (it reaches ii + 96) covers everything the NEXT block can read (< ii + 88)
+  // and lands while this block runs; 128 rows never overwrite a live sample.  Rows 0..7 are mirrored at 128..135 so
+  // the 8 samples of an interpolation are always 8 consecutive rows: one base address, immediate offsets.
   extern __shared__ __align__(16) unsigned char mm_smem[];
-  float (*ring)[BLK] = reinterpret_cast<float (*)[BLK]>(mm_smem);                        // [RD][BLK]
-  float (*s_mmse)[132] = reinterpret_cast<float (*)[132]>(mm_smem + sizeof(float) * RD * BLK);   // [8][132]
+  float (*ring)[BLK] = reinterpret_cast<float (*)[BLK]>(mm_smem);                        // [RD + 8][BLK]
+  float (*s_mmse)[132] = reinterpret_cast<float (*)[132]>(mm_smem + sizeof(float) * (RD + 8) * BLK);   // [8][132]
   for (int i = threadIdx.x; i < 129 * 8; i += BLK) s_mmse[7 - (i & 7)][i >> 3] = mmse_g[i];   // [k][imu] = taps[imu][7-k]
   __syncthreads();
   int idx = blockIdx.x * BLK + threadIdx.x;
   if (mode == 2) {
+    if (n_list < 0) n_list = *W.tail.n_list;             // device-driven tail: the list was built on the device
     if (idx >= n_list) return;
     const int4 it = list[idx];
     idx = it.x * G.nch + it.y;
@@ -726,39 +740,45 @@ __global__ void __launch_bounds__(BLK) k_mm_stateless_v2(Geom G, DevBatch W, con
   const int oo_end = (mode == 1) ? G.sym_target : G.n_dem;
   const unsigned ni = (unsigned)((mode == 1 ? G.ne_dem : G.n_dem) - 8);
   int pf = (int)ii;                // samples [pf-RD, pf) are in (or on their way to) the ring
-  int ready = 0;                   // samples below `ready` have landed
   const int tid = threadIdx.x;
   const int nch = G.nch;
+  const MmConst K = G.mm;
   gp += (long)pf * nch;
+  auto refill = [&](int want) {
+    for (; pf < want; pf++, gp += nch) {
+      const int rr = pf & (RD - 1);
+      cp_async4(&ring[rr][tid], gp);
+      if (rr < 8) cp_async4(&ring[rr + RD][tid], gp);
+    }
+    cp_async_commit();
+  };
   {
     int want = (int)ii + 8 + AHEAD; if (want > avail) want = avail;
-    for (; pf < want; pf++, gp += nch) cp_async4(&ring[pf & (RD - 1)][tid], gp);
-    cp_async_commit();
+    refill(want);
     cp_async_wait<0>();
-    ready = pf;
     if (G.dem_grid && ii == 0) ring[0][tid] = 0.0f;      // demod_out[0] of a window is never written by the reference
   }
-  int step = 0;
   while (oo < oo_end && ii < ni) {
-    if ((step & (PERIOD - 1)) == 0 && step) {
-      cp_async_wait<0>();          // the previous refill (issued PERIOD steps ago) has long landed
-      ready = pf;
+    cp_async_wait<0>();              // the refill issued a block ago has long landed
+    {
       int want = (int)ii + 8 + AHEAD; if (want > avail) want = avail;
-      for (; pf < want; pf++, gp += nch) cp_async4(&ring[pf & (RD - 1)][tid], gp);
-      cp_async_commit();
+      refill(want);
     }
-    step++;
-    if ((int)ii + 8 > ready) { cp_async_wait<0>(); ready = pf; }     // never taken for bounded inputs
-    int imu = __float2int_rn(st.mu * 128.0f);
-    imu = imu < 0 ? 0 : (imu > 128 ? 128 : imu);
-    float out = 0.0f;
+#pragma unroll 1
+    for (int t = 0; t < PERIOD && oo < oo_end && ii < ni; t++) {
+      int imu = __float2int_rn(st.mu * 128.0f);
+      imu = imu < 0 ? 0 : (imu > 128 ? 128 : imu);
+      const float *rp = &ring[ii & (RD - 1)][tid];
+      const float *mp = &s_mmse[0][imu];
+      float out = 0.0f;
 #pragma unroll
-    for (int k = 0; k < 8; k++) out = out + ring[(ii + k) & (RD - 1)][tid] * s_mmse[k][imu];
-    if (soft_row) soft_row[oo] = out;
-    if (!(out < 0)) word |= 1u << (oo & 31);
-    if ((oo & 31) == 31) { bits_row[oo >> 5] = word; word = 0; }
-    ii += (unsigned)mm_update(G.mm, st, out);
-    oo++;
+      for (int k = 0; k < 8; k++) out = out + rp[k * BLK] * mp[k * 132];
+      if (soft_row) soft_row[oo] = out;
+      if (!(out < 0)) word |= 1u << (oo & 31);
+      if ((oo & 31) == 31) { bits_row[oo >> 5] = word; word = 0; }
+      ii += (unsigned)mm_update(K, st, out);
+      oo++;
+    }
   }
   cp_async_wait<0>();
   if (mode == 1) save[idx] = MmSave{st.mu, st.omega, st.last, ii, oo, word};
@@ -778,7 +798,8 @@ __global__ void k_search_warp(Geom G, DevTables T, DevBatch W)
   const int lane = threadIdx.x & 31;
   if (idx >= W.B * G.nch) return;
   const int nsym = W.nsym[idx];
-  if (nsym <= 0) return;
+  const bool staged = W.tail.stage != nullptr;
+  if (nsym <= 0) { if (staged && lane == 0) W.tail.cnt[idx] = 0; return; }
   const int b = idx / G.nch, c = idx - b * G.nch;
   const uint32_t *__restrict__ row = W.bits + (long)idx * G.bw;
   const uint32_t wl = row[lane < G.bw ? lane : 0];           // words 0..31 cover lags 0..(625+72)
@@ -802,7 +823,8 @@ __global__ void k_search_warp(Geom G, DevTables T, DevBatch W)
   // lazy tail: the rows hold the first G.sym_target symbols; the true count is >= 1386 for this geometry,
   // so both limits are 625, and symbol counts are emitted RELATIVE to it (the host adds the true count)
   const int nsym_eff = G.early ? 0 : nsym;
-  HitEmitter em{G, W, b, c, nsym, G.early != 0};
+  int n_staged = 0;
+  HitEmitter em{G, W, b, c, nsym, G.early != 0, staged ? &n_staged : nullptr};
   int len = G.early ? (1 << 20) : nsym;
   if (G.search & 1) {
     const int limit0 = (len - 68 < 625) ? len - 68 : 625;
@@ -842,6 +864,96 @@ __global__ void k_search_warp(Geom G, DevTables T, DevBatch W)
         em(1, found, len_le - found, (uint32_t)(lo >> 8));
       }
       start = found + 40;
+    }
+  }
+  if (staged && lane == 0) W.tail.cnt[idx] = n_staged < TAIL_MAXW ? n_staged : TAIL_MAXW;
+}
+
+// ---- device-driven tail ------------------------------------------------------------------------------------------
+// positions of every window's hits in the final list (= the reference's visiting order: slot, channel, then the order
+// the search loops produced them) and the list of windows that have hits; one block, contiguous chunks per thread
+__global__ void __launch_bounds__(1024) k_tail_scan(Geom G, DevBatch W)
+{
+  __shared__ int s_h[1024], s_w[1024];
+  const int n = W.B * G.nch, t = threadIdx.x;
+  const int per = (n + 1023) / 1024, i0 = t * per, i1 = (i0 + per < n) ? i0 + per : n;
+  int h = 0, w = 0;
+  for (int i = i0; i < i1; i++) { const int c = W.tail.cnt[i]; h += c; w += c > 0; }
+  s_h[t] = h; s_w[t] = w;
+  __syncthreads();
+  for (int d = 1; d < 1024; d <<= 1) {
+    const int a = (t >= d) ? s_h[t - d] : 0, b = (t >= d) ? s_w[t - d] : 0;
+    __syncthreads();
+    s_h[t] += a; s_w[t] += b;
+    __syncthreads();
+  }
+  int hb = s_h[t] - h, wb = s_w[t] - w;                  // exclusive prefixes of this thread's chunk
+  for (int i = i0; i < i1; i++) {
+    const int c = W.tail.cnt[i];
+    W.tail.base[i] = hb;
+    if (c > 0) { W.tail.list[wb++] = make_int4(i / G.nch, i % G.nch, 0, 0); hb += c; }
+  }
+  if (t == 1023) { W.hit_count[0] = (unsigned)s_h[1023]; *W.tail.n_list = s_w[1023]; }
+}
+
+// the hits of every listed window, in order, with their final symbol counts
+__global__ void k_tail_compact(Geom G, DevBatch W)
+{
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= *W.tail.n_list) return;
+  const int4 it = W.tail.list[l];
+  const int key = it.x * G.nch + it.y;
+  const int cnt = W.tail.cnt[key], base = W.tail.base[key];
+  const int nsym = W.nsym[key];
+  for (int i = 0; i < cnt; i++) {
+    DevHit h = W.tail.stage[(long)key * TAIL_MAXW + i];
+    if (G.early) h.n_symbols += nsym;                   // the search ran on the prefix: counts were relative
+    int c = h.n_symbols < 3125 ? h.n_symbols : 3125;
+    if (c < 0) c = 0;
+    h.sym_count = (uint32_t)c;
+    if ((unsigned)(base + i) < W.hit_cap) W.tail.sorted[base + i] = h;
+  }
+}
+
+// arena layout: exclusive scan of the symbol counts in list order (one block)
+__global__ void __launch_bounds__(1024) k_tail_offsets(DevBatch W)
+{
+  __shared__ unsigned long long s_sum[1024];
+  unsigned n = W.hit_count[0];
+  if (n > W.hit_cap) n = W.hit_cap;
+  const int t = threadIdx.x;
+  const unsigned per = (n + 1023) / 1024, i0 = t * per, i1 = (i0 + per < n) ? i0 + per : n;
+  unsigned long long sum = 0;
+  for (unsigned i = i0; i < i1; i++) sum += W.tail.sorted[i].sym_count;
+  s_sum[t] = sum;
+  __syncthreads();
+  for (int d = 1; d < 1024; d <<= 1) {
+    const unsigned long long a = (t >= d) ? s_sum[t - d] : 0;
+    __syncthreads();
+    s_sum[t] += a;
+    __syncthreads();
+  }
+  unsigned long long off = s_sum[t] - sum;
+  for (unsigned i = i0; i < i1; i++) {
+    DevHit &h = W.tail.sorted[i];
+    h.sym_offset = off;
+    if (off + h.sym_count > W.arena_cap) h.sym_count = 0;
+    off += h.sym_count ? h.sym_count : 0;
+  }
+  if (t == 1023) *W.arena_used = s_sum[1023] < W.arena_cap ? s_sum[1023] : W.arena_cap;
+}
+
+__global__ void k_gather_sorted(Geom G, DevBatch W)
+{
+  unsigned n = W.hit_count[0];
+  if (n > W.hit_cap) n = W.hit_cap;
+  for (unsigned h = blockIdx.x; h < n; h += gridDim.x) {
+    const DevHit hit = W.tail.sorted[h];
+    const uint32_t *row = W.bits + ((long)hit.b * G.nch + hit.chi) * G.bw;
+    uint8_t *dst = W.arena + hit.sym_offset;
+    for (unsigned i = threadIdx.x; i < hit.sym_count; i += blockDim.x) {
+      const int s = hit.offset + (int)i;
+      dst[i] = (row[s >> 5] >> (s & 31)) & 1;
     }
   }
 }
@@ -1048,7 +1160,7 @@ void launch_demod_mm_v2(const Geom &G, const DevTables &T, const DevBatch &W, fl
     k_demod_all<<<grid, DM_WARPS * 32, 0, s>>>(G, W, T.atan_tab, demT, i_end);
   }
   constexpr int BLK = 64;
-  const size_t smem = sizeof(float) * MM_RD * BLK + sizeof(float) * 8 * 132;
+  const size_t smem = sizeof(float) * (MM_RD + 8) * BLK + sizeof(float) * 8 * 132;
   k_mm_stateless_v2<BLK><<<cdiv((long)W.B * G.nch, BLK), BLK, smem, s>>>(G, W, T.mmse, demT, G.early ? 1 : 0,
                                                                             reinterpret_cast<MmSave *>(W.mm_save), nullptr, 0);
 }
@@ -1064,9 +1176,31 @@ void launch_mm_resume_list(const Geom &G, const DevTables &T, const DevBatch &W,
     k_demod_list<<<grid, 128, 0, s>>>(G, W, T.atan_tab, demT, reinterpret_cast<const int4 *>(list4), G.ne_dem);
   }
   constexpr int BLK = 64;
-  const size_t smem = sizeof(float) * MM_RD * BLK + sizeof(float) * 8 * 132;
+  const size_t smem = sizeof(float) * (MM_RD + 8) * BLK + sizeof(float) * 8 * 132;
   k_mm_stateless_v2<BLK><<<cdiv(n_list, BLK), BLK, smem, s>>>(G, W, T.mmse, demT, 2, reinterpret_cast<MmSave *>(W.mm_save),
                                                                reinterpret_cast<const int4 *>(list4), n_list);
+}
+
+void launch_tail_scan(const Geom &G, const DevBatch &W, cudaStream_t s)
+{
+  k_tail_scan<<<1, 1024, 0, s>>>(G, W);
+}
+
+void launch_tail_resume(const Geom &G, const DevTables &T, const DevBatch &W, float *demT, cudaStream_t s)
+{
+  // one warp per block: the few hundred serial chains of a batch's hit windows spread over as many SMs as possible
+  constexpr int BLK = 32;
+  const size_t smem = sizeof(float) * (MM_RD + 8) * BLK + sizeof(float) * 8 * 132;
+  // the list length lives on the device: launch for the worst case, blocks past the list end return at once
+  k_mm_stateless_v2<BLK><<<cdiv((long)W.B * G.nch, BLK), BLK, smem, s>>>(G, W, T.mmse, demT, 2, reinterpret_cast<MmSave *>(W.mm_save),
+                                                                            W.tail.list, -1);
+}
+
+void launch_tail_finish(const Geom &G, const DevBatch &W, cudaStream_t s)
+{
+  k_tail_compact<<<cdiv((long)W.B * G.nch, 128), 128, 0, s>>>(G, W);
+  k_tail_offsets<<<1, 1024, 0, s>>>(W);
+  k_gather_sorted<<<296, 128, 0, s>>>(G, W);
 }
 
 void launch_search_warp(const Geom &G, const DevTables &T, const DevBatch &W, cudaStream_t s)

@@ -20,6 +20,21 @@ struct DevTables {
   const uint32_t *le_white;  // [nch] 16 whitening bits
 };
 
+// Device-driven tail of the throughput mode: the search kernel stages each window's hits in the window's own slots (the
+// warp replays the reference's search loops in order, so they arrive in visiting order: BR before LE, ascending lag),
+// a scan over the windows turns the counts into positions, and everything after that -- the list of windows to resume,
+// the hit list in the reference's order, the layout of the symbol arena -- is laid out by small kernels without a host
+// round trip (btb200_api.cu, polyphase mode).  stage == nullptr: hits are appended with atomics and sorted on the host.
+constexpr int TAIL_MAXW = 32;        // hits a window can hold: <= 10 access codes (68 apart) + <= 16 LE (40 apart) in 625 lags
+struct TailBufs {
+  DevHit *stage = nullptr;           // [B*nch][TAIL_MAXW]
+  int *cnt = nullptr;                // [B*nch] hits of a window
+  int *base = nullptr;               // [B*nch] position of the window's first hit in `sorted`
+  int4 *list = nullptr;              // windows with hits, in (slot, channel) order: {b, chi, 0, 0}
+  int *n_list = nullptr;             // [1]
+  DevHit *sorted = nullptr;          // the hit list in the reference's visiting order, symbol counts and arena offsets final
+};
+
 struct DevBatch {
   const c32 *x;              // input
   c32 *Y;                    // [G][nch]
@@ -41,6 +56,7 @@ struct DevBatch {
   unsigned hit_cap;
   unsigned long long arena_cap;
   int B;
+  TailBufs tail;
 };
 
 // implementation selectors (tests compare tuned kernels against the v1 baseline)
@@ -61,6 +77,11 @@ void launch_mm_chained_list(const Geom &G, const DevTables &T, const DevBatch &W
                             int *res4, cudaStream_t s);
 void launch_search(const Geom &G, const DevTables &T, const DevBatch &W, cudaStream_t s);
 void launch_gather(const Geom &G, const DevBatch &W, cudaStream_t s);
+// device-driven tail (W.tail.stage != nullptr): positions + resume list; resume of the listed windows (lazy tail);
+// final hit list (W.tail.sorted, count in W.hit_count[0]), arena layout (W.arena_used) and symbol gather
+void launch_tail_scan(const Geom &G, const DevBatch &W, cudaStream_t s);
+void launch_tail_resume(const Geom &G, const DevTables &T, const DevBatch &W, float *demT, cudaStream_t s);
+void launch_tail_finish(const Geom &G, const DevBatch &W, cudaStream_t s);
 void launch_demod_mm_v2(const Geom &G, const DevTables &T, const DevBatch &W, float *demT, cudaStream_t s);
 void launch_mm_resume_list(const Geom &G, const DevTables &T, const DevBatch &W, float *demT, const int *list4,
                            int n_list, cudaStream_t s);

@@ -10,7 +10,7 @@
 //   u_j[r]  = sum_{q<Q} x'[n_j + r + M q] h'[r + M q]    n_j = b S + fns + j D,  j < 850
 //   |Y_c[j]| = | sum_r e^{-j 2 pi a_c r / M} u_j[r] |
 //
-// One block = one tile of 2 x 64 outputs (64 per parity of j: outputs two apart are exactly one tap apart, 2 D = M)
+// One block = one tile of 2 x 48 outputs (48 per parity of j: outputs two apart are exactly one tap apart, 2 D = M)
 // of one slot.  Thread = (branch r, parity p, run k of 16 outputs): it slides its 16 accumulators through the 201
 // taps -- per step ONE new input sample and ONE new tap feed 16 complex-by-real MACs (the last 16 taps sit in a
 // statically rotated register window) -- so shared-memory traffic is 12 bytes per 32 FMA.  Inputs and taps stream
@@ -20,12 +20,13 @@
 // = 32 output groups x 4 channels), |Z|^2 summed over the tile's valid outputs.
 #include "rx_nest.cuh"
 #include "rx_tma.cuh"
+#include "rx_packed.cuh"
 
 namespace btb200 {
 
 namespace {
 
-constexpr int RING_CHUNKS = 6;       // ring capacity in chunks of 16 steps
+constexpr int RING_CHUNKS = NEST_K + 2;   // ring capacity in chunks of 16 steps: K + 1 live, one in flight
 constexpr int CH = 16;               // steps per chunk
 
 struct NestSmem { size_t ring, taps, wb, n2r, epart, bar, total; };
@@ -38,7 +39,7 @@ __host__ __device__ inline NestSmem nest_layout(const NestPlan &P)
   const size_t ring = (size_t)RING_CHUNKS * CH * P.M * sizeof(c32);
   const size_t u = (size_t)2 * NEST_TO * (P.M + 1) * sizeof(c32);         // U / V tile, row pitch M + 1
   L.ring = take(ring > u ? ring : u, 128);
-  L.taps = take((size_t)2 * CH * P.M * sizeof(float), 128);
+  L.taps = take((size_t)2 * CH * P.M * sizeof(float2), 128);
   L.wb = take((size_t)P.N2 * P.ncol * sizeof(c32), 16);
   L.n2r = take((size_t)P.N2 * sizeof(int), 16);
   L.epart = take((size_t)32 * P.ncol * sizeof(float), 16);
@@ -55,19 +56,21 @@ __global__ void k_nest_prerot(const c32 *__restrict__ x, c32 *__restrict__ xr, l
   xr[i] = c32{v.re * p.re - v.im * p.im, v.re * p.im + v.im * p.re};
 }
 
-template <int N1>
-__global__ void __launch_bounds__(800, 1) k_nest(NestPlan P)
+// MT: the number of branches as a compile-time constant (100 = the benchmark configuration: every shared-memory
+// access of the tap loop then has an immediate offset), or 0 for "read it from the plan"
+template <int N1, int MT>
+__global__ void __launch_bounds__(2 * NEST_K * 100, 1) k_nest(NestPlan P)
 {
   extern __shared__ __align__(128) unsigned char smem[];
   const NestSmem L = nest_layout(P);
   c32 *ring = reinterpret_cast<c32 *>(smem + L.ring);
-  float *taps = reinterpret_cast<float *>(smem + L.taps);
+  float2 *taps = reinterpret_cast<float2 *>(smem + L.taps);
   c32 *WBs = reinterpret_cast<c32 *>(smem + L.wb);
   int *n2r = reinterpret_cast<int *>(smem + L.n2r);
   float *epart = reinterpret_cast<float *>(smem + L.epart);
   uint64_t *bar = reinterpret_cast<uint64_t *>(smem + L.bar);          // [0..5] ring slots, [6..7] tap buffers
 
-  const int M = P.M, N2 = P.N2, ncol = P.ncol;
+  const int M = MT ? MT : P.M, N2 = MT ? MT / N1 : P.N2, ncol = P.ncol;
   const int tid = threadIdx.x, nthr = blockDim.x;                      // nthr = 2 * NEST_K * M
   const int r = tid % M, pk = tid / M, p = pk & 1, k = pk >> 1;
   const int b = blockIdx.x / P.tiles_per_slot, tile = blockIdx.x - b * P.tiles_per_slot;
@@ -75,7 +78,7 @@ __global__ void __launch_bounds__(800, 1) k_nest(NestPlan P)
   const long n_base = (long)b * P.S + P.fns + (long)M * i0;            // sample of ring step 0, branch 0, parity 0
   const int n_chunks = P.q_rows / CH;                                  // compute chunks
   const int n_ring = n_chunks + NEST_K;                                // ring chunks the tile reads (+1 for the parity offset)
-  const unsigned ring_bytes = (unsigned)(CH * M * sizeof(c32)), tap_bytes = (unsigned)(CH * M * sizeof(float));
+  const unsigned ring_bytes = (unsigned)(CH * M * sizeof(c32)), tap_bytes = (unsigned)(CH * M * sizeof(float2));
 
   if (tid == 0) {
     for (int i = 0; i < RING_CHUNKS + 2; i++) mbar_init(&bar[i], 1);
@@ -90,7 +93,7 @@ __global__ void __launch_bounds__(800, 1) k_nest(NestPlan P)
   auto load_taps = [&](int c) {
     uint64_t *bb = &bar[RING_CHUNKS + (c & 1)];
     mbar_expect_tx(bb, tap_bytes);
-    tma_bulk_g2s(taps + (size_t)(c & 1) * CH * M, P.hq + (size_t)c * CH * M, tap_bytes, bb);
+    tma_bulk_g2s(taps + (size_t)(c & 1) * CH * M, P.hq2 + (size_t)c * CH * M, tap_bytes, bb);
   };
   if (tid == 0) {
     for (int m = 0; m < RING_CHUNKS && m < n_ring; m++) load_ring(m);
@@ -101,26 +104,38 @@ __global__ void __launch_bounds__(800, 1) k_nest(NestPlan P)
   for (int i = tid; i < N2; i += nthr) n2r[i] = P.n2_of_rho[i];
 
   // ---- 1. branch sums: 16 outputs i0 + 16 k + o of parity p, branch r
-  float ar[NEST_R], ai[NEST_R], H[NEST_R];
+  // packed fp32 (FFMA2): accumulator = (re, im) of one output, input = (re, im) as loaded, tap = (h, h) as loaded.
+  // A 3-register FFMA whose operands share a register bank issues at half rate; the packed form reads register
+  // PAIRS, one of which (the input) is reused by all 16 MACs of a step, so it runs at the full fp32 rate.
+  u64 acc[NEST_R], H[NEST_R];
 #pragma unroll
-  for (int o = 0; o < NEST_R; o++) { ar[o] = 0.0f; ai[o] = 0.0f; H[o] = 0.0f; }
+  for (int o = 0; o < NEST_R; o++) { acc[o] = 0ull; H[o] = 0ull; }
   const int ring_samples = RING_CHUNKS * CH * M;
+  const u64 *ring64 = reinterpret_cast<const u64 *>(ring);
   for (int c = 0; c < n_chunks; c++) {
     if (c == 0) { for (int m = 0; m < NEST_K && m < n_ring; m++) mbar_wait(&bar[m], 0); }
     if (c + NEST_K < n_ring) mbar_wait(&bar[(c + NEST_K) % RING_CHUNKS], (unsigned)(((c + NEST_K) / RING_CHUNKS) & 1));
     mbar_wait(&bar[RING_CHUNKS + (c & 1)], (unsigned)((c >> 1) & 1));
-    int off = (int)(((long)M * (NEST_R * k + CH * c) + (long)P.D * p + r) % ring_samples);
-    const float *tp = taps + (size_t)(c & 1) * CH * M + r;
+    int off = (int)(((long)M * (NEST_R * k + CH * c) + (long)(M / 2) * p + r) % ring_samples);
+    const u64 *tp = reinterpret_cast<const u64 *>(taps + (size_t)(c & 1) * CH * M + r);
+    if (off + CH * M <= ring_samples) {
+      // the 16 steps do not cross the end of the ring (4 chunks in 5): one base address, immediate offsets
+      const u64 *xp = ring64 + off;
 #pragma unroll
-    for (int s = 0; s < CH; s++) {
-      const c32 X = ring[off];
-      off += M; if (off >= ring_samples) off -= ring_samples;
-      H[s] = tp[s * M];                               // tap q = 16 c + s; H[i] holds the latest tap with q = i (mod 16)
+      for (int s = 0; s < CH; s++) {
+        const u64 X = xp[s * M];
+        H[s] = tp[s * M];                             // tap q = 16 c + s; H[i] holds the latest tap with q = i (mod 16)
 #pragma unroll
-      for (int o = 0; o < NEST_R; o++) {
-        const float h = H[(s - o) & (NEST_R - 1)];    // tap q = 16 c + s - o
-        ar[o] = fmaf(X.re, h, ar[o]);
-        ai[o] = fmaf(X.im, h, ai[o]);
+        for (int o = 0; o < NEST_R; o++) acc[o] = pk_fma(X, H[(s - o) & (NEST_R - 1)], acc[o]);   // tap q = 16 c + s - o
+      }
+    } else {
+#pragma unroll
+      for (int s = 0; s < CH; s++) {
+        const u64 X = ring64[off];
+        off += M; if (off >= ring_samples) off -= ring_samples;
+        H[s] = tp[s * M];
+#pragma unroll
+        for (int o = 0; o < NEST_R; o++) acc[o] = pk_fma(X, H[(s - o) & (NEST_R - 1)], acc[o]);
       }
     }
     __syncthreads();                                  // ring chunk c and tap chunk c are free
@@ -130,11 +145,12 @@ __global__ void __launch_bounds__(800, 1) k_nest(NestPlan P)
       if (c + 2 < n_chunks) load_taps(c + 2);
     }
   }
-  // ---- the tile's branch sums to shared memory (the ring is dead): U[out][r], out = p * 64 + 16 k + o
+  // ---- the tile's branch sums to shared memory (the ring is dead): U[out][r], out = p * TO + 16 k + o
   const int UP = M + 1;
   c32 *U = ring;
 #pragma unroll
-  for (int o = 0; o < NEST_R; o++) U[(size_t)(p * NEST_TO + NEST_R * k + o) * UP + r] = c32{ar[o], ai[o]};
+  for (int o = 0; o < NEST_R; o++)
+    reinterpret_cast<u64 *>(U)[(size_t)(p * NEST_TO + NEST_R * k + o) * UP + r] = acc[o];
   __syncthreads();
 
   // ---- 2. N1-point DFTs, in place: V[out][k1 * N2 + n2] = sum_n1 U[out][(N2 n1 + N1 n2) mod M] W_N1^{n1 k1}
@@ -178,22 +194,23 @@ __global__ void __launch_bounds__(800, 1) k_nest(NestPlan P)
   for (int item = tid; item < 32 * n_cg; item += nthr) {
     const int og = item & 31, cg = item >> 5;
     const int col0 = cg * NEST_NCOL, k1 = col0 / P.CPC;
-    float zr[4][NEST_NCOL], zi[4][NEST_NCOL];
+    constexpr int NI = 2 * NEST_TO / 32;              // outputs per thread
+    float zr[NI][NEST_NCOL], zi[NI][NEST_NCOL];
 #pragma unroll
-    for (int i = 0; i < 4; i++)
+    for (int i = 0; i < NI; i++)
 #pragma unroll
       for (int j = 0; j < NEST_NCOL; j++) { zr[i][j] = 0.0f; zi[i][j] = 0.0f; }
     const c32 *vrow = U + (size_t)og * UP + k1 * N2;
     const c32 *wrow = WBs + col0;
 #pragma unroll 5
     for (int n2 = 0; n2 < N2; n2++) {
-      c32 v[4], w[NEST_NCOL];
+      c32 v[NI], w[NEST_NCOL];
 #pragma unroll
-      for (int i = 0; i < 4; i++) v[i] = vrow[(size_t)32 * i * UP + n2];
+      for (int i = 0; i < NI; i++) v[i] = vrow[(size_t)32 * i * UP + n2];
 #pragma unroll
       for (int j = 0; j < NEST_NCOL; j++) w[j] = wrow[n2 * ncol + j];
 #pragma unroll
-      for (int i = 0; i < 4; i++)
+      for (int i = 0; i < NI; i++)
 #pragma unroll
         for (int j = 0; j < NEST_NCOL; j++) {
           zr[i][j] = fmaf(v[i].re, w[j].re, zr[i][j]); zr[i][j] = fmaf(-v[i].im, w[j].im, zr[i][j]);
@@ -204,7 +221,7 @@ __global__ void __launch_bounds__(800, 1) k_nest(NestPlan P)
 #pragma unroll
     for (int j = 0; j < NEST_NCOL; j++) e[j] = 0.0f;
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
+    for (int i = 0; i < NI; i++) {
       const int out = og + 32 * i, pp = out / NEST_TO, idx = i0 + (out - pp * NEST_TO);
       if (idx < n_par[pp]) {
 #pragma unroll
@@ -237,18 +254,18 @@ __global__ void k_nest_reduce(NestPlan P, int B)
 
 size_t nest_smem_bytes(const NestPlan &P) { return nest_layout(P).total; }
 
-#define NEST_DISPATCH(CALL) do { if (P.N1 == 4) { CALL(4); } else if (P.N1 == 2) { CALL(2); } else { CALL(1); } } while (0)
+#define NEST_DISPATCH(CALL) do { if (P.N1 == 4 && P.M == 100) { CALL(4, 100); } else if (P.N1 == 4) { CALL(4, 0); } else if (P.N1 == 2) { CALL(2, 0); } else { CALL(1, 0); } } while (0)
 
 int nest_setup(const NestPlan &P)
 {
   if (2 * P.D != P.M || P.N1 * P.N2 != P.M || (P.N1 != 1 && P.N1 != 2 && P.N1 != 4)) return -1;
-  if (2 * NEST_K * P.M > 800 || P.q_rows % CH != 0 || P.q_rows < P.Q + CH || P.ncol % NEST_NCOL != 0) return -1;
-  if (((CH * P.M * sizeof(float)) & 15) != 0) return -1;                    // TMA bulk copies move multiples of 16 bytes
+  if (P.M > 100 || P.q_rows % CH != 0 || P.q_rows < P.Q + CH || P.ncol % NEST_NCOL != 0) return -1;
+  if (((CH * P.M * sizeof(float2)) & 15) != 0) return -1;                    // TMA bulk copies move multiples of 16 bytes
   if ((((long)P.S * sizeof(c32)) & 15) != 0 || (((long)P.fns * sizeof(c32)) & 15) != 0 || ((NEST_TO * P.M * sizeof(c32)) & 15) != 0)
     return -1;                                                             // ... from 16-byte aligned addresses
   if (nest_smem_bytes(P) > 227 * 1024) return -1;
   cudaError_t e = cudaSuccess;
-#define NEST_OPT(N1_) e = cudaFuncSetAttribute((const void *)k_nest<N1_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nest_smem_bytes(P))
+#define NEST_OPT(N1_, MT_) e = cudaFuncSetAttribute((const void *)k_nest<N1_, MT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nest_smem_bytes(P))
   NEST_DISPATCH(NEST_OPT);
 #undef NEST_OPT
   return e == cudaSuccess ? 0 : -1;
@@ -265,7 +282,7 @@ void launch_nest(const NestPlan &P, int B, cudaStream_t s)
   const dim3 grid((unsigned)(B * P.tiles_per_slot));
   const int threads = 2 * NEST_K * P.M;
   const size_t smem = nest_smem_bytes(P);
-#define NEST_RUN(N1_) k_nest<N1_><<<grid, threads, smem, s>>>(P)
+#define NEST_RUN(N1_, MT_) k_nest<N1_, MT_><<<grid, threads, smem, s>>>(P)
   NEST_DISPATCH(NEST_RUN);
 #undef NEST_RUN
   const int n = B * P.nch;

@@ -6,9 +6,9 @@
 namespace btb200 {
 
 constexpr int NEST_R = 16;           // outputs a thread slides through the taps
-constexpr int NEST_K = 4;            // runs per parity per tile
+constexpr int NEST_K = 3;            // runs per parity per tile
 constexpr int NEST_TO = NEST_R * NEST_K;   // outputs per parity per tile
-constexpr int NEST_NCOL = 4;         // channels per thread in the DFT stage
+constexpr int NEST_NCOL = 5;         // channels per thread in the DFT stage
 
 struct NestPlan {
   int M = 0, D = 0, Q = 0, q_rows = 0;   // branches, decimation (2 D = M), taps per branch, rows of hq (multiple of 16)
@@ -16,7 +16,7 @@ struct NestPlan {
   int S = 0, fns = 0, n_noise = 0;
   int tiles_per_slot = 0;
   int period = 0;
-  const float *hq = nullptr;         // [q_rows][M]  h'[r + M q], zero padded
+  const float2 *hq2 = nullptr;       // [q_rows][M]  (h, h) with h = h'[r + M q], zero padded: operands of the packed FMAs
   const int *n2_of_rho = nullptr;    // [N2]
   const c32 *WB = nullptr;           // [N2][ncol]
   const int *col_chan = nullptr;     // [ncol]

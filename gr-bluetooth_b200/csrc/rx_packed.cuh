@@ -16,6 +16,8 @@ __device__ __forceinline__ u64 pk_xsubp(u64 x, u64 p)
 { u64 d; asm("{.reg .b64 m1; mov.b64 m1, 0xbf800000bf800000; fma.rn.f32x2 %0, %2, m1, %1;}" : "=l"(d) : "l"(x), "l"(p)); return d; }
 // (x + p cannot be written fma(p, +1, x): ptxas folds the multiply by one and then contracts p's FMUL2 into a
 // real FFMA2.  Sums of products are therefore written x - (-p) with one factor negated: pk_neg + pk_xsubp.)
+// a * b + c, one rounding per half (tolerance-mode kernels only: the exact path never fuses)
+__device__ __forceinline__ u64 pk_fma(u64 a, u64 b, u64 c) { u64 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
 __device__ __forceinline__ u64 pk_neg(u64 a) { return a ^ 0x8000000080000000ull; }
 __device__ __forceinline__ float pk_lo(u64 v) { return __uint_as_float((unsigned)(v & 0xffffffffull)); }
 __device__ __forceinline__ float pk_hi(u64 v) { return __uint_as_float((unsigned)(v >> 32)); }

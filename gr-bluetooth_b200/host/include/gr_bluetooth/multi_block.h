@@ -36,6 +36,7 @@ class GR_BLUETOOTH_API multi_block : virtual public gr::sync_block {
   uint64_t d_cumulative_count = 0;       // samples elapsed, as in the reference
   btb200_ctx *d_ctx = nullptr;
   unsigned d_batch_slots = 1;            // windows handed to the GPU per work() call when available
+  bool d_stateless = false;
 
   // one callback per detected packet, in the reference's visiting order
   virtual void handle_hit(const btb200_hit &hit, const char *symbols, int n_symbols, double freq) = 0;
@@ -47,7 +48,7 @@ class GR_BLUETOOTH_API multi_block : virtual public gr::sync_block {
  public:
   virtual ~multi_block();
   // environment knobs (the make() signatures stay the reference's):
-  //   BTB200_MM_MODE=chained|stateless   BTB200_BATCH_SLOTS=n   BTB200_DEVICE=k
+  //   BTB200_MM_MODE=chained|stateless   BTB200_DDC=exact|polyphase   BTB200_BATCH_SLOTS=n   BTB200_DEVICE=k
   unsigned batch_slots() const { return d_batch_slots; }
   double samples_per_slot() const { return d_samples_per_slot; }
   virtual int work(int noutput_items, gr_vector_const_void_star &input_items,

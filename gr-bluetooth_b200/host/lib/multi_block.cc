@@ -29,6 +29,10 @@ multi_block::multi_block(double sample_rate, double center_freq, double squelch_
   // reference semantics by default: one clock-recovery state shared by all channel-windows
   const char *mm = std::getenv("BTB200_MM_MODE");
   cfg.mm_mode = (!force_chained && mm && std::string(mm) == "stateless") ? BTB200_MM_STATELESS : BTB200_MM_CHAINED;
+  d_stateless = cfg.mm_mode == BTB200_MM_STATELESS;
+  // BTB200_DDC=polyphase selects the throughput front end (stateless mode only; tolerance-level floats)
+  const char *dd = std::getenv("BTB200_DDC");
+  if (d_stateless && dd && std::string(dd) == "polyphase") cfg.ddc_mode = BTB200_DDC_POLYPHASE;
   const char *bs = std::getenv("BTB200_BATCH_SLOTS");
   d_batch_slots = bs ? (unsigned)std::atoi(bs) : 16u;
   if (d_batch_slots < 1) d_batch_slots = 1;
@@ -61,8 +65,11 @@ int multi_block::process_windows(int noutput_items, gr_vector_const_void_star &i
   if (n > (int)d_batch_slots) n = (int)d_batch_slots;
   static thread_local std::vector<btb200_hit> hits;
   static thread_local std::vector<uint8_t> symbols;
-  hits.resize(4096);
-  symbols.resize(4096u * 3125u / 4);
+  // every hit may carry 3125 symbols (classic_packet::make keeps MAX_SYMBOLS, lib/packet_impl.cc:52-58); the hit
+  // buffer grows and the batch is re-run when dense traffic overflows it -- a silently dropped or symbol-less hit
+  // would print a wrong line
+  if (hits.size() < 1024) hits.resize(1024);
+  symbols.resize(hits.size() * 3125u);
   btb200_hits out;
   std::memset(&out, 0, sizeof out);
   out.hits = hits.data();
@@ -74,6 +81,19 @@ int multi_block::process_windows(int noutput_items, gr_vector_const_void_star &i
                           (size_t)(n - 1) * S + H, first_slot, (uint32_t)n, &out);
   if (rc != BTB200_OK)
     throw std::runtime_error(std::string("btb200_process: ") + btb200_strerror(rc) + " (" + btb200_last_error(d_ctx) + ")");
+  if (out.overflow) {
+    // more hits than the buffer holds: this only happens in stateless (batch) mode, where the batch can simply be
+    // processed again; the chained stream state has already advanced and cannot be replayed
+    if (hits.size() >= (1u << 20) || !d_stateless)
+      throw std::runtime_error("btb200_process: hit buffer overflow (" + std::to_string(out.overflow) + " hits dropped)");
+    hits.resize(hits.size() * 4);
+    return process_windows(noutput_items, input_items);
+  }
+  for (uint32_t i = 0; i < out.count; i++) {
+    const int expect = out.hits[i].n_symbols < 3125 ? out.hits[i].n_symbols : 3125;
+    if ((int)out.hits[i].sym_count < (expect > 0 ? expect : 0))
+      throw std::runtime_error("btb200_process: symbol arena exhausted");
+  }
   uint32_t cur_slot = (uint32_t)first_slot;
   for (uint32_t i = 0; i < out.count; i++) {
     const btb200_hit &h = out.hits[i];

@@ -135,3 +135,64 @@ def generate(fs, fc, nslots, seed=1234, laps=None, occupancy=0.05, snr_db=17.0, 
             iq[start:end] += sig[:end - start].astype(np.complex64)
             truth.append(dict(slot=slot, channel=ch, lap=lap, start_sample=start, nsym=len(bits), kind=0))
     return iq, truth
+
+
+def _draw_burst(brng, fs, S, slot, ch, laps, occupancy, le_adv_occupancy):
+    """The random draws of one (slot, channel) cell, in generate()'s order.  -> None or a dict describing the burst."""
+    if brng.random() >= occupancy:
+        return None
+    if le_adv_occupancy > 0 and ch in LE_ADV_CHANNELS and brng.random() < le_adv_occupancy / occupancy:
+        bits = ble_adv_packet(LE_ADV_CHANNELS[ch], brng)
+        bits = np.concatenate([bits[:2] ^ 1, bits])
+        start = slot * S + int(brng.uniform(0, 200e-6) * fs)
+        return dict(kind=1, bits=bits, start=start, h=0.5, phase=brng.random(), lap=LE_ADV_AA)
+    lap = int(laps[int(brng.integers(0, len(laps)))])
+    hdr = np.repeat(brng.integers(0, 2, 18).astype(np.uint8), 3)
+    pay = brng.integers(0, 2, int(brng.integers(0, 367))).astype(np.uint8)
+    ac = access_code(lap)
+    bits = np.concatenate([np.array([0, 1, 0, 1], np.uint8) ^ ac[0] ^ 1, ac, hdr, pay])
+    start = slot * S + int(brng.uniform(0, 200e-6) * fs)
+    return dict(kind=0, bits=bits, start=start, h=0.32, phase=brng.random(), lap=lap)
+
+
+def generate_range(fs, fc, slot0, nslots, seed=1234, laps=None, occupancy=0.05, snr_db=17.0, sigma=50.0,
+                   burst_seed=5678, le_adv_occupancy=0.0, as_int16=False):
+    """Slots [slot0, slot0 + nslots) of ONE unbounded synthetic stream defined by (seed, burst_seed): the noise of
+    every slot comes from its own generator and the bursts from one sequential draw order, so any two calls agree
+    sample for sample where their ranges overlap -- what time-sharding across GPUs needs.
+    Same signal model as generate().  -> (iq, truth) with absolute slot numbers / sample positions in truth;
+    iq is complex64 [nslots * S], or with as_int16 the ROUNDED samples as interleaved int16 [2 * nslots * S]."""
+    laps = DEFAULT_LAPS if laps is None else laps
+    S = int(625 * fs / 1e6)
+    sps = fs / 1e6
+    n = nslots * S
+    iq = np.empty(n, np.complex64)
+    v = iq.view(np.float32)
+    for k in range(nslots):
+        rng = np.random.default_rng([seed, slot0 + k])
+        v[2 * k * S:2 * (k + 1) * S] = rng.standard_normal(2 * S, dtype=np.float32) * np.float32(sigma)
+    amp = sigma * np.sqrt(2.0 * 10 ** (snr_db / 10.0) * 1e6 / fs)
+    brng = np.random.default_rng(burst_seed)
+    lo, hi = band_channels(fs, fc)
+    truth = []
+    base = slot0 * S
+    for slot in range(slot0 + nslots):
+        for ch in range(lo, hi + 1):
+            bst = _draw_burst(brng, fs, S, slot, ch, laps, occupancy, le_adv_occupancy)
+            if bst is None or slot < slot0 - 1:
+                continue                       # a burst is shorter than a slot: older ones cannot reach the range
+            start, bits = bst["start"], bst["bits"]
+            end = start + len(bits) * int(sps)
+            if end <= base or start >= base + n:
+                continue
+            sig = gfsk(bits, sps, h=bst["h"])
+            k = np.arange(len(sig))
+            f_off = (2402e6 + ch * 1e6 - fc) / fs
+            sig = amp * sig * np.exp(2j * np.pi * f_off * (start + k)) * np.exp(2j * np.pi * bst["phase"])
+            a, b = max(start, base), min(start + len(sig), base + n)
+            iq[a - base:b - base] += sig[a - start:b - start].astype(np.complex64)
+            if slot >= slot0:
+                truth.append(dict(slot=slot, channel=ch, lap=bst["lap"], start_sample=start, nsym=len(bits), kind=bst["kind"]))
+    if as_int16:
+        return np.round(iq.view(np.float32)).astype(np.int16), truth
+    return iq, truth

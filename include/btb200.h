@@ -195,13 +195,26 @@ typedef struct btb200_hits {
   uint32_t    cap;
   uint32_t    count;             /* out; ordered by (slot, channel, kind, offset) = reference visiting order */
   uint32_t    overflow;          /* out: hits dropped because cap was too small */
-  uint8_t    *symbols;           /* caller-allocated arena, may be NULL (no symbols wanted) */
+  uint8_t    *symbols;           /* caller-allocated arena, may be NULL (no symbols wanted).  Borrowed symbols: pass
+                                  * symbols = NULL and symbols_cap = UINT64_MAX; collect() then sets `symbols` to the
+                                  * context's own pinned arena (no copy; valid until the next submit on this context)
+                                  * and sym_offset of each hit points into it */
   uint64_t    symbols_cap;
   uint64_t    symbols_used;      /* out */
 } btb200_hits;
 
 typedef struct btb200_ctx btb200_ctx;
 
+/* Exactness contract of BTB200_DDC_EXACT (what "bit-exact with the reference" rests on):
+ *  - every float operation of the sample path rounds once, sums run in ascending index order (the reference built
+ *    with -ffp-contract=off; GNU Radio's VOLK kernels would order sums differently on another machine);
+ *  - demod_out[0] of a window, which the reference never writes (lib/multi_block.cc:164) yet reads, is 0.0f;
+ *  - the interpolator index imu = rint(mu * 128) is clamped to 0..128 where GNU Radio's mmse_fir_interpolator_ff
+ *    throws; mu stays inside [0, 1) by construction, so the clamp never acts on finite input;
+ *  - snr = 10 log10(on / off) is evaluated by the host's libm on the device's exact fp64 energies.
+ * Rates: 625 * fs / 1 MHz must be a multiple of the decimation (int)(fs / 1 MHz) / 2 (all windows share one decimation
+ * grid): true for the even integer Msps rates, not for e.g. 5, 7, 9, 13 Msps, which the reference's block accepts --
+ * btb200_create returns BTB200_ERR_ARG for those (btb200_last_error(NULL) says why). */
 BTB200_API int  btb200_create(const btb200_config *cfg, btb200_ctx **out);
 BTB200_API void btb200_destroy(btb200_ctx *ctx);
 BTB200_API int  btb200_get_info(const btb200_ctx *ctx, btb200_info *out);
@@ -301,6 +314,21 @@ enum {
 };
 BTB200_API int64_t btb200_get_stage(btb200_ctx *ctx, int stage, uint32_t slot_in_batch,
                          uint32_t chan_index, void *dst, size_t cap);
+
+/* Debug entry for known-answer tests of the access-code search kernel alone (classic_packet::sniff_ac
+ * lib/packet_impl.cc:247-268 + check_ac :471-510 + acgen :309-364, as run by the loop of
+ * lib/multi_sniffer_impl.cc:107-126): the caller's symbol stream (one symbol per byte, air order) is cut into windows
+ * that start every `stride` symbols and hold stride + 72 symbols; each window goes through the SAME kernel the receive
+ * path uses (lags 0 .. min(len - 68, 625) - 1, first hit, skip 68, search on).  Hits come back with slot = window index,
+ * channel = 0, offset = lag inside the window, lap, n_symbols = window length - offset; no symbols, snr = 0.
+ * stride <= 625.  BR search only. */
+BTB200_API int  btb200_search_bits(btb200_ctx *ctx, const uint8_t *symbols, size_t n_symbols, uint32_t stride,
+                        btb200_hits *out);
+
+/* device-side stopwatch on the context's compute stream (CUDA events): start() records now; stop() records, waits and
+ * returns the milliseconds in between -- brackets any sequence of submit/collect calls of the contexts of one device */
+BTB200_API int  btb200_timer_start(btb200_ctx *ctx);
+BTB200_API int  btb200_timer_stop(btb200_ctx *ctx, float *ms);
 
 /* timing of the last batch, milliseconds, CUDA events on the ctx stream:
  * [0] H2D copy, [1] channel FIR, [2] noise FIR, [3] energy/squelch,

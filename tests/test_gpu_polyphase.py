@@ -184,3 +184,27 @@ def test_polyphase_rejects_unsupported_configurations():
         g.multi_sniffer(8e6, 2476.5e6, 10.0, mm_mode=g.MM_CHAINED, ddc=g.DDC_POLYPHASE)
     with pytest.raises(g.Btb200Error):
         g.multi_sniffer(8e6, 2476.5e6, 10.0, mm_mode=g.MM_STATELESS, squelch=g.SQUELCH_EAGER, ddc=g.DDC_POLYPHASE)
+
+
+def test_search_kernel_kat_channel37(kats):
+    """SURVEY 7.3 minimum slice on the GPU: the access-code search kernel alone on the reference's demodulated
+    capture samples/channel37.dem (committed as packed bits): 3 997 342 symbols -> the 33 hits of the reference's own
+    sniff_ac loop, exact offsets and LAPs (lib/packet_impl.cc:247-268, 309-364, 471-510)."""
+    import os
+    from conftest import GOLDEN
+    z = np.load(os.path.join(GOLDEN, "channel37_bits.npz"))
+    sym = np.unpackbits(z["packed"])[:int(z["n"])]
+    blk = g.multi_sniffer(8e6, 2476.5e6, 10.0, mm_mode=g.MM_STATELESS, max_slots=64)
+    want = [tuple(h) for h in kats["channel37_hits"]]
+    for stride in (625, 557):
+        got = blk.search_bits(sym, stride=stride)
+        # windows overlap by 72 symbols: a code that starts in the overlap is found by both neighbours
+        got = sorted(set(got))
+        assert got == want, (stride, len(got))
+    assert len(want) == 33 and want[0] == (66136, 0xF2F57B) and sum(1 for _, l in want if l == 0x24D952) == 31
+    # acgen KATs through the uploaded affine tables (SURVEY section 4): sync(lap) = C ^ T0[b0] ^ T1[b1] ^ T2[b2]
+    lut = blk.stage("ac_lut")
+    for lap, word in ((0x9E8B33, 0x4E7A2CCE331A3AE2), (0x24D952, 0xB093654ABEDEF6FA), (0, 0xB0000002C7820E7E)):
+        s = int(lut[768]) ^ int(lut[lap & 0xFF]) ^ int(lut[256 + ((lap >> 8) & 0xFF)]) ^ int(lut[512 + (lap >> 16)])
+        assert s == word
+    blk.close()

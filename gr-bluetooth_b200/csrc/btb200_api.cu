@@ -293,13 +293,13 @@ int setup_pfb(btb200_ctx *ctx)
   K.gain = P.demod_gain;
   K.phi_step = (float)(-2.0 * F.phi / F.M);
   int rc;
-  if ((rc = upload(ctx, &K.hq, F.hq))) return rc;
-  if ((rc = upload(ctx, &K.n2_of_rho, F.n2_of_rho))) return rc;
-  if ((rc = upload_raw<c32>(ctx, &K.WB, F.WB.data(), F.WB.size()))) return rc;
-  if ((rc = upload(ctx, &K.col_chan, F.col_chan))) return rc;
+  {
+    std::vector<unsigned char> blob(pfb_table_bytes(K));
+    pfb_pack_tables(K, reinterpret_cast<const c32 *>(F.WB.data()), F.hq.data(), P.atan_tab.data(),
+                    reinterpret_cast<const c32 *>(F.kappa.data()), F.col_chan.data(), F.n2_of_rho.data(), blob.data());
+    if ((rc = upload(ctx, &K.tables, blob))) return rc;
+  }
   if ((rc = upload(ctx, &K.chan_col, F.chan_col))) return rc;
-  if ((rc = upload_raw<c32>(ctx, &K.kappa, F.kappa.data(), F.kappa.size()))) return rc;
-  K.atan_tab = ctx->T.atan_tab;
   const size_t B = ctx->max_slots;
   const size_t Gtot = (B - 1) * (size_t)P.grid_per_slot + P.n_ddc;
   if ((rc = dev_alloc(ctx, &K.dem, Gtot * P.nch))) return rc;

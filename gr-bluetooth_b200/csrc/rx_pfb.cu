@@ -34,6 +34,7 @@
 #include "rx_pfb.cuh"
 #include "rx_tma.cuh"
 #include <cstdio>
+#include <cstring>
 
 namespace btb200 {
 
@@ -43,7 +44,7 @@ constexpr int PFB_THREADS = 256;
 constexpr int PFB_R = 8;             // outputs a thread slides in stage 1
 constexpr int VP = PFB_TT + 1;       // row pitch of V (odd: conflict-free stores from the branch stage)
 
-struct PfbSmem { size_t xs, v, wb, hq, atan, kap, cch, n2r, bar, total; };
+struct PfbSmem { size_t xs, v, tab, wb, hq, atan, kap, cch, n2r, tab_bytes, bar, total; };
 
 __host__ __device__ inline PfbSmem pfb_layout(const PfbPlan &P)
 {
@@ -54,12 +55,16 @@ __host__ __device__ inline PfbSmem pfb_layout(const PfbPlan &P)
   const size_t vbytes = (size_t)P.N1 * P.N2 * VP * sizeof(c32), zbytes = (size_t)PFB_TT * ZP * sizeof(c32);
   L.xs = take((size_t)P.span * sizeof(c32), 128);
   L.v = take(vbytes > zbytes ? vbytes : zbytes, 16);
+  // the tables sit in shared memory exactly as in the global blob (pfb_pack_tables): one bulk copy fetches them
+  L.tab = take(0, 128);
   L.wb = take((size_t)P.N2 * P.ncol * sizeof(c32), 16);
   L.hq = take((size_t)P.Q * P.M * sizeof(float), 16);
-  L.atan = take(257 * sizeof(float), 16);
+  L.atan = take(260 * sizeof(float), 16);
   L.kap = take((size_t)P.ncol * sizeof(c32), 16);
   L.cch = take((size_t)P.ncol * sizeof(int), 16);
-  L.n2r = take((size_t)P.N2 * sizeof(int), 16);
+  L.n2r = take((size_t)((P.N2 + 3) & ~3) * sizeof(int), 16);
+  L.tab_bytes = ((o + 15) & ~(size_t)15) - L.tab;
+  o = L.tab + L.tab_bytes;
   L.bar = take(8, 8);
   L.total = o;
   return L;
@@ -79,16 +84,11 @@ __device__ __forceinline__ float atan2_tab(const float *__restrict__ T, float y,
     alpha -= (float)idx;
     base = fmaf(T[idx + 1] - T[idx], alpha, T[idx]);
   }
+  // quadrant fix-up of the reference, folded: (xa > ya ? base : pi/2 - base), mirrored for x < 0, signed like y
   const float pi = 3.14159265358979323846f, hp = 1.57079632679489661923f;
-  float angle;
-  if (xa > ya) {
-    if (x >= 0.0f) angle = (y >= 0.0f) ? base : -base;
-    else angle = (y >= 0.0f) ? pi - base : base - pi;
-  } else {
-    if (y >= 0.0f) angle = (x >= 0.0f) ? hp - base : hp + base;
-    else angle = (x >= 0.0f) ? -hp + base : -hp - base;
-  }
-  return angle;
+  float angle = (xa > ya) ? base : hp - base;
+  if (x < 0.0f) angle = pi - angle;
+  return copysignf(angle, y);
 }
 
 template <int N1, int Q>
@@ -122,26 +122,21 @@ __global__ void __launch_bounds__(PFB_THREADS, 2) k_pfb(PfbPlan P, const c32 *__
 
   // ---- 0. stage the input span (TMA bulk copy when it is aligned and inside the batch) and the tables
   const bool bulk = s0 >= 0 && s0 + P.span <= n_samples && ((s0 | P.span) & 1) == 0;
-  if (bulk) {
-    if (tid == 0) { mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
-    __syncthreads();
-    if (tid == 0) {
-      const unsigned bytes = (unsigned)P.span * (unsigned)sizeof(c32);
-      mbar_expect_tx(bar, bytes);
-      tma_bulk_g2s(xs, x + s0, bytes, bar);
-    }
-  } else {
+  if (tid == 0) { mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
+  __syncthreads();
+  if (tid == 0) {
+    const unsigned tbytes = (unsigned)L.tab_bytes, bytes = bulk ? (unsigned)P.span * (unsigned)sizeof(c32) : 0u;
+    mbar_expect_tx(bar, tbytes + bytes);
+    tma_bulk_g2s(smem + L.tab, P.tables, tbytes, bar);
+    if (bulk) tma_bulk_g2s(xs, x + s0, bytes, bar);
+  }
+  if (!bulk) {
     for (int i = tid; i < P.span; i += PFB_THREADS) {
       const long n = s0 + i;
       xs[i] = (n >= 0 && n < n_samples) ? x[n] : c32{0.0f, 0.0f};
     }
   }
-  for (int i = tid; i < N2 * ncol; i += PFB_THREADS) WBs[i] = P.WB[i];
-  for (int i = tid; i < P.Q * M; i += PFB_THREADS) hqs[i] = P.hq[i];
-  for (int i = tid; i < 257; i += PFB_THREADS) atans[i] = P.atan_tab[i];
-  for (int i = tid; i < ncol; i += PFB_THREADS) { kaps[i] = P.kappa[i]; cch[i] = P.col_chan[i]; }
-  for (int i = tid; i < N2; i += PFB_THREADS) n2r[i] = P.n2_of_rho[i];
-  if (bulk) mbar_wait(bar, 0);
+  mbar_wait(bar, 0);
   __syncthreads();
   if (P.phi_step != 0.0f) {
     // x'[i] = x[i] e^{-j 2 pi phi i / M}: the phase origin is the tile's (any origin common to Z[g] and Z[g-1] does)
@@ -249,26 +244,38 @@ __global__ void __launch_bounds__(PFB_THREADS, 2) k_pfb(PfbPlan P, const c32 *__
   }
   __syncthreads();
 
-  // ---- 3. demod of the own points (local t = 1 .. n_own) and the tile's energy sums
-  for (int idx = tid; idx < n_own * ncol; idx += PFB_THREADS) {
-    const int t = 1 + idx / ncol, col = idx - (t - 1) * ncol;
-    const int ch = cch[col];
-    if (ch < 0) continue;
-    const c32 z1 = zs[t * ZP + col], z0 = zs[(t - 1) * ZP + col], k = kaps[col];
-    const float pr = z1.re * z0.re + z1.im * z0.im, pi = z1.im * z0.re - z1.re * z0.im;    // z1 conj(z0)
-    const float qr = pr * k.re - pi * k.im, qi = pr * k.im + pi * k.re;
-    P.dem[(gs + t) * (long)P.nch + ch] = P.gain * atan2_tab(atans, qi, qr);
-  }
-  if (tid < ncol) {
+  // ---- 3. demod of the own points (local t = 1 .. n_own) and the tile's energy sums.  thread = (column, row group):
+  // rows t = 1 + rg, 1 + rg + RG, ...; the |Z|^2 of its rows ride along and are reduced across the row groups.
+  {
+    const int RG = PFB_THREADS / ncol;                   // row groups (3 for 80 columns)
+    const int col = tid % ncol, rg = tid / ncol;
     float sa = 0.0f, sb = 0.0f;
-    for (int t = 1; t <= n_own; t++) {
-      const c32 z = zs[t * ZP + tid];
-      const float m = z.re * z.re + z.im * z.im;
-      sa += m;
-      if (in_seg0 + t - 1 < P.rem) sb += m;
+    if (rg < RG) {
+      const int ch = cch[col];
+      const c32 k = kaps[col];
+      float *drow = P.dem + (gs + 1 + rg) * (long)P.nch + ch;
+      for (int t = 1 + rg; t <= n_own; t += RG, drow += (long)RG * P.nch) {
+        const c32 z1 = zs[t * ZP + col], z0 = zs[(t - 1) * ZP + col];
+        const float m = z1.re * z1.re + z1.im * z1.im;
+        sa += m;
+        if (in_seg0 + t - 1 < P.rem) sb += m;
+        if (ch >= 0) {
+          const float pr = z1.re * z0.re + z1.im * z0.im, pi = z1.im * z0.re - z1.re * z0.im;    // z1 conj(z0)
+          const float qr = pr * k.re - pi * k.im, qi = pr * k.im + pi * k.re;
+          *drow = P.gain * atan2_tab(atans, qi, qr);
+        }
+      }
     }
-    P.E[(tile * ncol + tid) * 2] = sa;
-    P.E[(tile * ncol + tid) * 2 + 1] = sb;
+    __syncthreads();                                     // the Z tile is dead: its first rows carry the partial sums
+    float *part = reinterpret_cast<float *>(zs);
+    if (rg < RG) { part[(rg * ncol + col) * 2] = sa; part[(rg * ncol + col) * 2 + 1] = sb; }
+    __syncthreads();
+    if (tid < ncol) {
+      float ta = 0.0f, tb = 0.0f;
+      for (int g2 = 0; g2 < RG; g2++) { ta += part[(g2 * ncol + tid) * 2]; tb += part[(g2 * ncol + tid) * 2 + 1]; }
+      P.E[(tile * ncol + tid) * 2] = ta;
+      P.E[(tile * ncol + tid) * 2 + 1] = tb;
+    }
   }
 }
 
@@ -308,6 +315,21 @@ __global__ void k_i16_to_c32(const int16_t *__restrict__ src, c32 *__restrict__ 
 }  // namespace
 
 size_t pfb_smem_bytes(const PfbPlan &P) { return pfb_layout(P).total; }
+
+size_t pfb_table_bytes(const PfbPlan &P) { return pfb_layout(P).tab_bytes; }
+
+void pfb_pack_tables(const PfbPlan &P, const c32 *WB, const float *hq, const float *atan_tab, const c32 *kappa,
+                     const int *col_chan, const int *n2_of_rho, unsigned char *blob)
+{
+  const PfbSmem L = pfb_layout(P);
+  memset(blob, 0, L.tab_bytes);
+  memcpy(blob + (L.wb - L.tab), WB, (size_t)P.N2 * P.ncol * sizeof(c32));
+  memcpy(blob + (L.hq - L.tab), hq, (size_t)P.Q * P.M * sizeof(float));
+  memcpy(blob + (L.atan - L.tab), atan_tab, 257 * sizeof(float));
+  memcpy(blob + (L.kap - L.tab), kappa, (size_t)P.ncol * sizeof(c32));
+  memcpy(blob + (L.cch - L.tab), col_chan, (size_t)P.ncol * sizeof(int));
+  memcpy(blob + (L.n2r - L.tab), n2_of_rho, (size_t)P.N2 * sizeof(int));
+}
 
 template <int N1, int Q>
 static int pfb_optin(const PfbPlan &P)

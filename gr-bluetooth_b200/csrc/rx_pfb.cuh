@@ -20,20 +20,20 @@ struct PfbPlan {
   int span = 0;                    // samples staged per tile: (TT - 1) * D + Q * M
   float gain = 0;                  // demod gain (lib/multi_block.cc:88)
   float phi_step = 0;              // pre-rotation: x'[i] = x[i] e^{j pi phi_step i}, phi_step = -2 phi / M (0: none)
-  // device tables
-  const float *hq = nullptr;       // [Q][M]  h'[r + M q], h'[k] = h[Nc-1-k], zero padded
-  const int *n2_of_rho = nullptr;  // [N2]    n2 with (N1 n2) mod N2 == rho
-  const c32 *WB = nullptr;         // [N2][ncol]  W_N2^{n2 k2(col)}
-  const int *col_chan = nullptr;   // [ncol]  channel index of a column, -1: padding
+  // device tables: ONE blob in the kernel's shared-memory layout (pfb_pack_tables), fetched per tile by a bulk copy:
+  //   WB [N2][ncol] c32 W_N2^{n2 k2(col)} | hq [Q][M] f32 h'[r + M q] | atan [257] | kappa [ncol] c32
+  //   e^{-j 2 pi a_c D / M} | col_chan [ncol] i32 (-1: padding) | n2_of_rho [N2] i32
+  const unsigned char *tables = nullptr;
   const int *chan_col = nullptr;   // [nch]   column of a channel
-  const c32 *kappa = nullptr;      // [ncol]  e^{-j 2 pi a_c D / M}: constant of the differential product
-  const float *atan_tab = nullptr; // [257]
   // outputs
   float *dem = nullptr;            // [Gtot][nch]  demod floats on the global decimation grid
   float *E = nullptr;              // [segments * tps][ncol][2]  per-tile sums of |Z|^2 (all points / points below rem)
 };
 
 size_t pfb_smem_bytes(const PfbPlan &P);
+size_t pfb_table_bytes(const PfbPlan &P);
+void pfb_pack_tables(const PfbPlan &P, const c32 *WB, const float *hq, const float *atan_tab, const c32 *kappa,
+                     const int *col_chan, const int *n2_of_rho, unsigned char *blob);
 int  pfb_setup(const PfbPlan &P);                                 // opt in to the dynamic shared memory; 0 or -1
 long pfb_tiles(const PfbPlan &P, int B);
 // input samples (from x[0]) the tiles below `tile_end` read

@@ -782,38 +782,42 @@ static int submit_impl(btb200_ctx *ctx, const void *iq, int kind, size_t n_sampl
     if (host) CK(cudaEventRecord(ctx->ev_h2d, ctx->copy_stream));
   }
   if (ctx->poly) {
-    // throughput mode: polyphase channelizer with fused demod + energy, noise estimate for every window, then the
-    // same clock recovery / search as the exact mode, reading the demod floats from the global grid
+    // throughput mode: polyphase channelizer with fused demod + energy, clock recovery of the searchable prefix,
+    // access-code search, resume of the clock-recovery chains of the windows with hits, the noise estimate of every
+    // window (it only feeds the squelch, which is settled on the host at collect time), then the hit list in the
+    // reference's order, the arena layout and the symbol gather -- all laid out on the device, no host round trip
+    // inside a batch.  Everything runs in order on the compute stream: the resume is a few dozen latency-bound warps,
+    // and next to a compute-bound kernel (tried: second stream, high priority, beside the estimator or beside the
+    // next batch) they are starved of issue slots and take 4-5x longer, which costs more than the overlap saves
+    // (measured per step: 3.7 ms in order, 4.0 overlapped with the next batch, 6.5 beside the estimator).
+    // BTB200_TAIL_STREAM2=1 keeps the overlapped variant for experiments.
     CK(cudaMemsetAsync(W.hit_count, 0, 4 * sizeof(unsigned), s));
     CK(cudaEventRecord(ctx->ev[1], s));
     if (!front_done) front_range(0, ntile);
     launch_pfb_energy(ctx->PF, (int)n_slots, ctx->d_eon_all, s); ctx->launches++;
     CK(cudaMemcpyAsync(ctx->h_eon_all, ctx->d_eon_all, nbc * sizeof(double), cudaMemcpyDeviceToHost, s));
     CK(cudaEventRecord(ctx->ev[2], s));
-    enqueue_noise_estimate(ctx, G, W, (long)need, s);
-    CK(cudaMemcpyAsync(ctx->h_esum, ctx->F.esum, nbc * sizeof(double), cudaMemcpyDeviceToHost, s));
-    CK(cudaEventRecord(ctx->ev[3], s));
     launch_fill_pass(W, (int)nbc, 1, s); ctx->launches++;
-    CK(cudaEventRecord(ctx->ev[4], s));
     launch_demod_mm_v2(G, ctx->T, W, ctx->d_dem, s); ctx->launches++;
-    CK(cudaEventRecord(ctx->ev[5], s));
+    CK(cudaEventRecord(ctx->ev[3], s));
     launch_search_warp(G, ctx->T, W, s); ctx->launches++;
-    CK(cudaEventRecord(ctx->ev[6], s));
-    // the tail -- resume of the windows with hits, hit list in the reference's order, arena layout, symbol gather --
-    // is laid out on the device and runs on the second (high-priority) stream under the next batches' kernels
-    // The tail is a handful of latency-bound kernels (the resumed clock-recovery chains): run under another batch's
-    // compute-bound kernels they are starved of issue slots and take 5x longer, and that batch's own clock recovery
-    // slows down with them (measured: 4.0 ms per step overlapped on a second stream, 3.7 in order) -- so the tail stays
-    // on the compute stream.  BTB200_TAIL_STREAM2=1 restores the overlapped variant.
+    launch_tail_scan(G, W, s); ctx->launches++;
+    CK(cudaEventRecord(ctx->ev[4], s));
     static const bool tail_inline = std::getenv("BTB200_TAIL_STREAM2") == nullptr;
     cudaStream_t s2 = tail_inline ? s : ctx->stream2;
-    if (!tail_inline) CK(cudaStreamWaitEvent(s2, ctx->ev[6], 0));
-    launch_tail_scan(G, W, s2);
-    if (G.early) launch_tail_resume(G, ctx->T, W, ctx->d_dem, s2);
-    launch_tail_finish(G, W, s2);
-    ctx->launches += G.early ? 5 : 4;
-    CK(cudaMemcpyAsync(ctx->h_counts, W.hit_count, 4 * sizeof(unsigned), cudaMemcpyDeviceToHost, s2));
-    CK(cudaEventRecord(ctx->ev[7], s2));
+    if (G.early) {
+      if (!tail_inline) CK(cudaStreamWaitEvent(s2, ctx->ev[4], 0));
+      launch_tail_resume(G, ctx->T, W, ctx->d_dem, s2); ctx->launches++;
+      if (!tail_inline) CK(cudaEventRecord(ctx->ev_tail, s2));
+    }
+    enqueue_noise_estimate(ctx, G, W, (long)need, s);
+    CK(cudaMemcpyAsync(ctx->h_esum, ctx->F.esum, nbc * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CK(cudaEventRecord(ctx->ev[5], s));
+    if (G.early && !tail_inline) CK(cudaStreamWaitEvent(s, ctx->ev_tail, 0));
+    launch_tail_finish(G, W, s); ctx->launches += 3;
+    CK(cudaEventRecord(ctx->ev[6], s));
+    CK(cudaMemcpyAsync(ctx->h_counts, W.hit_count, 4 * sizeof(unsigned), cudaMemcpyDeviceToHost, s));
+    CK(cudaEventRecord(ctx->ev[7], s));
     CK(cudaGetLastError());
     ctx->pending = true;
     ctx->pend_slots = n_slots;
@@ -1085,12 +1089,15 @@ int collect_poly(btb200_ctx *ctx, btb200_hits *out)
   ctx->fast_off.assign(ctx->h_noise, ctx->h_noise + nbc);
   CK(cudaEventSynchronize(ctx->ev[8]));
   ctx->last_slots = ctx->pend_slots;
-  for (int i = 0; i < 6; i++) {
-    float ms = 0;
-    cudaEventElapsedTime(&ms, ctx->ev[i], ctx->ev[i + 1]);
-    ctx->timing[i] = ms;
-  }
-  cudaEventElapsedTime(&ctx->timing[6], ctx->ev[6], ctx->ev[8]);
+  // order of the throughput mode's stream: channelizer | clock recovery (prefix) | search | noise estimate with the
+  // resume beside it | tail (hit list, arena, gather, copies)
+  cudaEventElapsedTime(&ctx->timing[0], ctx->ev[0], ctx->ev[1]);
+  cudaEventElapsedTime(&ctx->timing[1], ctx->ev[1], ctx->ev[2]);
+  cudaEventElapsedTime(&ctx->timing[4], ctx->ev[2], ctx->ev[3]);
+  cudaEventElapsedTime(&ctx->timing[5], ctx->ev[3], ctx->ev[4]);
+  cudaEventElapsedTime(&ctx->timing[2], ctx->ev[4], ctx->ev[5]);
+  ctx->timing[3] = 0.0f;
+  cudaEventElapsedTime(&ctx->timing[6], ctx->ev[5], ctx->ev[8]);
   cudaEventElapsedTime(&ctx->timing[7], ctx->ev[0], ctx->ev[8]);
   if (!out) return BTB200_OK;
   out->count = 0;

@@ -1188,8 +1188,10 @@ void launch_tail_scan(const Geom &G, const DevBatch &W, cudaStream_t s)
 
 void launch_tail_resume(const Geom &G, const DevTables &T, const DevBatch &W, float *demT, cudaStream_t s)
 {
-  // one warp per block: the few hundred serial chains of a batch's hit windows spread over as many SMs as possible
-  constexpr int BLK = 32;
+  // Two warps per block: the resumed chains are latency-bound (one dependent chain of ~80 instructions per symbol)
+  // and their demod fetches are one sector per lane, so more than two warps on an SM queue up behind the load/store
+  // unit (measured per 512 slots / 2268 windows: 64-thread blocks 0.9 ms, 32-thread 0.9 ms, 128-thread 2.5 ms).
+  constexpr int BLK = 64;
   const size_t smem = sizeof(float) * (MM_RD + 8) * BLK + sizeof(float) * 8 * 132;
   // the list length lives on the device: launch for the worst case, blocks past the list end return at once
   k_mm_stateless_v2<BLK><<<cdiv((long)W.B * G.nch, BLK), BLK, smem, s>>>(G, W, T.mmse, demT, 2, reinterpret_cast<MmSave *>(W.mm_save),

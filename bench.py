@@ -506,6 +506,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--e2e-contexts", type=int, default=3,
                     help="contexts the pipelined loops cycle through (batches in flight = contexts)")
+    ap.add_argument("--tile", type=int, default=200, help="hopper workload: how many times the capture is played (BASELINE: 1000)")
     ap.add_argument("--snr-mode", default="exact", choices=["exact", "fast"],
                     help="exact-mode runs only: exact = reference arithmetic for every printed snr; fast = guarded estimate")
     args = ap.parse_args()

@@ -71,7 +71,7 @@ class Hits(C.Structure):
 EXPORTS = ["btb200_process_channels", "btb200_create", "btb200_destroy", "btb200_get_info", "btb200_process", "btb200_process_device",
            "btb200_submit", "btb200_submit_i16", "btb200_process_i16", "btb200_collect_begin", "btb200_collect", "btb200_host_alloc", "btb200_host_free",
            "btb200_get_mm_state", "btb200_set_mm_state", "btb200_reset", "btb200_get_stage",
-           "btb200_search_bits", "btb200_timer_start", "btb200_timer_stop",
+           "btb200_search_bits", "btb200_timer_start", "btb200_timer_stop", "btb200_set_window_mask",
            "btb200_last_timing", "btb200_launch_count", "btb200_strerror", "btb200_last_error",
            "btb200_version"]
 
@@ -106,6 +106,7 @@ def lib():
         L.btb200_get_stage.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_uint32, C.c_void_p, C.c_size_t]
         L.btb200_get_stage.restype = C.c_int64
         L.btb200_search_bits.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32, C.POINTER(Hits)]
+        L.btb200_set_window_mask.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
         L.btb200_timer_start.argtypes = [C.c_void_p]
         L.btb200_timer_stop.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
         L.btb200_last_timing.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
@@ -357,6 +358,11 @@ class multi_block:
             raise Btb200Error(-7, "hit buffer too small")
         hits = self._hits[:h.count]
         return [(int(x["slot"]) * stride + int(x["offset"]), int(x["lap"])) for x in hits]
+
+    def set_window_mask(self, mask):
+        """mask[slot_in_batch, chan_index] != 0: the channel-windows the NEXT submit/process demodulates and searches."""
+        m = np.ascontiguousarray(mask, dtype=np.uint8)
+        self._check(self._L.btb200_set_window_mask(self._ctx, m.ctypes.data, m.shape[0]))
 
     def timer_start(self):
         self._check(self._L.btb200_timer_start(self._ctx))

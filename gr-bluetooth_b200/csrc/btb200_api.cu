@@ -95,6 +95,8 @@ struct btb200_ctx {
   bool fast_snr = false;
   FastNoisePlan F{};
   double *h_esum = nullptr;
+  std::vector<int> win_mask;         // pass flags for the next submit (btb200_set_window_mask), empty: none
+  int *h_mask = nullptr;             // pinned staging of the mask
   bool use_nest = false;             // rx_nest.cu (fused polyphase + DFT) instead of the two kernels of rx_fast.cu
   PfbDesign nfd;
   NestPlan NP{};
@@ -275,6 +277,21 @@ void enqueue_noise_estimate(btb200_ctx *ctx, const Geom &G, const DevBatch &W, l
     launch_noise_fast(ctx->F, W.x, W.B, G.S, G.fns, G.D, G.n_noise, G.nch, s);
     ctx->launches += 2;
   }
+}
+
+// the pass flags of a lazy-squelch batch: all ones, or the caller's window mask (consumed)
+int enqueue_pass_flags(btb200_ctx *ctx, const DevBatch &W, size_t nbc, cudaStream_t s)
+{
+  if (ctx->win_mask.size() == nbc) {
+    if (!ctx->h_mask) CK(cudaMallocHost(&ctx->h_mask, (size_t)ctx->max_slots * ctx->plan.nch * sizeof(int)));
+    std::memcpy(ctx->h_mask, ctx->win_mask.data(), nbc * sizeof(int));
+    CK(cudaMemcpyAsync(W.pass, ctx->h_mask, nbc * sizeof(int), cudaMemcpyHostToDevice, s));
+  } else {
+    launch_fill_pass(W, (int)nbc, 1, s);
+  }
+  ctx->win_mask.clear();
+  ctx->launches++;
+  return 0;
 }
 
 // Tables and buffers of the polyphase channelizer (rx_pfb.cu)
@@ -578,7 +595,7 @@ void teardown(btb200_ctx *ctx)
   for (void *p : {(void *)ctx->h_energy, (void *)ctx->h_noise, (void *)ctx->h_pass, (void *)ctx->h_counts,
                   (void *)ctx->h_hits, (void *)ctx->h_arena, (void *)ctx->h_ph, (void *)ctx->h_groups,
                   (void *)ctx->h_list, (void *)ctx->h_eon, (void *)ctx->h_eoff, (void *)ctx->h_esum,
-                  (void *)ctx->h_list2, (void *)ctx->h_nsym, (void *)ctx->h_eon_all})
+                  (void *)ctx->h_list2, (void *)ctx->h_nsym, (void *)ctx->h_eon_all, (void *)ctx->h_mask})
     if (p) cudaFreeHost(p);
   for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
   for (auto &e : ctx->evl) if (e) cudaEventDestroy(e);
@@ -797,7 +814,7 @@ static int submit_impl(btb200_ctx *ctx, const void *iq, int kind, size_t n_sampl
     launch_pfb_energy(ctx->PF, (int)n_slots, ctx->d_eon_all, s); ctx->launches++;
     CK(cudaMemcpyAsync(ctx->h_eon_all, ctx->d_eon_all, nbc * sizeof(double), cudaMemcpyDeviceToHost, s));
     CK(cudaEventRecord(ctx->ev[2], s));
-    launch_fill_pass(W, (int)nbc, 1, s); ctx->launches++;
+    if (int rcm = enqueue_pass_flags(ctx, W, nbc, s)) return rcm;
     launch_demod_mm_v2(G, ctx->T, W, ctx->d_dem, s); ctx->launches++;
     CK(cudaEventRecord(ctx->ev[3], s));
     launch_search_warp(G, ctx->T, W, s); ctx->launches++;
@@ -862,7 +879,7 @@ static int submit_impl(btb200_ctx *ctx, const void *iq, int kind, size_t n_sampl
       CK(cudaMemcpyAsync(ctx->h_esum, ctx->F.esum, nbc * sizeof(double), cudaMemcpyDeviceToHost, s));
     }
     CK(cudaEventRecord(ctx->ev[3], s));
-    launch_fill_pass(W, (int)nbc, 1, s); ctx->launches++;
+    if (int rcm = enqueue_pass_flags(ctx, W, nbc, s)) return rcm;
   } else {
     launch_noise_fir(G, ctx->T, W, ctx->impl, s); ctx->launches++;
     CK(cudaEventRecord(ctx->ev[3], s));
@@ -907,6 +924,16 @@ static int submit_impl(btb200_ctx *ctx, const void *iq, int kind, size_t n_sampl
   ctx->pendW = W;
   ctx->pendG = G;
   ctx->pend_early = G.early != 0;
+  return BTB200_OK;
+}
+
+int btb200_set_window_mask(btb200_ctx *ctx, const uint8_t *mask, uint32_t n_slots)
+{
+  if (!ctx || !mask || n_slots == 0 || n_slots > ctx->max_slots) return BTB200_ERR_ARG;
+  if (!ctx->lazy) return BTB200_ERR_ARG;             // stateless mode with the lazy squelch only
+  const size_t n = (size_t)n_slots * ctx->plan.nch;
+  ctx->win_mask.resize(n);
+  for (size_t i = 0; i < n; i++) ctx->win_mask[i] = mask[i] ? 1 : 0;
   return BTB200_OK;
 }
 

@@ -4,12 +4,15 @@
 // work() until the file is consumed.
 //   -f/--freq Hz   -r/--rate sps   -i/--input-file FILE   -S (all-piconet sniffer, default)
 //   -L (LAP printer)   -l HEXLAP [-p] (follow one piconet: multi_hopper)   -s/--snr dB   -N/--nsamples n   -2/--input-shorts
+// and, not in the reference: --tile N (play the file N times back to back, as one stream; BASELINE configs[3]),
+// --stats (one JSON line on stderr: samples, seconds, Msamples/s through work())
 #include "gr_bluetooth/multi_sniffer.h"
 #include "gr_bluetooth/multi_LAP.h"
 #include "gr_bluetooth/multi_hopper.h"
 #include "gr_bluetooth/multi_UAP.h"
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -31,6 +34,8 @@ int main(int argc, char **argv)
   long nsamples = -1;
   bool shorts = false, hop_mode = false, tun = false, have_lap = false, sniff = false;
   int target_lap = 0;
+  long tile = 1;
+  bool stats = false;
   for (int i = 1; i < argc; i++) {
     std::string a = argv[i];
     auto next = [&]() -> const char * { return i + 1 < argc ? argv[++i] : ""; };
@@ -44,6 +49,8 @@ int main(int argc, char **argv)
     else if (a == "-L" || a == "--lap-printer") sniff = false;
     else if (a == "-l" || a == "--lap") { target_lap = (int)std::strtol(next(), nullptr, 16); have_lap = true; }     // apps/btrx:45
     else if (a == "-p" || a == "--hop") hop_mode = true;
+    else if (a == "--tile") tile = std::atol(next());
+    else if (a == "--stats") stats = true;
     else if (a == "-w" || a == "--wireshark") tun = true;           // apps/btrx:57-58; BTB200_TUN_FILE redirects the frames to a file
     else { std::fprintf(stderr, "unknown option %s\n", a.c_str()); return 2; }
   }
@@ -67,17 +74,23 @@ int main(int argc, char **argv)
     return 1;
   }
   const long H = blk->history(), S = (long)blk->samples_per_slot();
+  if (tile < 1) tile = 1;
+  const long file_total = total;
+  total *= tile;
   std::vector<gr_complex> buf((size_t)(H - 1 + total));
   if (shorts) {
-    std::vector<short> tmp((size_t)total * 2);
-    if (std::fread(tmp.data(), 4, (size_t)total, f) != (size_t)total) return 2;
-    for (long i = 0; i < total; i++) buf[(size_t)(H - 1 + i)] = gr_complex(tmp[2 * i], tmp[2 * i + 1]);
-  } else if (std::fread(&buf[(size_t)(H - 1)], 8, (size_t)total, f) != (size_t)total) return 2;
+    std::vector<short> tmp((size_t)file_total * 2);
+    if (std::fread(tmp.data(), 4, (size_t)file_total, f) != (size_t)file_total) return 2;
+    for (long i = 0; i < file_total; i++) buf[(size_t)(H - 1 + i)] = gr_complex(tmp[2 * i], tmp[2 * i + 1]);
+  } else if (std::fread(&buf[(size_t)(H - 1)], 8, (size_t)file_total, f) != (size_t)file_total) return 2;
   std::fclose(f);
+  for (long t = 1; t < tile; t++)
+    std::memcpy(&buf[(size_t)(H - 1 + t * file_total)], &buf[(size_t)(H - 1)], (size_t)file_total * sizeof(gr_complex));
 
   gr_vector_const_void_star inv(1);
   gr_vector_void_star outv;
   long consumed = 0;                    // new samples consumed so far
+  const auto t_start = std::chrono::steady_clock::now();
   const long ncalls = (total + S - 1) / S;
   long k = 0;
   while (k < ncalls) {
@@ -91,5 +104,10 @@ int main(int argc, char **argv)
     k += got / S;
   }
   std::fflush(stdout);
+  if (stats) {
+    const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
+    std::fprintf(stderr, "{\"samples\": %ld, \"seconds\": %.6f, \"msamples_per_s\": %.3f, \"work_calls_slots\": %ld, \"device_ms\": %.3f}\n",
+                 consumed, sec, consumed / sec / 1e6, k, blk->device_ms());
+  }
   return 0;
 }

@@ -37,6 +37,7 @@ class GR_BLUETOOTH_API multi_block : virtual public gr::sync_block {
   btb200_ctx *d_ctx = nullptr;
   unsigned d_batch_slots = 1;            // windows handed to the GPU per work() call when available
   bool d_stateless = false;
+  double d_device_ms = 0;                // device time of the batches processed so far (CUDA events, btb200_last_timing)
 
   // one callback per detected packet, in the reference's visiting order
   virtual void handle_hit(const btb200_hit &hit, const char *symbols, int n_symbols, double freq) = 0;
@@ -51,6 +52,7 @@ class GR_BLUETOOTH_API multi_block : virtual public gr::sync_block {
   //   BTB200_MM_MODE=chained|stateless   BTB200_DDC=exact|polyphase   BTB200_BATCH_SLOTS=n   BTB200_DEVICE=k
   unsigned batch_slots() const { return d_batch_slots; }
   double samples_per_slot() const { return d_samples_per_slot; }
+  double device_ms() const { return d_device_ms; }
   virtual int work(int noutput_items, gr_vector_const_void_star &input_items,
                    gr_vector_void_star &output_items) = 0;
 };

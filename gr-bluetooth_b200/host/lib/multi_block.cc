@@ -81,6 +81,7 @@ int multi_block::process_windows(int noutput_items, gr_vector_const_void_star &i
                           (size_t)(n - 1) * S + H, first_slot, (uint32_t)n, &out);
   if (rc != BTB200_OK)
     throw std::runtime_error(std::string("btb200_process: ") + btb200_strerror(rc) + " (" + btb200_last_error(d_ctx) + ")");
+  { float tm[8]; if (btb200_last_timing(d_ctx, tm) == BTB200_OK) d_device_ms += tm[7]; }
   if (out.overflow) {
     // more hits than the buffer holds: this only happens in stateless (batch) mode, where the batch can simply be
     // processed again; the chained stream state has already advanced and cannot be replayed

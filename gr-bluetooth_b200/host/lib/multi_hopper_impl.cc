@@ -8,6 +8,8 @@
 #include "multi_hopper_impl.h"
 #include "btb200.h"
 #include <cstdio>
+#include <cstdlib>
+#include <cstring>
 #include <stdexcept>
 #include <string>
 
@@ -32,15 +34,87 @@ multi_hopper_impl::multi_hopper_impl(double sample_rate, double center_freq, dou
   if (tun) d_host->set_tun_fd(btb200_host::open_tun_output());     /* lib/multi_hopper_impl.cc:56-64 */
   d_res.resize((size_t)(hi - lo + 1));
   d_symbols.resize((size_t)(hi - lo + 1) * 3125);
+  // BTB200_MM_MODE=stateless: once CLK1-27 is known, follow the piconet in BATCHES of slots.  The hop channel of
+  // every future slot is known then (lib/multi_hopper_impl.cc:152-166: clock = clkn + offset, channel = hop(clock)), so
+  // the slots no longer have to be visited one work() call at a time; each window starts from the constructor's
+  // clock-recovery state instead of the chained one (the throughput semantics of the sniffer block).
+  const char *mm = std::getenv("BTB200_MM_MODE");
+  if (mm && std::string(mm) == "stateless") {
+    btb200_config cfg;
+    std::memset(&cfg, 0, sizeof cfg);
+    cfg.abi_version = BTB200_ABI_VERSION;
+    cfg.sample_rate = sample_rate;
+    cfg.center_freq = center_freq;
+    cfg.squelch_threshold = squelch_threshold;
+    cfg.extra_history_symbols = 3125;
+    cfg.search = BTB200_SEARCH_BR;
+    cfg.mm_mode = BTB200_MM_STATELESS;
+    cfg.max_slots_per_call = d_batch_slots;
+    const char *dv = std::getenv("BTB200_DEVICE");
+    cfg.device = dv ? std::atoi(dv) : 0;
+    const char *dd = std::getenv("BTB200_DDC");
+    if (dd && std::string(dd) == "polyphase") cfg.ddc_mode = BTB200_DDC_POLYPHASE;
+    int rc = btb200_create(&cfg, &d_hop_ctx);
+    if (rc != BTB200_OK)
+      throw std::runtime_error(std::string("btb200_create (hop-along): ") + btb200_strerror(rc) + " (" + btb200_last_error(nullptr) + ")");
+    d_batched = true;
+    d_mask.resize((size_t)d_batch_slots * (size_t)(hi - lo + 1));
+    d_hits.resize(4096);
+  }
 }
 
-multi_hopper_impl::~multi_hopper_impl() {}
+multi_hopper_impl::~multi_hopper_impl() { if (d_hop_ctx) btb200_destroy(d_hop_ctx); }
 
-int multi_hopper_impl::work(int, gr_vector_const_void_star &input_items, gr_vector_void_star &)
+// hop-along over as many whole windows as the scheduler supplied: one masked channel per slot, first access code of
+// each window, packets handed to the piconet logic in slot order
+int multi_hopper_impl::hopalong_batch(int noutput_items, gr_vector_const_void_star &input_items)
+{
+  const int S = (int)d_samples_per_slot, H = (int)history();
+  int n = 1 + (noutput_items > 0 ? (noutput_items - 1) / S : 0);
+  if (n > (int)d_batch_slots) n = (int)d_batch_slots;
+  const uint32_t clkn0 = (uint32_t)((int)(d_cumulative_count / d_samples_per_slot) & 0x7ffffff);
+  const int lo = (int)((d_low_freq - 2402000000.0) / 1e6), nch = (int)d_res.size();
+  std::fill(d_mask.begin(), d_mask.begin() + (size_t)n * nch, 0);
+  bool any = false;
+  for (int k = 0; k < n; k++) {
+    const auto pl = d_host->plan(clkn0 + (uint32_t)k);
+    if (pl.n_channels == 1) { d_mask[(size_t)k * nch + (pl.first_channel - lo)] = 1; any = true; }
+  }
+  if (any) {
+    for (;;) {
+      btb200_hits out;
+      std::memset(&out, 0, sizeof out);
+      out.hits = d_hits.data();
+      out.cap = (uint32_t)d_hits.size();
+      out.symbols = nullptr;
+      out.symbols_cap = UINT64_MAX;                      // borrowed symbols: no second host copy
+      int rc = btb200_set_window_mask(d_hop_ctx, d_mask.data(), (uint32_t)n);
+      if (rc == BTB200_OK)
+        rc = btb200_process(d_hop_ctx, reinterpret_cast<const float *>(input_items[0]), (size_t)(n - 1) * S + H, clkn0, (uint32_t)n, &out);
+      if (rc != BTB200_OK)
+        throw std::runtime_error(std::string("btb200_process (hop-along): ") + btb200_strerror(rc) + " (" + btb200_last_error(d_hop_ctx) + ")");
+      { float tm[8]; if (btb200_last_timing(d_hop_ctx, tm) == BTB200_OK) d_device_ms += tm[7]; }
+      if (out.overflow) { d_hits.resize(d_hits.size() * 4); continue; }
+      uint32_t last_slot = 0xffffffffu;
+      for (uint32_t i = 0; i < out.count; i++) {
+        const btb200_hit &h = out.hits[i];
+        if (h.kind != 0 || h.slot == last_slot) continue;    // one sniff_ac per slot: the first access code only
+        last_slot = h.slot;
+        d_host->hop_packet(d_host->plan(h.slot), reinterpret_cast<const char *>(out.symbols + h.sym_offset), (int)h.sym_count);
+      }
+      break;
+    }
+  }
+  d_cumulative_count += (uint64_t)n * (uint64_t)S;
+  return n * S;
+}
+
+int multi_hopper_impl::work(int noutput_items, gr_vector_const_void_star &input_items, gr_vector_void_star &)
 {
   const int S = (int)d_samples_per_slot;
   const uint32_t clkn = (uint32_t)((int)(d_cumulative_count / d_samples_per_slot) & 0x7ffffff);
   const auto pl = d_host->plan(clkn);
+  if (d_batched && pl.hopalong) return hopalong_batch(noutput_items, input_items);
   if (pl.n_channels > 0) {
     int rc = btb200_process_channels(d_ctx, reinterpret_cast<const float *>(input_items[0]), history(), clkn,
                                      pl.first_channel, pl.n_channels, pl.stop_lap, d_res.data(), d_symbols.data(),

@@ -15,7 +15,14 @@ class multi_hopper_impl : virtual public multi_hopper {
   std::unique_ptr<btb200_host::HopperHost> d_host;
   std::vector<btb200_chan_result> d_res;
   std::vector<uint8_t> d_symbols;
+  // throughput variant of the hop-along phase (BTB200_MM_MODE=stateless): a second, stateless context processes
+  // batches of slots with one masked channel per slot
+  btb200_ctx *d_hop_ctx = nullptr;
+  std::vector<uint8_t> d_mask;
+  std::vector<btb200_hit> d_hits;
+  bool d_batched = false;
   void handle_hit(const btb200_hit &, const char *, int, double) {}
+  int hopalong_batch(int noutput_items, gr_vector_const_void_star &input_items);
 
  public:
   multi_hopper_impl(double sample_rate, double center_freq, double squelch_threshold, int LAP, bool aliased, bool tun);

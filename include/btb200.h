@@ -271,6 +271,12 @@ BTB200_API int btb200_process_channels(btb200_ctx *ctx, const float *iq, size_t 
  * (A' = a third context, or A again after collect(A) -- bench.py's end-to-end loop). */
 BTB200_API int  btb200_submit(btb200_ctx *ctx, const float *iq, int iq_on_device, size_t n_samples,
                    uint64_t first_slot, uint32_t n_slots);
+/* Window mask for the NEXT submit/process of a BTB200_MM_STATELESS context: mask[slot_in_batch * n_channels + chan_index]
+ * != 0 selects the channel-windows to demodulate and search; the others are skipped as if squelched.  This is the batched
+ * form of multi_hopper's hop-along phase (lib/multi_hopper_impl.cc:152-209: once CLK1-27 is known the hop channel of
+ * every slot is known in advance, one channel per slot).  The mask is consumed by that one call. */
+BTB200_API int  btb200_set_window_mask(btb200_ctx *ctx, const uint8_t *mask, uint32_t n_slots);
+
 /* int16 input: interleaved (re, im) int16 pairs, what the reference's flowgraph feeds through
  * interleaved_short_to_complex in front of the block (apps/btrx:141-159).  Same batches as btb200_submit /
  * btb200_process with half the host-to-device bytes; the conversion to complex64 is exact, so results are identical

@@ -65,8 +65,11 @@ multi_hopper_impl::multi_hopper_impl(double sample_rate, double center_freq, dou
 
 multi_hopper_impl::~multi_hopper_impl() { if (d_hop_ctx) btb200_destroy(d_hop_ctx); }
 
-// hop-along over as many whole windows as the scheduler supplied: one masked channel per slot, first access code of
-// each window, packets handed to the piconet logic in slot order
+// Batched form of the block (BTB200_MM_MODE=stateless): as many whole windows as the scheduler supplied go through the
+// stateless receive path at once.  While the clock is unknown every channel is demodulated and searched (the scan of
+// lib/multi_hopper_impl.cc:93-137); from the slot on which CLK1-27 is acquired -- it can happen in the middle of a batch --
+// only the predicted hop channel counts (hopalong(), :152-209), and batches that start with the clock known mask
+// everything else out before the GPU sees it.  Per (slot, channel) the reference runs ONE sniff_ac: the first access code.
 int multi_hopper_impl::hopalong_batch(int noutput_items, gr_vector_const_void_star &input_items)
 {
   const int S = (int)d_samples_per_slot, H = (int)history();
@@ -74,11 +77,14 @@ int multi_hopper_impl::hopalong_batch(int noutput_items, gr_vector_const_void_st
   if (n > (int)d_batch_slots) n = (int)d_batch_slots;
   const uint32_t clkn0 = (uint32_t)((int)(d_cumulative_count / d_samples_per_slot) & 0x7ffffff);
   const int lo = (int)((d_low_freq - 2402000000.0) / 1e6), nch = (int)d_res.size();
-  std::fill(d_mask.begin(), d_mask.begin() + (size_t)n * nch, 0);
-  bool any = false;
-  for (int k = 0; k < n; k++) {
-    const auto pl = d_host->plan(clkn0 + (uint32_t)k);
-    if (pl.n_channels == 1) { d_mask[(size_t)k * nch + (pl.first_channel - lo)] = 1; any = true; }
+  const bool masked = d_host->plan(clkn0).hopalong;
+  bool any = !masked;
+  if (masked) {
+    std::fill(d_mask.begin(), d_mask.begin() + (size_t)n * nch, 0);
+    for (int k = 0; k < n; k++) {
+      const auto pl = d_host->plan(clkn0 + (uint32_t)k);
+      if (pl.n_channels == 1) { d_mask[(size_t)k * nch + (pl.first_channel - lo)] = 1; any = true; }
+    }
   }
   if (any) {
     for (;;) {
@@ -88,19 +94,31 @@ int multi_hopper_impl::hopalong_batch(int noutput_items, gr_vector_const_void_st
       out.cap = (uint32_t)d_hits.size();
       out.symbols = nullptr;
       out.symbols_cap = UINT64_MAX;                      // borrowed symbols: no second host copy
-      int rc = btb200_set_window_mask(d_hop_ctx, d_mask.data(), (uint32_t)n);
+      int rc = masked ? btb200_set_window_mask(d_hop_ctx, d_mask.data(), (uint32_t)n) : BTB200_OK;
       if (rc == BTB200_OK)
         rc = btb200_process(d_hop_ctx, reinterpret_cast<const float *>(input_items[0]), (size_t)(n - 1) * S + H, clkn0, (uint32_t)n, &out);
       if (rc != BTB200_OK)
-        throw std::runtime_error(std::string("btb200_process (hop-along): ") + btb200_strerror(rc) + " (" + btb200_last_error(d_hop_ctx) + ")");
+        throw std::runtime_error(std::string("btb200_process (hopper batch): ") + btb200_strerror(rc) + " (" + btb200_last_error(d_hop_ctx) + ")");
       { float tm[8]; if (btb200_last_timing(d_hop_ctx, tm) == BTB200_OK) d_device_ms += tm[7]; }
       if (out.overflow) { d_hits.resize(d_hits.size() * 4); continue; }
-      uint32_t last_slot = 0xffffffffu;
+      uint32_t last_slot = 0xffffffffu, done_slot = 0xffffffffu;
+      int last_chan = -1;
       for (uint32_t i = 0; i < out.count; i++) {
         const btb200_hit &h = out.hits[i];
-        if (h.kind != 0 || h.slot == last_slot) continue;    // one sniff_ac per slot: the first access code only
-        last_slot = h.slot;
-        d_host->hop_packet(d_host->plan(h.slot), reinterpret_cast<const char *>(out.symbols + h.sym_offset), (int)h.sym_count);
+        if (h.kind != 0) continue;
+        if (h.slot == last_slot && h.channel == last_chan) continue;       // first access code of a channel-window only
+        last_slot = h.slot; last_chan = h.channel;
+        if (h.slot == done_slot) continue;                                   // the reference left this slot's channel loop
+        const char *sp = reinterpret_cast<const char *>(out.symbols + h.sym_offset);
+        const auto pl = d_host->plan(h.slot);
+        if (pl.hopalong) {
+          if (pl.n_channels == 1 && (int)h.channel == pl.first_channel) {      // one channel per slot in this phase
+            d_host->hop_packet(pl, sp, (int)h.sym_count);
+            done_slot = h.slot;
+          }
+        } else if (d_host->scan_packet(h.slot, h.channel, sp, (int)h.sym_count)) {
+          done_slot = h.slot;                                                // `break`, multi_hopper_impl.cc:129,133
+        }
       }
       break;
     }
@@ -114,7 +132,7 @@ int multi_hopper_impl::work(int noutput_items, gr_vector_const_void_star &input_
   const int S = (int)d_samples_per_slot;
   const uint32_t clkn = (uint32_t)((int)(d_cumulative_count / d_samples_per_slot) & 0x7ffffff);
   const auto pl = d_host->plan(clkn);
-  if (d_batched && pl.hopalong) return hopalong_batch(noutput_items, input_items);
+  if (d_batched) return hopalong_batch(noutput_items, input_items);
   if (pl.n_channels > 0) {
     int rc = btb200_process_channels(d_ctx, reinterpret_cast<const float *>(input_items[0]), history(), clkn,
                                      pl.first_channel, pl.n_channels, pl.stop_lap, d_res.data(), d_symbols.data(),

@@ -71,7 +71,7 @@ class Hits(C.Structure):
 EXPORTS = ["btb200_process_channels", "btb200_create", "btb200_destroy", "btb200_get_info", "btb200_process", "btb200_process_device",
            "btb200_submit", "btb200_submit_i16", "btb200_process_i16", "btb200_collect_begin", "btb200_collect", "btb200_host_alloc", "btb200_host_free",
            "btb200_get_mm_state", "btb200_set_mm_state", "btb200_reset", "btb200_get_stage",
-           "btb200_search_bits", "btb200_timer_start", "btb200_timer_stop", "btb200_set_window_mask",
+           "btb200_search_bits", "btb200_timer_start", "btb200_timer_stop", "btb200_set_window_mask", "btb200_hop_candidates", "btb200_hop_select",
            "btb200_last_timing", "btb200_launch_count", "btb200_strerror", "btb200_last_error",
            "btb200_version"]
 
@@ -107,6 +107,9 @@ def lib():
         L.btb200_get_stage.restype = C.c_int64
         L.btb200_search_bits.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32, C.POINTER(Hits)]
         L.btb200_set_window_mask.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
+        L.btb200_hop_candidates.argtypes = [C.c_int, C.c_uint32, C.c_int, C.c_int, C.c_uint32, C.c_int, C.c_void_p, C.c_uint32,
+                                            C.POINTER(C.c_uint32)]
+        L.btb200_hop_select.argtypes = [C.c_uint32, C.c_int, C.c_uint32]
         L.btb200_timer_start.argtypes = [C.c_void_p]
         L.btb200_timer_stop.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
         L.btb200_last_timing.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
@@ -419,6 +422,19 @@ def format_hit_line(hit):
         return "time %6d, snr=%.1f, channel %2d, LAP %06x " % (hit["slot"] & 0x7ffffff, hit["snr"],
                                                                hit["channel"], hit["lap"])
     return "time %6d, snr=%.1f, " % (hit["slot"] & 0x7ffffff, hit["snr"])
+
+
+def hop_candidates(address28, clock6, first_channel, afh=False, aliased=False, device=0):
+    """GPU candidate search of the hop reversal -> ascending uint32 array of CLK1-27 candidates."""
+    out = np.zeros(1 << 16, np.uint32)
+    n = C.c_uint32()
+    rc = lib().btb200_hop_candidates(device, address28, int(afh), int(aliased), clock6, first_channel, out.ctypes.data, len(out), C.byref(n))
+    if rc:
+        raise Btb200Error(rc)
+    if n.value > len(out):
+        out = np.zeros(n.value, np.uint32)
+        lib().btb200_hop_candidates(device, address28, int(afh), int(aliased), clock6, first_channel, out.ctypes.data, len(out), C.byref(n))
+    return out[:n.value].copy()
 
 
 def version():

@@ -5,6 +5,7 @@
 #include <sys/ioctl.h>
 #include <unistd.h>
 #include "bt_host.h"
+#include "../../csrc/hop_select.hpp"
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -545,7 +546,7 @@ bool Piconet::uap_from_header(ClassicPacket &pkt)
 void Piconet::reset()
 {
   std::printf("no candidates remaining! starting over . . .\n");
-  if (d_hop_reversal_inited) { d_clock_candidates.clear(); d_sequence.clear(); d_sequence.shrink_to_fit(); }
+  if (d_hop_reversal_inited) d_clock_candidates.clear();
   d_got_first_packet = false;
   d_packets_observed = 0;
   d_hop_reversal_inited = false;
@@ -557,78 +558,26 @@ void Piconet::reset()
   d_looks_like_afh = false;
 }
 
-// 5-bit butterfly permutation of the hop selection kernel (Core spec vol 2 part B 2.6; piconet_impl.cc:165-199)
-static int perm5(int z, int p_high, int p_low)
-{
-  static const int index1[14] = {0, 2, 1, 3, 0, 1, 0, 3, 1, 0, 2, 1, 0, 1};
-  static const int index2[14] = {1, 3, 2, 4, 4, 3, 2, 4, 4, 3, 4, 3, 3, 2};
-  int zb[5], p[14];
-  for (int i = 0; i < 9; i++) p[i] = (p_low >> i) & 1;
-  for (int i = 0; i < 5; i++) p[i + 9] = (p_high >> i) & 1;
-  for (int i = 0; i < 5; i++) zb[i] = (z >> i) & 1;
-  for (int i = 13; i >= 0; i--)
-    if (p[i]) { const int t = zb[index1[i]]; zb[index1[i]] = zb[index2[i]]; zb[index2[i]] = t; }
-  int out = 0;
-  for (int i = 0; i < 5; i++) out += zb[i] << i;
-  return out;
-}
+// hop selection kernel evaluated per clock value: csrc/hop_select.hpp (shared with the GPU candidate search)
+int Piconet::hop_select(uint32_t addr, bool afh, uint32_t clock) { return btb200::hop_select(addr, afh, clock); }
 
-// the complete hopping sequence, index = CLK1-27 (piconet_impl.cc:131-159, 214-255)
-void Piconet::gen_hops()
-{
-  const int address = (int)((((uint32_t)d_uap << 24) | d_lap) & 0xfffffff);
-  int bank[CHANNELS];
-  for (int i = 0; i < CHANNELS; i++) bank[i] = (i * 2) % CHANNELS;
-  const int a1 = (address >> 23) & 0x1f, bb = (address >> 19) & 0x0f;
-  const int c1 = ((address >> 4) & 0x10) + ((address >> 3) & 0x08) + ((address >> 2) & 0x04) + ((address >> 1) & 0x02) + (address & 0x01);
-  const int d1 = (address >> 10) & 0x1ff;
-  const int e = ((address >> 7) & 0x40) + ((address >> 6) & 0x20) + ((address >> 5) & 0x10) + ((address >> 4) & 0x08) +
-                ((address >> 3) & 0x04) + ((address >> 2) & 0x02) + ((address >> 1) & 0x01);
-  // permutation table for the two control words used per (c, d): [z][c][d]
-  std::vector<char> perm((size_t)32 * 32 * 512);
-  for (int z = 0; z < 32; z++)
-    for (int ph = 0; ph < 32; ph++)
-      for (int pl = 0; pl < 512; pl++) perm[((size_t)z * 32 + ph) * 512 + pl] = (char)perm5(z, ph, pl);
-  d_sequence.assign((size_t)SEQUENCE_LENGTH, 0);
-  size_t index = 0;
-  int f = 0;
-  for (int h = 0; h < 4; h++)
-    for (int i = 0; i < 32; i++) {
-      const int a = a1 ^ i;
-      for (int j = 0; j < 32; j++) {
-        const int cc = c1 ^ j, cf = cc ^ 0x1f;
-        for (int k = 0; k < 512; k++) {
-          const int d = d1 ^ k;
-          for (int x = 0; x < 32; x++) {
-            const int pin = ((x + a) % 32) ^ bb;
-            int pout = perm[((size_t)pin * 32 + cc) * 512 + d];
-            d_sequence[index] = (char)bank[(pout + e + f) % CHANNELS];
-            if (d_afh) {
-              d_sequence[index + 1] = d_sequence[index];
-            } else {
-              pout = perm[((size_t)pin * 32 + cf) * 512 + d];
-              d_sequence[index + 1] = (char)bank[(pout + e + f + 32) % CHANNELS];
-            }
-            index += 2;
-          }
-          f += 16;
-        }
-      }
-    }
-}
+Piconet::candidate_fn Piconet::s_candidate_fn = nullptr;
 
 int Piconet::init_hop_reversal(bool aliased)
 {
   std::printf("\nCalculating complete hopping sequence.\n");
-  gen_hops();
+  d_hop_addr = (((uint32_t)d_uap << 24) | d_lap) & 0xfffffffu;
   d_aliased = aliased;
   const uint32_t clock = (d_clk_offset + d_first_pkt_time) & 0x3f;
   // candidates: clock values with the known low bits whose hop lands on the first observed channel
   d_clock_candidates.clear();
-  const char first_channel = (char)d_pattern_channels[0];
-  for (uint32_t i = clock; i < (uint32_t)SEQUENCE_LENGTH; i += 0x40) {
-    const char obs = d_aliased ? aliased_channel(d_sequence[i]) : d_sequence[i];
-    if (obs == first_channel) d_clock_candidates.push_back(i);
+  const int first_channel = d_pattern_channels[0];
+  if (!(s_candidate_fn && s_candidate_fn(d_hop_addr, d_afh, d_aliased, clock, first_channel, d_clock_candidates))) {
+    d_clock_candidates.clear();
+    for (uint32_t c = clock; c < (uint32_t)SEQUENCE_LENGTH; c += 0x40) {
+      const int hc = hop_select(d_hop_addr, d_afh, c);
+      if ((d_aliased ? (int)aliased_channel((char)hc) : hc) == first_channel) d_clock_candidates.push_back(c);
+    }
   }
   d_num_candidates = (int)d_clock_candidates.size();
   d_winnowed = 0;
@@ -642,7 +591,7 @@ int Piconet::winnow(int offset, char channel)
 {
   int n = 0;
   for (int i = 0; i < d_num_candidates; i++) {
-    const char s = d_sequence[(size_t)((d_clock_candidates[(size_t)i] + (uint32_t)offset) % (uint32_t)SEQUENCE_LENGTH)];
+    const char s = hop((int)((d_clock_candidates[(size_t)i] + (uint32_t)offset) % (uint32_t)SEQUENCE_LENGTH));
     const char obs = d_aliased ? aliased_channel(s) : s;
     if (obs == channel) d_clock_candidates[(size_t)n++] = d_clock_candidates[(size_t)i];
   }

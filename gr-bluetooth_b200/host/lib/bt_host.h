@@ -118,7 +118,16 @@ class Piconet {
   // observed channel, then winnowed with every later observation.
   int init_hop_reversal(bool aliased);                          // :96-129
   int winnow();                                                 // :345-368
-  char hop(int clock) const { return d_sequence[(size_t)clock]; }   // :279-282
+  // Channel of the basic hop sequence at CLK1-27 = clock.  The reference tabulates all 2^27 entries (128 MiB,
+  // piconet_impl.cc:214-255) before it can look one up (:279-282); here the hop selection kernel (Core spec vol 2
+  // part B 2.6) is evaluated on demand from the clock's bit fields -- same values, no table.
+  char hop(int clock) const { return (char)hop_select(d_hop_addr, d_afh, (uint32_t)clock); }
+  static int hop_select(uint32_t address28, bool afh, uint32_t clock);
+  // candidate search of the hop reversal on another engine (the GPU kernel behind btb200_hop_candidates): fills `out`
+  // with every clock = clock6 (mod 64) below 2^27 whose hop is first_channel, ascending; returns false to decline
+  typedef bool (*candidate_fn)(uint32_t address28, bool afh, bool aliased, uint32_t clock6, int first_channel,
+                               std::vector<uint32_t> &out);
+  static candidate_fn s_candidate_fn;
   static char aliased_channel(char channel) { return (char)(((channel + 24) % 25) + 26); }   // :520-523
 
  private:
@@ -127,12 +136,11 @@ class Piconet {
   static const int CHANNELS = 79, ALIASED_CHANNELS = 25;
   int d_pattern_indices[MAX_PATTERN_LENGTH];
   uint8_t d_pattern_channels[MAX_PATTERN_LENGTH];
-  std::vector<char> d_sequence;
+  uint32_t d_hop_addr = 0;            // UAP/LAP bits the hop kernel uses
   std::vector<uint32_t> d_clock_candidates;
   int d_num_candidates = 0, d_winnowed = 0;
   bool d_hop_reversal_inited = false, d_aliased = false, d_afh = false, d_looks_like_afh = false;
   int winnow(int offset, char channel);                         // :303-343
-  void gen_hops();                                              // :214-255
   uint32_t d_lap;
   std::deque<std::shared_ptr<ClassicPacket>> d_queue;
   bool d_got_first_packet = false, d_have_uap = false, d_have_nap = false, d_have_clk6 = false, d_have_clk27 = false;

@@ -13,6 +13,24 @@
 #include <stdexcept>
 #include <string>
 
+namespace {
+// candidate search of the hop reversal on the GPU (btb200_hop_candidates); declining lets the host logic do it
+int g_hop_device = 0;
+bool gpu_hop_candidates(uint32_t address28, bool afh, bool aliased, uint32_t clock6, int first_channel, std::vector<uint32_t> &out)
+{
+  uint32_t n = 0;
+  out.resize(1u << 16);
+  int rc = btb200_hop_candidates(g_hop_device, address28, afh, aliased, clock6, first_channel, out.data(), (uint32_t)out.size(), &n);
+  if (rc == BTB200_OK && n > out.size()) {
+    out.resize(n);
+    rc = btb200_hop_candidates(g_hop_device, address28, afh, aliased, clock6, first_channel, out.data(), (uint32_t)out.size(), &n);
+  }
+  if (rc != BTB200_OK) return false;
+  out.resize(n);
+  return true;
+}
+}  // namespace
+
 namespace gr {
 namespace bluetooth {
 
@@ -34,6 +52,8 @@ multi_hopper_impl::multi_hopper_impl(double sample_rate, double center_freq, dou
   if (tun) d_host->set_tun_fd(btb200_host::open_tun_output());     /* lib/multi_hopper_impl.cc:56-64 */
   d_res.resize((size_t)(hi - lo + 1));
   d_symbols.resize((size_t)(hi - lo + 1) * 3125);
+  { const char *dv0 = std::getenv("BTB200_DEVICE"); g_hop_device = dv0 ? std::atoi(dv0) : 0; }
+  btb200_host::Piconet::s_candidate_fn = gpu_hop_candidates;
   // BTB200_MM_MODE=stateless: once CLK1-27 is known, follow the piconet in BATCHES of slots.  The hop channel of
   // every future slot is known then (lib/multi_hopper_impl.cc:152-166: clock = clkn + offset, channel = hop(clock)), so
   // the slots no longer have to be visited one work() call at a time; each window starts from the constructor's

@@ -331,6 +331,15 @@ BTB200_API int64_t btb200_get_stage(btb200_ctx *ctx, int stage, uint32_t slot_in
 BTB200_API int  btb200_search_bits(btb200_ctx *ctx, const uint8_t *symbols, size_t n_symbols, uint32_t stride,
                         btb200_hits *out);
 
+/* Hop reversal, candidate search (lib/piconet_impl.cc:96-129 walks a 2^27-entry table the reference has to generate
+ * first, :214-255): every CLK1-27 value = clock6 (mod 64) whose basic-hop channel -- folded by the aliasing receiver when
+ * `aliased` -- equals first_channel, ascending, for address28 = (UAP << 24 | LAP) & 0xfffffff.  The hop selection kernel
+ * is evaluated per clock value on the GPU, no table.  *count receives the number of candidates (out holds min(count, cap)). */
+/* the hop selection kernel itself, evaluated on the host (same source as the device code): channel 0..78 at CLK1-27 = clock */
+BTB200_API int  btb200_hop_select(uint32_t address28, int afh, uint32_t clock);
+BTB200_API int  btb200_hop_candidates(int device, uint32_t address28, int afh, int aliased, uint32_t clock6, int first_channel,
+                           uint32_t *out, uint32_t cap, uint32_t *count);
+
 /* device-side stopwatch on the context's compute stream (CUDA events): start() records now; stop() records, waits and
  * returns the milliseconds in between -- brackets any sequence of submit/collect calls of the contexts of one device */
 BTB200_API int  btb200_timer_start(btb200_ctx *ctx);

@@ -208,3 +208,50 @@ def test_search_kernel_kat_channel37(kats):
         s = int(lut[768]) ^ int(lut[lap & 0xFF]) ^ int(lut[256 + ((lap >> 8) & 0xFF)]) ^ int(lut[512 + (lap >> 16)])
         assert s == word
     blk.close()
+
+
+def test_hop_candidates_kernel_equals_host_kernel():
+    """the candidate search of the hop reversal on the GPU == the same hop selection kernel evaluated on the
+    host (whose values the CPU tier pins to the reference through the hopper digest: 26555 candidates for headset1)."""
+    L = g.lib()
+    rng = np.random.default_rng(5)
+    for addr, afh, aliased in ((0xAF24D952 & 0xFFFFFFF, False, False), (0x6148_31DD & 0xFFFFFFF, False, False),
+                               (int(rng.integers(0, 1 << 28)), True, False), (int(rng.integers(0, 1 << 28)), False, True)):
+        clock6, ch = int(rng.integers(0, 64)), None
+        ch = L.btb200_hop_select(addr, int(afh), clock6 + 64 * 12345)
+        if aliased:
+            ch = ((ch + 24) % 25) + 26
+        got = g.hop_candidates(addr, clock6, ch, afh=afh, aliased=aliased)
+        assert len(got) > 1000 and np.all(np.diff(got.astype(np.int64)) > 0) and np.all(got % 64 == clock6)
+        assert clock6 + 64 * 12345 in set(got.tolist())
+        # spot-check membership both ways on a sample of clocks
+        sample = clock6 + 64 * rng.integers(0, 1 << 21, 4000)
+        gs = set(got.tolist())
+        for c in sample:
+            h = L.btb200_hop_select(addr, int(afh), int(c))
+            if aliased:
+                h = ((h + 24) % 25) + 26
+            assert (h == ch) == (int(c) in gs)
+
+
+def test_window_mask_selects_channel_windows():
+    """btb200_set_window_mask: only the masked channel-windows are searched; their hits equal the unmasked run's."""
+    ex = load_excerpt("keyboard1", "stateless")
+    P = O.Plan(ex["fs"], ex["fc"])
+    n = 16
+    x = np.concatenate([np.zeros(P.H - 1, np.complex64), ex["iq"]])[:(n - 1) * P.S + P.H]
+    for ddc in (g.DDC_EXACT, g.DDC_POLYPHASE):
+        blk = g.multi_sniffer(ex["fs"], ex["fc"], 10.0, mm_mode=g.MM_STATELESS, max_slots=n, ddc=ddc)
+        full, _, _ = blk.process(x, 0, n)
+        assert len(full) > 2
+        mask = np.zeros((n, P.nch), np.uint8)
+        keep = [(int(h["slot"]), int(h["channel"]) - P.ch_lo) for h in full[::2]]
+        for s_, c_ in keep:
+            mask[s_, c_] = 1
+        blk.set_window_mask(mask)
+        part, _, _ = blk.process(x, 0, n)
+        want = full[[(int(h["slot"]), int(h["channel"]) - P.ch_lo) in set(keep) for h in full]]
+        assert np.array_equal(part[["slot", "channel", "kind", "offset", "lap"]], want[["slot", "channel", "kind", "offset", "lap"]])
+        again, _, _ = blk.process(x, 0, n)          # the mask was consumed
+        assert len(again) == len(full)
+        blk.close()

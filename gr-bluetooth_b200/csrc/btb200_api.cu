@@ -58,6 +58,7 @@ struct btb200_ctx {
   cudaEvent_t evl[3]{};      // lazy squelch: noise FIR / energies
   cudaEvent_t ev_tail = nullptr;
   cudaEvent_t ev_user[2] = {};
+  cudaEvent_t ev_res = nullptr;       // throughput mode: end of the resume
   bool lazy_timed = false;
   // device allocations
   std::vector<void *> allocs;
@@ -404,6 +405,7 @@ int setup(btb200_ctx *ctx)
   for (auto &e : ctx->evl) CK(cudaEventCreate(&e));
   CK(cudaEventCreateWithFlags(&ctx->ev_tail, cudaEventDisableTiming));
   for (auto &e : ctx->ev_user) CK(cudaEventCreate(&e));
+  CK(cudaEventCreate(&ctx->ev_res));
 
   int rc;
   if ((rc = upload_raw<c32>(ctx, &ctx->T.chan_rtaps, P.chan_rtaps.data(), P.chan_rtaps.size()))) return rc;
@@ -601,6 +603,7 @@ void teardown(btb200_ctx *ctx)
   for (auto &e : ctx->evl) if (e) cudaEventDestroy(e);
   if (ctx->ev_tail) cudaEventDestroy(ctx->ev_tail);
   for (auto &e : ctx->ev_user) if (e) cudaEventDestroy(e);
+  if (ctx->ev_res) cudaEventDestroy(ctx->ev_res);
   if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
   if (ctx->stream && ctx->owns_stream) cudaStreamDestroy(ctx->stream);
 }
@@ -827,6 +830,7 @@ static int submit_impl(btb200_ctx *ctx, const void *iq, int kind, size_t n_sampl
       launch_tail_resume(G, ctx->T, W, ctx->d_dem, s2); ctx->launches++;
       if (!tail_inline) CK(cudaEventRecord(ctx->ev_tail, s2));
     }
+    CK(cudaEventRecord(ctx->ev_res, s));
     enqueue_noise_estimate(ctx, G, W, (long)need, s);
     CK(cudaMemcpyAsync(ctx->h_esum, ctx->F.esum, nbc * sizeof(double), cudaMemcpyDeviceToHost, s));
     CK(cudaEventRecord(ctx->ev[5], s));
@@ -1116,14 +1120,14 @@ int collect_poly(btb200_ctx *ctx, btb200_hits *out)
   ctx->fast_off.assign(ctx->h_noise, ctx->h_noise + nbc);
   CK(cudaEventSynchronize(ctx->ev[8]));
   ctx->last_slots = ctx->pend_slots;
-  // order of the throughput mode's stream: channelizer | clock recovery (prefix) | search | noise estimate with the
-  // resume beside it | tail (hit list, arena, gather, copies)
+  // order of the throughput mode's stream: channelizer | clock recovery (prefix) | search | resume | noise estimate |
+  // tail (hit list, arena, gather, copies)
   cudaEventElapsedTime(&ctx->timing[0], ctx->ev[0], ctx->ev[1]);
   cudaEventElapsedTime(&ctx->timing[1], ctx->ev[1], ctx->ev[2]);
   cudaEventElapsedTime(&ctx->timing[4], ctx->ev[2], ctx->ev[3]);
   cudaEventElapsedTime(&ctx->timing[5], ctx->ev[3], ctx->ev[4]);
-  cudaEventElapsedTime(&ctx->timing[2], ctx->ev[4], ctx->ev[5]);
-  ctx->timing[3] = 0.0f;
+  cudaEventElapsedTime(&ctx->timing[3], ctx->ev[4], ctx->ev_res);       // [3]: resume of the windows with hits
+  cudaEventElapsedTime(&ctx->timing[2], ctx->ev_res, ctx->ev[5]);
   cudaEventElapsedTime(&ctx->timing[6], ctx->ev[5], ctx->ev[8]);
   cudaEventElapsedTime(&ctx->timing[7], ctx->ev[0], ctx->ev[8]);
   if (!out) return BTB200_OK;

@@ -347,7 +347,9 @@ BTB200_API int  btb200_timer_stop(btb200_ctx *ctx, float *ms);
 
 /* timing of the last batch, milliseconds, CUDA events on the ctx stream:
  * [0] H2D copy, [1] channel FIR, [2] noise FIR, [3] energy/squelch,
- * [4] demod+clock recovery, [5] access-code search, [6] D2H + host, [7] total device */
+ * [4] demod+clock recovery, [5] access-code search, [6] D2H + host, [7] total device.
+ * BTB200_DDC_POLYPHASE: [1] channelizer (with demod and energies), [2] noise estimate, [3] resume of the clock recovery
+ * of the windows with hits, [4] clock recovery of the searchable prefix, [5] search, [6] hit list + gather + copies */
 BTB200_API int  btb200_last_timing(const btb200_ctx *ctx, float ms[8]);
 /* number of kernel launches issued by this ctx so far */
 BTB200_API uint64_t btb200_launch_count(const btb200_ctx *ctx);

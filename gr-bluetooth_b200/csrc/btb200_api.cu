@@ -268,11 +268,12 @@ int setup_fast(btb200_ctx *ctx)
 }
 
 // off-channel energy estimate of every window of the batch -> F.esum
-void enqueue_noise_estimate(btb200_ctx *ctx, const Geom &G, const DevBatch &W, long n_samples, cudaStream_t s)
+void enqueue_noise_estimate(btb200_ctx *ctx, const Geom &G, const DevBatch &W, long n_samples, cudaStream_t s,
+                            const NestResume *resume = nullptr)
 {
   if (ctx->use_nest) {
     launch_nest_prerot(ctx->NP, W.x, n_samples, s);
-    launch_nest(ctx->NP, W.B, s);
+    launch_nest(ctx->NP, W.B, s, resume);
     ctx->launches += 3;
   } else {
     launch_noise_fast(ctx->F, W.x, W.B, G.S, G.fns, G.D, G.n_noise, G.nch, s);
@@ -823,15 +824,24 @@ static int submit_impl(btb200_ctx *ctx, const void *iq, int kind, size_t n_sampl
     launch_search_warp(G, ctx->T, W, s); ctx->launches++;
     launch_tail_scan(G, W, s); ctx->launches++;
     CK(cudaEventRecord(ctx->ev[4], s));
+    // The resume of the windows with hits rides in the first blocks of the noise estimator's launch (rx_nest.cuh,
+    // NestResume): those blocks own their SMs, so the latency-bound chains run at full speed while the other SMs work
+    // through the estimator's tiles.  (A separate launch next to a compute-bound kernel starves the chains: 4-5x slower.)
     static const bool tail_inline = std::getenv("BTB200_TAIL_STREAM2") == nullptr;
+    static const bool fuse_resume = std::getenv("BTB200_NO_FUSED_RESUME") == nullptr;
     cudaStream_t s2 = tail_inline ? s : ctx->stream2;
-    if (G.early) {
+    NestResume nr{};
+    const bool fused = G.early && fuse_resume && tail_inline && ctx->use_nest && nest_can_resume(ctx->NP);
+    if (fused) {
+      nr.G = G; nr.W = W; nr.mmse = ctx->T.mmse; nr.demT = ctx->d_dem; nr.save = W.mm_save;
+      nr.n_blocks = (int)((nbc + NEST_RESUME_BLK - 1) / NEST_RESUME_BLK);
+    } else if (G.early) {
       if (!tail_inline) CK(cudaStreamWaitEvent(s2, ctx->ev[4], 0));
       launch_tail_resume(G, ctx->T, W, ctx->d_dem, s2); ctx->launches++;
       if (!tail_inline) CK(cudaEventRecord(ctx->ev_tail, s2));
     }
     CK(cudaEventRecord(ctx->ev_res, s));
-    enqueue_noise_estimate(ctx, G, W, (long)need, s);
+    enqueue_noise_estimate(ctx, G, W, (long)need, s, fused ? &nr : nullptr);
     CK(cudaMemcpyAsync(ctx->h_esum, ctx->F.esum, nbc * sizeof(double), cudaMemcpyDeviceToHost, s));
     CK(cudaEventRecord(ctx->ev[5], s));
     if (G.early && !tail_inline) CK(cudaStreamWaitEvent(s, ctx->ev_tail, 0));

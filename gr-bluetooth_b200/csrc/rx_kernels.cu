@@ -6,6 +6,7 @@
 
 #include "rx_packed.cuh"
 #include "rx_tma.cuh"
+#include "rx_mm.cuh"
 
 namespace btb200 {
 
@@ -686,105 +687,14 @@ __device__ __forceinline__ void cp_async4(void *smem_dst, const void *gsrc)
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(gsrc));
 }
 
-struct MmSave { float mu, omega, last; unsigned ii; int oo; uint32_t word; };
-// ring depth of the clock-recovery kernel: a refill reaches ii+96 and the reader is at most 40 samples further
-// when the next one is issued, so 128 slots never overwrite a live sample; 36 KB per 64 windows keeps six
-// blocks per SM resident = the whole 512-slot batch in ONE wave (the loop is latency-bound, not issue-bound)
-constexpr int MM_RD = 128;
-
-// mode 0: every window from the constructor state to the end (reference loop).
-// mode 1 (lazy tail, first pass): every window, stop at G.sym_target symbols, demod floats exist for i < G.ne_dem
-//         (enough for sym_target symbols at the loop's maximum advance); the loop state is saved.
-// mode 2 (lazy tail, resume): LISTED windows continue from the saved state to the end.
+// the stateless clock-recovery loop lives in rx_mm.cuh (shared with rx_nest.cu)
 template <int BLK>
 __global__ void __launch_bounds__(BLK) k_mm_stateless_v2(Geom G, DevBatch W, const float *__restrict__ mmse_g,
                                                          const float *__restrict__ demT, int mode,
                                                          MmSave *__restrict__ save, const int4 *__restrict__ list, int n_list)
 {
-  constexpr int RD = MM_RD;        // ring depth (demod samples per window)
-  constexpr int AHEAD = 88;        // refill target: ii + 8 + AHEAD
-  constexpr int PERIOD = 8;        // steps between refills
-  // The loop advances ii by at most 5 samples per step (|demod| <= gain*pi bounds mm_val), so the refill issued at
-  // the start of a block of PERIOD steps (it reaches ii + 96) covers everything the NEXT block can read (< ii + 88)
-  // and lands while this block runs; 128 rows never overwrite a live sample.  Rows 0..7 are mirrored at 128..135 so
-  // the 8 samples of an interpolation are always 8 consecutive rows: one base address, immediate offsets.
   extern __shared__ __align__(16) unsigned char mm_smem[];
-  float (*ring)[BLK] = reinterpret_cast<float (*)[BLK]>(mm_smem);                        // [RD + 8][BLK]
-  float (*s_mmse)[132] = reinterpret_cast<float (*)[132]>(mm_smem + sizeof(float) * (RD + 8) * BLK);   // [8][132]
-  for (int i = threadIdx.x; i < 129 * 8; i += BLK) s_mmse[7 - (i & 7)][i >> 3] = mmse_g[i];   // [k][imu] = taps[imu][7-k]
-  __syncthreads();
-  int idx = blockIdx.x * BLK + threadIdx.x;
-  if (mode == 2) {
-    if (n_list < 0) n_list = *W.tail.n_list;             // device-driven tail: the list was built on the device
-    if (idx >= n_list) return;
-    const int4 it = list[idx];
-    idx = it.x * G.nch + it.y;
-  } else {
-    if (idx >= W.B * G.nch) return;
-    if (!W.pass[idx]) { W.nsym[idx] = 0; return; }
-  }
-  const int b = idx / G.nch, c = idx - b * G.nch;
-  const float *gp = demT + ((long)b * G.dem_rows) * G.nch + c;     // next sample to prefetch
-  uint32_t *__restrict__ bits_row = W.bits + (long)idx * G.bw;
-  float *soft_row = W.soft ? W.soft + (long)idx * G.n_dem_pad : nullptr;
-  MmState st{G.mu0, G.mm.omega_mid, 0.0f};
-  unsigned ii = 0;
-  int oo = 0;
-  uint32_t word = 0;
-  if (mode == 2) {
-    const MmSave sv = save[idx];
-    st = MmState{sv.mu, sv.omega, sv.last};
-    ii = sv.ii; oo = sv.oo; word = sv.word;
-  }
-  const int avail = (mode == 1) ? G.ne_dem : G.n_dem;            // demod floats that exist
-  const int oo_end = (mode == 1) ? G.sym_target : G.n_dem;
-  const unsigned ni = (unsigned)((mode == 1 ? G.ne_dem : G.n_dem) - 8);
-  int pf = (int)ii;                // samples [pf-RD, pf) are in (or on their way to) the ring
-  const int tid = threadIdx.x;
-  const int nch = G.nch;
-  const MmConst K = G.mm;
-  gp += (long)pf * nch;
-  auto refill = [&](int want) {
-    for (; pf < want; pf++, gp += nch) {
-      const int rr = pf & (RD - 1);
-      cp_async4(&ring[rr][tid], gp);
-      if (rr < 8) cp_async4(&ring[rr + RD][tid], gp);
-    }
-    cp_async_commit();
-  };
-  {
-    int want = (int)ii + 8 + AHEAD; if (want > avail) want = avail;
-    refill(want);
-    cp_async_wait<0>();
-    if (G.dem_grid && ii == 0) ring[0][tid] = 0.0f;      // demod_out[0] of a window is never written by the reference
-  }
-  while (oo < oo_end && ii < ni) {
-    cp_async_wait<0>();              // the refill issued a block ago has long landed
-    {
-      int want = (int)ii + 8 + AHEAD; if (want > avail) want = avail;
-      refill(want);
-    }
-#pragma unroll 1
-    for (int t = 0; t < PERIOD && oo < oo_end && ii < ni; t++) {
-      int imu = __float2int_rn(st.mu * 128.0f);
-      imu = imu < 0 ? 0 : (imu > 128 ? 128 : imu);
-      const float *rp = &ring[ii & (RD - 1)][tid];
-      const float *mp = &s_mmse[0][imu];
-      float out = 0.0f;
-#pragma unroll
-      for (int k = 0; k < 8; k++) out = out + rp[k * BLK] * mp[k * 132];
-      if (soft_row) soft_row[oo] = out;
-      if (!(out < 0)) word |= 1u << (oo & 31);
-      if ((oo & 31) == 31) { bits_row[oo >> 5] = word; word = 0; }
-      ii += (unsigned)mm_update(K, st, out);
-      oo++;
-    }
-  }
-  cp_async_wait<0>();
-  if (mode == 1) save[idx] = MmSave{st.mu, st.omega, st.last, ii, oo, word};
-  if (oo & 31) bits_row[oo >> 5] = word;
-  for (int w = (oo + 31) >> 5; w < G.bw; w++) bits_row[w] = 0;
-  W.nsym[idx] = oo;
+  mm_stateless_block<BLK>(G, W, mmse_g, demT, mode, save, list, n_list, mm_smem, (int)blockIdx.x);
 }
 
 // Access-code search, one warp per channel-window (lib/multi_sniffer_impl.cc:107-148 +
@@ -1160,7 +1070,7 @@ void launch_demod_mm_v2(const Geom &G, const DevTables &T, const DevBatch &W, fl
     k_demod_all<<<grid, DM_WARPS * 32, 0, s>>>(G, W, T.atan_tab, demT, i_end);
   }
   constexpr int BLK = 64;
-  const size_t smem = sizeof(float) * (MM_RD + 8) * BLK + sizeof(float) * 8 * 132;
+  const size_t smem = mm_smem_bytes(BLK);
   k_mm_stateless_v2<BLK><<<cdiv((long)W.B * G.nch, BLK), BLK, smem, s>>>(G, W, T.mmse, demT, G.early ? 1 : 0,
                                                                             reinterpret_cast<MmSave *>(W.mm_save), nullptr, 0);
 }
@@ -1176,7 +1086,7 @@ void launch_mm_resume_list(const Geom &G, const DevTables &T, const DevBatch &W,
     k_demod_list<<<grid, 128, 0, s>>>(G, W, T.atan_tab, demT, reinterpret_cast<const int4 *>(list4), G.ne_dem);
   }
   constexpr int BLK = 64;
-  const size_t smem = sizeof(float) * (MM_RD + 8) * BLK + sizeof(float) * 8 * 132;
+  const size_t smem = mm_smem_bytes(BLK);
   k_mm_stateless_v2<BLK><<<cdiv(n_list, BLK), BLK, smem, s>>>(G, W, T.mmse, demT, 2, reinterpret_cast<MmSave *>(W.mm_save),
                                                                reinterpret_cast<const int4 *>(list4), n_list);
 }
@@ -1192,7 +1102,7 @@ void launch_tail_resume(const Geom &G, const DevTables &T, const DevBatch &W, fl
   // and their demod fetches are one sector per lane, so more than two warps on an SM queue up behind the load/store
   // unit (measured per 512 slots / 2268 windows: 64-thread blocks 0.9 ms, 32-thread 0.9 ms, 128-thread 2.5 ms).
   constexpr int BLK = 64;
-  const size_t smem = sizeof(float) * (MM_RD + 8) * BLK + sizeof(float) * 8 * 132;
+  const size_t smem = mm_smem_bytes(BLK);
   // the list length lives on the device: launch for the worst case, blocks past the list end return at once
   k_mm_stateless_v2<BLK><<<cdiv((long)W.B * G.nch, BLK), BLK, smem, s>>>(G, W, T.mmse, demT, 2, reinterpret_cast<MmSave *>(W.mm_save),
                                                                             W.tail.list, -1);

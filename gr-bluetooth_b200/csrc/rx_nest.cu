@@ -21,6 +21,7 @@
 #include "rx_nest.cuh"
 #include "rx_tma.cuh"
 #include "rx_packed.cuh"
+#include "rx_mm.cuh"
 
 namespace btb200 {
 
@@ -59,9 +60,16 @@ __global__ void k_nest_prerot(const c32 *__restrict__ x, c32 *__restrict__ xr, l
 // MT: the number of branches as a compile-time constant (100 = the benchmark configuration: every shared-memory
 // access of the tap loop then has an immediate offset), or 0 for "read it from the plan"
 template <int N1, int MT>
-__global__ void __launch_bounds__(2 * NEST_K * 100, 1) k_nest(NestPlan P)
+__global__ void __launch_bounds__(2 * NEST_K * 100, 1) k_nest(NestPlan P, NestResume R)
 {
   extern __shared__ __align__(128) unsigned char smem[];
+  if ((int)blockIdx.x < R.n_blocks) {
+    // the first blocks resume clock-recovery chains instead (one block per SM: the chains get the SM to themselves)
+    mm_stateless_block<NEST_RESUME_BLK>(R.G, R.W, R.mmse, R.demT, 2, reinterpret_cast<MmSave *>(R.save), R.W.tail.list, -1,
+                                        smem, (int)blockIdx.x);
+    return;
+  }
+  const int tile_index = (int)blockIdx.x - R.n_blocks;
   const NestSmem L = nest_layout(P);
   c32 *ring = reinterpret_cast<c32 *>(smem + L.ring);
   float2 *taps = reinterpret_cast<float2 *>(smem + L.taps);
@@ -73,7 +81,7 @@ __global__ void __launch_bounds__(2 * NEST_K * 100, 1) k_nest(NestPlan P)
   const int M = MT ? MT : P.M, N2 = MT ? MT / N1 : P.N2, ncol = P.ncol;
   const int tid = threadIdx.x, nthr = blockDim.x;                      // nthr = 2 * NEST_K * M
   const int r = tid % M, pk = tid / M, p = pk & 1, k = pk >> 1;
-  const int b = blockIdx.x / P.tiles_per_slot, tile = blockIdx.x - b * P.tiles_per_slot;
+  const int b = tile_index / P.tiles_per_slot, tile = tile_index - b * P.tiles_per_slot;
   const int i0 = tile * NEST_TO;                                       // first output index (per parity) of the tile
   const long n_base = (long)b * P.S + P.fns + (long)M * i0;            // sample of ring step 0, branch 0, parity 0
   const int n_chunks = P.q_rows / CH;                                  // compute chunks
@@ -235,7 +243,7 @@ __global__ void __launch_bounds__(2 * NEST_K * 100, 1) k_nest(NestPlan P)
   for (int col = tid; col < ncol; col += nthr) {
     float sum = 0.0f;
     for (int og = 0; og < 32; og++) sum += epart[og * ncol + col];
-    P.E2[(size_t)blockIdx.x * ncol + col] = sum;
+    P.E2[(size_t)tile_index * ncol + col] = sum;
   }
 }
 
@@ -277,12 +285,19 @@ void launch_nest_prerot(const NestPlan &P, const c32 *x, long n_samples, cudaStr
   k_nest_prerot<<<(unsigned)((n_samples + 255) / 256), 256, 0, s>>>(x, P.xr, n_samples, P.phasor, P.period);
 }
 
-void launch_nest(const NestPlan &P, int B, cudaStream_t s)
+bool nest_can_resume(const NestPlan &P)
 {
-  const dim3 grid((unsigned)(B * P.tiles_per_slot));
+  return 2 * NEST_K * P.M >= NEST_RESUME_BLK && nest_smem_bytes(P) >= mm_smem_bytes(NEST_RESUME_BLK);
+}
+
+void launch_nest(const NestPlan &P, int B, cudaStream_t s, const NestResume *resume)
+{
+  NestResume R{};
+  if (resume && nest_can_resume(P)) R = *resume;
+  const dim3 grid((unsigned)(B * P.tiles_per_slot + R.n_blocks));
   const int threads = 2 * NEST_K * P.M;
   const size_t smem = nest_smem_bytes(P);
-#define NEST_RUN(N1_, MT_) k_nest<N1_, MT_><<<grid, threads, smem, s>>>(P)
+#define NEST_RUN(N1_, MT_) k_nest<N1_, MT_><<<grid, threads, smem, s>>>(P, R)
   NEST_DISPATCH(NEST_RUN);
 #undef NEST_RUN
   const int n = B * P.nch;

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include "rx_math.cuh"
+#include "rx_kernels.cuh"
 
 namespace btb200 {
 
@@ -27,11 +28,27 @@ struct NestPlan {
   double *esum = nullptr;            // [B][nch]  sum over the window's noise outputs
 };
 
+// The estimator's launch can carry the resume of the clock-recovery chains of the windows with hits (lazy tail,
+// rx_mm.cuh) in its FIRST n_blocks blocks: each of them owns an SM for the duration (the estimator runs one block per
+// SM), so the latency-bound chains are not starved of issue slots by compute-bound neighbours, while the other SMs
+// work through the estimator's tiles.  n_blocks = 0: estimator only.
+struct NestResume {
+  Geom G;
+  DevBatch W;
+  const float *mmse = nullptr;
+  const float *demT = nullptr;
+  void *save = nullptr;
+  int n_blocks = 0;                  // blocks of NEST_RESUME_BLK windows: enough for every window of the batch
+};
+constexpr int NEST_RESUME_BLK = 64;
+
 size_t nest_smem_bytes(const NestPlan &P);
 int  nest_setup(const NestPlan &P);      // 0, or -1 when the configuration is outside the kernel's limits
 // xr[n] = x[n] * phasor[(n0 + n) % period] for n < n_samples
 void launch_nest_prerot(const NestPlan &P, const c32 *x, long n_samples, cudaStream_t s);
 // esum[b][c] = sum_j |noise DDC output j of window b, channel c|^2 (lib/multi_block.cc:253-287) from P.xr
-void launch_nest(const NestPlan &P, int B, cudaStream_t s);
+// true when launch_nest can carry the resume for this plan (block size and shared memory suffice)
+bool nest_can_resume(const NestPlan &P);
+void launch_nest(const NestPlan &P, int B, cudaStream_t s, const NestResume *resume = nullptr);
 
 }  // namespace btb200

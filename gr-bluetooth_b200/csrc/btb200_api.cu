@@ -105,6 +105,7 @@ struct btb200_ctx {
   std::vector<double> fast_off;      // [B][nch] fast off-channel energy of the last batch
   // polyphase (throughput) mode: rx_pfb.cu
   bool poly = false;
+  bool dense_tail = false;           // throughput mode: recent batches had hits in so many windows that the lazy tail does not pay
   PfbDesign pfd;
   PfbPlan PF{};
   double *d_eon_all = nullptr, *h_eon_all = nullptr;   // [B][nch] on-channel window energies from the channelizer
@@ -738,7 +739,9 @@ static int submit_impl(btb200_ctx *ctx, const void *iq, int kind, size_t n_sampl
   if (n_slots > ctx->max_slots) return BTB200_ERR_TOO_MANY;
   const Plan &P = ctx->plan;
   Geom G = ctx->G;
-  G.early = (ctx->early && ctx->impl == IMPL_TUNED) ? 1 : 0;
+  // lazy tail unless the stream is so busy that most windows would be resumed anyway (same results either way)
+  G.early = (ctx->early && ctx->impl == IMPL_TUNED && !(ctx->poly && ctx->dense_tail)) ? 1 : 0;
+  if (!G.early) { G.ne_dem = P.n_dem; G.sym_target = P.n_dem; }
   const size_t need = (size_t)(n_slots - 1) * P.S + P.H;
   if (n_samples < need) return BTB200_ERR_SHORT_INPUT;
   CK(cudaSetDevice(ctx->device));
@@ -1121,6 +1124,13 @@ int collect_poly(btb200_ctx *ctx, btb200_hits *out)
   unsigned long long used = 0;
   std::memcpy(&used, ctx->h_counts + 2, sizeof used);
   if (used > kArenaCap) used = kArenaCap;
+  {
+    // adapt the tail policy to the traffic: resuming a window's clock recovery costs ~3x the share it has in a pass
+    // over ALL windows (compact list, one sector per lane), so past ~a quarter of the windows the full pass is cheaper
+    const double frac = (double)ctx->h_counts[1] / (double)((size_t)ctx->pend_slots * P.nch);
+    if (frac > 0.25) ctx->dense_tail = true;
+    else if (frac < 0.15) ctx->dense_tail = false;
+  }
   const bool want_sym = out && (out->symbols || borrow_symbols(out));
   if (nh) CK(cudaMemcpyAsync(ctx->h_hits, ctx->pendW.tail.sorted, (size_t)nh * sizeof(DevHit), cudaMemcpyDeviceToHost, cs));
   if (want_sym && used) CK(cudaMemcpyAsync(ctx->h_arena, ctx->W.arena, used, cudaMemcpyDeviceToHost, cs));

@@ -803,7 +803,7 @@ __global__ void __launch_bounds__(1024) k_tail_scan(Geom G, DevBatch W)
     W.tail.base[i] = hb;
     if (c > 0) { W.tail.list[wb++] = make_int4(i / G.nch, i % G.nch, 0, 0); hb += c; }
   }
-  if (t == 1023) { W.hit_count[0] = (unsigned)s_h[1023]; *W.tail.n_list = s_w[1023]; }
+  if (t == 1023) { W.hit_count[0] = (unsigned)s_h[1023]; W.hit_count[1] = (unsigned)s_w[1023]; *W.tail.n_list = s_w[1023]; }
 }
 
 // the hits of every listed window, in order, with their final symbol counts

@@ -1,5 +1,5 @@
 """CPU tier: the JSON line bench.py prints keeps the driver's contract.  Checked on the line committed from the last
-B200 run of the round (profiles/r1_bench_line_final.json) and on the argument surface of bench.py itself."""
+B200 run of the round (profiles/r2_bench_line.json) and on the argument surface of bench.py itself."""
 import json
 import os
 import subprocess
@@ -7,7 +7,7 @@ import sys
 
 from conftest import ROOT
 
-LINE = os.path.join(ROOT, "profiles", "r1_bench_line_final.json")
+LINE = os.path.join(ROOT, "profiles", "r2_bench_line.json")
 
 
 def test_committed_bench_line_has_every_contract_key():
@@ -29,6 +29,8 @@ def test_committed_bench_line_has_every_contract_key():
     for k in ("value", "unit", "cores", "kind", "sample"):
         assert k in c, k
     assert c["kind"] in ("reference", "port") and c["cores"] >= 1
+    assert {"frac_step", "achieved_step"} <= set(r) and r["traffic"] is None or r["traffic"] > 0
+    assert d["config"]["ddc"] in ("poly", "exact") and "exact_mode" in d and "occupancy_sweep" in d
     assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(d["clocks"])
     assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
 
@@ -36,5 +38,5 @@ def test_committed_bench_line_has_every_contract_key():
 def test_bench_argument_surface():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--help"], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0
-    for flag in ("--gpus", "--steps", "--warmup", "--impl"):
+    for flag in ("--gpus", "--steps", "--warmup", "--impl", "--workload", "--ddc", "--input"):
         assert flag in out.stdout

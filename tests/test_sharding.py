@@ -74,3 +74,18 @@ def test_two_rank_sharding_equals_single_process():
         assert p.exitcode == 0
     assert len(single) >= 3
     assert np.array_equal(merged, single)
+
+
+def test_one_stream_generator_is_range_independent():
+    """bench.py --gpus N: every rank generates ITS slots of one synthetic stream (synth.generate_range); any two ranges must
+    agree sample for sample where they overlap, bursts that straddle a range boundary included, and so must the truths."""
+    from gr_bluetooth_b200 import synth
+    fs, fc, S = 8e6, 2476.5e6, 5000
+    a, ta = synth.generate_range(fs, fc, 0, 24, occupancy=0.3)
+    b, tb = synth.generate_range(fs, fc, 7, 9, occupancy=0.3)
+    c, tc = synth.generate_range(fs, fc, 16, 8, occupancy=0.3)
+    assert np.array_equal(a[7 * S:16 * S], b) and np.array_equal(a[16 * S:], c)
+    assert [t for t in ta if 7 <= t["slot"] < 16] == tb and [t for t in ta if t["slot"] >= 16] == tc
+    assert len(tb) > 10
+    i16, _ = synth.generate_range(fs, fc, 7, 9, occupancy=0.3, as_int16=True)
+    assert i16.dtype == np.int16 and np.array_equal(i16, np.round(b.view(np.float32)).astype(np.int16))

@@ -6,6 +6,7 @@
 #include <unistd.h>
 #include "bt_host.h"
 #include "../../csrc/hop_select.hpp"
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -109,31 +110,37 @@ ClassicPacket::ClassicPacket(const char *stream, int length, uint32_t clkn_, dou
   std::memset(d_payload_header, 0, sizeof d_payload_header);
 }
 
+// A packet header follows the access code when the 4-symbol trailer alternates from the sync word's last bit and the
+// 54 header symbols look like 18 bits sent three times each (1/3 FEC).  Both checks are Hamming distances of packed
+// words: trailer ^ expected pattern, and (h ^ h>>1 | h>>1 ^ h>>2) sampled at every third position counts the triples
+// whose three copies disagree.  Present when fewer than ID_THRESHOLD (5, packet.h:185) symbols are off
+// (classic_packet_impl::header_present, packet_impl.cc:1205-1242).
 bool ClassicPacket::header_present() const
 {
   if (d_length < 126) return false;
-  const char *s = &d_sym[67];
-  int be = 0;
-  const char msb = s[0];
-  be += s[1] ^ !msb;
-  be += s[2] ^ msb;
-  be += s[3] ^ !msb;
-  be += s[4] ^ msb;
-  s += 5;
-  for (int a = 0; a < 54; a += 3)
-    be += ((s[a] ^ s[a + 1]) | (s[a + 1] ^ s[a + 2]) | (s[a + 2] ^ s[a]));
-  return be < 5;                                   // ID_THRESHOLD, packet.h:185
+  uint64_t trailer = 0, hdr = 0;
+  for (int i = 0; i < 5; i++) trailer |= (uint64_t)(d_sym[67 + i] & 1) << i;
+  for (int i = 0; i < 54; i++) hdr |= (uint64_t)(d_sym[72 + i] & 1) << i;
+  const uint64_t want4 = (trailer & 1) ? 0xAull : 0x5ull;      // symbols 1..4 after a 1: 0,1,0,1; after a 0: 1,0,1,0
+  int off = __builtin_popcountll(((trailer >> 1) & 0xF) ^ want4);
+  uint64_t every_third = 0;
+  for (int t = 0; t < 18; t++) every_third |= 1ull << (3 * t);
+  const uint64_t d01 = hdr ^ (hdr >> 1), d12 = (hdr >> 1) ^ (hdr >> 2);
+  off += __builtin_popcountll((d01 | d12) & every_third);
+  return off < 5;
 }
 
+// 1/3 repetition code: majority vote; the block is accepted while fewer than a quarter of the triples disagree
+// (classic_packet_impl::unfec13, packet_impl.cc:367-384)
 bool ClassicPacket::unfec13(const char *in, char *out, int length)
 {
-  int be = 0;
+  int split = 0;
   for (int i = 0; i < length; i++) {
-    const int a = 3 * i, b = a + 1, c = a + 2;
-    out[i] = (char)((in[a] & in[b]) | (in[b] & in[c]) | (in[c] & in[a]));
-    be += ((in[a] ^ in[b]) | (in[b] ^ in[c]) | (in[c] ^ in[a]));
+    const int ones = (in[3 * i] & 1) + (in[3 * i + 1] & 1) + (in[3 * i + 2] & 1);
+    out[i] = (char)(ones >> 1);
+    split += (ones == 1 || ones == 2);
   }
-  return be < (length / 4);
+  return split < length / 4;
 }
 
 // (15,10) shortened Hamming blocks.  The reference's correction switch can never match (its
@@ -167,25 +174,59 @@ void ClassicPacket::unwhiten(const char *in, char *out, int clock, int length, i
   }
 }
 
+// Payload CRC: CRC-16/CCITT, LSB first (polynomial 0x1021 reflected = 0x8408), register preset with the bit-reversed UAP
+// in its upper byte (classic_packet_impl::crcgen, packet_impl.cc:529-548).  Whole bytes go through a 256-entry table.
 uint16_t ClassicPacket::crcgen(const char *payload, int length, int uap)
 {
-  uint16_t reg = (uint16_t)((reverse8((uint8_t)uap) << 8) & 0xff00);
-  for (int i = 0; i < length; i++) {
-    const char byte = payload[i];
-    reg = (uint16_t)((reg >> 1) | (((reg & 0x0001) ^ (byte & 0x01)) << 15));
-    reg ^= ((reg & 0x8000) >> 5);
-    reg ^= ((reg & 0x8000) >> 12);
+  static const struct Table {
+    uint16_t t[256];
+    Table()
+    {
+      for (int v = 0; v < 256; v++) {
+        uint16_t r = (uint16_t)v;
+        for (int b = 0; b < 8; b++) r = (uint16_t)((r >> 1) ^ ((r & 1) ? 0x8408 : 0));
+        t[v] = r;
+      }
+    }
+  } crc;
+  uint16_t reg = (uint16_t)(reverse8((uint8_t)uap) << 8);
+  int i = 0;
+  for (; i + 8 <= length; i += 8) {
+    uint8_t byte = 0;
+    for (int b = 0; b < 8; b++) byte |= (uint8_t)((payload[i + b] & 1) << b);
+    reg = (uint16_t)((reg >> 8) ^ crc.t[(reg ^ byte) & 0xff]);
   }
+  for (; i < length; i++) reg = (uint16_t)((reg >> 1) ^ (((reg ^ payload[i]) & 1) ? 0x8408 : 0));
   return reg;
 }
 
+// The HEC is an 8-bit LFSR (x^8 + x^7 + x^5 + x^2 + x + 1) preset with the UAP and clocked over the 10 header bits, so
+// for a received (header data, HEC) pair the UAP that would have produced it is a GF(2)-LINEAR function of the 18 bits:
+// two XOR tables, built once from the responses to the 18 unit vectors (classic_packet_impl::UAP_from_hec,
+// packet_impl.cc:593-606 runs the register backwards for every call).
 int ClassicPacket::uap_from_hec(uint16_t data, uint8_t hec)
 {
-  for (int i = 9; i >= 0; i--) {
-    if (hec & 0x80) hec ^= 0x65;
-    hec = (uint8_t)((hec << 1) | (((hec >> 7) ^ (data >> i)) & 0x01));
-  }
-  return reverse8(hec);
+  static const struct Tables {
+    uint8_t by_hec[256], by_data[1024];
+    static uint8_t unit(uint16_t data, uint8_t hec)
+    {
+      // one backward pass of the register for a single input pattern
+      for (int i = 9; i >= 0; i--) {
+        if (hec & 0x80) hec ^= 0x65;
+        hec = (uint8_t)((hec << 1) | (((hec >> 7) ^ (data >> i)) & 1));
+      }
+      return reverse8(hec);
+    }
+    Tables()
+    {
+      uint8_t hb[8], db[10];
+      for (int b = 0; b < 8; b++) hb[b] = unit(0, (uint8_t)(1u << b));
+      for (int b = 0; b < 10; b++) db[b] = unit((uint16_t)(1u << b), 0);
+      for (int v = 0; v < 256; v++) { uint8_t r = 0; for (int b = 0; b < 8; b++) if (v >> b & 1) r ^= hb[b]; by_hec[v] = r; }
+      for (int v = 0; v < 1024; v++) { uint8_t r = 0; for (int b = 0; b < 10; b++) if (v >> b & 1) r ^= db[b]; by_data[v] = r; }
+    }
+  } lin;
+  return lin.by_hec[hec] ^ lin.by_data[data & 0x3ff];
 }
 
 uint8_t ClassicPacket::try_clock(int clock)
@@ -227,22 +268,60 @@ bool ClassicPacket::payload_crc() const
   return crc == check;
 }
 
+// ---- payload formats, one row per TYPE code of the packet header (Core spec vol 2 part B 6.5) ---------------------
+// The reference spreads this over seven member functions with a switch on the type inside each (DM, DH, EV3, EV4,
+// EV5, HV, fhs: packet_impl.cc:688-1042) and two more switches that pick among them (crc_check :609-668,
+// decode_payload :1092-1158); here the differences are data.  Return values keep the reference's meaning:
+// 0 = this cannot be such a packet, 1 = plausible, 10 = CRC correct, 1000 = FHS with correct CRC.
+namespace {
+enum class Body : uint8_t { None, Fhs, Acl, Scan, Ev4, Sco };
+struct PayloadFormat {
+  Body body;           // how the payload is parsed
+  bool fec23;          // Acl: protected by the (15,10) code
+  uint8_t hdr_bytes;   // Acl: payload header length
+  uint16_t limit;      // Acl: largest payload (header + body + CRC) in bytes; Scan: bytes tried
+  uint8_t skip;        // Acl: voice symbols in front of the data field (DV)
+  bool crc;            // Acl: has a CRC (AUX1 has none)
+  bool in_discovery;   // crc_check() looks at this type (the others always count as "plausible")
+};
+const PayloadFormat kFormat[16] = {
+    /* 0 NULL  */ {Body::None, false, 0, 0, 0, false, false},
+    /* 1 POLL  */ {Body::None, false, 0, 0, 0, false, false},
+    /* 2 FHS   */ {Body::Fhs, true, 0, 20, 0, true, true},
+    /* 3 DM1   */ {Body::Acl, true, 1, 20, 0, true, true},
+    /* 4 DH1   */ {Body::Acl, false, 1, 30, 0, true, true},
+    /* 5 HV1   */ {Body::Sco, false, 0, 10, 0, false, true},
+    /* 6 HV2   */ {Body::Sco, false, 0, 20, 0, false, false},
+    /* 7 HV3/EV3 */ {Body::Scan, false, 0, 32, 0, true, true},
+    /* 8 DV    */ {Body::Acl, true, 1, 12, 80, true, true},
+    /* 9 AUX1  */ {Body::Acl, false, 1, 30, 0, false, false},
+    /* 10 DM3  */ {Body::Acl, true, 2, 125, 0, true, true},
+    /* 11 DH3  */ {Body::Acl, false, 2, 187, 0, true, true},
+    /* 12 EV4  */ {Body::Ev4, true, 0, 0, 0, true, true},
+    /* 13 EV5  */ {Body::Scan, false, 0, 182, 0, true, true},
+    /* 14 DM5  */ {Body::Acl, true, 2, 228, 0, true, true},
+    /* 15 DH5  */ {Body::Acl, false, 2, 343, 0, true, true},
+};
+}  // namespace
+
+// what a payload under the whitening of `clock` says about the CLK1-6 / UAP hypothesis (packet_impl.cc:609-668)
 int ClassicPacket::crc_check(int clock)
 {
-  int retval = 1;
-  switch (d_type) {
-    case 2: retval = fhs(clock); break;
-    case 8: case 3: case 10: case 14: retval = DM(clock); break;
-    case 4: case 11: case 15: retval = DH(clock); break;
-    case 7: retval = EV3(clock); break;
-    case 12: retval = EV4(clock); break;
-    case 13: retval = EV5(clock); break;
-    case 5: retval = HV(clock); break;
+  const PayloadFormat &f = kFormat[d_type & 15];
+  if (!f.in_discovery) return 1;
+  int verdict = 1;
+  switch (f.body) {
+    case Body::Fhs: verdict = fhs(clock); break;
+    case Body::Acl: verdict = acl(clock); break;
+    case Body::Scan: verdict = crc_scan(clock); break;
+    case Body::Ev4: verdict = EV4(clock); break;
+    case Body::Sco: verdict = sco(clock); break;
     default: break;
   }
-  if (retval == 0 && (d_type != 2 && d_type != 3 && d_type != 5)) return 1;
-  if (retval > 1 && (d_type == 7 || d_type == 13)) return 1;
-  return retval;
+  // only FHS, DM1 and HV1 are trusted to rule a clock OUT; a CRC hit on a guessed-length EV3/EV5 proves nothing
+  if (verdict == 0 && !(d_type == 2 || d_type == 3 || d_type == 5)) return 1;
+  if (verdict > 1 && (d_type == 7 || d_type == 13)) return 1;
+  return verdict;
 }
 
 int ClassicPacket::fhs(int clock)
@@ -292,60 +371,40 @@ bool ClassicPacket::decode_payload_header(const char *stream, int clock, int hea
   return true;
 }
 
-int ClassicPacket::DM(int clock)
+// ACL-style payload: payload header, body, CRC -- DM1/3/5, DH1/3/5, DV's data field, AUX1
+// (classic_packet_impl::DM / DH, packet_impl.cc:772-870)
+int ClassicPacket::acl(int clock)
 {
-  int header_bytes = 2, max_length;
-  const char *stream = &d_sym[126];
-  int size = d_length - 126;
-  switch (d_type) {
-    case 8: stream += 80; size -= 80; header_bytes = 1; max_length = 12; break;
-    case 3: header_bytes = 1; max_length = 20; break;
-    case 10: max_length = 125; break;
-    case 14: max_length = 228; break;
-    default: return 0;
+  const PayloadFormat &f = kFormat[d_type & 15];
+  if (f.body != Body::Acl) return 0;
+  const char *stream = &d_sym[126 + f.skip];
+  const int size = d_length - 126 - f.skip;
+  if (!decode_payload_header(stream, clock, f.hdr_bytes, size, f.fec23)) return 0;
+  if (d_payload_length > f.limit) return 1;
+  const int bits = d_payload_length * 8;
+  if (bits > size) return 1;
+  if (f.fec23) {
+    std::vector<char> corrected;
+    if (!unfec23(stream, bits, corrected)) return 0;
+    unwhiten(corrected.data(), d_payload.data(), clock, bits, 18);
+  } else {
+    unwhiten(stream, d_payload.data(), clock, bits, 18);
   }
-  if (!decode_payload_header(stream, clock, header_bytes, size, true)) return 0;
-  if (d_payload_length > max_length) return 1;
-  const int bitlength = d_payload_length * 8;
-  if (bitlength > size) return 1;
-  std::vector<char> corrected;
-  if (!unfec23(stream, bitlength, corrected)) return 0;
-  unwhiten(corrected.data(), d_payload.data(), clock, bitlength, 18);
-  if (payload_crc()) return 10;
-  return 1;
+  if (!f.crc) return 1;
+  return payload_crc() ? 10 : 1;
 }
 
-int ClassicPacket::DH(int clock)
-{
-  int header_bytes = 2, max_length;
-  const char *stream = &d_sym[126];
-  const int size = d_length - 126;
-  switch (d_type) {
-    case 9: case 4: header_bytes = 1; max_length = 30; break;
-    case 11: max_length = 187; break;
-    case 15: max_length = 343; break;
-    default: return 0;
-  }
-  if (!decode_payload_header(stream, clock, header_bytes, size, false)) return 0;
-  if (d_payload_length > max_length) return 1;
-  const int bitlength = d_payload_length * 8;
-  if (bitlength > size) return 1;
-  unwhiten(stream, d_payload.data(), clock, bitlength, 18);
-  if (d_type == 9) return 1;
-  if (payload_crc()) return 10;
-  return 1;
-}
-
-int ClassicPacket::EV3(int clock)
+// eSCO payloads of unknown length without FEC (EV3, EV5): grow the payload a byte at a time until a CRC fits
+// (classic_packet_impl::EV3 / EV5, packet_impl.cc:872-899, 950-977)
+int ClassicPacket::crc_scan(int clock)
 {
   const char *stream = &d_sym[126];
-  const int size = d_length - 126;
-  const int maxlength = 32;
-  for (d_payload_length = 0; d_payload_length < maxlength; d_payload_length++) {
+  const int size = d_length - 126, limit = kFormat[d_type & 15].limit;
+  for (d_payload_length = 0; d_payload_length < limit; d_payload_length++) {
     const int bits = d_payload_length * 8;
-    if ((bits + 8) > size) return 1;
+    if (bits + 8 > size) return 1;
     unwhiten(stream, &d_payload[(size_t)bits], clock, 8, 18 + bits);
-    if ((d_payload_length > 2) && payload_crc()) return 10;
+    if (d_payload_length > 2 && payload_crc()) return 10;
   }
   return 1;
 }
@@ -372,44 +431,25 @@ int ClassicPacket::EV4(int clock)
   return 1;
 }
 
-int ClassicPacket::EV5(int clock)
+// SCO voice: 240 symbols carrying 10, 20 or 30 bytes under 1/3, 2/3 or no FEC, no CRC (classic_packet_impl::HV,
+// packet_impl.cc:979-1042; the reference also sends EV3 candidates here as HV3)
+int ClassicPacket::sco(int clock)
 {
   const char *stream = &d_sym[126];
-  const int size = d_length - 126;
-  const int maxlength = 182;
-  for (d_payload_length = 0; d_payload_length < maxlength; d_payload_length++) {
-    const int bits = d_payload_length * 8;
-    if ((bits + 8) > size) return 1;
-    unwhiten(stream, &d_payload[(size_t)bits], clock, 8, 18 + bits);
-    if ((d_payload_length > 2) && payload_crc()) return 10;
-  }
-  return 1;
-}
-
-int ClassicPacket::HV(int clock)
-{
-  const char *stream = &d_sym[126];
-  const int size = d_length - 126;
-  if (size < 240) { d_payload_length = 0; return 1; }
-  switch (d_type) {
-    case 5: {
-      char corrected[80];
-      if (!unfec13(stream, corrected, 80)) return 0;
-      d_payload_length = 10;
-      unwhiten(corrected, d_payload.data(), clock, d_payload_length * 8, 18);
-      break;
-    }
-    case 6: {
-      std::vector<char> corrected;
-      if (!unfec23(stream, 160, corrected)) return 0;
-      d_payload_length = 20;
-      unwhiten(corrected.data(), d_payload.data(), clock, d_payload_length * 8, 18);
-      break;
-    }
-    case 7:
-      d_payload_length = 30;
-      unwhiten(stream, d_payload.data(), clock, d_payload_length * 8, 18);
-      break;
+  if (d_length - 126 < 240) { d_payload_length = 0; return 1; }
+  if (d_type == 5) {
+    char voice[80];
+    if (!unfec13(stream, voice, 80)) return 0;
+    d_payload_length = 10;
+    unwhiten(voice, d_payload.data(), clock, 80, 18);
+  } else if (d_type == 6) {
+    std::vector<char> voice;
+    if (!unfec23(stream, 160, voice)) return 0;
+    d_payload_length = 20;
+    unwhiten(voice.data(), d_payload.data(), clock, 160, 18);
+  } else if (d_type == 7) {
+    d_payload_length = 30;
+    unwhiten(stream, d_payload.data(), clock, 240, 18);
   }
   return 1;
 }
@@ -432,26 +472,22 @@ bool ClassicPacket::decode_header()
   return false;
 }
 
+// payload of a packet whose header decoded (classic_packet_impl::decode_payload, packet_impl.cc:1092-1158)
 void ClassicPacket::decode_payload()
 {
   d_payload_header_length = 0;
   const int clk = (int)d_clock;
-  switch (d_type) {
-    case 0: case 1: d_payload_length = 0; break;
-    case 2: fhs(clk); break;
-    case 3: DM(clk); break;
-    case 4: DH(clk); break;
-    case 5: HV(clk); break;
-    case 6: HV(clk); break;
-    case 7: if (EV3(clk) <= 1) HV(clk); break;
-    case 8: DM(clk); break;
-    case 9: DH(clk); break;
-    case 10: DM(clk); break;
-    case 11: DH(clk); break;
-    case 12: EV4(clk); break;
-    case 13: EV5(clk);        /* the reference falls through into DM5 here (packet_impl.cc:1146-1152) */
-    case 14: DM(clk); break;
-    case 15: DH(clk); break;
+  switch (kFormat[d_type & 15].body) {
+    case Body::None: d_payload_length = 0; break;
+    case Body::Fhs: fhs(clk); break;
+    case Body::Acl: acl(clk); break;
+    case Body::Sco: sco(clk); break;
+    case Body::Ev4: EV4(clk); break;
+    case Body::Scan:
+      // type 7 is EV3 when a CRC fits and HV3 otherwise; type 13 is EV5 (the reference then falls into its DM5 case,
+      // which does nothing for this type: packet_impl.cc:1146-1152)
+      if (crc_scan(clk) <= 1 && d_type == 7) sco(clk);
+      break;
   }
   d_have_payload = true;
 }
@@ -485,61 +521,58 @@ std::shared_ptr<ClassicPacket> Piconet::dequeue()
   return p;
 }
 
-// piconet_impl.cc:433-517: eliminate CLK1-6 candidates with the HEC (UAP consistency) and payload CRCs
+// CLK1-6 / UAP discovery (basic_rate_piconet_impl::UAP_from_header, piconet_impl.cc:433-517).  Every packet with a
+// header is tried under each of the up to 64 clock hypotheses still alive: the header's HEC yields the UAP that
+// hypothesis implies, and the payload CRC under that UAP and whitening says whether the pair is impossible (drop
+// it), possible (keep it) or certain (done).  A hypothesis survives only while it keeps implying the same UAP.
 bool Piconet::uap_from_header(ClassicPacket &pkt)
 {
-  int first_clock = 0, starting = 0, remaining = 0;
   const uint32_t clkn = pkt.clkn;
-  if (!d_got_first_packet) d_first_pkt_time = clkn;
+  const bool first = !d_got_first_packet;
+  if (first) d_first_pkt_time = clkn;
   if (d_packets_observed >= MAX_PATTERN_LENGTH) {
     std::printf("Oops. More hops than we can remember.\n");
     reset();
     return false;
   }
+  // remember when and where it was seen: the hop reversal replays these observations
   d_pattern_indices[d_packets_observed] = (int)(clkn - d_first_pkt_time);
   d_pattern_channels[d_packets_observed] = (uint8_t)pkt.channel;
   d_packets_observed++;
   d_total_packets_observed++;
-  for (int count = 0; count < 64; count++) {
-    if (!d_got_first_packet || d_clock6_candidates[count] > -1) {
-      const int clock = (int)(((uint32_t)count + clkn - d_first_pkt_time) % 64);
-      starting++;
-      const uint8_t uap = pkt.try_clock(clock);
-      int retval = -1;
-      if (!d_got_first_packet || uap == d_clock6_candidates[count]) retval = pkt.crc_check(clock);
-      switch (retval) {
-        case -1:
-        case 0:
-          d_clock6_candidates[count] = -1;
-          break;
-        case 1:
-          d_clock6_candidates[count] = uap;
-          first_clock = count;
-          remaining++;
-          break;
-        default:
-          std::printf("Correct CRC! UAP = 0x%x found after %d total packets.\n", uap, d_total_packets_observed);
-          d_clk_offset = ((uint32_t)count - (d_first_pkt_time & 0x3f)) & 0x3f;
-          d_uap = uap;
-          d_have_clk6 = true;
-          d_have_uap = true;
-          d_total_packets_observed = 0;
-          return true;
-      }
+
+  const uint32_t elapsed = clkn - d_first_pkt_time;
+  int tried = 0, alive = 0, survivor = 0;
+  for (int h = 0; h < 64; h++) {
+    if (!first && d_clock6_candidates[h] < 0) continue;               // hypothesis already ruled out
+    tried++;
+    const int clock = (int)(((uint32_t)h + elapsed) % 64);             // CLK1-6 of THIS packet under hypothesis h
+    const uint8_t uap = pkt.try_clock(clock);
+    const bool consistent = first || uap == d_clock6_candidates[h];
+    const int verdict = consistent ? pkt.crc_check(clock) : -1;
+    if (verdict > 1) {
+      // a payload CRC that checks out under this whitening and UAP settles both at once
+      std::printf("Correct CRC! UAP = 0x%x found after %d total packets.\n", uap, d_total_packets_observed);
+      d_clk_offset = ((uint32_t)h - (d_first_pkt_time & 0x3f)) & 0x3f;
+      d_uap = uap;
+      d_have_clk6 = d_have_uap = true;
+      d_total_packets_observed = 0;
+      return true;
     }
+    if (verdict == 1) { d_clock6_candidates[h] = uap; survivor = h; alive++; }
+    else d_clock6_candidates[h] = -1;
   }
   d_got_first_packet = true;
-  std::printf("reduced from %d to %d CLK1-6 candidates\n", starting, remaining);
-  if (remaining == 1) {
-    d_clk_offset = ((uint32_t)first_clock - (d_first_pkt_time & 0x3f)) & 0x3f;
-    d_uap = (uint8_t)d_clock6_candidates[first_clock];
-    d_have_clk6 = true;
-    d_have_uap = true;
+  std::printf("reduced from %d to %d CLK1-6 candidates\n", tried, alive);
+  if (alive == 1) {
+    d_clk_offset = ((uint32_t)survivor - (d_first_pkt_time & 0x3f)) & 0x3f;
+    d_uap = (uint8_t)d_clock6_candidates[survivor];
+    d_have_clk6 = d_have_uap = true;
     std::printf("We have a winner! UAP = 0x%x found after %d total packets.\n", d_uap, d_total_packets_observed);
     d_total_packets_observed = 0;
     return true;
   }
-  if (remaining == 0) reset();
+  if (alive == 0) reset();
   return false;
 }
 
@@ -587,25 +620,27 @@ int Piconet::init_hop_reversal(bool aliased)
   return d_num_candidates;
 }
 
+// keep the candidates whose hop `offset` slots after the first packet is the channel observed then
+// (basic_rate_piconet_impl::winnow, piconet_impl.cc:303-343)
 int Piconet::winnow(int offset, char channel)
 {
-  int n = 0;
-  for (int i = 0; i < d_num_candidates; i++) {
-    const char s = hop((int)((d_clock_candidates[(size_t)i] + (uint32_t)offset) % (uint32_t)SEQUENCE_LENGTH));
-    const char obs = d_aliased ? aliased_channel(s) : s;
-    if (obs == channel) d_clock_candidates[(size_t)n++] = d_clock_candidates[(size_t)i];
-  }
-  d_num_candidates = n;
-  if (n == 1) {
+  auto misses = [&](uint32_t cand) {
+    const char h = hop((int)((cand + (uint32_t)offset) % (uint32_t)SEQUENCE_LENGTH));
+    return (d_aliased ? aliased_channel(h) : h) != channel;
+  };
+  d_clock_candidates.resize((size_t)d_num_candidates);
+  d_clock_candidates.erase(std::remove_if(d_clock_candidates.begin(), d_clock_candidates.end(), misses), d_clock_candidates.end());
+  d_num_candidates = (int)d_clock_candidates.size();
+  if (d_num_candidates == 1) {
     d_clk_offset = (d_clock_candidates[0] - d_first_pkt_time) & 0x7ffffff;
     d_have_clk27 = true;
     std::printf("\nAcquired CLK1-27 offset = 0x%07x\n", d_clk_offset);
-  } else if (n == 0) {
+  } else if (d_num_candidates == 0) {
     reset();
   } else {
-    std::printf("%d CLK1-27 candidates remaining\n", n);
+    std::printf("%d CLK1-27 candidates remaining\n", d_num_candidates);
   }
-  return n;
+  return d_num_candidates;
 }
 
 int Piconet::winnow()
@@ -625,63 +660,76 @@ int Piconet::winnow()
 }
 
 // ---------------------------------------------------------------------------------------------
+// BLE link-layer printout (le_packet_impl constructor + print, packet_impl.cc:1529-1646), driven by a description of
+// each advertising PDU: which 6-byte device addresses lead the payload and what follows them.
+namespace {
+struct LePdu {
+  const char *addr[2];      // names of the leading device addresses (nullptr: none)
+  const char *data;         // name of the byte string after the first address (AdvData / ScanRspData), or nullptr
+  bool connect;             // CONNECT_REQ: link parameters follow the two addresses
+};
+const LePdu kLePdu[8] = {
+    /* 0 ADV_IND         */ {{"AdvA", nullptr}, "AdvData", false},
+    /* 1 ADV_DIRECT_IND  */ {{"AdvA", "InitA"}, nullptr, false},
+    /* 2 ADV_NONCONN_IND */ {{"AdvA", nullptr}, "AdvData", false},
+    /* 3 SCAN_REQ        */ {{"ScanA", "AdvA"}, nullptr, false},
+    /* 4 SCAN_RSP        */ {{"AdvA", nullptr}, "ScanRspData", false},
+    /* 5 CONNECT_REQ     */ {{"InitA", "AdvA"}, nullptr, true},
+    /* 6 ADV_SCAN_IND    */ {{"AdvA", nullptr}, "AdvData", false},
+    /* 7                 */ {{nullptr, nullptr}, nullptr, false},
+};
+
+uint64_t le_field(const uint8_t *p, int bytes)          // little-endian multi-byte field
+{
+  uint64_t v = 0;
+  for (int i = 0; i < bytes; i++) v |= (uint64_t)p[i] << (8 * i);
+  return v;
+}
+}  // namespace
+
 void le_print(const char *stream, int available, double freq)
 {
   const int index = le_freq_to_index(freq);
-  const int MAXS = 8 * (1 + 4 + 39 + 3);           // LE_MAX_SYMBOLS, packet.h:283-285
+  const int n_sym = 8 * (1 + 4 + 39 + 3);           // LE_MAX_SYMBOLS, packet.h:283-285
+  // de-whiten everything after the access address, then read the fields LSB first
   char link[8 * 47];
-  for (int i = 0; i < MAXS; i++) link[i] = (i < available) ? (stream[i] & 1) : 0;
   const uint8_t *w = whitening_sequence();
-  for (int i = 40, wi = le_whitening_index(index < 0 ? 0 : index); i < MAXS; i++, wi = (wi + 1) % 127) link[i] ^= w[wi];
+  int wi = le_whitening_index(index < 0 ? 0 : index);
+  for (int i = 0; i < n_sym; i++) {
+    link[i] = (i < available) ? (stream[i] & 1) : 0;
+    if (i >= 40) { link[i] ^= w[wi]; wi = (wi + 1) % 127; }
+  }
   const uint32_t aa = air_to_host(&link[8], 32);
-  const uint16_t header = (uint16_t)air_to_host(&link[40], 16);
+  const unsigned header = air_to_host(&link[40], 16);
   uint8_t pdu[48];
-  int pi = 0;
-  for (int i = 56; i + 8 < MAXS; pi++, i += 8) pdu[pi] = (uint8_t)air_to_host(&link[i], 8);
-  if (index >= 37) {
-    const int type = header & 0xf, txadd = (header >> 6) & 1, rxadd = (header >> 7) & 1;
-    const unsigned len = (header >> 8) & 0x3f;
-    std::printf("BTLE index=%02d, AA=%08x, PDUType=%d, TxAdd=%d, RxAdd=%d, Length=%d\n", index, aa, type, txadd, rxadd, len);
-    switch (type) {
-      case 0: case 2: case 4: case 6:
-        std::printf("  AdvA=%02x%02x%02x%02x%02x%02x\n", pdu[0], pdu[1], pdu[2], pdu[3], pdu[4], pdu[5]);
-        std::printf(type == 4 ? "\n  (char) ScanRspData=" : "\n  (char) AdvData=");
-        for (unsigned i = 6; i < len; i++) {
-          char c = (char)pdu[i];
-          if ((c < ' ') || (c > '~')) c = '.';
-          std::printf(" %c", c);
-        }
-        std::printf(type == 4 ? "\n  (byte) ScanRspData=" : "\n  (byte) AdvData=");
-        for (unsigned i = 6; i < len; i++) std::printf("%02x", pdu[i]);
-        std::printf("\n");
-        break;
-      case 1:
-        std::printf("  AdvA=%02x%02x%02x%02x%02x%02x\n  InitA=%02x%02x%02x%02x%02x%02x\n", pdu[0], pdu[1], pdu[2], pdu[3],
-                    pdu[4], pdu[5], pdu[6], pdu[7], pdu[8], pdu[9], pdu[10], pdu[11]);
-        break;
-      case 3:
-        std::printf("  ScanA=%02x%02x%02x%02x%02x%02x\n  AdvA=%02x%02x%02x%02x%02x%02x\n", pdu[0], pdu[1], pdu[2], pdu[3],
-                    pdu[4], pdu[5], pdu[6], pdu[7], pdu[8], pdu[9], pdu[10], pdu[11]);
-        break;
-      case 5: {
-        std::printf("  InitA=%02x%02x%02x%02x%02x%02x\n  AdvA=%02x%02x%02x%02x%02x%02x\n", pdu[0], pdu[1], pdu[2], pdu[3],
-                    pdu[4], pdu[5], pdu[6], pdu[7], pdu[8], pdu[9], pdu[10], pdu[11]);
-        const uint32_t AA = pdu[12] | ((uint32_t)pdu[13] << 8) | ((uint32_t)pdu[14] << 16) | ((uint32_t)pdu[15] << 24);
-        const uint32_t crcinit = pdu[16] | ((uint32_t)pdu[17] << 8) | ((uint32_t)pdu[18] << 16);
-        const uint16_t winoff = (uint16_t)(pdu[20] | (pdu[21] << 8)), interval = (uint16_t)(pdu[22] | (pdu[23] << 8));
-        const uint16_t latency = (uint16_t)(pdu[24] | (pdu[25] << 8)), timeout = (uint16_t)(pdu[26] | (pdu[27] << 8));
-        const uint64_t chm = pdu[28] | ((uint64_t)pdu[29] << 8) | ((uint64_t)pdu[30] << 16) | ((uint64_t)pdu[31] << 24) |
-                             ((uint64_t)pdu[32] << 32);
-        std::printf("  AA=%08x, CRCInit=%06x, WinSize=%d, WinOffset=%d\n", AA, crcinit, pdu[19], winoff);
-        std::printf("  Interval=%d, Latency=%d, Timeout=%d, ChM=%010lx, Hop=%d, SCA=%d\n", interval, latency, timeout,
-                    (unsigned long)chm, pdu[33] & 0x1f, (pdu[33] >> 5) & 7);
-        break;
-      }
-      default: break;
-    }
-  } else {
+  for (int b = 0, i = 56; i + 8 < n_sym; b++, i += 8) pdu[b] = (uint8_t)air_to_host(&link[i], 8);
+  if (index < 37) {
     std::printf("BTLE index=%02d, AA=%08x, LLID=%d, NESN=%d, SN=%d, MD=%d, Length=%d\n", index, aa, header & 3,
                 (header >> 2) & 1, (header >> 3) & 1, (header >> 4) & 1, (header >> 8) & 0x1f);
+    return;
+  }
+  const unsigned type = header & 0xf, len = (header >> 8) & 0x3f;
+  std::printf("BTLE index=%02d, AA=%08x, PDUType=%d, TxAdd=%d, RxAdd=%d, Length=%d\n", index, aa, type, (header >> 6) & 1,
+              (header >> 7) & 1, len);
+  if (type > 6) return;
+  const LePdu &d = kLePdu[type];
+  for (int a = 0; a < 2 && d.addr[a]; a++) {
+    const uint8_t *p = pdu + 6 * a;
+    std::printf("  %s=%02x%02x%02x%02x%02x%02x\n", d.addr[a], p[0], p[1], p[2], p[3], p[4], p[5]);
+  }
+  if (d.data) {
+    std::printf("\n  (char) %s=", d.data);
+    for (unsigned i = 6; i < len; i++) std::printf(" %c", (pdu[i] < ' ' || pdu[i] > '~') ? '.' : (char)pdu[i]);
+    std::printf("\n  (byte) %s=", d.data);
+    for (unsigned i = 6; i < len; i++) std::printf("%02x", pdu[i]);
+    std::printf("\n");
+  }
+  if (d.connect) {
+    const uint8_t *q = pdu + 12;      // AA(4) CRCInit(3) WinSize(1) WinOffset(2) Interval(2) Latency(2) Timeout(2) ChM(5) Hop/SCA(1)
+    std::printf("  AA=%08x, CRCInit=%06x, WinSize=%d, WinOffset=%d\n", (unsigned)le_field(q, 4), (unsigned)le_field(q + 4, 3), q[7],
+                (int)le_field(q + 8, 2));
+    std::printf("  Interval=%d, Latency=%d, Timeout=%d, ChM=%010lx, Hop=%d, SCA=%d\n", (int)le_field(q + 10, 2),
+                (int)le_field(q + 12, 2), (int)le_field(q + 14, 2), (unsigned long)le_field(q + 16, 5), q[21] & 0x1f, (q[21] >> 5) & 7);
   }
 }
 

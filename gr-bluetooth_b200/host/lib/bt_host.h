@@ -85,13 +85,12 @@ class ClassicPacket {
   bool decode_header();                                         // :1066-1090
   void decode_payload();                                        // :1092-1158
   bool decode_payload_header(const char *stream, int clock, int header_bytes, int size, bool fec);   // :726-770
+  // payload parsers, driven by the per-type format table in bt_host.cc
   int fhs(int clock);
-  int DM(int clock);
-  int DH(int clock);
-  int EV3(int clock);
+  int acl(int clock);           // DM1/3/5, DH1/3/5, DV data field, AUX1
+  int crc_scan(int clock);      // EV3, EV5: length found by trying CRCs
   int EV4(int clock);
-  int EV5(int clock);
-  int HV(int clock);
+  int sco(int clock);           // HV1/2/3
 };
 
 // UAP / CLK1-6 discovery state of one piconet (basic_rate_piconet_impl, piconet_impl.cc:63-80,370-547)

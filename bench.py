@@ -359,7 +359,7 @@ def run_ours(args):
     sweep = None
     if world == 1 and not args.no_sweep:
         sweep = {}
-        nsl = min(B, 256)
+        nsl = B
         for occ in (0.05, 0.2, 0.5):
             x_o, _ = shard(0, nsl, occ)
             r_o = measure(args.ddc, x_o, max(3, args.steps // 2), 3, nslots=nsl, stages=False, e2e=False, first_slot=LEAD)

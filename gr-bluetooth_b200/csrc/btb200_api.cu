@@ -1127,9 +1127,10 @@ int collect_poly(btb200_ctx *ctx, btb200_hits *out)
   {
     // adapt the tail policy to the traffic: resuming a window's clock recovery costs ~3x the share it has in a pass
     // over ALL windows (compact list, one sector per lane), so past ~a quarter of the windows the full pass is cheaper
+    // (a full pass is one latency-bound wave of ~1.5 ms whatever the batch size, so it only pays for long batches)
     const double frac = (double)ctx->h_counts[1] / (double)((size_t)ctx->pend_slots * P.nch);
-    if (frac > 0.25) ctx->dense_tail = true;
-    else if (frac < 0.15) ctx->dense_tail = false;
+    if (frac > 0.25 && ctx->pend_slots >= 384) ctx->dense_tail = true;
+    else if (frac < 0.15 || ctx->pend_slots < 384) ctx->dense_tail = false;
   }
   const bool want_sym = out && (out->symbols || borrow_symbols(out));
   if (nh) CK(cudaMemcpyAsync(ctx->h_hits, ctx->pendW.tail.sorted, (size_t)nh * sizeof(DevHit), cudaMemcpyDeviceToHost, cs));

@@ -254,6 +254,35 @@ def run_ours(args):
 
     xi16, truth = shard(rank)
 
+    def h2d_probe():
+        """Plain pinned-host -> device copies of one batch's int16 input on every rank at once: the feed rate this box
+        gives each GPU when all of them pull (the ceiling of any end-to-end number at this N)."""
+        n = ((B - 1) * S + int(625 * fs / 1e6 * 6.4)) * 4
+        h = torch.empty(n, dtype=torch.uint8).pin_memory()
+        d = torch.empty(n, dtype=torch.uint8, device=dev)
+        for _ in range(2):
+            d.copy_(h, non_blocking=True)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(8):
+            d.copy_(h, non_blocking=True)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        gbs = 8 * n / dt / 1e9
+        t = torch.tensor([gbs], dtype=torch.float64, device=dev)
+        lo = t.clone()
+        if world > 1:
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        del h, d
+        return {"min_gbs_per_gpu": round(float(lo.item()), 1), "aggregate_gbs": round(float(t.item()), 1)}
+
+    feed = h2d_probe()
+    numa_all = [numa]
+    if world > 1:
+        numa_all = [None] * world
+        dist.all_gather_object(numa_all, numa)
+
     def make_block(ddc, nslots=B):
         return g.multi_sniffer.make(fs, fc, SNR_DB, False, mm_mode=g.MM_STATELESS, device=local, max_slots=nslots,
                                     search=search, ddc=g.DDC_POLYPHASE if ddc == "poly" else g.DDC_EXACT,
@@ -450,7 +479,8 @@ def run_ours(args):
                            "timing": "value: CUDA events on the device's compute stream around K pipelined steps; "
                                      "e2e: wall clock between barriers; max over ranks",
                            "sharding": "one synthetic stream, contiguous slot ranges per rank with (H-1)-sample guard, no collective",
-                           "numa_node": numa},
+                           "numa_node_per_rank": numa_all,
+                           "h2d_copy_only": feed},
                 "e2e": {"value": e2e["value"], "unit": UNIT, "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
                         "ms_per_step": e2e["ms_per_step"], "h2d_gbs_per_gpu": round(e2e["h2d_gbs_per_gpu"], 2),
                         "clocks": e2e["clocks"], "same_hits_as_device_run": e2e["same_hits"],

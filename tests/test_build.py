@@ -79,3 +79,27 @@ def test_delay_line_fir_keeps_separate_roundings(sass):
 def test_no_fmad_flag_in_makefile():
     mk = open(os.path.join(ROOT, "gr-bluetooth_b200", "Makefile")).read()
     assert "--fmad=false" in mk and "-ffp-contract=off" in mk
+
+
+def test_throughput_mode_kernels_are_tma_fed_fma_kernels(sass):
+    """The polyphase channelizer and the noise estimator (rx_pfb.cu, rx_nest.cu): IQ tiles, sample ring and tables
+    arrive by TMA bulk copies on mbarriers (SASS UBLKCP / SYNCS), the arithmetic is fused multiply-add -- packed FFMA2 in the
+    estimator's tap loop -- and no tensor-core instruction appears anywhere (north_star: short FIRs, not a contraction)."""
+    pfb = body(sass, "k_pfbILi4ELi7")
+    assert any("UBLKCP" in l for l in pfb) and any("SYNCS.ARRIVE.TRANS64" in l for l in pfb)
+    assert sum(bool(re.search(r"\bFFMA\b", l)) for l in pfb) > 300
+    nest = body(sass, "k_nestILi4ELi100")
+    assert any("UBLKCP" in l for l in nest) and any("SYNCS.PHASECHK" in l for l in nest)
+    assert sum(" FFMA2 " in l for l in nest) >= 256
+    for name, lines in sass.items():
+        assert not any(re.search(r"\b(HMMA|UTC\w*MMA|LDTM|STTM)\b", l) for l in lines), name
+
+
+def test_clock_recovery_is_not_contracted_where_it_rides_in_the_estimator(sass):
+    """rx_nest.cu also carries the resume of the Mueller & Mueller loop (rx_mm.cuh): that code must keep one rounding per
+    operation (the 8-tap dot product is FMUL + FADD), so the file is built without contraction and its FMAs are explicit."""
+    mk = open(os.path.join(ROOT, "gr-bluetooth_b200", "Makefile")).read()
+    rule = mk[mk.index("build/rx_nest.o:"):]
+    assert "$(EXACT)" in rule.split("build/plan.o")[0] and "$(FAST)" not in rule.split("build/plan.o")[0].split("\n", 3)[2]
+    mm = body(sass, "k_mm_stateless_v2")
+    assert any(" FMUL " in l for l in mm) and any(" FADD " in l for l in mm) and not any(re.search(r"\bFFMA\b", l) for l in mm)

@@ -21,6 +21,31 @@ for kw in (dict(squelch=g.SQUELCH_EAGER), dict(squelch=g.SQUELCH_LAZY), dict(squ
         hits, syms, _ = blk.process(iq[w0:w0 + (B - 1) * S + H], first, B, want_symbols=True)
         print(kw, impl, len(hits))
         blk.close()
+# throughput mode: polyphase channelizer, fused estimator + resume, device-driven tail, int16 input, window mask;
+# both tail policies; also the 30 Msps geometry (N1 = 2) and an 8 Msps one (N1 = 1, pre-rotation by half a channel)
+for tail in (g.TAIL_LAZY, g.TAIL_FULL):
+    blk = g.multi_sniffer(fs, fc, 10.0, mm_mode=g.MM_STATELESS, max_slots=B, ddc=g.DDC_POLYPHASE, tail=tail)
+    S, H = blk.samples_per_slot, blk.history()
+    w0 = first * S - (H - 1)
+    seg = iq[w0:w0 + (B - 1) * S + H]
+    hits, syms, _ = blk.process(seg, first, B, want_symbols=True)
+    h16, _, _ = blk.process_i16(np.round(seg.view(np.float32)).astype(np.int16), first, B, want_symbols="borrow")
+    m = np.zeros((B, blk.info.n_channels), np.uint8); m[:, ::3] = 1
+    blk.set_window_mask(m)
+    hm, _, _ = blk.process(seg, first, B)
+    print("poly", tail, len(hits), len(h16), len(hm))
+    blk.close()
+for fs2, fc2 in ((30e6, 2414e6), (8e6, 2476.5e6)):
+    iq2, _ = synth.generate(fs2, fc2, nslots, seed=4, occupancy=0.2, snr_db=20.0, le_adv_occupancy=0.05)
+    blk = g.multi_sniffer(fs2, fc2, 10.0, mm_mode=g.MM_STATELESS, max_slots=B, ddc=g.DDC_POLYPHASE)
+    S, H = blk.samples_per_slot, blk.history()
+    w0 = first * S - (H - 1)
+    print("poly", fs2, len(blk.process(iq2[w0:w0 + (B - 1) * S + H], first, B, want_symbols=True)[0]))
+    blk.close()
+print("hop", len(g.hop_candidates(0x0F24D952 & 0xFFFFFFF, 5, 10)))
+blk = g.multi_sniffer(8e6, 2476.5e6, 10.0, mm_mode=g.MM_STATELESS, max_slots=8)
+print("kat", len(blk.search_bits(np.random.default_rng(1).integers(0, 2, 20000).astype(np.uint8))))
+blk.close()
 # chained, small rate
 z = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "keyboard1_chained.npz"))
 xi = z["iq_i16"].astype(np.float32)

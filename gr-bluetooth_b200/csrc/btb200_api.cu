@@ -241,10 +241,25 @@ int setup_fast(btb200_ctx *ctx)
     if (!std::getenv("BTB200_NO_NEST") && N.design_noise(P, NEST_NCOL, 16) == 0 && std::fabs(N.phi - phi) < 1e-9) {
       K.M = N.M; K.D = N.D; K.Q = N.Q; K.q_rows = N.q_rows; K.N1 = N.N1; K.N2 = N.N2; K.CPC = N.CPC; K.ncol = N.ncol;
       K.nch = P.nch; K.S = P.S; K.fns = P.fns; K.n_noise = P.n_noise;
-      K.tiles_per_slot = ((P.n_noise + 1) / 2 + NEST_TO - 1) / NEST_TO;
+      // throughput mode: the even outputs with end-corrected weights (half the work, rx_nest.cuh); the guarded mode of
+      // the exact path keeps every output (its guard band assumes the tighter estimate)
+      std::vector<float> wts;
+      if (ctx->poly && !std::getenv("BTB200_NEST_DENSE") && (P.n_noise % 2) == 0 && P.n_noise >= 32) {
+        K.stride = 2;
+        K.n_used = P.n_noise / 2 + 1;
+        wts.assign((size_t)K.n_used, 2.0f);
+        const size_t n = wts.size();
+        wts[0] = 1.3125f; wts[1] = 2.25f; wts[2] = 1.9375f;
+        wts[n - 3] = 1.9375f; wts[n - 2] = 2.25f; wts[n - 1] = 0.3125f;
+        K.tiles_per_slot = (K.n_used + 2 * NEST_TO - 1) / (2 * NEST_TO);
+      } else {
+        K.stride = 1;
+        K.tiles_per_slot = ((P.n_noise + 1) / 2 + NEST_TO - 1) / NEST_TO;
+      }
       K.period = F.period; K.phasor = F.phasor; K.esum = F.esum;
       // the last tile of a slot reads (tiles * 64 + q_rows + 16 * 5) * M samples past the slot's first noise sample
-      const long reach = (long)P.fns + ((long)K.tiles_per_slot * NEST_TO + K.q_rows + 16 * (NEST_K + 1)) * K.M;
+      const long reach = (long)P.fns + ((long)K.tiles_per_slot * (K.stride == 2 ? 2 : 1) * NEST_TO + K.q_rows + 16 * (2 * NEST_K + 2)) * K.M;
+      if (K.stride == 2) { if ((rc = upload(ctx, &K.weights, wts))) return rc; }
       if (reach <= P.H && nest_setup(K) == 0) {
         {
           std::vector<float2> h2(N.hq.size());

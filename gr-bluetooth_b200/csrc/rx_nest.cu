@@ -27,7 +27,11 @@ namespace btb200 {
 
 namespace {
 
-constexpr int RING_CHUNKS = NEST_K + 2;   // ring capacity in chunks of 16 steps: K + 1 live, one in flight
+constexpr int RING_MAX = 2 * NEST_K + 2;  // ring capacity in chunks of 16 steps: live chunks + one in flight (stride 1: K + 2, stride 2: 2 K + 2)
+// compute chunk c reads ring chunks c .. c + live_ahead: stride 1: runs 0..K-1 plus the half-step offset of the odd
+// sequence; stride 2: runs 0..2K-1, no offset
+__host__ __device__ inline int live_ahead(const NestPlan &P) { return P.stride == 2 ? 2 * NEST_K - 1 : NEST_K; }
+__host__ __device__ inline int ring_chunks(const NestPlan &P) { return live_ahead(P) + 2; }
 constexpr int CH = 16;               // steps per chunk
 
 struct NestSmem { size_t ring, taps, wb, n2r, epart, bar, total; };
@@ -37,14 +41,14 @@ __host__ __device__ inline NestSmem nest_layout(const NestPlan &P)
   NestSmem L{};
   size_t o = 0;
   auto take = [&o](size_t bytes, size_t align) { o = (o + align - 1) / align * align; const size_t r = o; o += bytes; return r; };
-  const size_t ring = (size_t)RING_CHUNKS * CH * P.M * sizeof(c32);
+  const size_t ring = (size_t)ring_chunks(P) * CH * P.M * sizeof(c32);
   const size_t u = (size_t)2 * NEST_TO * (P.M + 1) * sizeof(c32);         // U / V tile, row pitch M + 1
   L.ring = take(ring > u ? ring : u, 128);
   L.taps = take((size_t)2 * CH * P.M * sizeof(float2), 128);
   L.wb = take((size_t)P.N2 * P.ncol * sizeof(c32), 16);
   L.n2r = take((size_t)P.N2 * sizeof(int), 16);
   L.epart = take((size_t)32 * P.ncol * sizeof(float), 16);
-  L.bar = take((RING_CHUNKS + 2) * 8, 8);
+  L.bar = take((RING_MAX + 2) * 8, 8);
   L.total = o;
   return L;
 }
@@ -82,14 +86,19 @@ __global__ void __launch_bounds__(2 * NEST_K * 100, 1) k_nest(NestPlan P, NestRe
   const int tid = threadIdx.x, nthr = blockDim.x;                      // nthr = 2 * NEST_K * M
   const int r = tid % M, pk = tid / M, p = pk & 1, k = pk >> 1;
   const int b = tile_index / P.tiles_per_slot, tile = tile_index - b * P.tiles_per_slot;
-  const int i0 = tile * NEST_TO;                                       // first output index (per parity) of the tile
-  const long n_base = (long)b * P.S + P.fns + (long)M * i0;            // sample of ring step 0, branch 0, parity 0
+  const int RING_CHUNKS = ring_chunks(P), AHEAD = live_ahead(P);
+  const bool sub = P.stride == 2;
+  // stride 1: the tile is 48 outputs of each parity, run (p, k) = 16 outputs i0 + 16 k + o of parity p.
+  // stride 2: the tile is 96 consecutive outputs of the even sequence, run g = 2 k + p... = 16 outputs i0 + 16 g + o.
+  const int run = sub ? pk : k;                                        // run start, in units of 16 steps
+  const int i0 = tile * (sub ? 2 * NEST_TO : NEST_TO);                 // first output index (in its sequence) of the tile
+  const long n_base = (long)b * P.S + P.fns + (long)M * i0;            // sample of ring step 0, branch 0, even sequence
   const int n_chunks = P.q_rows / CH;                                  // compute chunks
-  const int n_ring = n_chunks + NEST_K;                                // ring chunks the tile reads (+1 for the parity offset)
+  const int n_ring = n_chunks + AHEAD;                                 // ring chunks the tile reads
   const unsigned ring_bytes = (unsigned)(CH * M * sizeof(c32)), tap_bytes = (unsigned)(CH * M * sizeof(float2));
 
   if (tid == 0) {
-    for (int i = 0; i < RING_CHUNKS + 2; i++) mbar_init(&bar[i], 1);
+    for (int i = 0; i < RING_MAX + 2; i++) mbar_init(&bar[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   __syncthreads();
@@ -99,7 +108,7 @@ __global__ void __launch_bounds__(2 * NEST_K * 100, 1) k_nest(NestPlan P, NestRe
     tma_bulk_g2s(ring + (size_t)(m % RING_CHUNKS) * CH * M, P.xr + n_base + (long)m * CH * M, ring_bytes, bb);
   };
   auto load_taps = [&](int c) {
-    uint64_t *bb = &bar[RING_CHUNKS + (c & 1)];
+    uint64_t *bb = &bar[RING_MAX + (c & 1)];
     mbar_expect_tx(bb, tap_bytes);
     tma_bulk_g2s(taps + (size_t)(c & 1) * CH * M, P.hq2 + (size_t)c * CH * M, tap_bytes, bb);
   };
@@ -121,10 +130,10 @@ __global__ void __launch_bounds__(2 * NEST_K * 100, 1) k_nest(NestPlan P, NestRe
   const int ring_samples = RING_CHUNKS * CH * M;
   const u64 *ring64 = reinterpret_cast<const u64 *>(ring);
   for (int c = 0; c < n_chunks; c++) {
-    if (c == 0) { for (int m = 0; m < NEST_K && m < n_ring; m++) mbar_wait(&bar[m], 0); }
-    if (c + NEST_K < n_ring) mbar_wait(&bar[(c + NEST_K) % RING_CHUNKS], (unsigned)(((c + NEST_K) / RING_CHUNKS) & 1));
-    mbar_wait(&bar[RING_CHUNKS + (c & 1)], (unsigned)((c >> 1) & 1));
-    int off = (int)(((long)M * (NEST_R * k + CH * c) + (long)(M / 2) * p + r) % ring_samples);
+    if (c == 0) { for (int m = 0; m < AHEAD && m < n_ring; m++) mbar_wait(&bar[m], 0); }
+    if (c + AHEAD < n_ring) mbar_wait(&bar[(c + AHEAD) % RING_CHUNKS], (unsigned)(((c + AHEAD) / RING_CHUNKS) & 1));
+    mbar_wait(&bar[RING_MAX + (c & 1)], (unsigned)((c >> 1) & 1));
+    int off = (int)(((long)M * (NEST_R * run + CH * c) + (sub ? 0 : (long)(M / 2) * p) + r) % ring_samples);
     const u64 *tp = reinterpret_cast<const u64 *>(taps + (size_t)(c & 1) * CH * M + r);
     if (off + CH * M <= ring_samples) {
       // the 16 steps do not cross the end of the ring (4 chunks in 5): one base address, immediate offsets
@@ -158,7 +167,7 @@ __global__ void __launch_bounds__(2 * NEST_K * 100, 1) k_nest(NestPlan P, NestRe
   c32 *U = ring;
 #pragma unroll
   for (int o = 0; o < NEST_R; o++)
-    reinterpret_cast<u64 *>(U)[(size_t)(p * NEST_TO + NEST_R * k + o) * UP + r] = acc[o];
+    reinterpret_cast<u64 *>(U)[(size_t)((sub ? 0 : p * NEST_TO) + NEST_R * run + o) * UP + r] = acc[o];
   __syncthreads();
 
   // ---- 2. N1-point DFTs, in place: V[out][k1 * N2 + n2] = sum_n1 U[out][(N2 n1 + N1 n2) mod M] W_N1^{n1 k1}
@@ -230,11 +239,17 @@ __global__ void __launch_bounds__(2 * NEST_K * 100, 1) k_nest(NestPlan P, NestRe
     for (int j = 0; j < NEST_NCOL; j++) e[j] = 0.0f;
 #pragma unroll
     for (int i = 0; i < NI; i++) {
-      const int out = og + 32 * i, pp = out / NEST_TO, idx = i0 + (out - pp * NEST_TO);
-      if (idx < n_par[pp]) {
-#pragma unroll
-        for (int j = 0; j < NEST_NCOL; j++) e[j] += zr[i][j] * zr[i][j] + zi[i][j] * zi[i][j];
+      const int out = og + 32 * i;
+      float wgt;
+      if (sub) {
+        const int u = i0 + out;
+        wgt = u < P.n_used ? P.weights[u] : 0.0f;
+      } else {
+        const int pp = out / NEST_TO, idx = i0 + (out - pp * NEST_TO);
+        wgt = idx < n_par[pp] ? 1.0f : 0.0f;
       }
+#pragma unroll
+      for (int j = 0; j < NEST_NCOL; j++) e[j] = fmaf(wgt, zr[i][j] * zr[i][j] + zi[i][j] * zi[i][j], e[j]);
     }
 #pragma unroll
     for (int j = 0; j < NEST_NCOL; j++) epart[og * ncol + col0 + j] = e[j];
@@ -269,6 +284,7 @@ int nest_setup(const NestPlan &P)
   if (2 * P.D != P.M || P.N1 * P.N2 != P.M || (P.N1 != 1 && P.N1 != 2 && P.N1 != 4)) return -1;
   if (P.M > 100 || P.q_rows % CH != 0 || P.q_rows < P.Q + CH || P.ncol % NEST_NCOL != 0) return -1;
   if (((CH * P.M * sizeof(float2)) & 15) != 0) return -1;                    // TMA bulk copies move multiples of 16 bytes
+  if (P.stride != 1 && !(P.stride == 2 && P.weights && P.n_used > 8)) return -1;
   if ((((long)P.S * sizeof(c32)) & 15) != 0 || (((long)P.fns * sizeof(c32)) & 15) != 0 || ((NEST_TO * P.M * sizeof(c32)) & 15) != 0)
     return -1;                                                             // ... from 16-byte aligned addresses
   if (nest_smem_bytes(P) > 227 * 1024) return -1;

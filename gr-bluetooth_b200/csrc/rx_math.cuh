@@ -125,6 +125,15 @@ BTB_HD int mm_update(const MmConst &K, MmState &s, float out)
   x1 = x1 - x2;
   s.omega = K.omega_mid + 0.5f * x1;
   float mu = s.mu + (s.omega + K.gain_mu * mm_val);
+#if defined(__CUDA_ARCH__)
+  // floor and float->int without the conversion unit: for 0 <= mu < 2^23 adding 2^23 with round-toward-zero drops the
+  // fraction exactly, the integer sits in the mantissa and subtracting 2^23 back is exact (same value as floorf)
+  if (mu >= 0.0f && mu < 8388608.0f) {
+    const float t = __fadd_rz(mu, 8388608.0f);
+    s.mu = mu - (t - 8388608.0f);
+    return __float_as_int(t) - 0x4B000000;
+  }
+#endif
   const float fl = floorf(mu);
   s.mu = mu - fl;
   return (int)fl;

@@ -99,7 +99,9 @@ __device__ __forceinline__ void mm_stateless_block(const Geom &G, const DevBatch
     }
 #pragma unroll 1
     for (int t = 0; t < PERIOD && oo < oo_end && ii < ni; t++) {
-      int imu = __float2int_rn(st.mu * 128.0f);
+      // rint(mu * 128) without the conversion unit: 0 <= mu < 1, so adding 1.5 * 2^23 rounds to nearest-even at the
+      // units place and leaves the integer in the mantissa (= __float2int_rn)
+      int imu = __float_as_int(__fadd_rn(st.mu * 128.0f, 12582912.0f)) - 0x4B400000;
       imu = imu < 0 ? 0 : (imu > 128 ? 128 : imu);
       const float *rp = &ring[ii & (RD - 1)][tid];
       const float *mp = &s_mmse[0][imu];

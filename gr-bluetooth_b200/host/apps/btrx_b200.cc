@@ -35,7 +35,7 @@ int main(int argc, char **argv)
   bool shorts = false, hop_mode = false, tun = false, have_lap = false, sniff = false;
   int target_lap = 0;
   long tile = 1;
-  bool stats = false;
+  bool stats = false, aliased = false;
   for (int i = 1; i < argc; i++) {
     std::string a = argv[i];
     auto next = [&]() -> const char * { return i + 1 < argc ? argv[++i] : ""; };
@@ -51,6 +51,7 @@ int main(int argc, char **argv)
     else if (a == "-p" || a == "--hop") hop_mode = true;
     else if (a == "--tile") tile = std::atol(next());
     else if (a == "--stats") stats = true;
+    else if (a == "--aliased") aliased = true;                      // apps/btrx:37-38: aliasing receiver (USRP2 firmware)
     else if (a == "-w" || a == "--wireshark") tun = true;           // apps/btrx:57-58; BTB200_TUN_FILE redirects the frames to a file
     else { std::fprintf(stderr, "unknown option %s\n", a.c_str()); return 2; }
   }
@@ -66,7 +67,7 @@ int main(int argc, char **argv)
   try {
     // mode selection of apps/btrx:140-159: -S sniffer; no LAP: LAP printer; LAP + -p: hopper; LAP alone: UAP discovery
     if (sniff) blk = gr::bluetooth::multi_sniffer::make(rate, freq, snr, tun);
-    else if (have_lap && hop_mode) blk = gr::bluetooth::multi_hopper::make(rate, freq, snr, target_lap, false, tun);
+    else if (have_lap && hop_mode) blk = gr::bluetooth::multi_hopper::make(rate, freq, snr, target_lap, aliased, tun);
     else if (have_lap) blk = gr::bluetooth::multi_UAP::make(rate, freq, snr, target_lap);
     else blk = gr::bluetooth::multi_LAP::make(rate, freq, snr);      // print the LAP of every frame detected (also -L)
   } catch (const std::exception &e) {

@@ -600,18 +600,21 @@ int Piconet::init_hop_reversal(bool aliased)
 {
   std::printf("\nCalculating complete hopping sequence.\n");
   d_hop_addr = (((uint32_t)d_uap << 24) | d_lap) & 0xfffffffu;
-  d_aliased = aliased;
+  // the reference picks its first candidates BEFORE it stores the new aliasing flag (piconet_impl.cc:118-124), i.e. with
+  // the flag of the previous attempt (false the first time): kept, the printed candidate counts depend on it
+  const bool aliased_for_candidates = d_aliased;
   const uint32_t clock = (d_clk_offset + d_first_pkt_time) & 0x3f;
   // candidates: clock values with the known low bits whose hop lands on the first observed channel
   d_clock_candidates.clear();
   const int first_channel = d_pattern_channels[0];
-  if (!(s_candidate_fn && s_candidate_fn(d_hop_addr, d_afh, d_aliased, clock, first_channel, d_clock_candidates))) {
+  if (!(s_candidate_fn && s_candidate_fn(d_hop_addr, d_afh, aliased_for_candidates, clock, first_channel, d_clock_candidates))) {
     d_clock_candidates.clear();
     for (uint32_t c = clock; c < (uint32_t)SEQUENCE_LENGTH; c += 0x40) {
       const int hc = hop_select(d_hop_addr, d_afh, c);
-      if ((d_aliased ? (int)aliased_channel((char)hc) : hc) == first_channel) d_clock_candidates.push_back(c);
+      if ((aliased_for_candidates ? (int)aliased_channel((char)hc) : hc) == first_channel) d_clock_candidates.push_back(c);
     }
   }
+  d_aliased = aliased;
   d_num_candidates = (int)d_clock_candidates.size();
   d_winnowed = 0;
   d_hop_reversal_inited = true;
@@ -849,7 +852,10 @@ HopperHost::SlotPlan HopperHost::plan(uint32_t clkn) const
     p.clock27 = (clkn + d_piconet.offset()) & 0x7ffffff;
     const int hopch = d_piconet.hop((int)p.clock27);
     p.obs_channel = d_aliased ? Piconet::aliased_channel((char)hopch) : hopch;
-    if (p.obs_channel >= d_ch_lo && p.obs_channel <= d_ch_hi) { p.first_channel = hopch; p.n_channels = 1; }
+    // the reference tests the OBSERVED channel against the band and then demodulates the hop channel itself
+    // (multi_hopper_impl.cc:158-168); with the aliasing receiver the latter can lie outside the band, where the
+    // reference dereferences a filter that does not exist -- such slots are skipped here
+    if (p.obs_channel >= d_ch_lo && p.obs_channel <= d_ch_hi && hopch >= d_ch_lo && hopch <= d_ch_hi) { p.first_channel = hopch; p.n_channels = 1; }
   } else {
     p.first_channel = d_ch_lo;
     p.n_channels = d_ch_hi - d_ch_lo + 1;

@@ -46,7 +46,6 @@ multi_hopper_impl::multi_hopper_impl(double sample_rate, double center_freq, dou
                      gr::io_signature::make(0, 0, 0)),
       multi_block(sample_rate, center_freq, squelch_threshold, 3125, BTB200_SEARCH_BR, /*force_chained=*/true)
 {
-  if (aliased) throw std::runtime_error("multi_hopper: the aliased receiver mode is not supported on the B200 path");
   const int lo = (int)((d_low_freq - 2402000000.0) / 1e6), hi = (int)((d_high_freq - 2402000000.0) / 1e6);
   d_host.reset(new btb200_host::HopperHost((uint32_t)LAP, aliased, lo, hi));
   if (tun) d_host->set_tun_fd(btb200_host::open_tun_output());     /* lib/multi_hopper_impl.cc:56-64 */

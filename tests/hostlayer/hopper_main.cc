@@ -31,8 +31,9 @@ int main(int argc, char **argv)
   std::fclose(f);
   const int chist = I.Nc + I.D * 8;
   std::printf("history set to %d samples: channel=%d, noise=%d\n", I.S + (chist > I.Nn ? chist : I.Nn), chist, I.Nn);
-  btb200_host::HopperHost host(lap, false, I.ch_lo, I.ch_hi);
-  if (argc > 5 && std::string(argv[5]) != "uap") host.set_tun_fd(open(argv[5], O_WRONLY | O_CREAT | O_TRUNC, 0644));
+  const bool aliased = argc > 5 && std::string(argv[5]) == "aliased";
+  btb200_host::HopperHost host(lap, aliased, I.ch_lo, I.ch_hi);
+  if (argc > 5 && std::string(argv[5]) != "uap" && !aliased) host.set_tun_fd(open(argv[5], O_WRONLY | O_CREAT | O_TRUNC, 0644));
   std::vector<btbo_chan_result> res((size_t)I.nch);
   std::vector<uint8_t> sym((size_t)I.nch * I.H);
   std::vector<int32_t> chis((size_t)I.nch);

@@ -95,6 +95,22 @@ def test_hopper_logic_reproduces_reference_digest(hopper_harness):
 
 
 @pytest.mark.skipif(not os.path.isdir(REF_SAMPLES), reason="needs the bundled captures")
+def test_hopper_logic_aliased_mode_equals_reference_build(hopper_harness):
+    """`btrx --aliased` (apps/btrx:37-38, 154): the hop reversal works on the 25 aliased channels -- including the
+    reference's quirk that the FIRST candidate set is still drawn with the previous flag (piconet_impl.cc:118-124) --
+    same stdout as the verbatim reference build on headset1 (the capture is not aliased, so the candidates run out)."""
+    from oracle import ref as R
+    if not R.available():
+        pytest.skip("oracle/_ref/btref not built")
+    path = os.path.join(REF_SAMPLES, "headset1.cfile")
+    want = subprocess.run([R.BTREF, "hop", "--fs", "8e6", "--fc", "2476.5e6", "--lap", "24d952", "--in", path, "--aliased"],
+                          capture_output=True, timeout=300).stdout.decode()
+    out = subprocess.run([hopper_harness, "8e6", "2476.5e6", "24d952", path, "aliased"], capture_output=True, timeout=300)
+    assert out.returncode == 0 and out.stdout.decode() == want
+    assert "26555 initial CLK1-27 candidates" in want and "no candidates remaining" in want
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_SAMPLES), reason="needs the bundled captures")
 def test_hopper_logic_keyboard1_equals_reference_build(hopper_harness):
     """BASELINE config 4 input (keyboard1, LAP 4831dd): same stdout as the verbatim reference build."""
     from oracle import ref as R

@@ -54,7 +54,7 @@ class Info(C.Structure):
 
 HIT_DTYPE = np.dtype([("slot", "<u4"), ("channel", "<u2"), ("kind", "<u2"), ("offset", "<i4"),
                       ("n_symbols", "<i4"), ("lap", "<u4"), ("flags", "<u4"), ("snr", "<f8"),
-                      ("sym_offset", "<u8"), ("sym_count", "<u4"), ("reserved", "<u4")], align=True)
+                      ("sym_offset", "<u8"), ("sym_count", "<u4"), ("ac_errors", "<u4")], align=True)
 
 
 class ChanResult(C.Structure):

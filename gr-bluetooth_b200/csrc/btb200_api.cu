@@ -1185,12 +1185,12 @@ int collect_poly(btb200_ctx *ctx, btb200_hits *out)
     o.kind = (uint16_t)h.kind;
     o.offset = h.offset;
     o.n_symbols = h.n_symbols;
-    o.lap = h.lap;
+    o.lap = h.kind == 0 ? (h.lap & 0xffffffu) : h.lap;       // BR: bits 24..31 carry the access code's symbol errors
     o.flags = ((std::fabs(snr - P.squelch_db) <= 1e-6) ? 1u : 0u) | 2u | 4u;
     o.snr = snr;
     o.sym_offset = 0;
     o.sym_count = 0;
-    o.reserved = 0;
+    o.ac_errors = h.kind == 0 ? (h.lap >> 24) : 0u;
     if (borrow) { o.sym_offset = h.sym_offset; o.sym_count = h.sym_count; }
     else if (out->symbols && h.sym_count && out->symbols_used + h.sym_count <= out->symbols_cap) {
       std::memcpy(out->symbols + out->symbols_used, ctx->h_arena + h.sym_offset, h.sym_count);
@@ -1306,14 +1306,14 @@ int btb200_collect(btb200_ctx *ctx, btb200_hits *out)
     o.kind = (uint16_t)h.kind;
     o.offset = h.offset;
     o.n_symbols = h.n_symbols;
-    o.lap = h.lap;
+    o.lap = h.kind == 0 ? (h.lap & 0xffffffu) : h.lap;       // BR: bits 24..31 carry the access code's symbol errors
     o.flags = (std::fabs(snr - P.squelch_db) <= 1e-6) ? 1u : 0u;
     if (!est_flag.empty() && est_flag[bc]) o.flags |= 2u;
     if (ctx->poly) o.flags |= 4u;
     o.snr = snr;
     o.sym_offset = 0;
     o.sym_count = 0;
-    o.reserved = 0;
+    o.ac_errors = h.kind == 0 ? (h.lap >> 24) : 0u;
     if (borrow) { o.sym_offset = h.sym_offset; o.sym_count = h.sym_count; }
     else if (out->symbols && h.sym_count && out->symbols_used + h.sym_count <= out->symbols_cap) {
       std::memcpy(out->symbols + out->symbols_used, ctx->h_arena + h.sym_offset, h.sym_count);
@@ -1508,7 +1508,7 @@ int btb200_search_bits(btb200_ctx *ctx, const uint8_t *symbols, size_t n_symbols
       btb200_hit &o = out->hits[out->count++];
       o = btb200_hit{};
       o.slot = (uint32_t)(w0 + (size_t)h.b * P.nch + h.chi);
-      o.offset = h.offset; o.n_symbols = h.n_symbols; o.lap = h.lap;
+      o.offset = h.offset; o.n_symbols = h.n_symbols; o.lap = h.lap & 0xffffffu; o.ac_errors = h.lap >> 24;
     }
   }
   ctx->last_slots = 0;

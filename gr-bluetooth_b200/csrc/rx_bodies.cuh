@@ -174,6 +174,11 @@ BTB_HD void window_search(const Geom &G, const uint64_t *__restrict__ ac_lut, co
         if (br_lag_test(ac_lut, lo, hi, &lap)) { found = lag; break; }
       }
       if (found < 0) break;
+      {
+        uint64_t lo; uint32_t hi;
+        bits_window(row, found, &lo, &hi);
+        lap |= (uint32_t)br_lag_errors(ac_lut, lo, hi) << 24;      // bits 24..31 of a BR hit's lap field: symbol errors of the access code
+      }
       emit(0, found, nsym - found, lap);
       start = found + 68;
     }

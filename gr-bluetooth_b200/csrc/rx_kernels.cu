@@ -750,7 +750,7 @@ __global__ void k_search_warp(Geom G, DevTables T, DevBatch W)
       if (lane == 0) {
         uint64_t lo; uint32_t hi;
         bits_window(row, found, &lo, &hi);
-        em(0, found, nsym_eff - found, (uint32_t)(lo >> 38) & 0xffffff);
+        em(0, found, nsym_eff - found, ((uint32_t)(lo >> 38) & 0xffffff) | ((uint32_t)br_lag_errors(T.ac_lut, lo, hi) << 24));
       }
       start = found + 68;
     }

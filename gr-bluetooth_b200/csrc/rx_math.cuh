@@ -178,6 +178,17 @@ BTB_HD int br_lag_test(const uint64_t *__restrict__ lut, uint64_t w_lo, uint32_t
   return errs < 7;
 }
 
+// check_ac's count for a lag that passed (lib/packet_impl.cc:471-510): symbols among the first 68 that differ from the
+// access code regenerated for the LAP read from the stream; 0..6
+BTB_HD int br_lag_errors(const uint64_t *__restrict__ lut, uint64_t w_lo, uint32_t w_hi)
+{
+  const uint32_t lap = (uint32_t)(w_lo >> 38) & 0xffffff;
+  const uint64_t sync = lut[768] ^ lut[lap & 0xff] ^ lut[256 + ((lap >> 8) & 0xff)] ^ lut[512 + (lap >> 16)];
+  const uint64_t rx_sync = (w_lo >> 4) | ((uint64_t)(w_hi & 0xf) << 60);
+  const uint32_t exp_pre = (sync & 1) ? 0x5u : 0xAu;
+  return popc64(rx_sync ^ sync) + popc32(((uint32_t)w_lo & 0xf) ^ exp_pre);
+}
+
 // nearest-valid-byte distances of the LE header tables (lib/packet_impl.cc:1327-1444 in closed form)
 BTB_HD int le_hdr_dist(uint32_t v, int which)
 {

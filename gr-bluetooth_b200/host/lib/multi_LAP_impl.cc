@@ -2,7 +2,9 @@
 // Window geometry: history + 68 symbols (multi_LAP_impl.cc:54).  The reference searches with
 // libbtbb's btbb_find_ac(max_ac_errs=1), an external library that is not part of the reference
 // tree; this block uses classic_packet::sniff_ac semantics instead (parity unpinned)
-// and reports the first access code per channel-window, like the reference's single call.
+// and reports the first access code per channel-window, like the reference's single call.  `err` is the number of
+// symbols among the first 68 that differ from the access code regenerated for the LAP (check_ac's count, < 7 accepted);
+// libbtbb reports the bit errors its BCH decoder corrected (<= max_ac_errs = 1 accepted) -- not the same acceptance rule.
 #include "multi_LAP_impl.h"
 #include "btb200.h"
 #include <cstdio>
@@ -34,7 +36,7 @@ void multi_LAP_impl::handle_hit(const btb200_hit &hit, const char *, int, double
   if ((int)hit.slot == d_last_slot && (int)hit.channel == d_last_channel) return;   // one report per channel-window
   d_last_slot = (int)hit.slot;
   d_last_channel = (int)hit.channel;
-  std::printf("GOT PACKET: ch=%d, LAP=%06x, err=%u at time slot %d\n", hit.channel, hit.lap, 0u, (int)hit.slot);
+  std::printf("GOT PACKET: ch=%d, LAP=%06x, err=%u at time slot %d\n", hit.channel, hit.lap, hit.ac_errors, (int)hit.slot);
 }
 
 }  // namespace bluetooth

@@ -187,7 +187,8 @@ typedef struct btb200_hit {
   uint64_t sym_offset;           /* into btb200_hits.symbols */
   uint32_t sym_count;            /* min(n_symbols, 3125) symbols copied (what classic_packet::make keeps,
                                   * lib/packet_impl.cc:52-58), one per byte, air order; 0 when the arena was full */
-  uint32_t reserved;
+  uint32_t ac_errors;            /* BR: symbols among the first 68 that differ from the access code of `lap` (check_ac's
+                                  * count, 0..6); LE: 0 */
 } btb200_hit;
 
 typedef struct btb200_hits {

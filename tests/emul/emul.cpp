@@ -126,7 +126,7 @@ int emul_run(double fs, double fc, double snr_db, int extra, int stateless, int 
         if (o->nhits < o->hits_cap) {
           emul_hit &h = o->hits[o->nhits];
           h.slot = first_slot + b; h.channel = (int16_t)(P.ch_lo + c); h.kind = (int16_t)kind;
-          h.offset = offset; h.n_symbols = n_symbols; h.lap = lap; h.snr = snr;
+          h.offset = offset; h.n_symbols = n_symbols; h.lap = kind == 0 ? (lap & 0xffffff) : lap; h.snr = snr;
         }
         o->nhits++;
       };

@@ -98,6 +98,7 @@ def test_polyphase_synthetic_wideband(fs, fc, nslots):
     blk = poly_block(fs, fc, B, keep_stages=True)
     hits, syms, ovf = blk.process(seg, first, B, want_symbols=True)
     assert ovf == 0 and np.all(hits["flags"] & 4)
+    assert np.all(hits["ac_errors"][hits["kind"] == 0] < 7) and np.all(hits["ac_errors"][hits["kind"] == 1] == 0)
     # energies of every window
     for j in range(B):
         for chi in range(0, P.nch, 7):

@@ -14,12 +14,30 @@ __device__ __forceinline__ void mm_cp_async4(void *smem_dst, const void *gsrc)
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(gsrc));
 }
 __device__ __forceinline__ void mm_cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-__device__ __forceinline__ void mm_cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::); }
+__device__ __forceinline__ void mm_cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+__device__ __forceinline__ void mm_cp_async_wait_prev() { asm volatile("cp.async.wait_group 1;\n" ::: "memory"); }
+
+// ld.shared with an explicit 32-bit address and an immediate offset
+template <int IMM>
+__device__ __forceinline__ float mm_lds(unsigned addr)
+{
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1+%2];\n" : "=f"(v) : "r"(addr), "n"(IMM));
+  return v;
+}
+// the 8-tap interpolation of one step, ascending order, one rounding per operation
+template <int BLK, int K = 0>
+__device__ __forceinline__ float mm_interp8(unsigned ra, unsigned ma, float acc)
+{
+  if constexpr (K == 8) return acc;
+  else return mm_interp8<BLK, K + 1>(ra, ma, acc + mm_lds<K * BLK * 4>(ra) * mm_lds<K * 132 * 4>(ma));
+}
 
 struct MmSave { float mu, omega, last; unsigned ii; int oo; uint32_t word; };
 // ring depth of the clock-recovery loop: a refill reaches ii+96 and the reader is at most 40 samples further
 // when the next one is issued, so 128 rows never overwrite a live sample
 constexpr int MM_RD = 128;
+constexpr int MM_MAXADV = 5;         // |demod| <= gain * pi bounds the timing error term: at most 5 samples per symbol
 constexpr size_t mm_smem_bytes(int blk) { return sizeof(float) * (MM_RD + 8) * blk + sizeof(float) * 8 * 132; }
 
 // mode 0: every window from the constructor state to the end (reference loop).
@@ -33,38 +51,46 @@ __device__ __forceinline__ void mm_stateless_block(const Geom &G, const DevBatch
                                                    const float *__restrict__ demT, int mode, MmSave *__restrict__ save,
                                                    const int4 *__restrict__ list, int n_list, unsigned char *mm_smem, int block)
 {
-
+  static_assert(BLK % 32 == 0, "whole warps");
   constexpr int RD = MM_RD;        // ring depth (demod samples per window)
-  constexpr int AHEAD = 88;        // refill target: ii + 8 + AHEAD
-  constexpr int PERIOD = 8;        // steps between refills
-  // The loop advances ii by at most 5 samples per step (|demod| <= gain*pi bounds mm_val), so the refill issued at
-  // the start of a block of PERIOD steps (it reaches ii + 96) covers everything the NEXT block can read (< ii + 88)
-  // and lands while this block runs; 128 rows never overwrite a live sample.  Rows 0..7 are mirrored at 128..135 so
-  // the 8 samples of an interpolation are always 8 consecutive rows: one base address, immediate offsets.
+  constexpr int PERIOD = 8;        // steps per block
+  constexpr int NEED = MM_MAXADV * PERIOD + 8;   // a block reads samples below ii + NEED
+  constexpr unsigned FULL = 0xffffffffu;
+  // Every chain has its own column of the ring, but the ROWS move in step for the 32 chains of a warp: row i holds
+  // sample i of each chain's window, the warp copies rows [pf, want) with want = (smallest ii of the warp) + RD, one
+  // cp.async per row -- for windows of consecutive channels that is one or two cache lines per instruction and ONE
+  // shared-memory wavefront (per-chain row schedules cost a wavefront per distinct row: 45 % of the shared-memory
+  // pipe, the unit that bounds this loop).  The loop advances ii by at most MM_MAXADV samples per step (|demod| <=
+  // gain pi bounds the timing error), so a block of PERIOD steps reads below ii + NEED; a chain that is further
+  // ahead of the slowest one than the landed rows allow sits the block out (chains drift apart by a few tens of
+  // samples over a window).  Two copy groups may be in flight.  Rows 0..7 are mirrored at RD..RD+7 so the 8 samples
+  // of an interpolation are always 8 consecutive rows: one base address, immediate offsets.
   float (*ring)[BLK] = reinterpret_cast<float (*)[BLK]>(mm_smem);                        // [RD + 8][BLK]
   float (*s_mmse)[132] = reinterpret_cast<float (*)[132]>(mm_smem + sizeof(float) * (RD + 8) * BLK);   // [8][132]
   for (int i = threadIdx.x; i < 129 * 8; i += blockDim.x) s_mmse[7 - (i & 7)][i >> 3] = mmse_g[i];   // [k][imu] = taps[imu][7-k]
+  if (threadIdx.x == 0) s_mmse[0][129] = __int_as_float((int)(0x4B400000u << 2));                    // spare column: see mmse_biased
   __syncthreads();
-  if (threadIdx.x >= BLK) return;
+  if (threadIdx.x >= BLK) return;                          // whole warps leave; the others stay complete to the end
   int idx = block * BLK + threadIdx.x;
+  bool live;
   if (mode == 2) {
     if (n_list < 0) n_list = *W.tail.n_list;             // device-driven tail: the list was built on the device
-    if (idx >= n_list) return;
-    const int4 it = list[idx];
-    idx = it.x * G.nch + it.y;
+    live = idx < n_list;
+    if (live) { const int4 it = list[idx]; idx = it.x * G.nch + it.y; }
   } else {
-    if (idx >= W.B * G.nch) return;
-    if (!W.pass[idx]) { W.nsym[idx] = 0; return; }
+    live = idx < W.B * G.nch;
+    if (live && !W.pass[idx]) { W.nsym[idx] = 0; live = false; }
   }
+  if (!live) idx = 0;
   const int b = idx / G.nch, c = idx - b * G.nch;
-  const float *gp = demT + ((long)b * G.dem_rows) * G.nch + c;     // next sample to prefetch
+  const float *gp = demT + ((long)b * G.dem_rows) * G.nch + c;     // sample 0 of the window
   uint32_t *__restrict__ bits_row = W.bits + (long)idx * G.bw;
   float *soft_row = W.soft ? W.soft + (long)idx * G.n_dem_pad : nullptr;
   MmState st{G.mu0, G.mm.omega_mid, 0.0f};
   unsigned ii = 0;
   int oo = 0;
   uint32_t word = 0;
-  if (mode == 2) {
+  if (mode == 2 && live) {
     const MmSave sv = save[idx];
     st = MmState{sv.mu, sv.omega, sv.last};
     ii = sv.ii; oo = sv.oo; word = sv.word;
@@ -72,50 +98,124 @@ __device__ __forceinline__ void mm_stateless_block(const Geom &G, const DevBatch
   const int avail = (mode == 1) ? G.ne_dem : G.n_dem;            // demod floats that exist
   const int oo_end = (mode == 1) ? G.sym_target : G.n_dem;
   const unsigned ni = (unsigned)((mode == 1 ? G.ne_dem : G.n_dem) - 8);
-  int pf = (int)ii;                // samples [pf-RD, pf) are in (or on their way to) the ring
   const int tid = threadIdx.x;
   const int nch = G.nch;
+  const unsigned ring_tid = (unsigned)__cvta_generic_to_shared(&ring[0][tid]);
+  // table address biased by the exponent bits of the magic constant: entry imu is at mmse_biased + 4 bits(1.5 2^23 + imu)
+  // (the bias is read back from shared memory so that ptxas cannot split it off again as an add per load)
+  const unsigned mmse_biased = (unsigned)__cvta_generic_to_shared(&s_mmse[0][0]) - (unsigned)__float_as_int(s_mmse[0][129]);
   const MmConst K = G.mm;
-  gp += (long)pf * nch;
-  auto refill = [&](int want) {
-    for (; pf < want; pf++, gp += nch) {
-      const int rr = pf & (RD - 1);
-      mm_cp_async4(&ring[rr][tid], gp);
-      if (rr < 8) mm_cp_async4(&ring[rr + RD][tid], gp);
-    }
-    mm_cp_async_commit();
-  };
-  {
-    int want = (int)ii + 8 + AHEAD; if (want > avail) want = avail;
-    refill(want);
-    mm_cp_async_wait_all();
-    if (G.dem_grid && ii == 0) ring[0][tid] = 0.0f;      // demod_out[0] of a window is never written by the reference
-  }
-  while (oo < oo_end && ii < ni) {
-    mm_cp_async_wait_all();              // the refill issued a block ago has long landed
+  bool done = !live || !(oo < oo_end && ii < ni);
+  // rows [pf - RD, pf) are in (or on their way to) the ring; pf is the same for the 32 chains of the warp
+  int pf = (int)__reduce_min_sync(FULL, done ? 0x7fffffffu : ii);
+  if (pf != 0x7fffffff) {
+    gp += (long)pf * nch;
+    auto refill = [&](int want) {
+      for (; pf < want; pf++, gp += nch) {
+        const int rr = pf & (RD - 1);
+        if (live) {
+          mm_cp_async4(&ring[rr][tid], gp);
+          if (rr < 8) mm_cp_async4(&ring[rr + RD][tid], gp);
+        }
+      }
+      mm_cp_async_commit();
+    };
     {
-      int want = (int)ii + 8 + AHEAD; if (want > avail) want = avail;
+      int want = pf + RD; if (want > avail) want = avail;
       refill(want);
+      mm_cp_async_wait_all();
+      if (G.dem_grid && live && ii == 0) ring[0][tid] = 0.0f;      // demod_out[0] of a window is never written by the reference
     }
+    // reach_prev = first row NOT covered by the copies issued before the most recent group (landed after wait_group 1)
+    int reach_prev = pf, reach_last = pf;
+    while (true) {
+      done = !live || !(oo < oo_end && ii < ni);
+      if (__all_sync(FULL, done)) break;
+      const int ii_min = (int)__reduce_min_sync(FULL, done ? 0x7fffffffu : ii);
+      if (ii_min + NEED > reach_prev) { mm_cp_async_wait_all(); reach_prev = reach_last; }
+      else mm_cp_async_wait_prev();
+      const int landed = reach_prev;
+      {
+        int want = ii_min + RD; if (want > avail) want = avail;      // rows from ii_min on stay
+        refill(want);
+        reach_prev = reach_last;
+        reach_last = pf;
+      }
+      if (done || ((int)ii + NEED > landed && landed < avail)) continue;     // finished, or too far ahead: sit this block out
+      if ((oo & 7) == 0 && oo + PERIOD <= oo_end && ii + (unsigned)(MM_MAXADV * PERIOD) < ni) {
+        // Fast block: PERIOD steps of straight-line code.  No exit tests inside (the loop cannot end within them: the
+        // advance per step is at most MM_MAXADV samples), the sliced bits collected in a byte, shared memory addressed
+        // explicitly.  Same arithmetic as mm_update / mmse_interp, operation for operation and rounding for rounding:
+        //   sl * out = +-out;  clip = 0.5 (|x + c| - |x - c|);
+        //   floor(m) and (int) floor(m) from tz = RZ(m + 2^23): fl = tz - 2^23, advance = bits(tz) - bits(2^23);
+        //   rint(128 (m - fl)) from ONE fused multiply-add: m - fl is exact and 1.5 2^23 - 128 fl = fma(tz, -128,
+        //   2^30 + 1.5 2^23) is an exact integer below 2^24, so fma(m, 128, that) rounds 128 (m - fl) + 1.5 2^23
+        //   once, like fadd(128 mu, 1.5 2^23) = the magic rint of the slow path.
+        // A step whose m is outside [0, 2^23) (never, for finite input) flags the block, which is then redone by the
+        // step-by-step loop below from the saved state.
+        const MmState st0 = st;
+        const unsigned ii0 = ii;
+        constexpr int SH = (BLK == 32 ? 7 : BLK == 64 ? 8 : BLK == 128 ? 9 : BLK == 256 ? 10 : -1);
+        static_assert(SH > 0, "BLK must be 32, 64, 128 or 256");
+        constexpr unsigned RMASK = (unsigned)(RD - 1) << SH;
+        unsigned iiw = ii << SH;
+        unsigned tb = umin((unsigned)__float_as_int(__fmaf_rn(st.mu, 128.0f, 12582912.0f)), 0x4B400080u);
+        unsigned byte = 0, bad = 0;
+        float mu = st.mu, omega = st.omega, last = st.last;
+  #pragma unroll
+        for (int t = 0; t < PERIOD; t++) {
+          const unsigned ma = mmse_biased + (tb << 2);
+          const unsigned ra = ring_tid + (iiw & RMASK);
+          const float out = mm_interp8<BLK>(ra, ma, 0.0f);
+          if (soft_row) soft_row[oo + t] = out;
+          const bool neg = out < 0;
+          if (!neg) byte |= 1u << t;
+          const float a = (last < 0) ? -out : out;
+          const float b = neg ? -last : last;
+          const float mm_val = a - b;
+          last = out;
+          const float x = (omega + K.gain_omega * mm_val) - K.omega_mid;
+          omega = K.omega_mid + 0.5f * (fabsf(x + K.omega_lim) - fabsf(x - K.omega_lim));
+          const float m = mu + (omega + K.gain_mu * mm_val);
+          const float tz = __fadd_rz(m, 8388608.0f);
+          const unsigned tzb = (unsigned)__float_as_int(tz);
+          tb = umin((unsigned)__float_as_int(__fmaf_rn(m, 128.0f, __fmaf_rn(tz, -128.0f, 1086324736.0f))), 0x4B400080u);
+          iiw += SH >= 8 ? (tzb << SH) : ((tzb - 0x4B000000u) << SH);        // bits(2^23) << 8 is 0 mod 2^32
+          bad |= tzb - 0x4B000000u;
+          mu = m - (tz - 8388608.0f);
+        }
+        if (bad < 0x800000u) {
+          st = MmState{mu, omega, last};
+          ii = ii0 + ((iiw - (ii0 << SH)) >> SH);
+          word |= byte << (oo & 31);
+          oo += PERIOD;
+          if ((oo & 31) == 0) { bits_row[(oo >> 5) - 1] = word; word = 0; }
+          continue;
+        }
+        st = st0;
+        ii = ii0;
+      }
 #pragma unroll 1
-    for (int t = 0; t < PERIOD && oo < oo_end && ii < ni; t++) {
-      // rint(mu * 128) without the conversion unit: 0 <= mu < 1, so adding 1.5 * 2^23 rounds to nearest-even at the
-      // units place and leaves the integer in the mantissa (= __float2int_rn)
-      int imu = __float_as_int(__fadd_rn(st.mu * 128.0f, 12582912.0f)) - 0x4B400000;
-      imu = imu < 0 ? 0 : (imu > 128 ? 128 : imu);
-      const float *rp = &ring[ii & (RD - 1)][tid];
-      const float *mp = &s_mmse[0][imu];
-      float out = 0.0f;
+      for (int t = 0; t < PERIOD && oo < oo_end && ii < ni; t++) {
+        // rint(mu * 128) without the conversion unit: 0 <= mu < 1, so adding 1.5 * 2^23 rounds to nearest-even at the
+        // units place and leaves the integer in the mantissa (= __float2int_rn)
+        int imu = __float_as_int(__fadd_rn(st.mu * 128.0f, 12582912.0f)) - 0x4B400000;
+        imu = imu < 0 ? 0 : (imu > 128 ? 128 : imu);
+        const float *rp = &ring[ii & (RD - 1)][tid];
+        const float *mp = &s_mmse[0][imu];
+        float out = 0.0f;
 #pragma unroll
-      for (int k = 0; k < 8; k++) out = out + rp[k * BLK] * mp[k * 132];
-      if (soft_row) soft_row[oo] = out;
-      if (!(out < 0)) word |= 1u << (oo & 31);
-      if ((oo & 31) == 31) { bits_row[oo >> 5] = word; word = 0; }
-      ii += (unsigned)mm_update(K, st, out);
-      oo++;
+        for (int k = 0; k < 8; k++) out = out + rp[k * BLK] * mp[k * 132];
+        if (soft_row) soft_row[oo] = out;
+        if (!(out < 0)) word |= 1u << (oo & 31);
+        if ((oo & 31) == 31) { bits_row[oo >> 5] = word; word = 0; }
+        ii += (unsigned)mm_update(K, st, out);
+        oo++;
+      }
     }
+    mm_cp_async_wait_all();
   }
-  mm_cp_async_wait_all();
+  if (!live) return;
   if (mode == 1) save[idx] = MmSave{st.mu, st.omega, st.last, ii, oo, word};
   if (oo & 31) bits_row[oo >> 5] = word;
   for (int w = (oo + 31) >> 5; w < G.bw; w++) bits_row[w] = 0;

@@ -102,4 +102,9 @@ def test_clock_recovery_is_not_contracted_where_it_rides_in_the_estimator(sass):
     rule = mk[mk.index("build/rx_nest.o:"):]
     assert "$(EXACT)" in rule.split("build/plan.o")[0] and "$(FAST)" not in rule.split("build/plan.o")[0].split("\n", 3)[2]
     mm = body(sass, "k_mm_stateless_v2")
-    assert any(" FMUL " in l for l in mm) and any(" FADD " in l for l in mm) and not any(re.search(r"\bFFMA\b", l) for l in mm)
+    assert any(" FMUL " in l for l in mm) and any(" FADD " in l for l in mm)
+    # the only fused multiply-adds are the exact ones of the table index (rx_mm.cuh: 128 mu + 1.5 2^23 with the floor
+    # folded in: both products are exact, one rounding, same value as the reference's rint(128 mu))
+    for l in mm:
+        if re.search(r"\bFFMA\b", l):
+            assert re.search(r", 128, |12582912|1\.0863247", l), l

@@ -244,7 +244,22 @@ int setup_fast(btb200_ctx *ctx)
       // throughput mode: the even outputs with end-corrected weights (half the work, rx_nest.cuh); the guarded mode of
       // the exact path keeps every output (its guard band assumes the tighter estimate)
       std::vector<float> wts;
-      if (ctx->poly && !std::getenv("BTB200_NEST_DENSE") && (P.n_noise % 2) == 0 && P.n_noise >= 32) {
+      // BTB200_NEST_FOLD: 0 = every output, 1 = the even outputs, 2 = every 4th output (default where it fits)
+      int fold_req = 2;
+      if (const char *e = std::getenv("BTB200_NEST_FOLD")) fold_req = std::atoi(e);
+      if (std::getenv("BTB200_NEST_DENSE")) fold_req = 0;
+      const bool sub_ok = ctx->poly && (P.n_noise % 2) == 0 && P.n_noise >= 32;
+      if (sub_ok && fold_req >= 2 && P.n_noise >= 128 && NEST_RUNS_V * 2 * N.M <= 2 * NEST_K * 100) {
+        // every 4th output, weights by least squares over the band of |y|^2 (+-90 kHz of the 2 Msps output rate)
+        K.fold = 2;
+        K.stride = 4;
+        const double omega = 2.0 * M_PI * 90e3 * P.D / P.fs;
+        if (nest_quadrature(P.n_noise, K.stride, 2, 12, omega, wts) < 0) return BTB200_ERR_ARG;
+        K.n_used = (int)wts.size();
+        const int MV = K.fold * N.M, Qv = (P.Nn + MV - 1) / MV;
+        K.q_rows_v = (Qv + 15 + 15) / 16 * 16;
+        K.tiles_per_slot = (K.n_used + NEST_R * NEST_RUNS_V - 1) / (NEST_R * NEST_RUNS_V);
+      } else if (sub_ok && fold_req >= 1) {
         K.stride = 2;
         K.n_used = P.n_noise / 2 + 1;
         wts.assign((size_t)K.n_used, 2.0f);
@@ -257,13 +272,19 @@ int setup_fast(btb200_ctx *ctx)
         K.tiles_per_slot = ((P.n_noise + 1) / 2 + NEST_TO - 1) / NEST_TO;
       }
       K.period = F.period; K.phasor = F.phasor; K.esum = F.esum;
-      // the last tile of a slot reads (tiles * 64 + q_rows + 16 * 5) * M samples past the slot's first noise sample
-      const long reach = (long)P.fns + ((long)K.tiles_per_slot * (K.stride == 2 ? 2 : 1) * NEST_TO + K.q_rows + 16 * (2 * NEST_K + 2)) * K.M;
-      if (K.stride == 2) { if ((rc = upload(ctx, &K.weights, wts))) return rc; }
+      // the last tile of a slot reads (outputs of the tiles + tap rows + the ring's look-ahead) rows of K.fold * M samples
+      // past the slot's first noise sample
+      const long reach = K.fold > 1
+          ? (long)P.fns + ((long)K.tiles_per_slot * NEST_R * NEST_RUNS_V + K.q_rows_v + 16 * (NEST_RUNS_V + 1)) * K.fold * K.M
+          : (long)P.fns + ((long)K.tiles_per_slot * (K.stride == 2 ? 2 : 1) * NEST_TO + K.q_rows + 16 * (2 * NEST_K + 2)) * K.M;
+      if (K.stride >= 2) { if ((rc = upload(ctx, &K.weights, wts))) return rc; }
       if (reach <= P.H && nest_setup(K) == 0) {
         {
-          std::vector<float2> h2(N.hq.size());
-          for (size_t i = 0; i < h2.size(); i++) h2[i] = make_float2(N.hq[i], N.hq[i]);
+          // flat in the tap index k = row * (row length) + branch: the folded mode reads the same array with rows of fold * M
+          size_t n_h2 = N.hq.size();
+          if (K.fold > 1 && (size_t)K.q_rows_v * K.fold * K.M > n_h2) n_h2 = (size_t)K.q_rows_v * K.fold * K.M;
+          std::vector<float2> h2(n_h2, make_float2(0.0f, 0.0f));
+          for (size_t i = 0; i < N.hq.size(); i++) h2[i] = make_float2(N.hq[i], N.hq[i]);
           if ((rc = upload(ctx, &K.hq2, h2))) return rc;
         }
         if ((rc = upload(ctx, &K.n2_of_rho, N.n2_of_rho))) return rc;

@@ -213,6 +213,77 @@ int PfbDesign::design_noise(const Plan &P, int cols_per_thread, int row_pad)
   return 0;
 }
 
+double nest_quadrature(int N, int s, int n_extra, int n_free, double omega_max, std::vector<float> &w)
+{
+  if (N < 16 || s < 1 || n_extra < 0 || n_free < 1 || !(omega_max > 0)) return -1.0;
+  const int n_used = (N - 1) / s + 1 + n_extra;
+  std::vector<int> idx;                                   // the free weights: n_free at either end (all, if they overlap)
+  for (int m = 0; m < n_used; m++)
+    if (m < n_free || m >= n_used - n_free) idx.push_back(m);
+  const int nu = (int)idx.size(), nw = 400, rows = 2 * nw + nu;
+  const long double reg = 1e-4L;                          // sqrt of the Tikhonov weight
+  typedef long double ld;
+  std::vector<ld> A((size_t)rows * nu, 0.0L), b((size_t)rows, 0.0L);
+  std::vector<ld> Tre(nw), Tim(nw);
+  for (int k = 0; k < nw; k++) {
+    const ld om = (ld)omega_max * k / (nw - 1);
+    // target sum_{j<N} e^{i om j} minus the contribution of the pinned weights
+    ld tr = 0, ti = 0;
+    for (int j = 0; j < N; j++) { tr += cosl(om * j); ti += sinl(om * j); }
+    Tre[k] = tr; Tim[k] = ti;
+    ld rr = tr, ri = ti;
+    for (int m = 0; m < n_used; m++) { rr -= (ld)s * cosl(om * s * m); ri -= (ld)s * sinl(om * s * m); }
+    for (int u = 0; u < nu; u++) {
+      A[(size_t)(2 * k) * nu + u] = cosl(om * s * idx[u]);
+      A[(size_t)(2 * k + 1) * nu + u] = sinl(om * s * idx[u]);
+    }
+    b[2 * k] = rr; b[2 * k + 1] = ri;
+  }
+  for (int u = 0; u < nu; u++) A[(size_t)(2 * nw + u) * nu + u] = reg;
+  // Householder QR, column by column; b is transformed along
+  for (int c = 0; c < nu; c++) {
+    ld norm = 0;
+    for (int r = c; r < rows; r++) norm += A[(size_t)r * nu + c] * A[(size_t)r * nu + c];
+    norm = sqrtl(norm);
+    if (norm == 0) return -2.0;
+    const ld alpha = A[(size_t)c * nu + c] > 0 ? -norm : norm;
+    std::vector<ld> v((size_t)rows, 0.0L);
+    for (int r = c; r < rows; r++) v[r] = A[(size_t)r * nu + c];
+    v[c] -= alpha;
+    ld vv = 0;
+    for (int r = c; r < rows; r++) vv += v[r] * v[r];
+    if (vv == 0) continue;
+    for (int cc = c; cc < nu; cc++) {
+      ld dot = 0;
+      for (int r = c; r < rows; r++) dot += v[r] * A[(size_t)r * nu + cc];
+      const ld f = 2 * dot / vv;
+      for (int r = c; r < rows; r++) A[(size_t)r * nu + cc] -= f * v[r];
+    }
+    ld dot = 0;
+    for (int r = c; r < rows; r++) dot += v[r] * b[r];
+    const ld f = 2 * dot / vv;
+    for (int r = c; r < rows; r++) b[r] -= f * v[r];
+  }
+  std::vector<ld> dw((size_t)nu, 0.0L);
+  for (int c = nu - 1; c >= 0; c--) {
+    ld acc = b[c];
+    for (int cc = c + 1; cc < nu; cc++) acc -= A[(size_t)c * nu + cc] * dw[cc];
+    dw[c] = acc / A[(size_t)c * nu + c];
+  }
+  w.assign((size_t)n_used, (float)s);
+  for (int u = 0; u < nu; u++) w[(size_t)idx[u]] = (float)((ld)s + dw[u]);
+  // residual with the weights as stored (float)
+  double worst = 0;
+  for (int k = 0; k < nw; k++) {
+    const ld om = (ld)omega_max * k / (nw - 1);
+    ld rr = -Tre[k], ri = -Tim[k];
+    for (int m = 0; m < n_used; m++) { rr += (ld)w[m] * cosl(om * s * m); ri += (ld)w[m] * sinl(om * s * m); }
+    const double e = (double)sqrtl(rr * rr + ri * ri);
+    if (e > worst) worst = e;
+  }
+  return worst;
+}
+
 // classic_packet::acgen, lib/packet_impl.cc:309-364: (64,30) BCH sync word.
 uint64_t sync_word(uint32_t lap)
 {

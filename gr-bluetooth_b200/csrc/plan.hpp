@@ -69,6 +69,16 @@ struct PfbDesign {
   int q_rows = 0;                    // rows of hq (noise variant: padded)
 };
 
+// Quadrature weights of the sub-sampled off-channel energy sum (rx_nest.cu, throughput mode).  check_snr sums |y_j|^2
+// over the N outputs j < N of the noise DDC (lib/multi_block.cc:279-284); |y|^2 is band-limited far below the
+// reference's output rate (the Hann low-pass of 22.5 kHz + 10 kHz transition leaves y within ~+-45 kHz at 2 Msps), so
+//     sum_{j<N} g(j)  ~=  sum_{m<n_used} w[m] g(s m),     n_used = (N-1)/s + 1 + n_extra
+// for every g band-limited to |omega| <= omega_max (radians per output).  Interior weights are s; the n_free weights
+// at either end are the least-squares solution over a grid of complex exponentials in the band (Householder QR,
+// Tikhonov-regularised towards s).  Returns the largest residual |sum_m w e^{i w s m} - sum_j e^{i w j}| over the
+// grid (the worst-case error for a unit-amplitude in-band tone; the sum itself is N), or a negative value on error.
+double nest_quadrature(int N, int s, int n_extra, int n_free, double omega_max, std::vector<float> &w);
+
 // Free-running rotator of one DDC object (GNU Radio's gr::blocks::rotator):
 // phase multiplies output i, then advances; renormalised every 512 outputs.
 struct Rotator {

@@ -30,7 +30,7 @@ namespace {
 constexpr int RING_MAX = 2 * NEST_K + 2;  // ring capacity in chunks of 16 steps: live chunks + one in flight (stride 1: K + 2, stride 2: 2 K + 2)
 // compute chunk c reads ring chunks c .. c + live_ahead: stride 1: runs 0..K-1 plus the half-step offset of the odd
 // sequence; stride 2: runs 0..2K-1, no offset
-__host__ __device__ inline int live_ahead(const NestPlan &P) { return P.stride == 2 ? 2 * NEST_K - 1 : NEST_K; }
+__host__ __device__ inline int live_ahead(const NestPlan &P) { return P.fold > 1 ? NEST_RUNS_V - 1 : P.stride == 2 ? 2 * NEST_K - 1 : NEST_K; }
 __host__ __device__ inline int ring_chunks(const NestPlan &P) { return live_ahead(P) + 2; }
 constexpr int CH = 16;               // steps per chunk
 
@@ -41,10 +41,12 @@ __host__ __device__ inline NestSmem nest_layout(const NestPlan &P)
   NestSmem L{};
   size_t o = 0;
   auto take = [&o](size_t bytes, size_t align) { o = (o + align - 1) / align * align; const size_t r = o; o += bytes; return r; };
-  const size_t ring = (size_t)ring_chunks(P) * CH * P.M * sizeof(c32);
-  const size_t u = (size_t)2 * NEST_TO * (P.M + 1) * sizeof(c32);         // U / V tile, row pitch M + 1
+  const int MV = P.fold * P.M;                                            // row length of the tap loop
+  const int n_out = P.fold > 1 ? NEST_R * NEST_RUNS_V : 2 * NEST_TO;      // outputs per tile
+  const size_t ring = (size_t)ring_chunks(P) * CH * MV * sizeof(c32);
+  const size_t u = (size_t)n_out * (MV + 1) * sizeof(c32);                // U / V tile, row pitch MV + 1
   L.ring = take(ring > u ? ring : u, 128);
-  L.taps = take((size_t)2 * CH * P.M * sizeof(float2), 128);
+  L.taps = take((size_t)2 * CH * MV * sizeof(float2), 128);
   L.wb = take((size_t)P.N2 * P.ncol * sizeof(c32), 16);
   L.n2r = take((size_t)P.N2 * sizeof(int), 16);
   L.epart = take((size_t)32 * P.ncol * sizeof(float), 16);
@@ -63,7 +65,8 @@ __global__ void k_nest_prerot(const c32 *__restrict__ x, c32 *__restrict__ xr, l
 
 // MT: the number of branches as a compile-time constant (100 = the benchmark configuration: every shared-memory
 // access of the tap loop then has an immediate offset), or 0 for "read it from the plan"
-template <int N1, int MT>
+// FOLD: 1 = every output or the even ones (P.stride); F >= 2 = every (2 F)-th output through F M virtual branches
+template <int N1, int MT, int FOLD>
 __global__ void __launch_bounds__(2 * NEST_K * 100, 1) k_nest(NestPlan P, NestResume R)
 {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -82,20 +85,24 @@ __global__ void __launch_bounds__(2 * NEST_K * 100, 1) k_nest(NestPlan P, NestRe
   float *epart = reinterpret_cast<float *>(smem + L.epart);
   uint64_t *bar = reinterpret_cast<uint64_t *>(smem + L.bar);          // [0..5] ring slots, [6..7] tap buffers
 
+  constexpr bool FV = FOLD > 1;
   const int M = MT ? MT : P.M, N2 = MT ? MT / N1 : P.N2, ncol = P.ncol;
-  const int tid = threadIdx.x, nthr = blockDim.x;                      // nthr = 2 * NEST_K * M
-  const int r = tid % M, pk = tid / M, p = pk & 1, k = pk >> 1;
+  const int MV = FOLD * M;                                             // row length of the tap loop (virtual branches)
+  const int tid = threadIdx.x, nthr = blockDim.x;                      // nthr = 2 * NEST_K * M, or NEST_RUNS_V * MV
+  const int r = tid % MV, pk = tid / MV, p = pk & 1, k = pk >> 1;
   const int b = tile_index / P.tiles_per_slot, tile = tile_index - b * P.tiles_per_slot;
   const int RING_CHUNKS = ring_chunks(P), AHEAD = live_ahead(P);
-  const bool sub = P.stride == 2;
+  const bool sub = FV || P.stride == 2;
   // stride 1: the tile is 48 outputs of each parity, run (p, k) = 16 outputs i0 + 16 k + o of parity p.
   // stride 2: the tile is 96 consecutive outputs of the even sequence, run g = 2 k + p... = 16 outputs i0 + 16 g + o.
+  // fold F:   the tile is 16 NEST_RUNS_V consecutive outputs of the sub-sampled sequence, run = tid / MV.
   const int run = sub ? pk : k;                                        // run start, in units of 16 steps
-  const int i0 = tile * (sub ? 2 * NEST_TO : NEST_TO);                 // first output index (in its sequence) of the tile
-  const long n_base = (long)b * P.S + P.fns + (long)M * i0;            // sample of ring step 0, branch 0, even sequence
-  const int n_chunks = P.q_rows / CH;                                  // compute chunks
+  constexpr int N_OUT = FV ? NEST_R * NEST_RUNS_V : 2 * NEST_TO;       // outputs per tile
+  const int i0 = tile * (sub ? N_OUT : NEST_TO);                       // first output index (in its sequence) of the tile
+  const long n_base = (long)b * P.S + P.fns + (long)MV * i0;           // sample of ring step 0, branch 0, first sequence
+  const int n_chunks = (FV ? P.q_rows_v : P.q_rows) / CH;              // compute chunks
   const int n_ring = n_chunks + AHEAD;                                 // ring chunks the tile reads
-  const unsigned ring_bytes = (unsigned)(CH * M * sizeof(c32)), tap_bytes = (unsigned)(CH * M * sizeof(float2));
+  const unsigned ring_bytes = (unsigned)(CH * MV * sizeof(c32)), tap_bytes = (unsigned)(CH * MV * sizeof(float2));
 
   if (tid == 0) {
     for (int i = 0; i < RING_MAX + 2; i++) mbar_init(&bar[i], 1);
@@ -105,12 +112,12 @@ __global__ void __launch_bounds__(2 * NEST_K * 100, 1) k_nest(NestPlan P, NestRe
   auto load_ring = [&](int m) {
     uint64_t *bb = &bar[m % RING_CHUNKS];
     mbar_expect_tx(bb, ring_bytes);
-    tma_bulk_g2s(ring + (size_t)(m % RING_CHUNKS) * CH * M, P.xr + n_base + (long)m * CH * M, ring_bytes, bb);
+    tma_bulk_g2s(ring + (size_t)(m % RING_CHUNKS) * CH * MV, P.xr + n_base + (long)m * CH * MV, ring_bytes, bb);
   };
   auto load_taps = [&](int c) {
     uint64_t *bb = &bar[RING_MAX + (c & 1)];
     mbar_expect_tx(bb, tap_bytes);
-    tma_bulk_g2s(taps + (size_t)(c & 1) * CH * M, P.hq2 + (size_t)c * CH * M, tap_bytes, bb);
+    tma_bulk_g2s(taps + (size_t)(c & 1) * CH * MV, P.hq2 + (size_t)c * CH * MV, tap_bytes, bb);
   };
   if (tid == 0) {
     for (int m = 0; m < RING_CHUNKS && m < n_ring; m++) load_ring(m);
@@ -127,21 +134,21 @@ __global__ void __launch_bounds__(2 * NEST_K * 100, 1) k_nest(NestPlan P, NestRe
   u64 acc[NEST_R], H[NEST_R];
 #pragma unroll
   for (int o = 0; o < NEST_R; o++) { acc[o] = 0ull; H[o] = 0ull; }
-  const int ring_samples = RING_CHUNKS * CH * M;
+  const int ring_samples = RING_CHUNKS * CH * MV;
   const u64 *ring64 = reinterpret_cast<const u64 *>(ring);
   for (int c = 0; c < n_chunks; c++) {
     if (c == 0) { for (int m = 0; m < AHEAD && m < n_ring; m++) mbar_wait(&bar[m], 0); }
     if (c + AHEAD < n_ring) mbar_wait(&bar[(c + AHEAD) % RING_CHUNKS], (unsigned)(((c + AHEAD) / RING_CHUNKS) & 1));
     mbar_wait(&bar[RING_MAX + (c & 1)], (unsigned)((c >> 1) & 1));
-    int off = (int)(((long)M * (NEST_R * run + CH * c) + (sub ? 0 : (long)(M / 2) * p) + r) % ring_samples);
-    const u64 *tp = reinterpret_cast<const u64 *>(taps + (size_t)(c & 1) * CH * M + r);
-    if (off + CH * M <= ring_samples) {
+    int off = (int)(((long)MV * (NEST_R * run + CH * c) + (sub ? 0 : (long)(M / 2) * p) + r) % ring_samples);
+    const u64 *tp = reinterpret_cast<const u64 *>(taps + (size_t)(c & 1) * CH * MV + r);
+    if (off + CH * MV <= ring_samples) {
       // the 16 steps do not cross the end of the ring (4 chunks in 5): one base address, immediate offsets
       const u64 *xp = ring64 + off;
 #pragma unroll
       for (int s = 0; s < CH; s++) {
-        const u64 X = xp[s * M];
-        H[s] = tp[s * M];                             // tap q = 16 c + s; H[i] holds the latest tap with q = i (mod 16)
+        const u64 X = xp[s * MV];
+        H[s] = tp[s * MV];                            // tap q = 16 c + s; H[i] holds the latest tap with q = i (mod 16)
 #pragma unroll
         for (int o = 0; o < NEST_R; o++) acc[o] = pk_fma(X, H[(s - o) & (NEST_R - 1)], acc[o]);   // tap q = 16 c + s - o
       }
@@ -149,8 +156,8 @@ __global__ void __launch_bounds__(2 * NEST_K * 100, 1) k_nest(NestPlan P, NestRe
 #pragma unroll
       for (int s = 0; s < CH; s++) {
         const u64 X = ring64[off];
-        off += M; if (off >= ring_samples) off -= ring_samples;
-        H[s] = tp[s * M];
+        off += MV; if (off >= ring_samples) off -= ring_samples;
+        H[s] = tp[s * MV];
 #pragma unroll
         for (int o = 0; o < NEST_R; o++) acc[o] = pk_fma(X, H[(s - o) & (NEST_R - 1)], acc[o]);
       }
@@ -163,7 +170,7 @@ __global__ void __launch_bounds__(2 * NEST_K * 100, 1) k_nest(NestPlan P, NestRe
     }
   }
   // ---- the tile's branch sums to shared memory (the ring is dead): U[out][r], out = p * TO + 16 k + o
-  const int UP = M + 1;
+  const int UP = MV + 1;
   c32 *U = ring;
 #pragma unroll
   for (int o = 0; o < NEST_R; o++)
@@ -172,7 +179,8 @@ __global__ void __launch_bounds__(2 * NEST_K * 100, 1) k_nest(NestPlan P, NestRe
 
   // ---- 2. N1-point DFTs, in place: V[out][k1 * N2 + n2] = sum_n1 U[out][(N2 n1 + N1 n2) mod M] W_N1^{n1 k1}
   {
-    constexpr int ITEMS = 16 / N1;                    // 2 * NEST_TO * N2 items on 8 * N1 * N2 threads
+    constexpr int ITEMS = 16 / (N1 * FOLD);           // N_OUT * N2 items on 6 * N1 * N2 (or NEST_RUNS_V * FOLD * N1 * N2) threads
+    static_assert(ITEMS >= 1 && ITEMS * N1 * FOLD == 16, "fold and N1 must divide 16");
     float vr[ITEMS][N1], vi[ITEMS][N1];
 #pragma unroll
     for (int j = 0; j < ITEMS; j++) {
@@ -180,7 +188,15 @@ __global__ void __launch_bounds__(2 * NEST_K * 100, 1) k_nest(NestPlan P, NestRe
       const int out = it / N2, rho = it - out * N2, n2 = n2r[rho];
       float ur[N1], ui[N1];
 #pragma unroll
-      for (int n1 = 0; n1 < N1; n1++) { const c32 u = U[(size_t)out * UP + (N2 * n1 + N1 * n2) % M]; ur[n1] = u.re; ui[n1] = u.im; }
+      for (int n1 = 0; n1 < N1; n1++) {
+        const c32 *up = U + (size_t)out * UP + (N2 * n1 + N1 * n2) % M;
+        c32 u = up[0];
+        if constexpr (FV) {
+#pragma unroll
+          for (int f = 1; f < FOLD; f++) { const c32 t = up[f * M]; u.re += t.re; u.im += t.im; }    // virtual branches r + M f
+        }
+        ur[n1] = u.re; ui[n1] = u.im;
+      }
       if constexpr (N1 == 1) { vr[j][0] = ur[0]; vi[j][0] = ui[0]; }
       else if constexpr (N1 == 2) {
         vr[j][0] = ur[0] + ur[1]; vi[j][0] = ui[0] + ui[1];
@@ -208,10 +224,11 @@ __global__ void __launch_bounds__(2 * NEST_K * 100, 1) k_nest(NestPlan P, NestRe
   // ---- 3. N2-point DFTs at the channel bins + |Z|^2 over the valid outputs.  item = (og, cg): outputs og + 32 i
   const int n_cg = ncol / NEST_NCOL;
   const int n_par[2] = {(P.n_noise + 1) / 2, P.n_noise / 2};            // outputs of each parity in a slot
-  for (int item = tid; item < 32 * n_cg; item += nthr) {
-    const int og = item & 31, cg = item >> 5;
+  constexpr int OG = FV ? 16 : 32;                    // output groups: a thread takes outputs og + OG i
+  for (int item = tid; item < OG * n_cg; item += nthr) {
+    const int og = item & (OG - 1), cg = item / OG;
     const int col0 = cg * NEST_NCOL, k1 = col0 / P.CPC;
-    constexpr int NI = 2 * NEST_TO / 32;              // outputs per thread
+    constexpr int NI = N_OUT / OG;                    // outputs per thread
     float zr[NI][NEST_NCOL], zi[NI][NEST_NCOL];
 #pragma unroll
     for (int i = 0; i < NI; i++)
@@ -223,7 +240,7 @@ __global__ void __launch_bounds__(2 * NEST_K * 100, 1) k_nest(NestPlan P, NestRe
     for (int n2 = 0; n2 < N2; n2++) {
       c32 v[NI], w[NEST_NCOL];
 #pragma unroll
-      for (int i = 0; i < NI; i++) v[i] = vrow[(size_t)32 * i * UP + n2];
+      for (int i = 0; i < NI; i++) v[i] = vrow[(size_t)OG * i * UP + n2];
 #pragma unroll
       for (int j = 0; j < NEST_NCOL; j++) w[j] = wrow[n2 * ncol + j];
 #pragma unroll
@@ -239,7 +256,7 @@ __global__ void __launch_bounds__(2 * NEST_K * 100, 1) k_nest(NestPlan P, NestRe
     for (int j = 0; j < NEST_NCOL; j++) e[j] = 0.0f;
 #pragma unroll
     for (int i = 0; i < NI; i++) {
-      const int out = og + 32 * i;
+      const int out = og + OG * i;
       float wgt;
       if (sub) {
         const int u = i0 + out;
@@ -257,7 +274,7 @@ __global__ void __launch_bounds__(2 * NEST_K * 100, 1) k_nest(NestPlan P, NestRe
   __syncthreads();
   for (int col = tid; col < ncol; col += nthr) {
     float sum = 0.0f;
-    for (int og = 0; og < 32; og++) sum += epart[og * ncol + col];
+    for (int og = 0; og < OG; og++) sum += epart[og * ncol + col];
     P.E2[(size_t)tile_index * ncol + col] = sum;
   }
 }
@@ -277,19 +294,26 @@ __global__ void k_nest_reduce(NestPlan P, int B)
 
 size_t nest_smem_bytes(const NestPlan &P) { return nest_layout(P).total; }
 
-#define NEST_DISPATCH(CALL) do { if (P.N1 == 4 && P.M == 100) { CALL(4, 100); } else if (P.N1 == 4) { CALL(4, 0); } else if (P.N1 == 2) { CALL(2, 0); } else { CALL(1, 0); } } while (0)
+#define NEST_DISPATCH(CALL) do { \
+    if (P.fold == 2) { if (P.N1 == 4 && P.M == 100) { CALL(4, 100, 2); } else if (P.N1 == 4) { CALL(4, 0, 2); } else if (P.N1 == 2) { CALL(2, 0, 2); } else { CALL(1, 0, 2); } } \
+    else if (P.N1 == 4 && P.M == 100) { CALL(4, 100, 1); } else if (P.N1 == 4) { CALL(4, 0, 1); } else if (P.N1 == 2) { CALL(2, 0, 1); } else { CALL(1, 0, 1); } } while (0)
 
 int nest_setup(const NestPlan &P)
 {
   if (2 * P.D != P.M || P.N1 * P.N2 != P.M || (P.N1 != 1 && P.N1 != 2 && P.N1 != 4)) return -1;
   if (P.M > 100 || P.q_rows % CH != 0 || P.q_rows < P.Q + CH || P.ncol % NEST_NCOL != 0) return -1;
   if (((CH * P.M * sizeof(float2)) & 15) != 0) return -1;                    // TMA bulk copies move multiples of 16 bytes
-  if (P.stride != 1 && !(P.stride == 2 && P.weights && P.n_used > 8)) return -1;
+  if (P.fold != 1 && P.fold != 2) return -1;
+  if (P.fold > 1) {
+    const int MV = P.fold * P.M, Qv = (P.Q * P.M + MV - 1) / MV;
+    if (P.stride != 2 * P.fold || !P.weights || P.n_used <= 8 || P.q_rows_v % CH != 0 || P.q_rows_v < Qv + CH) return -1;
+    if (NEST_RUNS_V * MV > 2 * NEST_K * 100) return -1;                      // the kernel's launch bound
+  } else if (P.stride != 1 && !(P.stride == 2 && P.weights && P.n_used > 8)) return -1;
   if ((((long)P.S * sizeof(c32)) & 15) != 0 || (((long)P.fns * sizeof(c32)) & 15) != 0 || ((NEST_TO * P.M * sizeof(c32)) & 15) != 0)
     return -1;                                                             // ... from 16-byte aligned addresses
   if (nest_smem_bytes(P) > 227 * 1024) return -1;
   cudaError_t e = cudaSuccess;
-#define NEST_OPT(N1_, MT_) e = cudaFuncSetAttribute((const void *)k_nest<N1_, MT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nest_smem_bytes(P))
+#define NEST_OPT(N1_, MT_, F_) e = cudaFuncSetAttribute((const void *)k_nest<N1_, MT_, F_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nest_smem_bytes(P))
   NEST_DISPATCH(NEST_OPT);
 #undef NEST_OPT
   return e == cudaSuccess ? 0 : -1;
@@ -303,7 +327,8 @@ void launch_nest_prerot(const NestPlan &P, const c32 *x, long n_samples, cudaStr
 
 bool nest_can_resume(const NestPlan &P)
 {
-  return 2 * NEST_K * P.M >= NEST_RESUME_BLK && nest_smem_bytes(P) >= mm_smem_bytes(NEST_RESUME_BLK);
+  const int threads = P.fold > 1 ? NEST_RUNS_V * P.fold * P.M : 2 * NEST_K * P.M;
+  return threads >= NEST_RESUME_BLK && nest_smem_bytes(P) >= mm_smem_bytes(NEST_RESUME_BLK);
 }
 
 void launch_nest(const NestPlan &P, int B, cudaStream_t s, const NestResume *resume)
@@ -311,9 +336,9 @@ void launch_nest(const NestPlan &P, int B, cudaStream_t s, const NestResume *res
   NestResume R{};
   if (resume && nest_can_resume(P)) R = *resume;
   const dim3 grid((unsigned)(B * P.tiles_per_slot + R.n_blocks));
-  const int threads = 2 * NEST_K * P.M;
+  const int threads = P.fold > 1 ? NEST_RUNS_V * P.fold * P.M : 2 * NEST_K * P.M;
   const size_t smem = nest_smem_bytes(P);
-#define NEST_RUN(N1_, MT_) k_nest<N1_, MT_><<<grid, threads, smem, s>>>(P, R)
+#define NEST_RUN(N1_, MT_, F_) k_nest<N1_, MT_, F_><<<grid, threads, smem, s>>>(P, R)
   NEST_DISPATCH(NEST_RUN);
 #undef NEST_RUN
   const int n = B * P.nch;

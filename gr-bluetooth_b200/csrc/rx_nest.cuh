@@ -10,6 +10,7 @@ constexpr int NEST_R = 16;           // outputs a thread slides through the taps
 constexpr int NEST_K = 3;            // runs per parity per tile
 constexpr int NEST_TO = NEST_R * NEST_K;   // outputs per parity per tile
 constexpr int NEST_NCOL = 5;         // channels per thread in the DFT stage
+constexpr int NEST_RUNS_V = 3;       // fold >= 2: runs of 16 outputs per tile (threads = NEST_RUNS_V * fold * M)
 
 struct NestPlan {
   int M = 0, D = 0, Q = 0, q_rows = 0;   // branches, decimation (2 D = M), taps per branch, rows of hq (multiple of 16)
@@ -24,8 +25,16 @@ struct NestPlan {
   // closing 0.3125) to ~1e-4 relative -- measured <= 3.3e-4 with 25 dB bursts in half of the neighbouring channels,
   // 6e-5 at the benchmark's traffic.  Half the multiply-adds.
   int stride = 1;
-  int n_used = 0;                    // stride 2: outputs of the even sequence that carry weight (n_noise / 2 + 1)
-  const float *weights = nullptr;    // stride 2: [n_used]
+  int n_used = 0;                    // stride >= 2: outputs of the sub-sampled sequence that carry weight
+  const float *weights = nullptr;    // stride >= 2: [n_used]
+  // fold F >= 2: every (2 F)-th output only (stride = 2 F; |y|^2 lives within +-90 kHz, the sub-sampled sequence still
+  // runs at 2 Msps / (2 F)), weights from nest_quadrature() (plan.hpp: least squares over the band, end corrections
+  // included).  Outputs F M samples apart are one tap apart in a bank of MV = F M "virtual" branches with
+  // ceil(Nn / MV) taps each -- the SAME flat tap array h'[k] and the SAME contiguous input range read with row length
+  // MV -- so the tap loop is the one of the even-output mode with M -> MV; the F virtual branches r + M f of a real
+  // branch r are added up on the way into the N1-point DFTs.  1/F of the multiply-adds of the even-output mode.
+  int fold = 1;
+  int q_rows_v = 0;                  // fold >= 2: rows of the tap array read with row length fold * M (multiple of 16, >= ceil(Nn / MV) + 16)
   const float2 *hq2 = nullptr;       // [q_rows][M]  (h, h) with h = h'[r + M q], zero padded: operands of the packed FMAs
   const int *n2_of_rho = nullptr;    // [N2]
   const c32 *WB = nullptr;           // [N2][ncol]

@@ -195,4 +195,15 @@ int emul_pfb(double fs, double fc, int extra, const float *xf, long n_x, int n_g
   return 0;
 }
 
+// quadrature weights of the sub-sampled off-channel energy sum (plan.cpp: nest_quadrature); w: room for (N-1)/s+1+n_extra floats
+double emul_nest_quadrature(int N, int s, int n_extra, int n_free, double omega_max, float *w, int32_t *n_used)
+{
+  std::vector<float> v;
+  const double res = nest_quadrature(N, s, n_extra, n_free, omega_max, v);
+  if (res < 0) return res;
+  *n_used = (int32_t)v.size();
+  std::memcpy(w, v.data(), v.size() * sizeof(float));
+  return res;
+}
+
 }  // extern "C"

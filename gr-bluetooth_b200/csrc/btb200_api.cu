@@ -359,6 +359,12 @@ int setup_pfb(btb200_ctx *ctx)
   const size_t B = ctx->max_slots;
   const size_t Gtot = (B - 1) * (size_t)P.grid_per_slot + P.n_ddc;
   if ((rc = dev_alloc(ctx, &K.dem, Gtot * P.nch))) return rc;
+  if (!std::getenv("BTB200_NO_DEMC")) {
+    // channel-major copy for the resume of the clock-recovery chains (rx_mm.cuh, CM); rows padded so that the
+    // 16-byte groups around a window's ends stay inside the allocation
+    K.pitchC = (long)((Gtot + 3) / 4 * 4 + 8);
+    if ((rc = dev_alloc(ctx, &K.demC, (size_t)K.pitchC * P.nch))) return rc;
+  }
   if ((rc = dev_alloc(ctx, &K.E, (size_t)pfb_tiles(K, (int)B) * K.ncol * 2))) return rc;
   if ((rc = dev_alloc(ctx, &ctx->d_eon_all, B * P.nch))) return rc;
   CK(cudaMallocHost(&ctx->h_eon_all, B * P.nch * sizeof(double)));
@@ -873,6 +879,7 @@ static int submit_impl(btb200_ctx *ctx, const void *iq, int kind, size_t n_sampl
     const bool fused = G.early && fuse_resume && tail_inline && ctx->use_nest && nest_can_resume(ctx->NP);
     if (fused) {
       nr.G = G; nr.W = W; nr.mmse = ctx->T.mmse; nr.demT = ctx->d_dem; nr.save = W.mm_save;
+      nr.demC = ctx->PF.demC; nr.pitchC = ctx->PF.pitchC;
       nr.n_blocks = (int)((nbc + NEST_RESUME_BLK - 1) / NEST_RESUME_BLK);
     } else if (G.early) {
       if (!tail_inline) CK(cudaStreamWaitEvent(s2, ctx->ev[4], 0));

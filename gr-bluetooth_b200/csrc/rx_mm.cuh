@@ -13,6 +13,11 @@ __device__ __forceinline__ void mm_cp_async4(void *smem_dst, const void *gsrc)
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(gsrc));
 }
+__device__ __forceinline__ void mm_cp_async16(void *smem_dst, const void *gsrc)
+{
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc));
+}
 __device__ __forceinline__ void mm_cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 __device__ __forceinline__ void mm_cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 __device__ __forceinline__ void mm_cp_async_wait_prev() { asm volatile("cp.async.wait_group 1;\n" ::: "memory"); }
@@ -26,11 +31,12 @@ __device__ __forceinline__ float mm_lds(unsigned addr)
   return v;
 }
 // the 8-tap interpolation of one step, ascending order, one rounding per operation
-template <int BLK, int K = 0>
+// RS = bytes between consecutive samples of a chain in the ring
+template <int RS, int K = 0>
 __device__ __forceinline__ float mm_interp8(unsigned ra, unsigned ma, float acc)
 {
   if constexpr (K == 8) return acc;
-  else return mm_interp8<BLK, K + 1>(ra, ma, acc + mm_lds<K * BLK * 4>(ra) * mm_lds<K * 132 * 4>(ma));
+  else return mm_interp8<RS, K + 1>(ra, ma, acc + mm_lds<K * RS>(ra) * mm_lds<K * 132 * 4>(ma));
 }
 
 struct MmSave { float mu, omega, last; unsigned ii; int oo; uint32_t word; };
@@ -38,7 +44,8 @@ struct MmSave { float mu, omega, last; unsigned ii; int oo; uint32_t word; };
 // when the next one is issued, so 128 rows never overwrite a live sample
 constexpr int MM_RD = 128;
 constexpr int MM_MAXADV = 5;         // |demod| <= gain * pi bounds the timing error term: at most 5 samples per symbol
-constexpr size_t mm_smem_bytes(int blk) { return sizeof(float) * (MM_RD + 8) * blk + sizeof(float) * 8 * 132; }
+constexpr int MM_PC = MM_RD + 12;   // channel-major source: floats per chain in the ring (8 mirrored rows + pad, 16-byte multiple)
+constexpr size_t mm_smem_bytes(int blk) { return sizeof(float) * MM_PC * blk + sizeof(float) * 8 * 132; }
 
 // mode 0: every window from the constructor state to the end (reference loop).
 // mode 1 (lazy tail, first pass): every window, stop at G.sym_target symbols, demod floats exist for i < G.ne_dem
@@ -46,10 +53,21 @@ constexpr size_t mm_smem_bytes(int blk) { return sizeof(float) * (MM_RD + 8) * b
 // mode 2 (lazy tail, resume): LISTED windows continue from the saved state to the end.
 // The whole block calls this (the interpolator table is staged by all threads); threads >= BLK leave after that.
 // block = index of this group of BLK windows; mm_smem = mm_smem_bytes(BLK) bytes of shared memory.
-template <int BLK>
+//
+// CM (mode 2 in the throughput mode): the demod floats come from the CHANNEL-MAJOR copy demC[c * pitchC + grid row]
+// the channelizer writes next to the row-major one.  The listed windows are scattered over slots and channels, so
+// from the row-major grid every sample of every chain is its own 32-byte sector and its own 4-byte copy (one
+// load/store-unit pass per lane: 830 MB of sectors per 2 300 windows, and the unit the chains' own shared-memory
+// loads queue behind); from the channel-major copy a lane fetches 16 bytes = 4 consecutive samples of its window
+// per copy and uses every byte of every sector.  A copy lands as 16 contiguous bytes, so the ring is chain-major,
+// [chain][MM_PC] (rows are bank-conflicted 4-way between lanes, which two warps per SM do not notice); rows are
+// counted from the 16-byte boundary at or below the window's first grid row (`sh` rows earlier), the same for the
+// whole warp, so the copies are aligned for every lane.
+template <int BLK, bool CM = false>
 __device__ __forceinline__ void mm_stateless_block(const Geom &G, const DevBatch &W, const float *__restrict__ mmse_g,
                                                    const float *__restrict__ demT, int mode, MmSave *__restrict__ save,
-                                                   const int4 *__restrict__ list, int n_list, unsigned char *mm_smem, int block)
+                                                   const int4 *__restrict__ list, int n_list, unsigned char *mm_smem, int block,
+                                                   const float *__restrict__ demC = nullptr, long pitchC = 0)
 {
   static_assert(BLK % 32 == 0, "whole warps");
   constexpr int RD = MM_RD;        // ring depth (demod samples per window)
@@ -66,7 +84,9 @@ __device__ __forceinline__ void mm_stateless_block(const Geom &G, const DevBatch
   // samples over a window).  Two copy groups may be in flight.  Rows 0..7 are mirrored at RD..RD+7 so the 8 samples
   // of an interpolation are always 8 consecutive rows: one base address, immediate offsets.
   float (*ring)[BLK] = reinterpret_cast<float (*)[BLK]>(mm_smem);                        // [RD + 8][BLK]
-  float (*s_mmse)[132] = reinterpret_cast<float (*)[132]>(mm_smem + sizeof(float) * (RD + 8) * BLK);   // [8][132]
+  float *ringc = reinterpret_cast<float *>(mm_smem);                                     // CM: [BLK][MM_PC]
+  constexpr int PC = MM_PC;
+  float (*s_mmse)[132] = reinterpret_cast<float (*)[132]>(mm_smem + sizeof(float) * (CM ? PC : RD + 8) * BLK);   // [8][132]
   for (int i = threadIdx.x; i < 129 * 8; i += blockDim.x) s_mmse[7 - (i & 7)][i >> 3] = mmse_g[i];   // [k][imu] = taps[imu][7-k]
   if (threadIdx.x == 0) s_mmse[0][129] = __int_as_float((int)(0x4B400000u << 2));                    // spare column: see mmse_biased
   __syncthreads();
@@ -83,7 +103,10 @@ __device__ __forceinline__ void mm_stateless_block(const Geom &G, const DevBatch
   }
   if (!live) idx = 0;
   const int b = idx / G.nch, c = idx - b * G.nch;
-  const float *gp = demT + ((long)b * G.dem_rows) * G.nch + c;     // sample 0 of the window
+  // CM: rows count from the 16-byte boundary at or below the window's first grid row; gp is row 0 of that numbering
+  const int sh = CM ? (int)(((long)b * G.dem_rows) & 3) : 0;
+  const float *gp = CM ? demC + (long)c * pitchC + ((long)b * G.dem_rows - sh)
+                       : demT + ((long)b * G.dem_rows) * G.nch + c;     // sample 0 of the window
   uint32_t *__restrict__ bits_row = W.bits + (long)idx * G.bw;
   float *soft_row = W.soft ? W.soft + (long)idx * G.n_dem_pad : nullptr;
   MmState st{G.mu0, G.mm.omega_mid, 0.0f};
@@ -95,12 +118,14 @@ __device__ __forceinline__ void mm_stateless_block(const Geom &G, const DevBatch
     st = MmState{sv.mu, sv.omega, sv.last};
     ii = sv.ii; oo = sv.oo; word = sv.word;
   }
-  const int avail = (mode == 1) ? G.ne_dem : G.n_dem;            // demod floats that exist
+  ii += (unsigned)sh;                                            // CM: ii, ni and avail live in the shifted row numbering
+  // demod floats that exist (CM: the warp copies whole 16-byte groups, up to the group that holds the last row of any lane)
+  const int avail = CM ? ((G.n_dem + 3 + 3) & ~3) : (mode == 1) ? G.ne_dem : G.n_dem;
   const int oo_end = (mode == 1) ? G.sym_target : G.n_dem;
-  const unsigned ni = (unsigned)((mode == 1 ? G.ne_dem : G.n_dem) - 8);
+  const unsigned ni = (unsigned)((mode == 1 ? G.ne_dem : G.n_dem) - 8 + sh);
   const int tid = threadIdx.x;
   const int nch = G.nch;
-  const unsigned ring_tid = (unsigned)__cvta_generic_to_shared(&ring[0][tid]);
+  const unsigned ring_tid = CM ? (unsigned)__cvta_generic_to_shared(&ringc[tid * PC]) : (unsigned)__cvta_generic_to_shared(&ring[0][tid]);
   // table address biased by the exponent bits of the magic constant: entry imu is at mmse_biased + 4 bits(1.5 2^23 + imu)
   // (the bias is read back from shared memory so that ptxas cannot split it off again as an add per load)
   const unsigned mmse_biased = (unsigned)__cvta_generic_to_shared(&s_mmse[0][0]) - (unsigned)__float_as_int(s_mmse[0][129]);
@@ -109,13 +134,23 @@ __device__ __forceinline__ void mm_stateless_block(const Geom &G, const DevBatch
   // rows [pf - RD, pf) are in (or on their way to) the ring; pf is the same for the 32 chains of the warp
   int pf = (int)__reduce_min_sync(FULL, done ? 0x7fffffffu : ii);
   if (pf != 0x7fffffff) {
-    gp += (long)pf * nch;
+    if constexpr (CM) pf &= ~3; else gp += (long)pf * nch;
     auto refill = [&](int want) {
-      for (; pf < want; pf++, gp += nch) {
-        const int rr = pf & (RD - 1);
-        if (live) {
-          mm_cp_async4(&ring[rr][tid], gp);
-          if (rr < 8) mm_cp_async4(&ring[rr + RD][tid], gp);
+      if constexpr (CM) {
+        for (; pf < want; pf += 4) {                          // pf and want are multiples of 4
+          const int rr = pf & (RD - 1);
+          if (live) {
+            mm_cp_async16(&ringc[tid * PC + rr], gp + pf);
+            if (rr < 8) mm_cp_async16(&ringc[tid * PC + RD + rr], gp + pf);
+          }
+        }
+      } else {
+        for (; pf < want; pf++, gp += nch) {
+          const int rr = pf & (RD - 1);
+          if (live) {
+            mm_cp_async4(&ring[rr][tid], gp);
+            if (rr < 8) mm_cp_async4(&ring[rr + RD][tid], gp);
+          }
         }
       }
       mm_cp_async_commit();
@@ -124,7 +159,7 @@ __device__ __forceinline__ void mm_stateless_block(const Geom &G, const DevBatch
       int want = pf + RD; if (want > avail) want = avail;
       refill(want);
       mm_cp_async_wait_all();
-      if (G.dem_grid && live && ii == 0) ring[0][tid] = 0.0f;      // demod_out[0] of a window is never written by the reference
+      if (!CM && G.dem_grid && live && ii == 0) ring[0][tid] = 0.0f;   // demod_out[0] of a window is never written by the reference
     }
     // reach_prev = first row NOT covered by the copies issued before the most recent group (landed after wait_group 1)
     int reach_prev = pf, reach_last = pf;
@@ -136,7 +171,7 @@ __device__ __forceinline__ void mm_stateless_block(const Geom &G, const DevBatch
       else mm_cp_async_wait_prev();
       const int landed = reach_prev;
       {
-        int want = ii_min + RD; if (want > avail) want = avail;      // rows from ii_min on stay
+        int want = (CM ? (ii_min & ~3) : ii_min) + RD; if (want > avail) want = avail;      // rows from ii_min on stay
         refill(want);
         reach_prev = reach_last;
         reach_last = pf;
@@ -155,8 +190,10 @@ __device__ __forceinline__ void mm_stateless_block(const Geom &G, const DevBatch
         // step-by-step loop below from the saved state.
         const MmState st0 = st;
         const unsigned ii0 = ii;
-        constexpr int SH = (BLK == 32 ? 7 : BLK == 64 ? 8 : BLK == 128 ? 9 : BLK == 256 ? 10 : -1);
+        // byte address of a chain's row = ring_tid + (row << SH): rows are BLK floats apart, or 1 float (CM)
+        constexpr int SH = CM ? 2 : (BLK == 32 ? 7 : BLK == 64 ? 8 : BLK == 128 ? 9 : BLK == 256 ? 10 : -1);
         static_assert(SH > 0, "BLK must be 32, 64, 128 or 256");
+        constexpr int RS = CM ? 4 : BLK * 4;
         constexpr unsigned RMASK = (unsigned)(RD - 1) << SH;
         unsigned iiw = ii << SH;
         unsigned tb = umin((unsigned)__float_as_int(__fmaf_rn(st.mu, 128.0f, 12582912.0f)), 0x4B400080u);
@@ -166,7 +203,7 @@ __device__ __forceinline__ void mm_stateless_block(const Geom &G, const DevBatch
         for (int t = 0; t < PERIOD; t++) {
           const unsigned ma = mmse_biased + (tb << 2);
           const unsigned ra = ring_tid + (iiw & RMASK);
-          const float out = mm_interp8<BLK>(ra, ma, 0.0f);
+          const float out = mm_interp8<RS>(ra, ma, 0.0f);
           if (soft_row) soft_row[oo + t] = out;
           const bool neg = out < 0;
           if (!neg) byte |= 1u << t;
@@ -201,11 +238,11 @@ __device__ __forceinline__ void mm_stateless_block(const Geom &G, const DevBatch
         // units place and leaves the integer in the mantissa (= __float2int_rn)
         int imu = __float_as_int(__fadd_rn(st.mu * 128.0f, 12582912.0f)) - 0x4B400000;
         imu = imu < 0 ? 0 : (imu > 128 ? 128 : imu);
-        const float *rp = &ring[ii & (RD - 1)][tid];
+        const float *rp = CM ? &ringc[tid * PC + (ii & (RD - 1))] : &ring[ii & (RD - 1)][tid];
         const float *mp = &s_mmse[0][imu];
         float out = 0.0f;
 #pragma unroll
-        for (int k = 0; k < 8; k++) out = out + rp[k * BLK] * mp[k * 132];
+        for (int k = 0; k < 8; k++) out = out + rp[k * (CM ? 1 : BLK)] * mp[k * 132];
         if (soft_row) soft_row[oo] = out;
         if (!(out < 0)) word |= 1u << (oo & 31);
         if ((oo & 31) == 31) { bits_row[oo >> 5] = word; word = 0; }

@@ -72,8 +72,12 @@ __global__ void __launch_bounds__(2 * NEST_K * 100, 1) k_nest(NestPlan P, NestRe
   extern __shared__ __align__(128) unsigned char smem[];
   if ((int)blockIdx.x < R.n_blocks) {
     // the first blocks resume clock-recovery chains instead (one block per SM: the chains get the SM to themselves)
-    mm_stateless_block<NEST_RESUME_BLK>(R.G, R.W, R.mmse, R.demT, 2, reinterpret_cast<MmSave *>(R.save), R.W.tail.list, -1,
-                                        smem, (int)blockIdx.x);
+    if (R.demC)
+      mm_stateless_block<NEST_RESUME_BLK, true>(R.G, R.W, R.mmse, R.demT, 2, reinterpret_cast<MmSave *>(R.save), R.W.tail.list, -1,
+                                                smem, (int)blockIdx.x, R.demC, R.pitchC);
+    else
+      mm_stateless_block<NEST_RESUME_BLK>(R.G, R.W, R.mmse, R.demT, 2, reinterpret_cast<MmSave *>(R.save), R.W.tail.list, -1,
+                                          smem, (int)blockIdx.x);
     return;
   }
   const int tile_index = (int)blockIdx.x - R.n_blocks;

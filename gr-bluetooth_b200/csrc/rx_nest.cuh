@@ -55,6 +55,8 @@ struct NestResume {
   DevBatch W;
   const float *mmse = nullptr;
   const float *demT = nullptr;
+  const float *demC = nullptr;       // channel-major copy of the demod floats (rx_pfb.cuh), or null: read demT
+  long pitchC = 0;
   void *save = nullptr;
   int n_blocks = 0;                  // blocks of NEST_RESUME_BLK windows: enough for every window of the batch
 };

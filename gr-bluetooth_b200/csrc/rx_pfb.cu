@@ -53,7 +53,9 @@ __host__ __device__ inline PfbSmem pfb_layout(const PfbPlan &P)
   auto take = [&o](size_t bytes, size_t align) { o = (o + align - 1) / align * align; const size_t r = o; o += bytes; return r; };
   const int ZP = P.ncol | 1;
   const size_t vbytes = (size_t)P.N1 * P.N2 * VP * sizeof(c32), zbytes = (size_t)PFB_TT * ZP * sizeof(c32);
-  L.xs = take((size_t)P.span * sizeof(c32), 128);
+  // the staged input span; the epilogue reuses it for the demod tile of the channel-major copy ([ncol][TT + 1] floats)
+  const size_t xbytes = (size_t)P.span * sizeof(c32), dbytes = (size_t)P.ncol * (PFB_TT + 1) * sizeof(float);
+  L.xs = take(xbytes > dbytes ? xbytes : dbytes, 128);
   L.v = take(vbytes > zbytes ? vbytes : zbytes, 16);
   // the tables sit in shared memory exactly as in the global blob (pfb_pack_tables): one bulk copy fetches them
   L.tab = take(0, 128);
@@ -248,12 +250,14 @@ __global__ void __launch_bounds__(PFB_THREADS, 2) k_pfb(PfbPlan P, const c32 *__
   // rows t = 1 + rg, 1 + rg + RG, ...; the |Z|^2 of its rows ride along and are reduced across the row groups.
   {
     const int RG = PFB_THREADS / ncol;                   // row groups (3 for 80 columns)
+    constexpr int DTP = PFB_TT + 1;                      // pitch of the demod tile (channel-major copy)
     const int col = tid % ncol, rg = tid / ncol;
     float sa = 0.0f, sb = 0.0f;
     if (rg < RG) {
       const int ch = cch[col];
       const c32 k = kaps[col];
       float *drow = P.dem + (gs + 1 + rg) * (long)P.nch + ch;
+      float *dt = reinterpret_cast<float *>(xs) + col * DTP;   // the staged input is dead: demod tile [col][t], odd pitch
       for (int t = 1 + rg; t <= n_own; t += RG, drow += (long)RG * P.nch) {
         const c32 z1 = zs[t * ZP + col], z0 = zs[(t - 1) * ZP + col];
         const float m = z1.re * z1.re + z1.im * z1.im;
@@ -262,11 +266,24 @@ __global__ void __launch_bounds__(PFB_THREADS, 2) k_pfb(PfbPlan P, const c32 *__
         if (ch >= 0) {
           const float pr = z1.re * z0.re + z1.im * z0.im, pi = z1.im * z0.re - z1.re * z0.im;    // z1 conj(z0)
           const float qr = pr * k.re - pi * k.im, qi = pr * k.im + pi * k.re;
-          *drow = P.gain * atan2_tab(atans, qi, qr);
+          const float d = P.gain * atan2_tab(atans, qi, qr);
+          *drow = d;
+          if (P.demC) dt[t] = d;
         }
       }
     }
     __syncthreads();                                     // the Z tile is dead: its first rows carry the partial sums
+    if (P.demC) {
+      // channel-major copy: a warp writes the tile's run of each of its channels (lanes = consecutive grid points)
+      const int lane = tid & 31;
+      for (int cl = tid >> 5; cl < ncol; cl += PFB_THREADS / 32) {
+        const int ch = cch[cl];
+        if (ch < 0) continue;
+        const float *dt = reinterpret_cast<const float *>(xs) + cl * DTP;
+        float *crow = P.demC + (long)ch * P.pitchC + gs;
+        for (int t = 1 + lane; t <= n_own; t += 32) crow[t] = dt[t];
+      }
+    }
     float *part = reinterpret_cast<float *>(zs);
     if (rg < RG) { part[(rg * ncol + col) * 2] = sa; part[(rg * ncol + col) * 2 + 1] = sb; }
     __syncthreads();

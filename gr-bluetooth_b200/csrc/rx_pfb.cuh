@@ -28,6 +28,10 @@ struct PfbPlan {
   // outputs
   float *dem = nullptr;            // [Gtot][nch]  demod floats on the global decimation grid
   float *E = nullptr;              // [segments * tps][ncol][2]  per-tile sums of |Z|^2 (all points / points below rem)
+  // optional channel-major copy of the demod floats, demC[c * pitchC + g]: what the resume of the clock-recovery
+  // chains of the windows with hits reads (rx_mm.cuh, CM) -- a window is a contiguous run of its channel's row there
+  float *demC = nullptr;
+  long pitchC = 0;                 // floats per channel row (multiple of 4, >= Gtot + 8)
 };
 
 size_t pfb_smem_bytes(const PfbPlan &P);

@@ -249,6 +249,48 @@ def test_synthetic_wideband_equals_oracle(fs, fc, nslots, squelch):
     blk.close()
 
 
+def test_benchmark_batch_spot_check_equals_oracle():
+    """The BENCHMARKED geometry (100 Msps, 79 channels, one batch of 512 slots = 32 M samples, bench.py's own synthetic
+    stream) against the oracle on windows sampled from the start, the middle and the end of the batch: exact mode bit
+    for bit (hit records with the f64 snr, symbols), throughput mode on the set of detected packets."""
+    from gr_bluetooth_b200 import synth
+    fs, fc, B, first = 100e6, 2441e6, 512, 7
+    xi, truth = synth.generate_range(fs, fc, 0, B + first, seed=1234, occupancy=0.05, as_int16=True)
+    iq = xi.astype(np.float32).view(np.complex64)
+    P = O.Plan(fs, fc)
+    S, H = P.S, P.H
+    w0 = first * S - (H - 1)
+    seg = iq[w0:w0 + (B - 1) * S + H]
+    spots = [first, first + 1, first + 255, first + 256, first + B - 2, first + B - 1]
+    want, bits = [], {}
+    for s0 in spots[::2]:
+        o = P.run(iq, first_call=s0, num_calls=2, stateless=True, threads=8, want_bits=True)
+        want += oracle_hit_tuples(o["hits"])
+        for h in o["hits"]:
+            bits[(int(h["slot"]), int(h["channel"]), int(h["offset"]))] = o["bits"][int(h["slot"]) - s0, int(h["channel"]) - P.ch_lo]
+    assert len(want) >= 10
+    blk = g.multi_sniffer(fs, fc, 10.0, mm_mode=g.MM_STATELESS, max_slots=B)
+    hits, syms, ovf = blk.process(seg, first, B, want_symbols=True)
+    blk.close()
+    assert ovf == 0
+    sel = np.isin(hits["slot"], spots)
+    assert gpu_hit_tuples(hits[sel]) == want
+    for h in hits[sel]:
+        off, cnt = int(h["offset"]), int(h["sym_count"])
+        row = bits[(int(h["slot"]), int(h["channel"]), off)]
+        assert cnt == max(0, min(int(h["n_symbols"]), 3125))
+        assert np.array_equal(syms[int(h["sym_offset"]):int(h["sym_offset"]) + cnt], row[off:off + cnt])
+    # throughput mode, same batch: the packets found in the sampled windows
+    blk = g.multi_sniffer(fs, fc, 10.0, mm_mode=g.MM_STATELESS, max_slots=B, ddc=g.DDC_POLYPHASE)
+    ph, _, ovf = blk.process_i16(xi[2 * w0:2 * (w0 + (B - 1) * S + H)], first, B, want_symbols=True)
+    blk.close()
+    key = lambda rows: {(int(h[0]), int(h[1]), int(h[2]), int(h[5]) if h[2] == 0 else 0) for h in rows}
+    a = key(gpu_hit_tuples(ph[np.isin(ph["slot"], spots)]))
+    b = key(want)
+    assert ovf == 0 and len(a & b) >= 0.9 * len(a | b), (sorted(a ^ b))
+    assert {k for k in a if k[2] == 0} == {k for k in b if k[2] == 0}
+
+
 def test_edge_inputs():
     blk = g.multi_sniffer(2e6, 2476e6, 10.0, mm_mode=g.MM_STATELESS, max_slots=4, squelch=g.SQUELCH_EAGER)
     H, S = blk.history(), blk.samples_per_slot

@@ -256,3 +256,75 @@ def test_window_mask_selects_channel_windows():
         again, _, _ = blk.process(x, 0, n)          # the mask was consumed
         assert len(again) == len(full)
         blk.close()
+
+
+def _with_env(env, fn):
+    import os
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        return fn()
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+@pytest.mark.parametrize("fs,fc", [(100e6, 2441e6), (30e6, 2414e6)])
+def test_noise_estimator_subsampled_sums_agree(fs, fc):
+    """rx_nest.cu evaluates every output of the noise DDCs (BTB200_NEST_FOLD=0), the even ones with Euler-Maclaurin end
+    weights (1) or every 4th one through 2 M virtual branches with least-squares weights (2, the default): the window
+    sums of |y|^2 agree to fp32 rounding (< 1e-4 relative; the mode's snr tolerance is 5e-3 dB = 1.2e-3), on traffic
+    with strong bursts in a third of the channel-slots, and the hit lists are the same."""
+    from gr_bluetooth_b200 import synth
+    nslots, first = 13, 7
+    iq, _ = synth.generate(fs, fc, nslots, seed=21, occupancy=0.3, snr_db=25.0)
+    P = O.Plan(fs, fc)
+    B = nslots - first
+    w0 = first * P.S - (P.H - 1)
+    seg = iq[w0:w0 + (B - 1) * P.S + P.H]
+
+    def run():
+        blk = poly_block(fs, fc, B, keep_stages=True)
+        hits, syms, ovf = blk.process(seg, first, B, want_symbols=True)
+        z = np.array([[blk.stage("noise", j, chi)[0] for chi in range(P.nch)] for j in range(B)])
+        blk.close()
+        return hits, syms, z
+
+    h0, s0, z0 = _with_env({"BTB200_NEST_FOLD": "0"}, run)
+    h1, s1, z1 = _with_env({"BTB200_NEST_FOLD": "1"}, run)
+    h2, s2, z2 = _with_env({"BTB200_NEST_FOLD": "2"}, run)
+    d1, d2 = np.abs(z1 / z0 - 1), np.abs(z2 / z0 - 1)
+    print("%g Msps: even outputs vs all: median %.1e max %.1e; every 4th vs all: median %.1e max %.1e"
+          % (fs / 1e6, np.median(d1), d1.max(), np.median(d2), d2.max()))
+    assert d1.max() < 1e-4 and d2.max() < 1e-4
+    key = lambda h: [(int(x["slot"]), int(x["channel"]), int(x["kind"]), int(x["lap"]), int(x["offset"])) for x in h]
+    assert key(h0) == key(h1) == key(h2) and len(h0) > 0
+    assert np.array_equal(s0, s2)
+
+
+def test_resume_from_channel_major_copy_equals_row_major():
+    """The resume of the clock-recovery chains reads the channel-major copy of the demod floats (16-byte copies, rx_mm.cuh
+    CM); same floats, same loop: hits and symbols equal the run without the copy (BTB200_NO_DEMC=1) and the full tail."""
+    from gr_bluetooth_b200 import synth
+    fs, fc, nslots, first = 100e6, 2441e6, 16, 7
+    iq, _ = synth.generate(fs, fc, nslots, seed=31, occupancy=0.15, snr_db=20.0)
+    P = O.Plan(fs, fc)
+    B = nslots - first
+    w0 = first * P.S - (P.H - 1)
+    seg = iq[w0:w0 + (B - 1) * P.S + P.H]
+
+    def run(**kw):
+        blk = poly_block(fs, fc, B, **kw)
+        out = blk.process(seg, first, B, want_symbols=True)
+        blk.close()
+        return out
+
+    ha, sa, _ = run()
+    hb, sb, _ = _with_env({"BTB200_NO_DEMC": "1"}, run)
+    hc, sc, _ = run(tail=g.TAIL_FULL) if hasattr(g, "TAIL_FULL") else (ha, sa, 0)
+    assert len(ha) > 20
+    assert np.array_equal(ha, hb) and np.array_equal(sa, sb)
+    assert np.array_equal(ha, hc) and np.array_equal(sa, sc)

@@ -105,3 +105,55 @@ def test_polyphase_equals_direct_form(emul, name, geom):
     for dd in (dm, dp):
         assert np.median(dd) < tol_med, np.median(dd)
         assert np.quantile(dd, 0.999) < tol_999, np.quantile(dd, 0.999)
+
+
+def exact_noise_energies(P, iq, b, n_out):
+    """|y_j|^2, j < n_out, of window b's noise DDCs (lib/multi_block.cc:253-287) for every channel, float64 (FFT convolution
+    with the oracle's prototype; the DDC's unit-modulus rotator does not change |y|)."""
+    h = np.asarray(P.noise_proto(), np.float64)[::-1]
+    Nn, D = len(h), P.D
+    L = (n_out - 1) * D + Nn
+    n0 = b * P.S + P.fns
+    seg = iq[n0:n0 + L].astype(np.complex128)
+    F = 1 << int(np.ceil(np.log2(L + Nn)))
+    Hf = np.fft.fft(h, F)
+    n = np.arange(L)
+    g = np.empty((P.nch, n_out))
+    for c in range(P.nch):
+        f = 2402e6 + (P.ch_lo + c) * 1e6 + 790e3 - P.fc
+        y = np.fft.ifft(np.fft.fft(seg * np.exp(-2j * np.pi * f / P.fs * n), F) * Hf)[Nn - 1:Nn - 1 + n_out * D:D]
+        g[c] = np.abs(y) ** 2
+    return g
+
+
+@pytest.mark.parametrize("s,n_extra,n_free,khz", [(4, 2, 12, 90.0), (2, 2, 8, 90.0)])
+def test_subsampled_noise_energy_quadrature(emul, s, n_extra, n_free, khz):
+    """The estimator of the throughput mode sums |y|^2 over every s-th noise-DDC output with the weights of
+    nest_quadrature() (plan.cpp).  With exact |y_j|^2 (float64, the oracle's prototype) of the benchmark's synthetic
+    traffic -- light and with 25 dB bursts in half of all channel-slots -- the weighted sub-sampled sum reproduces the
+    reference's sum over all 850 outputs to < 2e-5 relative (the mode's tolerance on the snr is 5e-3 dB = 1.2e-3);
+    what the kernel adds on top is fp32 rounding."""
+    from gr_bluetooth_b200 import synth
+    fs, fc = 100e6, 2441e6
+    P = O.Plan(fs, fc)
+    N = P.n_noise
+    emul.emul_nest_quadrature.restype = C.c_double
+    emul.emul_nest_quadrature.argtypes = [C.c_int] * 4 + [C.c_double, C.c_void_p, C.c_void_p]
+    w = np.zeros(N, np.float32)
+    n_used = C.c_int32(0)
+    omega = 2 * np.pi * khz * 1e3 * P.D / fs
+    res = emul.emul_nest_quadrature(N, s, n_extra, n_free, omega, w.ctypes.data, C.byref(n_used))
+    n = n_used.value
+    assert n == (N - 1) // s + 1 + n_extra and 0 <= res < 1e-3
+    w = w[:n].astype(np.float64)
+    assert np.all(w[n_free:n - n_free] == s) and abs(w.sum() - N) < 1e-3       # exact for a constant
+    worst = 0.0
+    for occ, snr, seed in ((0.05, 17.0, 5), (0.5, 25.0, 6)):
+        iq, _ = synth.generate(fs, fc, 4, seed=seed, occupancy=occ, snr_db=snr)
+        for b in (0, 1):
+            g = exact_noise_energies(P, iq, b, s * n)
+            ref = g[:, :N].sum(axis=1)
+            est = (g[:, ::s][:, :n] * w[None, :]).sum(axis=1)
+            worst = max(worst, float(np.max(np.abs(est / ref - 1))))
+    print("stride %d: worst relative deviation of the weighted sub-sampled sum %.2e (design residual %.1e)" % (s, worst, res))
+    assert worst < 2e-5

@@ -99,6 +99,7 @@ struct btb200_ctx {
   std::vector<int> win_mask;         // pass flags for the next submit (btb200_set_window_mask), empty: none
   int *h_mask = nullptr;             // pinned staging of the mask
   bool use_nest = false;             // rx_nest.cu (fused polyphase + DFT) instead of the two kernels of rx_fast.cu
+  long nest_reach = 0;               // samples from a window's first one that the estimator's tiles read
   PfbDesign nfd;
   NestPlan NP{};
   double phi = 0;                    // common fractional MHz offset of the noise DDCs
@@ -278,6 +279,7 @@ int setup_fast(btb200_ctx *ctx)
           ? (long)P.fns + ((long)K.tiles_per_slot * NEST_R * NEST_RUNS_V + K.q_rows_v + 16 * (NEST_RUNS_V + 1)) * K.fold * K.M
           : (long)P.fns + ((long)K.tiles_per_slot * (K.stride == 2 ? 2 : 1) * NEST_TO + K.q_rows + 16 * (2 * NEST_K + 2)) * K.M;
       if (K.stride >= 2) { if ((rc = upload(ctx, &K.weights, wts))) return rc; }
+      ctx->nest_reach = reach;
       if (reach <= P.H && nest_setup(K) == 0) {
         {
           // flat in the tap index k = row * (row length) + branch: the folded mode reads the same array with rows of fold * M
@@ -309,9 +311,10 @@ void enqueue_noise_estimate(btb200_ctx *ctx, const Geom &G, const DevBatch &W, l
                             const NestResume *resume = nullptr)
 {
   if (ctx->use_nest) {
-    launch_nest_prerot(ctx->NP, W.x, n_samples, s);
+    const bool rotated = ctx->poly && ctx->PF.xr == ctx->NP.xr;   // the channelizer already wrote the rotated copy
+    if (!rotated) launch_nest_prerot(ctx->NP, W.x, n_samples, s);
     launch_nest(ctx->NP, W.B, s, resume);
-    ctx->launches += 3;
+    ctx->launches += rotated ? 2 : 3;
   } else {
     launch_noise_fast(ctx->F, W.x, W.B, G.S, G.fns, G.D, G.n_noise, G.nch, s);
     ctx->launches += 2;
@@ -614,6 +617,12 @@ int setup(btb200_ctx *ctx)
     if (ctx->poly && !ctx->fast_snr) {
       ctx->last_error = "polyphase mode: the noise estimator does not fit this configuration";
       return BTB200_ERR_ARG;
+    }
+    // throughput mode: the channelizer writes the estimator's rotated copy of the input along the way (rx_pfb.cuh)
+    // when its tiles cover every sample the estimator reads of the batch's last window
+    if (ctx->poly && ctx->use_nest && ctx->nest_reach > 0 && !std::getenv("BTB200_NO_FUSED_PREROT") &&
+        (long)P.fcs + (long)P.n_ddc * P.D >= ctx->nest_reach) {
+      ctx->PF.xr = ctx->NP.xr; ctx->PF.phasor = ctx->NP.phasor; ctx->PF.period = ctx->NP.period;
     }
   }
   reset_stream_state(ctx);

@@ -27,16 +27,34 @@ template <int IMM>
 __device__ __forceinline__ float mm_lds(unsigned addr)
 {
   float v;
-  asm volatile("ld.shared.f32 %0, [%1+%2];\n" : "=f"(v) : "r"(addr), "n"(IMM));
+  asm volatile("ld.volatile.shared.f32 %0, [%1+%2];\n" : "=f"(v) : "r"(addr), "n"(IMM));
   return v;
 }
 // the 8-tap interpolation of one step, ascending order, one rounding per operation
-// RS = bytes between consecutive samples of a chain in the ring
-template <int RS, int K = 0>
+// ld.shared.v4 with an explicit 32-bit address and an immediate offset
+template <int IMM>
+__device__ __forceinline__ float4 mm_lds4(unsigned addr)
+{
+  float4 v;
+  asm volatile("ld.volatile.shared.v4.f32 {%0, %1, %2, %3}, [%4+%5];\n" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr), "n"(IMM));
+  return v;
+}
+// The 8-tap interpolation of one step, ascending order, one rounding per operation.  RS = bytes between consecutive
+// samples of a chain in the ring; ma = address of the 8 taps of the step's fraction, contiguous ([imu][8] table).
+// A chain is ONE dependent instruction stream with at most a few warps per scheduler to hide behind, and the
+// assembler sinks every load to its first use, where it costs its full latency -- sixteen times per step with
+// scalar loads.  So: the loads are volatile (kept in program order), the eight samples go first (their address
+// follows from the integer advance, before the rounded fraction is known), the taps arrive as two 16-byte loads,
+// and the first multiply cannot be placed before the last load has been issued.
+template <int RS>
 __device__ __forceinline__ float mm_interp8(unsigned ra, unsigned ma, float acc)
 {
-  if constexpr (K == 8) return acc;
-  else return mm_interp8<RS, K + 1>(ra, ma, acc + mm_lds<K * RS>(ra) * mm_lds<K * 132 * 4>(ma));
+  const float x0 = mm_lds<0 * RS>(ra), x1 = mm_lds<1 * RS>(ra), x2 = mm_lds<2 * RS>(ra), x3 = mm_lds<3 * RS>(ra);
+  const float x4 = mm_lds<4 * RS>(ra), x5 = mm_lds<5 * RS>(ra), x6 = mm_lds<6 * RS>(ra), x7 = mm_lds<7 * RS>(ra);
+  const float4 tb = mm_lds4<16>(ma), ta = mm_lds4<0>(ma);      // the first multiply needs ta: both loads are out before it
+  acc = acc + x0 * ta.x; acc = acc + x1 * ta.y; acc = acc + x2 * ta.z; acc = acc + x3 * ta.w;
+  acc = acc + x4 * tb.x; acc = acc + x5 * tb.y; acc = acc + x6 * tb.z; acc = acc + x7 * tb.w;
+  return acc;
 }
 
 struct MmSave { float mu, omega, last; unsigned ii; int oo; uint32_t word; };
@@ -86,9 +104,10 @@ __device__ __forceinline__ void mm_stateless_block(const Geom &G, const DevBatch
   float (*ring)[BLK] = reinterpret_cast<float (*)[BLK]>(mm_smem);                        // [RD + 8][BLK]
   float *ringc = reinterpret_cast<float *>(mm_smem);                                     // CM: [BLK][MM_PC]
   constexpr int PC = MM_PC;
-  float (*s_mmse)[132] = reinterpret_cast<float (*)[132]>(mm_smem + sizeof(float) * (CM ? PC : RD + 8) * BLK);   // [8][132]
-  for (int i = threadIdx.x; i < 129 * 8; i += blockDim.x) s_mmse[7 - (i & 7)][i >> 3] = mmse_g[i];   // [k][imu] = taps[imu][7-k]
-  if (threadIdx.x == 0) s_mmse[0][129] = __int_as_float((int)(0x4B400000u << 2));                    // spare column: see mmse_biased
+  // interpolator taps, [imu][8]: entry k of row imu = taps[imu][7 - k] multiplies sample k of the step (two 16-byte loads)
+  float *s_mmse = reinterpret_cast<float *>(mm_smem + sizeof(float) * (CM ? PC : RD + 8) * BLK);     // [130][8]
+  for (int i = threadIdx.x; i < 129 * 8; i += blockDim.x) s_mmse[(i & ~7) + 7 - (i & 7)] = mmse_g[i];
+  if (threadIdx.x == 0) s_mmse[129 * 8] = __int_as_float((int)(0x4B400000u << 5));                   // spare row: see mmse_biased
   __syncthreads();
   if (threadIdx.x >= BLK) return;                          // whole warps leave; the others stay complete to the end
   int idx = block * BLK + threadIdx.x;
@@ -126,9 +145,9 @@ __device__ __forceinline__ void mm_stateless_block(const Geom &G, const DevBatch
   const int tid = threadIdx.x;
   const int nch = G.nch;
   const unsigned ring_tid = CM ? (unsigned)__cvta_generic_to_shared(&ringc[tid * PC]) : (unsigned)__cvta_generic_to_shared(&ring[0][tid]);
-  // table address biased by the exponent bits of the magic constant: entry imu is at mmse_biased + 4 bits(1.5 2^23 + imu)
-  // (the bias is read back from shared memory so that ptxas cannot split it off again as an add per load)
-  const unsigned mmse_biased = (unsigned)__cvta_generic_to_shared(&s_mmse[0][0]) - (unsigned)__float_as_int(s_mmse[0][129]);
+  // table address biased by the exponent bits of the magic constant: row imu is at mmse_biased + 32 bits(1.5 2^23 + imu)
+  // mod 2^32 (the bias is read back from shared memory so that ptxas cannot split it off again as an add per load)
+  const unsigned mmse_biased = (unsigned)__cvta_generic_to_shared(&s_mmse[0]) - (unsigned)__float_as_int(s_mmse[129 * 8]);
   const MmConst K = G.mm;
   bool done = !live || !(oo < oo_end && ii < ni);
   // rows [pf - RD, pf) are in (or on their way to) the ring; pf is the same for the 32 chains of the warp
@@ -201,7 +220,7 @@ __device__ __forceinline__ void mm_stateless_block(const Geom &G, const DevBatch
         float mu = st.mu, omega = st.omega, last = st.last;
   #pragma unroll
         for (int t = 0; t < PERIOD; t++) {
-          const unsigned ma = mmse_biased + (tb << 2);
+          const unsigned ma = mmse_biased + (tb << 5);
           const unsigned ra = ring_tid + (iiw & RMASK);
           const float out = mm_interp8<RS>(ra, ma, 0.0f);
           if (soft_row) soft_row[oo + t] = out;
@@ -239,10 +258,10 @@ __device__ __forceinline__ void mm_stateless_block(const Geom &G, const DevBatch
         int imu = __float_as_int(__fadd_rn(st.mu * 128.0f, 12582912.0f)) - 0x4B400000;
         imu = imu < 0 ? 0 : (imu > 128 ? 128 : imu);
         const float *rp = CM ? &ringc[tid * PC + (ii & (RD - 1))] : &ring[ii & (RD - 1)][tid];
-        const float *mp = &s_mmse[0][imu];
+        const float *mp = &s_mmse[imu * 8];
         float out = 0.0f;
 #pragma unroll
-        for (int k = 0; k < 8; k++) out = out + rp[k * (CM ? 1 : BLK)] * mp[k * 132];
+        for (int k = 0; k < 8; k++) out = out + rp[k * (CM ? 1 : BLK)] * mp[k];
         if (soft_row) soft_row[oo] = out;
         if (!(out < 0)) word |= 1u << (oo & 31);
         if ((oo & 31) == 31) { bits_row[oo >> 5] = word; word = 0; }

@@ -140,6 +140,28 @@ __global__ void __launch_bounds__(PFB_THREADS, 2) k_pfb(PfbPlan P, const c32 *__
   }
   mbar_wait(bar, 0);
   __syncthreads();
+  if (P.xr) {
+    // the estimator's rotated copy of the tile's own samples: local indices [D, D + n_own D) of the staged span
+    const long n0 = s0 + D;
+    const int cnt = n_own * D;
+    int ph = (int)(n0 % P.period) + tid;
+    for (int i = tid; i < cnt; i += PFB_THREADS, ph += PFB_THREADS) {
+      while (ph >= P.period) ph -= P.period;
+      const long n = n0 + i;
+      if (n < n_samples) {
+        const c32 v = xs[D + i], w = P.phasor[ph];
+        P.xr[n] = c32{v.re * w.re - v.im * w.im, v.re * w.im + v.im * w.re};
+      }
+    }
+    if (tile == 0) {
+      // the samples in front of the first grid point (nobody's own)
+      for (long n = tid; n < n0 && n < n_samples; n += PFB_THREADS) {
+        const c32 v = x[n], w = P.phasor[(int)(n % P.period)];
+        P.xr[n] = c32{v.re * w.re - v.im * w.im, v.re * w.im + v.im * w.re};
+      }
+    }
+    if (P.phi_step != 0.0f) __syncthreads();
+  }
   if (P.phi_step != 0.0f) {
     // x'[i] = x[i] e^{-j 2 pi phi i / M}: the phase origin is the tile's (any origin common to Z[g] and Z[g-1] does)
     for (int i = tid; i < P.span; i += PFB_THREADS) {
@@ -258,17 +280,35 @@ __global__ void __launch_bounds__(PFB_THREADS, 2) k_pfb(PfbPlan P, const c32 *__
       const c32 k = kaps[col];
       float *drow = P.dem + (gs + 1 + rg) * (long)P.nch + ch;
       float *dt = reinterpret_cast<float *>(xs) + col * DTP;   // the staged input is dead: demod tile [col][t], odd pitch
-      for (int t = 1 + rg; t <= n_own; t += RG, drow += (long)RG * P.nch) {
-        const c32 z1 = zs[t * ZP + col], z0 = zs[(t - 1) * ZP + col];
-        const float m = z1.re * z1.re + z1.im * z1.im;
-        sa += m;
-        if (in_seg0 + t - 1 < P.rem) sb += m;
-        if (ch >= 0) {
-          const float pr = z1.re * z0.re + z1.im * z0.im, pi = z1.im * z0.re - z1.re * z0.im;    // z1 conj(z0)
+      // three rows per pass: the six loads go out together, then the arithmetic, then the stores (the shared-memory
+      // store of the demod tile would otherwise fence the next row's loads behind it)
+      constexpr int UB = 3;
+      for (int t = 1 + rg; t <= n_own; t += UB * RG, drow += (long)UB * RG * P.nch) {
+        c32 z1[UB], z0[UB];
+#pragma unroll
+        for (int u = 0; u < UB; u++) {
+          const int tt = t + u * RG <= n_own ? t + u * RG : t;
+          z1[u] = zs[tt * ZP + col]; z0[u] = zs[(tt - 1) * ZP + col];
+        }
+        float d[UB];
+#pragma unroll
+        for (int u = 0; u < UB; u++) {
+          const float m = z1[u].re * z1[u].re + z1[u].im * z1[u].im;
+          if (t + u * RG <= n_own) {
+            sa += m;
+            if (in_seg0 + t + u * RG - 1 < P.rem) sb += m;
+          }
+          const float pr = z1[u].re * z0[u].re + z1[u].im * z0[u].im, pi = z1[u].im * z0[u].re - z1[u].re * z0[u].im;    // z1 conj(z0)
           const float qr = pr * k.re - pi * k.im, qi = pr * k.im + pi * k.re;
-          const float d = P.gain * atan2_tab(atans, qi, qr);
-          *drow = d;
-          if (P.demC) dt[t] = d;
+          d[u] = P.gain * atan2_tab(atans, qi, qr);
+        }
+        if (ch >= 0) {
+#pragma unroll
+          for (int u = 0; u < UB; u++)
+            if (t + u * RG <= n_own) {
+              drow[(long)u * RG * P.nch] = d[u];
+              if (P.demC) dt[t + u * RG] = d[u];
+            }
         }
       }
     }

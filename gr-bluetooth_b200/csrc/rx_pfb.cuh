@@ -32,6 +32,13 @@ struct PfbPlan {
   // chains of the windows with hits reads (rx_mm.cuh, CM) -- a window is a contiguous run of its channel's row there
   float *demC = nullptr;
   long pitchC = 0;                 // floats per channel row (multiple of 4, >= Gtot + 8)
+  // optional second output: the input rotated by the noise DDCs' common fractional offset, xr[n] = x[n] phasor[n % period]
+  // -- what the noise estimator (rx_nest.cu) reads.  Every tile writes the samples of its own grid points from the
+  // span it has staged anyway (tile 0 also the fcs samples in front of the first grid point), which saves the
+  // estimator's own pass over the input (one read of the batch).  Covers samples [0, fcs + Gtot D).
+  c32 *xr = nullptr;
+  const c32 *phasor = nullptr;     // [period]
+  int period = 0;
 };
 
 size_t pfb_smem_bytes(const PfbPlan &P);

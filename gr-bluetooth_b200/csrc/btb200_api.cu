@@ -100,6 +100,7 @@ struct btb200_ctx {
   int *h_mask = nullptr;             // pinned staging of the mask
   bool use_nest = false;             // rx_nest.cu (fused polyphase + DFT) instead of the two kernels of rx_fast.cu
   long nest_reach = 0;               // samples from a window's first one that the estimator's tiles read
+  int *d_smflag = nullptr;           // k_nest2: per-SM "resume chains running" flags
   PfbDesign nfd;
   NestPlan NP{};
   double phi = 0;                    // common fractional MHz offset of the noise DDCs
@@ -260,6 +261,13 @@ int setup_fast(btb200_ctx *ctx)
         const int MV = K.fold * N.M, Qv = (P.Nn + MV - 1) / MV;
         K.q_rows_v = (Qv + 15 + 15) / 16 * 16;
         K.tiles_per_slot = (K.n_used + NEST_R * NEST_RUNS_V - 1) / (NEST_R * NEST_RUNS_V);
+        const char *v2e = std::getenv("BTB200_NEST_V2");
+        if (N.N1 == 4 && N.M == 100 && !(v2e && v2e[0] == '0')) {
+          // small blocks, three per SM (rx_nest.cu: k_nest2): single runs of 16 outputs, chunks of 8 tap rows
+          K.v2 = 1;
+          K.q_rows_v = (Qv + 15 + 7) / 8 * 8;
+          K.tiles_per_slot = (K.n_used + NEST_R - 1) / NEST_R;
+        }
       } else if (sub_ok && fold_req >= 1) {
         K.stride = 2;
         K.n_used = P.n_noise / 2 + 1;
@@ -275,11 +283,21 @@ int setup_fast(btb200_ctx *ctx)
       K.period = F.period; K.phasor = F.phasor; K.esum = F.esum;
       // the last tile of a slot reads (outputs of the tiles + tap rows + the ring's look-ahead) rows of K.fold * M samples
       // past the slot's first noise sample
-      const long reach = K.fold > 1
+      const long reach = K.v2
+          ? (long)P.fns + ((long)K.tiles_per_slot * NEST_R + K.q_rows_v + 8 * 4) * K.fold * K.M
+          : K.fold > 1
           ? (long)P.fns + ((long)K.tiles_per_slot * NEST_R * NEST_RUNS_V + K.q_rows_v + 16 * (NEST_RUNS_V + 1)) * K.fold * K.M
           : (long)P.fns + ((long)K.tiles_per_slot * (K.stride == 2 ? 2 : 1) * NEST_TO + K.q_rows + 16 * (2 * NEST_K + 2)) * K.M;
       if (K.stride >= 2) { if ((rc = upload(ctx, &K.weights, wts))) return rc; }
       ctx->nest_reach = reach;
+      if (K.v2) {
+        std::vector<float> h1((size_t)K.q_rows_v * K.fold * K.M, 0.0f);
+        for (size_t i = 0; i < N.hq.size() && i < h1.size(); i++) h1[i] = N.hq[i];
+        for (size_t i = h1.size(); i < N.hq.size(); i++) if (N.hq[i] != 0.0f) return BTB200_ERR_ARG;   // every tap inside the rows read
+        if ((rc = upload(ctx, &K.hq1, h1))) return rc;
+        if ((rc = dev_alloc(ctx, &ctx->d_smflag, 256))) return rc;
+        CK(cudaMemset(ctx->d_smflag, 0, 256 * sizeof(int)));
+      }
       if (reach <= P.H && nest_setup(K) == 0) {
         {
           // flat in the tap index k = row * (row length) + branch: the folded mode reads the same array with rows of fold * M
@@ -889,6 +907,8 @@ static int submit_impl(btb200_ctx *ctx, const void *iq, int kind, size_t n_sampl
     if (fused) {
       nr.G = G; nr.W = W; nr.mmse = ctx->T.mmse; nr.demT = ctx->d_dem; nr.save = W.mm_save;
       nr.demC = ctx->PF.demC; nr.pitchC = ctx->PF.pitchC;
+      static const bool share_sm = std::getenv("BTB200_RESUME_SHARED") != nullptr;
+      nr.sm_flag = (ctx->NP.v2 && !share_sm) ? ctx->d_smflag : nullptr;
       nr.n_blocks = (int)((nbc + NEST_RESUME_BLK - 1) / NEST_RESUME_BLK);
     } else if (G.early) {
       if (!tail_inline) CK(cudaStreamWaitEvent(s2, ctx->ev[4], 0));

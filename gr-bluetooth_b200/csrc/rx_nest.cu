@@ -296,7 +296,244 @@ __global__ void k_nest_reduce(NestPlan P, int B)
 
 }  // namespace
 
-size_t nest_smem_bytes(const NestPlan &P) { return nest_layout(P).total; }
+// ---------------------------------------------------------------------------------------------------------------
+// k_nest2: the folded estimator (fold 2) in small blocks.  k_nest's tile is 48 outputs on 600 threads with 180 KB of
+// shared memory: one block per SM, and by ncu only ~27 % of a tile's time is the tap loop at full FMA rate -- the rest
+// is the pipeline fill (nothing to do until the first 100 KB have landed), the chunk barriers and the DFT phases, which
+// nothing overlaps.  Here a block is ONE run of 16 outputs on 2 M threads (thread = virtual branch), chunks of 8 steps,
+// a ring of 4 chunks (51 KB: three chunks of look-ahead), taps as plain floats (paired in a register), the DFT matrix
+// fetched by a bulk copy into the dead ring while the branch sums are folded: ~70 KB, three blocks per SM, each in a
+// different phase.  Same arithmetic per output as k_nest<.., 2> (same tap array, same fold, same DFT, same weights).
+constexpr int N2_CH = 8;             // steps per chunk
+constexpr int N2_RC = 4;             // ring slots (chunks)
+constexpr int N2_OUT = NEST_R;       // outputs per tile
+constexpr int N2_OG = 8;             // output groups of the N2-point DFT stage
+
+struct Nest2Smem { size_t ring, wb_off, taps, n2r, epart, bar, total; };
+
+__host__ __device__ inline Nest2Smem nest2_layout(const NestPlan &P)
+{
+  Nest2Smem L{};
+  size_t o = 0;
+  auto take = [&o](size_t bytes, size_t align) { o = (o + align - 1) / align * align; const size_t r = o; o += bytes; return r; };
+  const int MV = 2 * P.M;
+  const size_t ring = (size_t)N2_RC * N2_CH * MV * sizeof(c32);
+  const size_t u = (size_t)N2_OUT * (MV + 1) * sizeof(c32);               // U / V tile, row pitch MV + 1
+  L.wb_off = (u + 127) / 128 * 128;                                       // the DFT matrix follows the U tile in the dead ring
+  const size_t after = L.wb_off + (size_t)P.N2 * P.ncol * sizeof(c32);
+  L.ring = take(ring > after ? ring : after, 128);
+  L.taps = take((size_t)2 * N2_CH * MV * sizeof(float), 128);
+  L.n2r = take((size_t)P.N2 * sizeof(int), 16);
+  L.epart = take((size_t)N2_OG * P.ncol * sizeof(float), 16);
+  L.bar = take((N2_RC + 3) * 8, 8);
+  L.total = o;
+  return L;
+}
+
+template <int V> struct IntC { static constexpr int value = V; };
+
+template <int N1, int MT>
+__global__ void __launch_bounds__(2 * MT, 3) k_nest2(NestPlan P, NestResume R)
+{
+  extern __shared__ __align__(128) unsigned char smem[];
+  unsigned smid;
+  asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+  const int tid = threadIdx.x;
+  if ((int)blockIdx.x < R.n_blocks) {
+    // resume of clock-recovery chains (see k_nest); with windows to resume the block claims its SM for the duration
+    __shared__ int s_live;
+    if (tid == 0) {
+      s_live = (int)blockIdx.x * NEST_RESUME_BLK < *R.W.tail.n_list;
+      if (s_live && R.sm_flag) atomicAdd(&R.sm_flag[smid & 255], NEST_RESUME_BLK / 32);
+    }
+    __syncthreads();
+    const bool live = s_live != 0;
+    if (R.demC)
+      mm_stateless_block<NEST_RESUME_BLK, true>(R.G, R.W, R.mmse, R.demT, 2, reinterpret_cast<MmSave *>(R.save), R.W.tail.list, -1,
+                                                smem, (int)blockIdx.x, R.demC, R.pitchC);
+    else
+      mm_stateless_block<NEST_RESUME_BLK>(R.G, R.W, R.mmse, R.demT, 2, reinterpret_cast<MmSave *>(R.save), R.W.tail.list, -1,
+                                          smem, (int)blockIdx.x);
+    if (live && R.sm_flag && tid < NEST_RESUME_BLK && (tid & 31) == 0) atomicSub(&R.sm_flag[smid & 255], 1);   // one per chain warp
+    return;
+  }
+  if (R.sm_flag) {
+    // an SM whose resume block is still running its chains: wait (bounded: ~4 ms) instead of taking issue slots from them
+    if (tid == 0) {
+      const volatile int *f = R.sm_flag + (smid & 255);
+      for (int spin = 0; spin < 4000 && *f > 0; spin++) __nanosleep(1000);
+    }
+    __syncthreads();
+  }
+  const int tile_index = (int)blockIdx.x - R.n_blocks;
+  const Nest2Smem L = nest2_layout(P);
+  c32 *ring = reinterpret_cast<c32 *>(smem + L.ring);
+  float *taps = reinterpret_cast<float *>(smem + L.taps);
+  c32 *WBs = reinterpret_cast<c32 *>(smem + L.ring + L.wb_off);
+  int *n2r = reinterpret_cast<int *>(smem + L.n2r);
+  float *epart = reinterpret_cast<float *>(smem + L.epart);
+  uint64_t *bar = reinterpret_cast<uint64_t *>(smem + L.bar);          // [0..3] ring slots, [4..5] tap buffers, [6] DFT matrix
+
+  constexpr int M = MT, N2 = MT / N1, MV = 2 * MT;
+  const int ncol = P.ncol, nthr = MV;
+  const int b = tile_index / P.tiles_per_slot, tile = tile_index - b * P.tiles_per_slot;
+  const int i0 = tile * N2_OUT;                                        // first output (of the sub-sampled sequence) of the tile
+  const long n_base = (long)b * P.S + P.fns + (long)MV * i0;           // sample of step 0, virtual branch 0
+  const int n_chunks = P.q_rows_v / N2_CH;
+  constexpr unsigned ring_bytes = N2_CH * MV * sizeof(c32), tap_bytes = N2_CH * MV * sizeof(float);
+
+  if (tid == 0) {
+    for (int i = 0; i < N2_RC + 3; i++) mbar_init(&bar[i], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
+  auto load_ring = [&](int m) {
+    uint64_t *bb = &bar[m % N2_RC];
+    mbar_expect_tx(bb, ring_bytes);
+    tma_bulk_g2s(ring + (size_t)(m % N2_RC) * N2_CH * MV, P.xr + n_base + (long)m * N2_CH * MV, ring_bytes, bb);
+  };
+  auto load_taps = [&](int c) {
+    uint64_t *bb = &bar[N2_RC + (c & 1)];
+    mbar_expect_tx(bb, tap_bytes);
+    tma_bulk_g2s(taps + (size_t)(c & 1) * N2_CH * MV, P.hq1 + (size_t)c * N2_CH * MV, tap_bytes, bb);
+  };
+  if (tid == 0) {
+    for (int m = 0; m < N2_RC && m < n_chunks; m++) load_ring(m);
+    load_taps(0);
+    if (n_chunks > 1) load_taps(1);
+  }
+  for (int i = tid; i < N2; i += nthr) n2r[i] = P.n2_of_rho[i];
+
+  // ---- 1. branch sums: outputs i0 + o, o < 16, virtual branch tid.  Step g = 8 c + s brings sample row g and tap row g;
+  // acc[o] += x[g] h[g - o]: the last 16 taps sit in a register window whose indices are static because chunks are
+  // processed in pairs (H index = g mod 16).
+  u64 acc[NEST_R], H[NEST_R];
+#pragma unroll
+  for (int o = 0; o < NEST_R; o++) { acc[o] = 0ull; H[o] = 0ull; }
+  const u64 *ring64 = reinterpret_cast<const u64 *>(ring);
+  auto chunk = [&](auto ofs_t, int c) {
+    constexpr int OFS = decltype(ofs_t)::value;
+    mbar_wait(&bar[c % N2_RC], (unsigned)((c / N2_RC) & 1));
+    mbar_wait(&bar[N2_RC + (c & 1)], (unsigned)((c >> 1) & 1));
+    const u64 *xp = ring64 + (size_t)(c % N2_RC) * N2_CH * MV + tid;
+    const float *tp = taps + (size_t)(c & 1) * N2_CH * MV + tid;
+#pragma unroll
+    for (int s = 0; s < N2_CH; s++) {
+      const u64 X = xp[s * MV];
+      const float h = tp[s * MV];
+      H[OFS + s] = pk_pack(h, h);
+#pragma unroll
+      for (int o = 0; o < NEST_R; o++) acc[o] = pk_fma(X, H[(OFS + s - o) & (NEST_R - 1)], acc[o]);
+    }
+    __syncthreads();                                  // ring chunk c and tap chunk c are free
+    if (tid == 0) {
+      fence_proxy_async();
+      if (c + N2_RC < n_chunks) load_ring(c + N2_RC);
+      if (c + 2 < n_chunks) load_taps(c + 2);
+    }
+  };
+  int c = 0;
+  for (; c + 1 < n_chunks; c += 2) { chunk(IntC<0>{}, c); chunk(IntC<N2_CH>{}, c + 1); }
+  if (c < n_chunks) chunk(IntC<0>{}, c);
+  // the ring is dead: the DFT matrix arrives behind the U tile while the branch sums are folded
+  const unsigned wb_bytes = (unsigned)(N2 * ncol * sizeof(c32));
+  if (tid == 0) { mbar_expect_tx(&bar[N2_RC + 2], wb_bytes); tma_bulk_g2s(WBs, P.WB, wb_bytes, &bar[N2_RC + 2]); }
+  constexpr int UP = MV + 1;
+  c32 *U = ring;
+#pragma unroll
+  for (int o = 0; o < NEST_R; o++) reinterpret_cast<u64 *>(U)[(size_t)o * UP + tid] = acc[o];
+  __syncthreads();
+
+  // ---- 2. fold the two virtual branches of a branch and N1-point DFTs, in place: V[out][k1 * N2 + n2]
+  {
+    constexpr int ITEMS = 16 / (N1 * 2);              // 16 N2 items on 2 N1 N2 threads
+    float vr[ITEMS][N1], vi[ITEMS][N1];
+#pragma unroll
+    for (int j = 0; j < ITEMS; j++) {
+      const int it = tid + j * nthr;
+      const int out = it / N2, rho = it - out * N2, n2 = n2r[rho];
+      float ur[N1], ui[N1];
+#pragma unroll
+      for (int n1 = 0; n1 < N1; n1++) {
+        const c32 *up = U + (size_t)out * UP + (N2 * n1 + N1 * n2) % M;
+        const c32 a = up[0], t = up[M];
+        ur[n1] = a.re + t.re; ui[n1] = a.im + t.im;
+      }
+      if constexpr (N1 == 1) { vr[j][0] = ur[0]; vi[j][0] = ui[0]; }
+      else if constexpr (N1 == 2) {
+        vr[j][0] = ur[0] + ur[1]; vi[j][0] = ui[0] + ui[1];
+        vr[j][1] = ur[0] - ur[1]; vi[j][1] = ui[0] - ui[1];
+      } else {
+        const float er = ur[0] + ur[2], ei = ui[0] + ui[2], fr = ur[0] - ur[2], fi = ui[0] - ui[2];
+        const float gr = ur[1] + ur[3], gi = ui[1] + ui[3], hr = ur[1] - ur[3], hi = ui[1] - ui[3];
+        vr[j][0] = er + gr; vi[j][0] = ei + gi;
+        vr[j][1] = fr + hi; vi[j][1] = fi - hr;       // f - j h
+        vr[j][2] = er - gr; vi[j][2] = ei - gi;
+        vr[j][3] = fr - hi; vi[j][3] = fi + hr;       // f + j h
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < ITEMS; j++) {
+      const int it = tid + j * nthr;
+      const int out = it / N2, rho = it - out * N2, n2 = n2r[rho];
+#pragma unroll
+      for (int k1 = 0; k1 < N1; k1++) U[(size_t)out * UP + k1 * N2 + n2] = c32{vr[j][k1], vi[j][k1]};
+    }
+    __syncthreads();
+  }
+
+  // ---- 3. N2-point DFTs at the channel bins + weighted |Z|^2.  item = (og, cg): outputs og and og + 8, 5 columns
+  mbar_wait(&bar[N2_RC + 2], 0);
+  const int n_cg = ncol / NEST_NCOL;
+  for (int item = tid; item < N2_OG * n_cg; item += nthr) {
+    const int og = item & (N2_OG - 1), cg = item / N2_OG;
+    const int col0 = cg * NEST_NCOL, k1 = col0 / P.CPC;
+    constexpr int NI = N2_OUT / N2_OG;
+    float zr[NI][NEST_NCOL], zi[NI][NEST_NCOL];
+#pragma unroll
+    for (int i = 0; i < NI; i++)
+#pragma unroll
+      for (int j = 0; j < NEST_NCOL; j++) { zr[i][j] = 0.0f; zi[i][j] = 0.0f; }
+    const c32 *vrow = U + (size_t)og * UP + k1 * N2;
+    const c32 *wrow = WBs + col0;
+#pragma unroll 5
+    for (int n2 = 0; n2 < N2; n2++) {
+      c32 v[NI], w[NEST_NCOL];
+#pragma unroll
+      for (int i = 0; i < NI; i++) v[i] = vrow[(size_t)N2_OG * i * UP + n2];
+#pragma unroll
+      for (int j = 0; j < NEST_NCOL; j++) w[j] = wrow[n2 * ncol + j];
+#pragma unroll
+      for (int i = 0; i < NI; i++)
+#pragma unroll
+        for (int j = 0; j < NEST_NCOL; j++) {
+          zr[i][j] = fmaf(v[i].re, w[j].re, zr[i][j]); zr[i][j] = fmaf(-v[i].im, w[j].im, zr[i][j]);
+          zi[i][j] = fmaf(v[i].re, w[j].im, zi[i][j]); zi[i][j] = fmaf(v[i].im, w[j].re, zi[i][j]);
+        }
+    }
+    float e[NEST_NCOL];
+#pragma unroll
+    for (int j = 0; j < NEST_NCOL; j++) e[j] = 0.0f;
+#pragma unroll
+    for (int i = 0; i < NI; i++) {
+      const int u = i0 + og + N2_OG * i;
+      const float wgt = u < P.n_used ? P.weights[u] : 0.0f;
+#pragma unroll
+      for (int j = 0; j < NEST_NCOL; j++) e[j] = fmaf(wgt, zr[i][j] * zr[i][j] + zi[i][j] * zi[i][j], e[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < NEST_NCOL; j++) epart[og * ncol + col0 + j] = e[j];
+  }
+  __syncthreads();
+  for (int col = tid; col < ncol; col += nthr) {
+    float sum = 0.0f;
+    for (int og = 0; og < N2_OG; og++) sum += epart[og * ncol + col];
+    P.E2[(size_t)tile_index * ncol + col] = sum;
+  }
+}
+
+size_t nest_smem_bytes(const NestPlan &P) { return P.v2 ? nest2_layout(P).total : nest_layout(P).total; }
 
 #define NEST_DISPATCH(CALL) do { \
     if (P.fold == 2) { if (P.N1 == 4 && P.M == 100) { CALL(4, 100, 2); } else if (P.N1 == 4) { CALL(4, 0, 2); } else if (P.N1 == 2) { CALL(2, 0, 2); } else { CALL(1, 0, 2); } } \
@@ -316,6 +553,12 @@ int nest_setup(const NestPlan &P)
   if ((((long)P.S * sizeof(c32)) & 15) != 0 || (((long)P.fns * sizeof(c32)) & 15) != 0 || ((NEST_TO * P.M * sizeof(c32)) & 15) != 0)
     return -1;                                                             // ... from 16-byte aligned addresses
   if (nest_smem_bytes(P) > 227 * 1024) return -1;
+  if (P.v2) {
+    if (P.fold != 2 || P.N1 != 4 || P.M != 100 || !P.hq1 || P.q_rows_v % N2_CH != 0) return -1;
+    if (((N2_CH * 2 * P.M * sizeof(float)) & 15) != 0 || ((N2_OUT * 2 * P.M * sizeof(c32)) & 15) != 0) return -1;
+    if (3 * (nest_smem_bytes(P) + 1024) > 228 * 1024) return -1;            // three blocks per SM
+    return cudaFuncSetAttribute((const void *)k_nest2<4, 100>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nest_smem_bytes(P)) == cudaSuccess ? 0 : -1;
+  }
   cudaError_t e = cudaSuccess;
 #define NEST_OPT(N1_, MT_, F_) e = cudaFuncSetAttribute((const void *)k_nest<N1_, MT_, F_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nest_smem_bytes(P))
   NEST_DISPATCH(NEST_OPT);
@@ -331,7 +574,7 @@ void launch_nest_prerot(const NestPlan &P, const c32 *x, long n_samples, cudaStr
 
 bool nest_can_resume(const NestPlan &P)
 {
-  const int threads = P.fold > 1 ? NEST_RUNS_V * P.fold * P.M : 2 * NEST_K * P.M;
+  const int threads = P.v2 ? 2 * P.M : P.fold > 1 ? NEST_RUNS_V * P.fold * P.M : 2 * NEST_K * P.M;
   return threads >= NEST_RESUME_BLK && nest_smem_bytes(P) >= mm_smem_bytes(NEST_RESUME_BLK);
 }
 
@@ -340,8 +583,16 @@ void launch_nest(const NestPlan &P, int B, cudaStream_t s, const NestResume *res
   NestResume R{};
   if (resume && nest_can_resume(P)) R = *resume;
   const dim3 grid((unsigned)(B * P.tiles_per_slot + R.n_blocks));
-  const int threads = P.fold > 1 ? NEST_RUNS_V * P.fold * P.M : 2 * NEST_K * P.M;
   const size_t smem = nest_smem_bytes(P);
+  if (P.v2) {
+    if (R.n_blocks == 0) R.sm_flag = nullptr;
+    if (R.sm_flag) cudaMemsetAsync(R.sm_flag, 0, 256 * sizeof(int), s);
+    k_nest2<4, 100><<<grid, 2 * P.M, smem, s>>>(P, R);
+    const int n = B * P.nch;
+    k_nest_reduce<<<(n + 127) / 128, 128, 0, s>>>(P, B);
+    return;
+  }
+  const int threads = P.fold > 1 ? NEST_RUNS_V * P.fold * P.M : 2 * NEST_K * P.M;
 #define NEST_RUN(N1_, MT_, F_) k_nest<N1_, MT_, F_><<<grid, threads, smem, s>>>(P, R)
   NEST_DISPATCH(NEST_RUN);
 #undef NEST_RUN

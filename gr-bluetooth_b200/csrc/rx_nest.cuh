@@ -34,6 +34,11 @@ struct NestPlan {
   // MV -- so the tap loop is the one of the even-output mode with M -> MV; the F virtual branches r + M f of a real
   // branch r are added up on the way into the N1-point DFTs.  1/F of the multiply-adds of the even-output mode.
   int fold = 1;
+  // v2 (fold 2, M = 100 = 4 x 25): the same tiles cut into single runs of 16 outputs, 2 M threads and ~70 KB of shared
+  // memory per block, THREE blocks per SM -- the pipeline fill, the per-tile DFT phases and the chunk barriers of one
+  // block hide behind the tap loops of the other two (rx_nest.cu: k_nest2).  hq1 = the tap array as plain floats.
+  int v2 = 0;
+  const float *hq1 = nullptr;
   int q_rows_v = 0;                  // fold >= 2: rows of the tap array read with row length fold * M (multiple of 16, >= ceil(Nn / MV) + 16)
   const float2 *hq2 = nullptr;       // [q_rows][M]  (h, h) with h = h'[r + M q], zero padded: operands of the packed FMAs
   const int *n2_of_rho = nullptr;    // [N2]
@@ -59,6 +64,9 @@ struct NestResume {
   long pitchC = 0;
   void *save = nullptr;
   int n_blocks = 0;                  // blocks of NEST_RESUME_BLK windows: enough for every window of the batch
+  // v2 (several blocks per SM): a resume block that has windows raises sm_flag[its SM] while its chains run and the
+  // estimator blocks that find the flag up wait (bounded) before they start -- the chains keep their SM to themselves
+  int *sm_flag = nullptr;            // [256], zero before the launch; null: share the SM
 };
 constexpr int NEST_RESUME_BLK = 64;
 

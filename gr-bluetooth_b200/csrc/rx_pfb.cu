@@ -72,25 +72,29 @@ __host__ __device__ inline PfbSmem pfb_layout(const PfbPlan &P)
   return L;
 }
 
-// gr::fast_atan2f with an approximate division: tolerance-mode demod
+// gr::fast_atan2f, tolerance-mode demod: branch-free (the reference's early returns and quadrant
+// ladder become selects -- divergent branches cost this epilogue more than the arithmetic), approximate reciprocal,
+// floor and fraction of the table position from one round-towards-zero add of 2^23 instead of two conversions.
 __device__ __forceinline__ float atan2_tab(const float *__restrict__ T, float y, float x)
 {
   const float ya = fabsf(y), xa = fabsf(x);
   const float mx = fmaxf(ya, xa), mn = fminf(ya, xa);
-  if (!(mx > 0.0f)) return 0.0f;
-  const float z = __fdividef(mn, mx);
-  float base = z;
-  if (!(z < 0.003921569f)) {
-    float alpha = z * 255.0f;
-    const int idx = ((int)alpha) & 0xff;
-    alpha -= (float)idx;
-    base = fmaf(T[idx + 1] - T[idx], alpha, T[idx]);
-  }
+  float rc;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(mx));
+  const float z = mn * rc;                               // NaN for x = y = 0: selected away at the end
+  const float alpha = z * 255.0f;
+  const float tz = __fadd_rz(alpha, 8388608.0f);         // 2^23 + floor(alpha), alpha in [0, 255]
+  const int idx = __float_as_int(tz) & 0xff;
+  const float frac = alpha - (tz - 8388608.0f);
+  const float t0 = T[idx], t1 = T[idx + 1];
+  float base = fmaf(t1 - t0, frac, t0);
+  base = (z < 0.003921569f) ? z : base;
   // quadrant fix-up of the reference, folded: (xa > ya ? base : pi/2 - base), mirrored for x < 0, signed like y
   const float pi = 3.14159265358979323846f, hp = 1.57079632679489661923f;
   float angle = (xa > ya) ? base : hp - base;
-  if (x < 0.0f) angle = pi - angle;
-  return copysignf(angle, y);
+  angle = (x < 0.0f) ? pi - angle : angle;
+  angle = copysignf(angle, y);
+  return (mx > 0.0f) ? angle : 0.0f;
 }
 
 template <int N1, int Q>
@@ -317,14 +321,14 @@ __global__ void __launch_bounds__(PFB_THREADS, 2) k_pfb(PfbPlan P, const c32 *__
     }
     __syncthreads();                                     // the Z tile is dead: its first rows carry the partial sums
     if (P.demC) {
-      // channel-major copy: a warp writes the tile's run of each of its channels (lanes = consecutive grid points)
-      const int lane = tid & 31;
-      for (int cl = tid >> 5; cl < ncol; cl += PFB_THREADS / 32) {
+      // channel-major copy: element (column, t) of the demod tile, a warp = 32 consecutive grid points of one channel;
+      // independent load/store pairs, four in flight per thread
+      const float *dtile = reinterpret_cast<const float *>(xs);
+#pragma unroll 4
+      for (int e = tid; e < ncol * PFB_TT; e += PFB_THREADS) {
+        const int cl = e / PFB_TT, t = e - cl * PFB_TT;
         const int ch = cch[cl];
-        if (ch < 0) continue;
-        const float *dt = reinterpret_cast<const float *>(xs) + cl * DTP;
-        float *crow = P.demC + (long)ch * P.pitchC + gs;
-        for (int t = 1 + lane; t <= n_own; t += 32) crow[t] = dt[t];
+        if (ch >= 0 && t >= 1 && t <= n_own) P.demC[(long)ch * P.pitchC + gs + t] = dtile[cl * DTP + t];
       }
     }
     float *part = reinterpret_cast<float *>(zs);

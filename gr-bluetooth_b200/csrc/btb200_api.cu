@@ -298,7 +298,17 @@ int setup_fast(btb200_ctx *ctx)
         if ((rc = dev_alloc(ctx, &ctx->d_smflag, 256))) return rc;
         CK(cudaMemset(ctx->d_smflag, 0, 256 * sizeof(int)));
       }
-      if (reach <= P.H && nest_setup(K) == 0) {
+      bool nest_ok = reach <= P.H && nest_setup(K) == 0;
+      if (!nest_ok && K.v2) {
+        // the small-block variant does not fit: the 48-output tiles of k_nest
+        const int MV = K.fold * N.M, Qv = (P.Nn + MV - 1) / MV;
+        K.v2 = 0;
+        K.q_rows_v = (Qv + 15 + 15) / 16 * 16;
+        K.tiles_per_slot = (K.n_used + NEST_R * NEST_RUNS_V - 1) / (NEST_R * NEST_RUNS_V);
+        ctx->nest_reach = (long)P.fns + ((long)K.tiles_per_slot * NEST_R * NEST_RUNS_V + K.q_rows_v + 16 * (NEST_RUNS_V + 1)) * K.fold * K.M;
+        nest_ok = ctx->nest_reach <= P.H && nest_setup(K) == 0;
+      }
+      if (nest_ok) {
         {
           // flat in the tap index k = row * (row length) + branch: the folded mode reads the same array with rows of fold * M
           size_t n_h2 = N.hq.size();

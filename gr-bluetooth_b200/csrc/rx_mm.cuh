@@ -46,12 +46,24 @@ __device__ __forceinline__ float4 mm_lds4(unsigned addr)
 // scalar loads.  So: the loads are volatile (kept in program order), the eight samples go first (their address
 // follows from the integer advance, before the rounded fraction is known), the taps arrive as two 16-byte loads,
 // and the first multiply cannot be placed before the last load has been issued.
+// byte permute with a selector the assembler cannot see through (0x3210 at run time: d = a); used to make a value wait
+// for another one's arrival without changing it
+__device__ __forceinline__ float mm_tie(float a, float other, unsigned sel)
+{
+  unsigned d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(__float_as_uint(a)), "r"(__float_as_uint(other)), "r"(sel));
+  return __uint_as_float(d);
+}
 template <int RS>
-__device__ __forceinline__ float mm_interp8(unsigned ra, unsigned ma, float acc)
+__device__ __forceinline__ float mm_interp8(unsigned ra, unsigned ma, float acc, unsigned sel)
 {
   const float x0 = mm_lds<0 * RS>(ra), x1 = mm_lds<1 * RS>(ra), x2 = mm_lds<2 * RS>(ra), x3 = mm_lds<3 * RS>(ra);
   const float x4 = mm_lds<4 * RS>(ra), x5 = mm_lds<5 * RS>(ra), x6 = mm_lds<6 * RS>(ra), x7 = mm_lds<7 * RS>(ra);
-  const float4 tb = mm_lds4<16>(ma), ta = mm_lds4<0>(ma);      // the first multiply needs ta: both loads are out before it
+  float4 tb = mm_lds4<16>(ma);
+  const float4 ta = mm_lds4<0>(ma);
+  // the upper taps pass through a permute that also reads the lower ones: no multiply can be scheduled between the
+  // two loads (where it would stall the second load behind the first one's latency); both are in flight together
+  tb.x = mm_tie(tb.x, ta.w, sel); tb.y = mm_tie(tb.y, ta.w, sel); tb.z = mm_tie(tb.z, ta.w, sel); tb.w = mm_tie(tb.w, ta.w, sel);
   acc = acc + x0 * ta.x; acc = acc + x1 * ta.y; acc = acc + x2 * ta.z; acc = acc + x3 * ta.w;
   acc = acc + x4 * tb.x; acc = acc + x5 * tb.y; acc = acc + x6 * tb.z; acc = acc + x7 * tb.w;
   return acc;
@@ -107,7 +119,10 @@ __device__ __forceinline__ void mm_stateless_block(const Geom &G, const DevBatch
   // interpolator taps, [imu][8]: entry k of row imu = taps[imu][7 - k] multiplies sample k of the step (two 16-byte loads)
   float *s_mmse = reinterpret_cast<float *>(mm_smem + sizeof(float) * (CM ? PC : RD + 8) * BLK);     // [130][8]
   for (int i = threadIdx.x; i < 129 * 8; i += blockDim.x) s_mmse[(i & ~7) + 7 - (i & 7)] = mmse_g[i];
-  if (threadIdx.x == 0) s_mmse[129 * 8] = __int_as_float((int)(0x4B400000u << 5));                   // spare row: see mmse_biased
+  if (threadIdx.x == 0) {
+    s_mmse[129 * 8] = __int_as_float((int)(0x4B400000u << 5));                                         // spare row: see mmse_biased
+    s_mmse[129 * 8 + 1] = __int_as_float(0x3210);                                                      // identity selector of mm_tie
+  }
   __syncthreads();
   if (threadIdx.x >= BLK) return;                          // whole warps leave; the others stay complete to the end
   int idx = block * BLK + threadIdx.x;
@@ -148,6 +163,7 @@ __device__ __forceinline__ void mm_stateless_block(const Geom &G, const DevBatch
   // table address biased by the exponent bits of the magic constant: row imu is at mmse_biased + 32 bits(1.5 2^23 + imu)
   // mod 2^32 (the bias is read back from shared memory so that ptxas cannot split it off again as an add per load)
   const unsigned mmse_biased = (unsigned)__cvta_generic_to_shared(&s_mmse[0]) - (unsigned)__float_as_int(s_mmse[129 * 8]);
+  const unsigned tie_sel = (unsigned)__float_as_int(*(volatile float *)&s_mmse[129 * 8 + 1]);
   const MmConst K = G.mm;
   bool done = !live || !(oo < oo_end && ii < ni);
   // rows [pf - RD, pf) are in (or on their way to) the ring; pf is the same for the 32 chains of the warp
@@ -222,7 +238,7 @@ __device__ __forceinline__ void mm_stateless_block(const Geom &G, const DevBatch
         for (int t = 0; t < PERIOD; t++) {
           const unsigned ma = mmse_biased + (tb << 5);
           const unsigned ra = ring_tid + (iiw & RMASK);
-          const float out = mm_interp8<RS>(ra, ma, 0.0f);
+          const float out = mm_interp8<RS>(ra, ma, 0.0f, tie_sel);
           if (soft_row) soft_row[oo + t] = out;
           const bool neg = out < 0;
           if (!neg) byte |= 1u << t;

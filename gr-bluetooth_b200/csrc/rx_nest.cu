@@ -547,8 +547,8 @@ int nest_setup(const NestPlan &P)
   if (P.fold != 1 && P.fold != 2) return -1;
   if (P.fold > 1) {
     const int MV = P.fold * P.M, Qv = (P.Q * P.M + MV - 1) / MV;
-    if (P.stride != 2 * P.fold || !P.weights || P.n_used <= 8 || P.q_rows_v % CH != 0 || P.q_rows_v < Qv + CH) return -1;
-    if (NEST_RUNS_V * MV > 2 * NEST_K * 100) return -1;                      // the kernel's launch bound
+    if (P.stride != 2 * P.fold || !P.weights || P.n_used <= 8 || P.q_rows_v < Qv + NEST_R - 1) return -1;
+    if (!P.v2 && (P.q_rows_v % CH != 0 || NEST_RUNS_V * MV > 2 * NEST_K * 100)) return -1;   // chunking and launch bound of k_nest
   } else if (P.stride != 1 && !(P.stride == 2 && P.weights && P.n_used > 8)) return -1;
   if ((((long)P.S * sizeof(c32)) & 15) != 0 || (((long)P.fns * sizeof(c32)) & 15) != 0 || ((NEST_TO * P.M * sizeof(c32)) & 15) != 0)
     return -1;                                                             // ... from 16-byte aligned addresses

@@ -456,8 +456,13 @@ def run_ours(args):
         gtot = (B - 1) * (S // I.decimation) + I.ddc_out_per_window
         fp32 = {"peak_fma_per_s": fma_peak, "peak_source": "sm_count x 128 lanes x sampled SM clock (%d MHz)" % clk_mhz, "kernels": {}}
         if args.ddc == "poly":
+            # the estimator evaluates every 4th noise-DDC output by default (BTB200_NEST_FOLD: 0 all, 1 even, 2 every 4th)
+            nest_stride = {0: 1, 1: 2}.get(int(os.environ.get("BTB200_NEST_FOLD", "2")), 4)
+            if os.environ.get("BTB200_NEST_DENSE"):
+                nest_stride = 1
+            n_est = (I.noise_out_per_window - 1) // nest_stride + 1 + (2 if nest_stride == 4 else 1 if nest_stride == 2 else 0)
             work = {"chan_fir": gtot * (M * 7 * 2 + 4.0 * M * I.n_channels / (4 if M % 4 == 0 and (M // 4) % 2 else 2 if (M // 2) % 2 else 1)),
-                    "noise_fir": B * I.noise_out_per_window * (2.0 * I.noise_taps + 4.0 * M * I.n_channels / (4 if M % 4 == 0 and (M // 4) % 2 else 2 if (M // 2) % 2 else 1))}
+                    "noise_fir": B * n_est * (2.0 * I.noise_taps + 4.0 * M * I.n_channels / (4 if M % 4 == 0 and (M // 4) % 2 else 2 if (M // 2) % 2 else 1))}
         else:
             work = {"chan_fir": 4.0 * gtot * I.n_channels * I.chan_taps}
         for k, w in work.items():

@@ -16,7 +16,17 @@ LIB_PATH = os.path.join(_HERE, "libbtb200.so")
 
 ABI_VERSION = 1
 MM_CHAINED, MM_STATELESS = 0, 1
-SEARCH_BR, SEARCH_LE = 1, 2
+SEARCH_BR, SEARCH_LE, SEARCH_BR_BCH = 1, 2, 4
+
+
+def bch_any(max_err=1):
+    """btb200_config.bch for BTB200_SEARCH_BR_BCH with LAP_ANY (include/btb200.h: BTB200_BCH_ANY)."""
+    return (max_err & 7) << 28
+
+
+def bch_lap(lap, max_err=2):
+    """btb200_config.bch for BTB200_SEARCH_BR_BCH with a given LAP (BTB200_BCH_LAP)."""
+    return (lap & 0xFFFFFF) | (1 << 24) | ((max_err & 7) << 28)
 SQUELCH_DEFAULT, SQUELCH_EAGER, SQUELCH_LAZY = 0, 1, 2
 SNR_EXACT, SNR_FAST_GUARDED = 0, 1
 TAIL_LAZY, TAIL_FULL = 0, 1
@@ -39,7 +49,7 @@ class Config(C.Structure):
                 ("mm_mode", C.c_int32), ("search", C.c_int32), ("device", C.c_int32),
                 ("max_slots_per_call", C.c_uint32), ("keep_stages", C.c_uint32),
                 ("squelch_mode", C.c_uint32), ("snr_mode", C.c_uint32), ("tail_mode", C.c_uint32),
-                ("ddc_mode", C.c_uint32), ("reserved", C.c_uint32)]
+                ("ddc_mode", C.c_uint32), ("bch", C.c_uint32)]
 
 
 class Info(C.Structure):
@@ -165,13 +175,13 @@ class multi_block:
 
     def __init__(self, sample_rate, center_freq, squelch_threshold, *, mm_mode=MM_CHAINED,
                  search=SEARCH_BR | SEARCH_LE, device=0, max_slots=64, keep_stages=False,
-                 squelch=SQUELCH_DEFAULT, snr_mode=SNR_EXACT, tail=TAIL_LAZY, ddc=DDC_EXACT):
+                 squelch=SQUELCH_DEFAULT, snr_mode=SNR_EXACT, tail=TAIL_LAZY, ddc=DDC_EXACT, bch=0):
         self._L = lib()
         cfg = Config(abi_version=ABI_VERSION, sample_rate=sample_rate, center_freq=center_freq,
                      squelch_threshold=squelch_threshold, extra_history_symbols=self.EXTRA_SYMBOLS,
                      mm_mode=mm_mode, search=search, device=device, max_slots_per_call=max_slots,
                      keep_stages=int(keep_stages), squelch_mode=squelch, snr_mode=snr_mode, tail_mode=tail,
-                     ddc_mode=ddc)
+                     ddc_mode=ddc, bch=bch)
         self._ctx = C.c_void_p()
         rc = self._L.btb200_create(C.byref(cfg), C.byref(self._ctx))
         if rc:

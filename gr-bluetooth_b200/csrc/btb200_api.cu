@@ -488,6 +488,21 @@ int setup(btb200_ctx *ctx)
   if ((rc = upload(ctx, &ctx->T.mmse, P.mmse))) return rc;
   if ((rc = upload(ctx, &ctx->T.atan_tab, P.atan_tab))) return rc;
   if ((rc = upload(ctx, &ctx->T.ac_lut, P.ac_lut))) return rc;
+  if (ctx->cfg.search & BTB200_SEARCH_BR_BCH) {
+    // libbtbb-style access-code test (rx_math.cuh: br_lag_test_bch): syndrome tables of the sync word's (64,30) code
+    const uint32_t bch = ctx->cfg.bch;
+    BchTables bt;
+    if (bt.build((int)(bch >> 28) & 7) != 0) { ctx->last_error = "BTB200_SEARCH_BR_BCH: max_ac_errors must be 0..2"; return BTB200_ERR_ARG; }
+    BchDev &B = ctx->T.bch;
+    if ((rc = upload(ctx, &B.par, bt.par))) return rc;
+    if (bt.syn.empty()) { bt.syn.push_back(0); bt.err.push_back(0); }
+    if ((rc = upload(ctx, &B.syn, bt.syn))) return rc;
+    if ((rc = upload(ctx, &B.err, bt.err))) return rc;
+    B.n = bt.max_err ? (int)bt.syn.size() : 0;
+    B.max_err = bt.max_err;
+    B.lap = (bch & (1u << 24)) ? (bch & 0xffffffu) : 0xffffffffu;
+    B.target = (bch & (1u << 24)) ? sync_word(bch & 0xffffffu) : 0;
+  }
   {
     // channel-group-interleaved tap banks for the tiled FIR: [group][k][16], zero taps for padding channels
     const int ng = (P.nch + 15) / 16;
@@ -726,6 +741,7 @@ int btb200_create(const btb200_config *cfg, btb200_ctx **out)
   if (!ctx) return BTB200_ERR_NOMEM;
   ctx->cfg = *cfg;
   if (ctx->cfg.search == 0) ctx->cfg.search = BTB200_SEARCH_BR | BTB200_SEARCH_LE;
+  if (ctx->cfg.search & BTB200_SEARCH_BR_BCH) ctx->cfg.search |= BTB200_SEARCH_BR;
   if (ctx->cfg.extra_history_symbols == 0) ctx->cfg.extra_history_symbols = 3125;
   ctx->max_slots = cfg->max_slots_per_call ? cfg->max_slots_per_call : kDefaultMaxSlots;
   ctx->device = cfg->device;
@@ -1526,7 +1542,7 @@ int btb200_search_bits(btb200_ctx *ctx, const uint8_t *symbols, size_t n_symbols
   const Plan &P = ctx->plan;
   Geom G = ctx->G;
   G.early = 0;
-  G.search = BTB200_SEARCH_BR;
+  G.search = BTB200_SEARCH_BR | (ctx->cfg.search & BTB200_SEARCH_BR_BCH);
   const int wlen = (int)stride + 72;
   if (G.bw < (wlen + 31) / 32 + 4) return BTB200_ERR_ARG;
   CK(cudaSetDevice(ctx->device));

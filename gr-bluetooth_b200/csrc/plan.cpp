@@ -285,17 +285,16 @@ double nest_quadrature(int N, int s, int n_extra, int n_free, double omega_max, 
 }
 
 // classic_packet::acgen, lib/packet_impl.cc:309-364: (64,30) BCH sync word.
-uint64_t sync_word(uint32_t lap)
+// the (64,30) code word of 30 information bits (bit k = sync-word bit 34 + k: 24 LAP bits, then the 6 Barker bits) with
+// the PN overlay applied: bits 0..33 parity, 34..63 information
+uint64_t sync_from_info(uint32_t info30)
 {
   // PN overlay p[0..63] for sync-word bit i (= access-code position 4+i)
   static const uint8_t pn_bytes[9] = {0x03, 0xF2, 0xA3, 0x3D, 0xD6, 0x9B, 0x12, 0x1C, 0x10};
   auto pn = [&](int pos) { return (pn_bytes[pos >> 3] >> (7 - (pos & 7))) & 1; };
   static const uint8_t gen[35] = {1,0,0,1,0,1,0,1,1,0,1,1,1,1,0,0,1,0,0,0,1,1,1,0,1,0,1,0,0,0,0,1,1,0,1};
   uint8_t info[30];
-  for (int i = 0; i < 24; i++) info[i] = (lap >> i) & 1;
-  const int msb = (lap >> 23) & 1;
-  const uint8_t bark[2][6] = {{0, 0, 1, 1, 0, 1}, {1, 1, 0, 0, 1, 0}};
-  for (int i = 0; i < 6; i++) info[24 + i] = bark[msb][i];
+  for (int i = 0; i < 30; i++) info[i] = (info30 >> i) & 1;
   uint8_t reg[34] = {0};
   for (int i = 29; i >= 0; i--) {
     const uint8_t fb = (uint8_t)((info[i] ^ pn(38 + i)) ^ reg[33]);
@@ -306,6 +305,45 @@ uint64_t sync_word(uint32_t lap)
   for (int i = 0; i < 34; i++) w |= (uint64_t)(reg[i] ^ pn(4 + i)) << i;
   for (int i = 0; i < 30; i++) w |= (uint64_t)info[i] << (34 + i);
   return w;
+}
+
+uint64_t sync_word(uint32_t lap)
+{
+  // information bits 24..29: the Barker sequence selected by the LAP's most significant bit
+  const int msb = (lap >> 23) & 1;
+  const uint32_t bark = msb ? 0x13u : 0x2Cu;      // bits 0..5 = {1,1,0,0,1,0} / {0,0,1,1,0,1}
+  return sync_from_info((lap & 0xffffffu) | (bark << 24));
+}
+
+int BchTables::build(int max_errors)
+{
+  if (max_errors < 0 || max_errors > 2) return -1;
+  max_err = max_errors;
+  const uint64_t c0 = sync_from_info(0);
+  par.assign(4 * 256 + 1, 0);
+  for (int byte = 0; byte < 4; byte++)
+    for (int v = 0; v < 256; v++) {
+      const uint32_t info = (uint32_t)v << (8 * byte);
+      if (info >> 30) continue;
+      par[(size_t)byte * 256 + v] = (sync_from_info(info) ^ c0) & kBchParityMask;
+    }
+  par[1024] = c0 & kBchParityMask;
+  // every error pattern of weight 1..max_err on sync-word bits 0..57 with its syndrome (received parity ^ parity of the
+  // received information bits), sorted by syndrome; distinct because the code's minimum distance is 14
+  auto syndrome_of = [&](uint64_t e) { return (e ^ sync_from_info((uint32_t)(e >> 34)) ^ c0) & kBchParityMask; };
+  std::vector<std::pair<uint64_t, uint64_t>> tab;
+  if (max_err >= 1)
+    for (int i = 0; i < 58; i++) tab.push_back({syndrome_of(1ull << i), 1ull << i});
+  if (max_err >= 2)
+    for (int i = 0; i < 58; i++)
+      for (int j = i + 1; j < 58; j++) tab.push_back({syndrome_of((1ull << i) | (1ull << j)), (1ull << i) | (1ull << j)});
+  std::sort(tab.begin(), tab.end());
+  syn.clear(); err.clear();
+  for (size_t i = 0; i < tab.size(); i++) {
+    if (tab[i].first == 0 || (i && tab[i].first == tab[i - 1].first)) return -2;
+    syn.push_back(tab[i].first); err.push_back(tab[i].second);
+  }
+  return 0;
 }
 
 int Plan::design(double fs_, double fc_, double squelch, int extra)

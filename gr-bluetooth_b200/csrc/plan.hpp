@@ -8,6 +8,7 @@
 // operation order as the reference so the uploaded tables are bit-identical.
 #pragma once
 #include <cstdint>
+#include <utility>
 #include <vector>
 
 namespace btb200 {
@@ -93,5 +94,20 @@ struct Rotator {
 // 64-bit sync word of a LAP, bit i = access-code symbol 4+i
 // (restates classic_packet::acgen, lib/packet_impl.cc:309-364)
 uint64_t sync_word(uint32_t lap);
+// the same code word generator for arbitrary information bits (bit k = sync-word bit 34 + k)
+uint64_t sync_from_info(uint32_t info30);
+
+// Tables of the libbtbb-style access-code search (BTB200_SEARCH_BR_BCH; what multi_LAP / multi_UAP call through
+// btbb_find_ac, lib/multi_LAP_impl.cc:93, lib/multi_UAP_impl.cc:95): syndrome decoding of the (64,30) code the sync
+// word is built on.  par: parity of the information bits as four byte tables + constant (the generator is affine);
+// syn/err: the syndromes of every error pattern of weight <= max_err on sync-word bits 0..57, sorted, with the patterns.
+constexpr uint64_t kBchParityMask = (1ull << 34) - 1;
+struct BchTables {
+  int max_err = 0;
+  std::vector<uint64_t> par;   // [4][256] + constant
+  std::vector<uint64_t> syn;   // sorted
+  std::vector<uint64_t> err;   // pattern of syn[i]
+  int build(int max_errors);   // 0, or negative (max_errors outside 0..2)
+};
 
 }  // namespace btb200

@@ -159,8 +159,10 @@ struct DevHit {
 // over one channel-window; emit() is called for every ac()/aa() invocation.
 template <class Emit>
 BTB_HD void window_search(const Geom &G, const uint64_t *__restrict__ ac_lut, const uint8_t *__restrict__ le_hdr_lut,
-                          const uint32_t *__restrict__ row, int nsym, int le_idx, uint32_t le_white, Emit emit)
+                          const uint32_t *__restrict__ row, int nsym, int le_idx, uint32_t le_white, Emit emit,
+                          const BchDev *bch = nullptr)
 {
+  const bool use_bch = (G.search & 4) && bch != nullptr;     // BTB200_SEARCH_BR_BCH: libbtbb-style test instead of sniff_ac's
   int len = nsym;
   if (G.search & 1) {
     const int limit0 = (len - 68 < 625) ? len - 68 : 625;   // absolute end of the BR search
@@ -171,10 +173,15 @@ BTB_HD void window_search(const Geom &G, const uint64_t *__restrict__ ac_lut, co
       for (int lag = start; lag < limit0; lag++) {
         uint64_t lo; uint32_t hi;
         bits_window(row, lag, &lo, &hi);
-        if (br_lag_test(ac_lut, lo, hi, &lap)) { found = lag; break; }
+        int ne = 0;
+        if (use_bch ? br_lag_test_bch(*bch, lo, hi, &lap, &ne) : br_lag_test(ac_lut, lo, hi, &lap)) {
+          found = lag;
+          if (use_bch) lap = (lap & 0xffffff) | ((uint32_t)ne << 24);
+          break;
+        }
       }
       if (found < 0) break;
-      {
+      if (!use_bch) {
         uint64_t lo; uint32_t hi;
         bits_window(row, found, &lo, &hi);
         lap |= (uint32_t)br_lag_errors(ac_lut, lo, hi) << 24;      // bits 24..31 of a BR hit's lap field: symbol errors of the access code

@@ -166,7 +166,7 @@ __global__ void k_search_v1(Geom G, DevTables T, DevBatch W)
   if (nsym <= 0) return;
   const int b = idx / G.nch, c = idx - b * G.nch;
   HitEmitter em{G, W, b, c, nsym};
-  window_search(G, T.ac_lut, T.le_hdr_lut, W.bits + (long)idx * G.bw, nsym, T.le_index[c], T.le_white[c], em);
+  window_search(G, T.ac_lut, T.le_hdr_lut, W.bits + (long)idx * G.bw, nsym, T.le_index[c], T.le_white[c], em, &T.bch);
 }
 
 // copy the symbols of every hit into the arena, one byte per symbol
@@ -724,7 +724,9 @@ __global__ void k_search_warp(Geom G, DevTables T, DevBatch W)
     const uint32_t hi = (uint32_t)(bb >> lane) & 0xff;
     const int lag = 32 * q + lane;
     uint32_t lap;
-    const bool fb = (G.search & 1) && lag < 625 && br_lag_test(T.ac_lut, lo, hi, &lap);
+    int bch_err;
+    const bool fb = (G.search & 1) && lag < 625 &&
+                    ((G.search & 4) ? br_lag_test_bch(T.bch, lo, hi, &lap, &bch_err) : br_lag_test(T.ac_lut, lo, hi, &lap));
     const bool fl = (G.search & 2) && le_idx >= 0 && lag < 625 && le_lag_test(T.le_hdr_lut, lo, le_white, le_idx >= 37);
     const uint32_t mb = __ballot_sync(0xffffffffu, fb), ml = __ballot_sync(0xffffffffu, fl);
     if (lane == q) { br_mask = mb; le_mask = ml; }
@@ -750,7 +752,12 @@ __global__ void k_search_warp(Geom G, DevTables T, DevBatch W)
       if (lane == 0) {
         uint64_t lo; uint32_t hi;
         bits_window(row, found, &lo, &hi);
-        em(0, found, nsym_eff - found, ((uint32_t)(lo >> 38) & 0xffffff) | ((uint32_t)br_lag_errors(T.ac_lut, lo, hi) << 24));
+        if (G.search & 4) {
+          uint32_t lap2 = 0; int ne = 0;
+          br_lag_test_bch(T.bch, lo, hi, &lap2, &ne);                 // the corrected LAP and the corrected-bit count
+          em(0, found, nsym_eff - found, (lap2 & 0xffffff) | ((uint32_t)ne << 24));
+        } else
+          em(0, found, nsym_eff - found, ((uint32_t)(lo >> 38) & 0xffffff) | ((uint32_t)br_lag_errors(T.ac_lut, lo, hi) << 24));
       }
       start = found + 68;
     }

@@ -18,6 +18,7 @@ struct DevTables {
   const uint8_t *le_hdr_lut; // [4*256]
   const int8_t *le_index;    // [nch]
   const uint32_t *le_white;  // [nch] 16 whitening bits
+  BchDev bch;                // BTB200_SEARCH_BR_BCH: libbtbb-style access-code test (rx_math.cuh)
 };
 
 // Device-driven tail of the throughput mode: the search kernel stages each window's hits in the window's own slots (the

@@ -189,6 +189,62 @@ BTB_HD int br_lag_errors(const uint64_t *__restrict__ lut, uint64_t w_lo, uint32
   return popc64(rx_sync ^ sync) + popc32(((uint32_t)w_lo & 0xf) ^ exp_pre);
 }
 
+// libbtbb-style access-code test (BTB200_SEARCH_BR_BCH): what multi_LAP / multi_UAP get from btbb_find_ac
+// (lib/multi_LAP_impl.cc:93, lib/multi_UAP_impl.cc:95).  libbtbb is an external library that is not part of the
+// reference tree; this restates its published algorithm (bluetooth_packet.c, the API level with
+// btbb_find_ac(stream, search_length, lap, max_ac_errors, &pkt) that the reference's call sites use) -- PARITY
+// UNPINNED, see DESIGN.md:
+//   * a given LAP: Hamming distance of the 64 received sync-word symbols to that LAP's sync word <= max_ac_errors;
+//   * LAP_ANY: the 7 top symbols (LAP MSB + Barker sequence) are replaced by the nearer of their two valid patterns,
+//     the syndrome of the (64,30) code word under the PN overlay is computed, a non-zero syndrome is looked up among
+//     the error patterns of weight <= max_ac_errors on sync-word bits 0..57 and corrected; the LAP is read from the
+//     corrected word, the error count is the weight of the pattern (Barker corrections are not counted).
+// The window is aligned like sniff_ac's: symbols 4..67 of the lag are the sync word, so a hit's offset is the
+// preamble's (libbtbb reports the sync word's position, 4 later, and also tries the first 4 positions of a stream).
+struct BchDev {
+  const uint64_t *par = nullptr;     // [4][256] + constant: parity bits of the information bits (plan.hpp BchTables)
+  const uint64_t *syn = nullptr;     // [n] sorted syndromes of the correctable error patterns
+  const uint64_t *err = nullptr;     // [n] the patterns
+  int n = 0;
+  int max_err = 0;
+  uint32_t lap = 0xffffffffu;        // 0xffffffff: LAP_ANY
+  uint64_t target = 0;               // sync word of `lap`
+};
+
+BTB_HD int br_lag_test_bch(const BchDev &B, uint64_t w_lo, uint32_t w_hi, uint32_t *lap_out, int *n_err)
+{
+  uint64_t sw = (w_lo >> 4) | ((uint64_t)(w_hi & 0xf) << 60);                      // symbols 4..67
+  if (B.lap != 0xffffffffu) {
+    const int e = popc64(sw ^ B.target);
+    *lap_out = B.lap; *n_err = e;
+    return e <= B.max_err;
+  }
+  const uint32_t top = (uint32_t)(sw >> 57);                                       // LAP MSB + Barker: 88 or 39
+  const uint32_t fix = popc32(top ^ 88u) < popc32(top ^ 39u) ? 88u : 39u;          // complements: no ties
+  sw = (sw & ((1ull << 57) - 1)) | ((uint64_t)fix << 57);
+  const uint32_t info = (uint32_t)(sw >> 34);
+  const uint64_t par = B.par[1024] ^ B.par[info & 0xff] ^ B.par[256 + ((info >> 8) & 0xff)] ^ B.par[512 + ((info >> 16) & 0xff)] ^
+                       B.par[768 + (info >> 24)];
+  const uint64_t syn = (sw ^ par) & ((1ull << 34) - 1);
+  int ne = 0;
+  if (syn) {
+    int lo = 0, hi = B.n - 1, at = -1;
+    while (lo <= hi) {
+      const int mid = (lo + hi) >> 1;
+      const uint64_t v = B.syn[mid];
+      if (v == syn) { at = mid; break; }
+      if (v < syn) lo = mid + 1; else hi = mid - 1;
+    }
+    if (at < 0) return 0;
+    const uint64_t e = B.err[at];
+    sw ^= e;
+    ne = popc64(e);
+  }
+  *lap_out = (uint32_t)(sw >> 34) & 0xffffff;
+  *n_err = ne;
+  return 1;
+}
+
 // nearest-valid-byte distances of the LE header tables (lib/packet_impl.cc:1327-1444 in closed form)
 BTB_HD int le_hdr_dist(uint32_t v, int which)
 {

@@ -130,7 +130,14 @@ enum {
 
 enum {
   BTB200_SEARCH_BR = 1,          /* classic_packet::sniff_ac */
-  BTB200_SEARCH_LE = 2           /* le_packet::sniff_aa */
+  BTB200_SEARCH_LE = 2,          /* le_packet::sniff_aa */
+  /* with BTB200_SEARCH_BR: the access-code test of libbtbb's btbb_find_ac -- what multi_LAP and multi_UAP call
+   * (lib/multi_LAP_impl.cc:93 with LAP_ANY and max_ac_errs 1, lib/multi_UAP_impl.cc:95 with the piconet's LAP and 2) --
+   * instead of sniff_ac's: syndrome decoding of the (64,30) code of the sync word with up to `max_ac_errors` corrected
+   * bits, or the Hamming distance to a given LAP's sync word; parameters in btb200_config.bch.  libbtbb is an external
+   * library outside the reference tree: restated from its published algorithm, PARITY UNPINNED.
+   * hit.lap is the corrected LAP, hit.ac_errors the corrected-bit count, hit.offset the preamble's position. */
+  BTB200_SEARCH_BR_BCH = 4
 };
 
 /* which block's window geometry / search */
@@ -154,8 +161,11 @@ typedef struct btb200_config {
   uint32_t snr_mode;             /* BTB200_SNR_* (lazy squelch only) */
   uint32_t tail_mode;            /* BTB200_TAIL_* (lazy squelch only) */
   uint32_t ddc_mode;             /* BTB200_DDC_* */
-  uint32_t reserved;
+  uint32_t bch;                  /* BTB200_SEARCH_BR_BCH: BTB200_BCH_ANY(max_ac_errors) or BTB200_BCH_LAP(lap, max_ac_errors),
+                                  * max_ac_errors 0..2; ignored (write 0) otherwise */
 } btb200_config;
+#define BTB200_BCH_ANY(max_err)      ((((uint32_t)(max_err)) & 7u) << 28)
+#define BTB200_BCH_LAP(lap, max_err) ((((uint32_t)(lap)) & 0xffffffu) | (1u << 24) | ((((uint32_t)(max_err)) & 7u) << 28))
 
 /* derived constants (lib/multi_block.cc:56-119, 299-342) */
 typedef struct btb200_info {

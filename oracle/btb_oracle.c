@@ -225,6 +225,97 @@ int btbo_check_ac(const uint8_t *stream, uint32_t lap)
   return 1;
 }
 
+/* ------------------------------------------------------------------------- */
+/* libbtbb-style access-code search: what multi_LAP / multi_UAP call through  */
+/* btbb_find_ac (lib/multi_LAP_impl.cc:93, lib/multi_UAP_impl.cc:95).         */
+/*                                                                             */
+/* PARITY UNPINNED.  libbtbb is an external, un-vendored dependency            */
+/* (cmake/Modules/FindBTBB.cmake; no version pinned by the reference, the call */
+/* sites use the API level btbb_init(max_ac_errors) / btbb_find_ac(stream,     */
+/* search_length, lap, max_ac_errors, &pkt) of the 2014/2015 releases).  This  */
+/* restates its published algorithm (bluetooth_packet.c) by BRUTE FORCE over   */
+/* the code the reference's own acgen defines, independent of the product's    */
+/* syndrome tables:                                                            */
+/*   given LAP: Hamming distance of the 64 sync-word symbols to acgen(LAP)'s   */
+/*              sync word <= max_ac_errors;                                    */
+/*   LAP_ANY:   the 7 top symbols (LAP MSB + Barker) are replaced by the nearer */
+/*              of their two valid patterns; the word is accepted if flipping  */
+/*              at most max_ac_errors of sync-word bits 0..57 makes it a code   */
+/*              word (parity regenerated from the information bits agrees);    */
+/*              LAP and error count come from the corrected word (Barker       */
+/*              corrections are not counted).                                  */
+/* The 68-symbol window is aligned like sniff_ac's (symbols 4..67 = sync word). */
+
+/* parity symbols (ac positions 4..37) of 30 information bits, acgen's encoder (:336-357) with the information given */
+static void bch_parity(const uint8_t info[30], uint8_t par[34])
+{
+  uint8_t cw[34];
+  memset(cw, 0, sizeof cw);
+  for (int i = 29; i >= 0; i--) {
+    uint8_t fb = (uint8_t)((info[i] ^ pn_bit(38 + i)) ^ cw[33]);
+    for (int j = 33; j > 0; j--) cw[j] = cw[j - 1] ^ (BCH_G[j] & fb);
+    cw[0] = BCH_G[0] & fb;
+  }
+  for (int i = 0; i < 34; i++) par[i] = cw[i] ^ pn_bit(4 + i);
+}
+
+static int bch_is_codeword(const uint8_t sw[64])
+{
+  uint8_t par[34];
+  bch_parity(sw + 34, par);
+  return memcmp(par, sw, 34) == 0;
+}
+
+/* stream: >= 68 symbols at the lag under test.  lap = 0xffffffff: LAP_ANY.  Returns 1 and the LAP / corrected-bit
+ * count when libbtbb's test accepts the lag. */
+int btbo_bch_lag(const uint8_t *stream, int max_ac_errors, uint32_t lap, uint32_t *lap_out, int *n_err)
+{
+  uint8_t sw[64];
+  for (int i = 0; i < 64; i++) sw[i] = stream[4 + i] & 1;
+  if (lap != 0xffffffffu) {
+    uint8_t ac[72];
+    int d = 0;
+    btbo_acgen_bits(lap, ac);
+    for (int i = 0; i < 64; i++) d += ac[4 + i] != sw[i];
+    *lap_out = lap; *n_err = d;
+    return d <= max_ac_errors;
+  }
+  /* LAP MSB + Barker sequence: the nearer of {0,0,0,1,1,0,1} (a23 = 0) and its complement */
+  static const uint8_t top0[7] = { 0, 0, 0, 1, 1, 0, 1 };
+  int d0 = 0;
+  for (int i = 0; i < 7; i++) d0 += sw[57 + i] != top0[i];
+  for (int i = 0; i < 7; i++) sw[57 + i] = (d0 < 7 - d0) ? top0[i] : (uint8_t)!top0[i];
+  for (int w = 0; w <= max_ac_errors && w <= 2; w++) {
+    if (w == 0) { if (bch_is_codeword(sw)) goto found; continue; }
+    for (int i = 0; i < 58; i++) {
+      sw[i] ^= 1;
+      if (w == 1) { if (bch_is_codeword(sw)) { *n_err = 1; goto found_e; } }
+      else
+        for (int j = i + 1; j < 58; j++) {
+          sw[j] ^= 1;
+          if (bch_is_codeword(sw)) { *n_err = 2; goto found_e; }
+          sw[j] ^= 1;
+        }
+      sw[i] ^= 1;
+    }
+  }
+  return 0;
+found:
+  *n_err = 0;
+found_e:
+  *lap_out = 0;
+  for (int i = 0; i < 24; i++) *lap_out |= (uint32_t)sw[34 + i] << i;
+  return 1;
+}
+
+/* btbb_find_ac over a symbol stream: first accepted lag < search_length, or -1 */
+int btbo_find_ac_bch(const uint8_t *stream, int search_length, uint32_t lap, int max_ac_errors, uint32_t *lap_out, int *n_err)
+{
+  for (int count = 0; count < search_length; count++)
+    if (btbo_bch_lag(stream + count, max_ac_errors, lap, lap_out, n_err)) return count;
+  return -1;
+}
+
 static inline uint32_t air_to_host(const uint8_t *air, int bits)   /* :104-136 */
 {
   uint32_t v = 0;

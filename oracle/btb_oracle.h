@@ -57,6 +57,11 @@ void btbo_acgen_bits(uint32_t lap, uint8_t ac[72]);
 void btbo_acgen_bytes(uint32_t lap, uint8_t out[9]);
 /* packet_impl.cc:471-510 */
 int  btbo_check_ac(const uint8_t *stream, uint32_t lap);
+/* libbtbb-style access-code test of one lag / search over a stream (btbb_find_ac as multi_LAP_impl.cc:93 and
+ * multi_UAP_impl.cc:95 call it; restated from libbtbb's published algorithm by brute force -- PARITY UNPINNED).
+ * lap = 0xffffffff: LAP_ANY. */
+int  btbo_bch_lag(const uint8_t *stream, int max_ac_errors, uint32_t lap, uint32_t *lap_out, int *n_err);
+int  btbo_find_ac_bch(const uint8_t *stream, int search_length, uint32_t lap, int max_ac_errors, uint32_t *lap_out, int *n_err);
 /* packet_impl.cc:247-268; returns lag or -1 */
 int  btbo_sniff_ac(const uint8_t *stream, int stream_length);
 /* packet_impl.cc:1452-1527; returns lag or -1 */

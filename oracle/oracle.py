@@ -80,6 +80,8 @@ def lib():
         L.btbo_sniff_ac.argtypes = [C.c_void_p, C.c_int]
         L.btbo_sniff_aa.argtypes = [C.c_void_p, C.c_int, C.c_double]
         L.btbo_lut.argtypes = [C.c_int, C.c_void_p, C.c_int]
+        L.btbo_bch_lag.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_int)]
+        L.btbo_find_ac_bch.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_int)]
         L.btbo_le_index.argtypes = [C.c_double]
         L.btbo_demod.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.btbo_mm_cr.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
@@ -259,6 +261,27 @@ def sniff_ac(stream, limit=None):
     s = np.ascontiguousarray(stream, np.uint8)
     limit = len(s) - 72 if limit is None else limit
     return lib().btbo_sniff_ac(_ptr(s), limit)
+
+
+LAP_ANY = 0xFFFFFFFF
+
+
+def bch_lag(stream, max_ac_errors=1, lap=LAP_ANY):
+    """libbtbb-style test of the lag at stream[0] (>= 68 symbols): (accepted, lap, corrected bits).  PARITY UNPINNED."""
+    s = np.ascontiguousarray(stream, np.uint8)
+    assert len(s) >= 68
+    lap_out, n_err = C.c_uint32(0), C.c_int(0)
+    ok = lib().btbo_bch_lag(_ptr(s), max_ac_errors, C.c_uint32(lap), C.byref(lap_out), C.byref(n_err))
+    return bool(ok), int(lap_out.value), int(n_err.value)
+
+
+def find_ac_bch(stream, search_length, lap=LAP_ANY, max_ac_errors=1):
+    """btbb_find_ac restated (lib/multi_LAP_impl.cc:93): first accepted lag < search_length or -1, LAP, corrected bits."""
+    s = np.ascontiguousarray(stream, np.uint8)
+    assert len(s) >= search_length + 67
+    lap_out, n_err = C.c_uint32(0), C.c_int(0)
+    off = lib().btbo_find_ac_bch(_ptr(s), search_length, C.c_uint32(lap), max_ac_errors, C.byref(lap_out), C.byref(n_err))
+    return int(off), int(lap_out.value), int(n_err.value)
 
 
 def sniff_aa(stream, freq, limit=None):

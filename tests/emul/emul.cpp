@@ -206,4 +206,30 @@ double emul_nest_quadrature(int N, int s, int n_extra, int n_free, double omega_
   return res;
 }
 
+// libbtbb-style access-code test of the product (rx_math.cuh: br_lag_test_bch with the tables of plan.cpp) on EVERY lag
+// of a symbol stream (one symbol per byte): lags/laps/errs of the accepted lags, up to cap; returns their number.
+// lap = 0xffffffff: LAP_ANY.
+int emul_bch_scan(const uint8_t *symbols, long n, int max_err, uint32_t lap, int32_t *lags, uint32_t *laps, int32_t *errs, int cap)
+{
+  BchTables T;
+  if (T.build(max_err)) return -1;
+  BchDev B;
+  B.par = T.par.data(); B.syn = T.syn.data(); B.err = T.err.data(); B.n = (int)T.syn.size(); B.max_err = max_err;
+  B.lap = lap; B.target = lap != 0xffffffffu ? sync_word(lap) : 0;
+  const long nw = (n + 31) / 32 + 4;
+  std::vector<uint32_t> row((size_t)nw, 0u);
+  for (long i = 0; i < n; i++) row[(size_t)(i >> 5)] |= (uint32_t)(symbols[i] & 1) << (i & 31);
+  int found = 0;
+  for (long lag = 0; lag + 68 <= n; lag++) {
+    uint64_t lo; uint32_t hi;
+    bits_window(row.data(), (int)lag, &lo, &hi);
+    uint32_t l = 0; int e = 0;
+    if (br_lag_test_bch(B, lo, hi, &l, &e)) {
+      if (found < cap) { lags[found] = (int32_t)lag; laps[found] = l; errs[found] = e; }
+      found++;
+    }
+  }
+  return found;
+}
+
 }  // extern "C"

@@ -361,15 +361,17 @@ class multi_block:
             raise Btb200Error(int(n), self._L.btb200_last_error(self._ctx).decode())
         return buf[:n].view(dt).copy()
 
-    def search_bits(self, symbols, stride=625):
+    def search_bits(self, symbols, stride=625, with_errors=False):
         """Known-answer entry: the access-code search kernel on a caller-supplied symbol stream (one symbol per byte),
-        cut into windows every `stride` symbols.  -> list of (absolute symbol offset, LAP)."""
+        cut into windows every `stride` symbols.  -> list of (absolute symbol offset, LAP[, ac_errors])."""
         sym = np.ascontiguousarray(symbols, dtype=np.uint8)
         h = self._hits_struct(False)
         self._check(self._L.btb200_search_bits(self._ctx, sym.ctypes.data, len(sym), stride, C.byref(h)))
         if h.overflow:
             raise Btb200Error(-7, "hit buffer too small")
         hits = self._hits[:h.count]
+        if with_errors:
+            return [(int(x["slot"]) * stride + int(x["offset"]), int(x["lap"]), int(x["ac_errors"])) for x in hits]
         return [(int(x["slot"]) * stride + int(x["offset"]), int(x["lap"])) for x in hits]
 
     def set_window_mask(self, mask):

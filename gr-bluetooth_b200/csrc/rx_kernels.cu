@@ -96,7 +96,7 @@ __global__ void k_mm_chained(Geom G, DevBatch W, const float *__restrict__ mmse)
 // the loop ends after the first channel whose packet has LAP == stop_lap and a header.
 // res[c] = {processed, nsym, ac_index, lap}
 __global__ void k_mm_chained_list(Geom G, DevBatch W, const float *__restrict__ mmse, const uint64_t *__restrict__ ac_lut,
-                                  int first, int n, uint32_t stop_lap, int4 *__restrict__ res)
+                                  BchDev bch, int first, int n, uint32_t stop_lap, int4 *__restrict__ res)
 {
   if (blockIdx.x != 0 || threadIdx.x != 0) return;
   MmState st = *W.mm_state;
@@ -115,7 +115,8 @@ __global__ void k_mm_chained_list(Geom G, DevBatch W, const float *__restrict__ 
           for (int lag = 0; lag < latest; lag++) {
             uint64_t lo; uint32_t hi, lap;
             bits_window(row, lag, &lo, &hi);
-            if (br_lag_test(ac_lut, lo, hi, &lap)) { r.z = lag; r.w = (int)lap; break; }
+            int ne;
+            if ((G.search & 4) ? br_lag_test_bch(bch, lo, hi, &lap, &ne) : br_lag_test(ac_lut, lo, hi, &lap)) { r.z = lag; r.w = (int)lap; break; }
           }
           if (r.z >= 0 && (uint32_t)r.w == stop_lap) {
             const int len = (nsym - r.z) < 3125 ? (nsym - r.z) : 3125;
@@ -1056,7 +1057,7 @@ void launch_mm(const Geom &G, const DevTables &T, const DevBatch &W, cudaStream_
 void launch_mm_chained_list(const Geom &G, const DevTables &T, const DevBatch &W, int first, int n, unsigned stop_lap,
                             int *res4, cudaStream_t s)
 {
-  k_mm_chained_list<<<1, 32, 0, s>>>(G, W, T.mmse, T.ac_lut, first, n, stop_lap, reinterpret_cast<int4 *>(res4));
+  k_mm_chained_list<<<1, 32, 0, s>>>(G, W, T.mmse, T.ac_lut, T.bch, first, n, stop_lap, reinterpret_cast<int4 *>(res4));
 }
 
 void launch_search(const Geom &G, const DevTables &T, const DevBatch &W, cudaStream_t s)

@@ -25,8 +25,9 @@ class GR_BLUETOOTH_API multi_block : virtual public gr::sync_block {
  protected:
   multi_block() {}   // to allow for pure virtual
   // extra_symbols: 3125 for sniffer/hopper, 68 for multi_LAP (set_symbol_history in the reference)
+  // bch: btb200_config.bch when search_mask carries BTB200_SEARCH_BR_BCH (the libbtbb-style access-code test)
   multi_block(double sample_rate, double center_freq, double squelch_threshold, int extra_symbols,
-              int search_mask, bool force_chained = false);
+              int search_mask, bool force_chained = false, unsigned bch = 0);
 
   static const int SYMBOLS_PER_BASIC_RATE_SLOT = 625;
 

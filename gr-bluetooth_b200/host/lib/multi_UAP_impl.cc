@@ -8,10 +8,12 @@
 // Piconet::uap_from_header of bt_host.cc (the same arithmetic as basic_rate_piconet_impl::UAP_from_header,
 // lib/piconet_impl.cc:433-517).
 //
-// Differences from the reference, stated: it calls libbtbb (btbb_find_ac with up to 2 bit errors, btbb_uap_from_
-// header) -- an external library that is not part of the reference tree, so parity there is unpinned; this block
-// uses classic_packet::sniff_ac semantics for the search (like multi_hopper) and gives the packets their real
-// CLKN.  Where the reference calls exit(0), work() returns -1 (gr::block::WORK_DONE).
+// Differences from the reference, stated: it calls libbtbb (btbb_find_ac for the piconet's LAP with up to 2 bit errors,
+// btbb_uap_from_header) -- an external library that is not part of the reference tree, so parity there is unpinned.
+// The search is the same test restated (BTB200_SEARCH_BR_BCH with the LAP: Hamming distance of the 64 sync-word
+// symbols to the LAP's sync word <= 2; BTB200_AC_SEARCH=sniff_ac selects sniff_ac's rule), the discovery is the
+// native one, and the packets get their real CLKN.  Where the reference calls exit(0), work() returns -1
+// (gr::block::WORK_DONE).
 #include "multi_UAP_impl.h"
 #include "btb200.h"
 #include <stdexcept>
@@ -28,7 +30,8 @@ multi_UAP::sptr multi_UAP::make(double sample_rate, double center_freq, double s
 multi_UAP_impl::multi_UAP_impl(double sample_rate, double center_freq, double squelch_threshold, int LAP)
     : gr::sync_block("bluetooth multi UAP block", gr::io_signature::make(1, 1, sizeof(gr_complex)),
                      gr::io_signature::make(0, 0, 0)),
-      multi_block(sample_rate, center_freq, squelch_threshold, 3125, BTB200_SEARCH_BR, /*force_chained=*/true)
+      multi_block(sample_rate, center_freq, squelch_threshold, 3125, BTB200_SEARCH_BR | BTB200_SEARCH_BR_BCH, /*force_chained=*/true,
+                  BTB200_BCH_LAP((unsigned)LAP, 2))
 {
   const int lo = (int)((d_low_freq - 2402000000.0) / 1e6), hi = (int)((d_high_freq - 2402000000.0) / 1e6);
   d_host.reset(new btb200_host::UapHost((uint32_t)LAP, lo, hi));

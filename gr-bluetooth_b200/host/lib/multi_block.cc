@@ -11,7 +11,7 @@ namespace gr {
 namespace bluetooth {
 
 multi_block::multi_block(double sample_rate, double center_freq, double squelch_threshold,
-                         int extra_symbols, int search_mask, bool force_chained)
+                         int extra_symbols, int search_mask, bool force_chained, unsigned bch)
     : gr::sync_block("bluetooth multi block", gr::io_signature::make(1, 1, sizeof(gr_complex)),
                      gr::io_signature::make(0, 0, 0))
 {
@@ -26,6 +26,11 @@ multi_block::multi_block(double sample_rate, double center_freq, double squelch_
   cfg.squelch_threshold = squelch_threshold;
   cfg.extra_history_symbols = (uint32_t)extra_symbols;
   cfg.search = search_mask;
+  cfg.bch = bch;
+  // BTB200_AC_SEARCH=sniff_ac: the blocks the reference builds on libbtbb (multi_LAP, multi_UAP) fall back to
+  // classic_packet::sniff_ac semantics (what this port used before the libbtbb-style test existed)
+  if (const char *acs = std::getenv("BTB200_AC_SEARCH"))
+    if (std::string(acs) == "sniff_ac") { cfg.search &= ~BTB200_SEARCH_BR_BCH; cfg.bch = 0; }
   // reference semantics by default: one clock-recovery state shared by all channel-windows
   const char *mm = std::getenv("BTB200_MM_MODE");
   cfg.mm_mode = (!force_chained && mm && std::string(mm) == "stateless") ? BTB200_MM_STATELESS : BTB200_MM_CHAINED;

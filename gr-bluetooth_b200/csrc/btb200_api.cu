@@ -935,7 +935,10 @@ static int submit_impl(btb200_ctx *ctx, const void *iq, int kind, size_t n_sampl
       nr.demC = ctx->PF.demC; nr.pitchC = ctx->PF.pitchC;
       static const bool share_sm = std::getenv("BTB200_RESUME_SHARED") != nullptr;
       nr.sm_flag = (ctx->NP.v2 && !share_sm) ? ctx->d_smflag : nullptr;
-      nr.n_blocks = (int)((nbc + NEST_RESUME_BLK - 1) / NEST_RESUME_BLK);
+      // chains per resume block: 64 (two warps on their SM), or 32 with BTB200_RESUME_BLK=32 (k_nest2 + channel-major copy)
+      static const int resume_blk = (std::getenv("BTB200_RESUME_BLK") && std::atoi(std::getenv("BTB200_RESUME_BLK")) == 32) ? 32 : 64;
+      nr.blk = (ctx->NP.v2 && ctx->PF.demC && resume_blk == 32) ? 32 : NEST_RESUME_BLK;
+      nr.n_blocks = (int)((nbc + nr.blk - 1) / nr.blk);
     } else if (G.early) {
       if (!tail_inline) CK(cudaStreamWaitEvent(s2, ctx->ev[4], 0));
       launch_tail_resume(G, ctx->T, W, ctx->d_dem, s2); ctx->launches++;

@@ -792,26 +792,39 @@ __global__ void k_search_warp(Geom G, DevTables T, DevBatch W)
 // the search loops produced them) and the list of windows that have hits; one block, contiguous chunks per thread
 __global__ void __launch_bounds__(1024) k_tail_scan(Geom G, DevBatch W)
 {
-  __shared__ int s_h[1024], s_w[1024];
-  const int n = W.B * G.nch, t = threadIdx.x;
-  const int per = (n + 1023) / 1024, i0 = t * per, i1 = (i0 + per < n) ? i0 + per : n;
+  // one block, a contiguous chunk of windows per WARP: coalesced reads, warp totals, a 32-entry prefix, then a second
+  // coalesced pass with warp scans (shuffles / ballots) that writes positions and the compacted window list
+  __shared__ int s_h[32], s_w[32];
+  constexpr unsigned FULL = 0xffffffffu;
+  const int n = W.B * G.nch, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int per_warp = ((n + 31) / 32 + 31) / 32 * 32;
+  const int i0 = wid * per_warp < n ? wid * per_warp : n, i1 = (i0 + per_warp < n) ? i0 + per_warp : n;
   int h = 0, w = 0;
-  for (int i = i0; i < i1; i++) { const int c = W.tail.cnt[i]; h += c; w += c > 0; }
-  s_h[t] = h; s_w[t] = w;
+  for (int i = i0 + lane; i < i1; i += 32) { const int c = W.tail.cnt[i]; h += c; w += c > 0; }
+  h = __reduce_add_sync(FULL, h); w = __reduce_add_sync(FULL, w);
+  if (lane == 0) { s_h[wid] = h; s_w[wid] = w; }
   __syncthreads();
-  for (int d = 1; d < 1024; d <<= 1) {
-    const int a = (t >= d) ? s_h[t - d] : 0, b = (t >= d) ? s_w[t - d] : 0;
-    __syncthreads();
-    s_h[t] += a; s_w[t] += b;
-    __syncthreads();
+  int hb = 0, wb = 0, ht = 0, wt = 0;                   // hits / windows with hits before this warp's chunk, and in total
+  for (int k = 0; k < 32; k++) {
+    const int a = s_h[k], b = s_w[k];
+    if (k < wid) { hb += a; wb += b; }
+    ht += a; wt += b;
   }
-  int hb = s_h[t] - h, wb = s_w[t] - w;                  // exclusive prefixes of this thread's chunk
-  for (int i = i0; i < i1; i++) {
-    const int c = W.tail.cnt[i];
-    W.tail.base[i] = hb;
-    if (c > 0) { W.tail.list[wb++] = make_int4(i / G.nch, i % G.nch, 0, 0); hb += c; }
+  for (int i = i0; i < i1; i += 32) {
+    const int idx = i + lane;
+    const int c = idx < i1 ? W.tail.cnt[idx] : 0;
+    int inc = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(FULL, inc, d); if (lane >= d) inc += t; }
+    const unsigned m = __ballot_sync(FULL, c > 0);
+    if (idx < i1) {
+      W.tail.base[idx] = hb + inc - c;
+      if (c > 0) W.tail.list[wb + __popc(m & ((1u << lane) - 1u))] = make_int4(idx / G.nch, idx % G.nch, 0, 0);
+    }
+    hb += __shfl_sync(FULL, inc, 31);
+    wb += __popc(m);
   }
-  if (t == 1023) { W.hit_count[0] = (unsigned)s_h[1023]; W.hit_count[1] = (unsigned)s_w[1023]; *W.tail.n_list = s_w[1023]; }
+  if (threadIdx.x == 0) { W.hit_count[0] = (unsigned)ht; W.hit_count[1] = (unsigned)wt; *W.tail.n_list = wt; }
 }
 
 // the hits of every listed window, in order, with their final symbol counts

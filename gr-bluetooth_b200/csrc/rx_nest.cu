@@ -343,18 +343,21 @@ __global__ void __launch_bounds__(2 * MT, 3) k_nest2(NestPlan P, NestResume R)
     // resume of clock-recovery chains (see k_nest); with windows to resume the block claims its SM for the duration
     __shared__ int s_live;
     if (tid == 0) {
-      s_live = (int)blockIdx.x * NEST_RESUME_BLK < *R.W.tail.n_list;
-      if (s_live && R.sm_flag) atomicAdd(&R.sm_flag[smid & 255], NEST_RESUME_BLK / 32);
+      s_live = (int)blockIdx.x * R.blk < *R.W.tail.n_list;
+      if (s_live && R.sm_flag) atomicAdd(&R.sm_flag[smid & 255], R.blk / 32);
     }
     __syncthreads();
     const bool live = s_live != 0;
-    if (R.demC)
+    if (R.demC && R.blk == 32)
+      mm_stateless_block<32, true>(R.G, R.W, R.mmse, R.demT, 2, reinterpret_cast<MmSave *>(R.save), R.W.tail.list, -1,
+                                   smem, (int)blockIdx.x, R.demC, R.pitchC);
+    else if (R.demC)
       mm_stateless_block<NEST_RESUME_BLK, true>(R.G, R.W, R.mmse, R.demT, 2, reinterpret_cast<MmSave *>(R.save), R.W.tail.list, -1,
                                                 smem, (int)blockIdx.x, R.demC, R.pitchC);
     else
       mm_stateless_block<NEST_RESUME_BLK>(R.G, R.W, R.mmse, R.demT, 2, reinterpret_cast<MmSave *>(R.save), R.W.tail.list, -1,
                                           smem, (int)blockIdx.x);
-    if (live && R.sm_flag && tid < NEST_RESUME_BLK && (tid & 31) == 0) atomicSub(&R.sm_flag[smid & 255], 1);   // one per chain warp
+    if (live && R.sm_flag && tid < R.blk && (tid & 31) == 0) atomicSub(&R.sm_flag[smid & 255], 1);   // one per chain warp
     return;
   }
   if (R.sm_flag) {

@@ -63,7 +63,8 @@ struct NestResume {
   const float *demC = nullptr;       // channel-major copy of the demod floats (rx_pfb.cuh), or null: read demT
   long pitchC = 0;
   void *save = nullptr;
-  int n_blocks = 0;                  // blocks of NEST_RESUME_BLK windows: enough for every window of the batch
+  int n_blocks = 0;                  // blocks of `blk` windows: enough for every window of the batch
+  int blk = 64;                      // windows (chains) per resume block: 64, or 32 (channel-major source only)
   // v2 (several blocks per SM): a resume block that has windows raises sm_flag[its SM] while its chains run and the
   // estimator blocks that find the flag up wait (bounded) before they start -- the chains keep their SM to themselves
   int *sm_flag = nullptr;            // [256], zero before the launch; null: share the SM

@@ -351,9 +351,18 @@ __global__ void k_pfb_energy(PfbPlan P, int B, const int *__restrict__ chan_col,
   if (idx >= B * P.nch) return;
   const int b = idx / P.nch, c = idx - b * P.nch;
   const int col = chan_col[c];
-  double sum = 0.0;
-  for (int s = b; s < b + P.nfull; s++)
-    for (int j = 0; j < P.tps; j++) sum += (double)P.E[(((long)s * P.tps + j) * P.ncol + col) * 2];
+  // the tiles of segments b .. b + nfull - 1 are consecutive: four independent partial sums keep four loads in flight
+  const float *e = P.E + ((long)b * P.tps * P.ncol + col) * 2;
+  const long st = (long)P.ncol * 2;
+  const int nt = P.nfull * P.tps;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  int k = 0;
+  for (; k + 3 < nt; k += 4) {
+    s0 += (double)e[(long)k * st]; s1 += (double)e[(long)(k + 1) * st];
+    s2 += (double)e[(long)(k + 2) * st]; s3 += (double)e[(long)(k + 3) * st];
+  }
+  for (; k < nt; k++) s0 += (double)e[(long)k * st];
+  double sum = (s0 + s1) + (s2 + s3);
   if (P.rem > 0)
     for (int j = 0; j * PFB_T < P.rem; j++) sum += (double)P.E[(((long)(b + P.nfull) * P.tps + j) * P.ncol + col) * 2 + 1];
   e_on[idx] = sum / (double)P.n_ddc;

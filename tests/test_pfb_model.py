@@ -157,3 +157,32 @@ def test_subsampled_noise_energy_quadrature(emul, s, n_extra, n_free, khz):
             worst = max(worst, float(np.max(np.abs(est / ref - 1))))
     print("stride %d: worst relative deviation of the weighted sub-sampled sum %.2e (design residual %.1e)" % (s, worst, res))
     assert worst < 2e-5
+
+
+@pytest.mark.parametrize("N,s", [(850, 4), (850, 2), (1250, 4), (128, 4), (333, 4), (64, 2)])
+def test_quadrature_weights_other_lengths(emul, N, s):
+    """nest_quadrature() for the window lengths of the other rates (n_noise = 850 at 100 / 30 / 8 Msps geometries with
+    D-dependent omega, odd and short lengths as edge cases): exact for a constant, in-band tones to the design residual,
+    interior weights pinned, nothing wild at the ends."""
+    emul.emul_nest_quadrature.restype = C.c_double
+    emul.emul_nest_quadrature.argtypes = [C.c_int] * 4 + [C.c_double, C.c_void_p, C.c_void_p]
+    w = np.zeros(N + 8, np.float32)
+    n_used = C.c_int32(0)
+    omega = 2 * np.pi * 90e3 / 2e6
+    res = emul.emul_nest_quadrature(N, s, 2, 12, omega, w.ctypes.data, C.byref(n_used))
+    n = n_used.value
+    assert n == (N - 1) // s + 1 + 2 and 0 <= res < 2e-3
+    w = w[:n].astype(np.float64)
+    assert abs(w.sum() - N) < 2e-3 and np.abs(w).max() < 12 * s
+    if n > 24:
+        assert np.all(w[12:n - 12] == s)
+    rng = np.random.default_rng(N + s)
+    j, m = np.arange(N), np.arange(n) * s
+    for om in rng.uniform(-omega, omega, 50):
+        ph = rng.uniform(0, 2 * np.pi)
+        full = np.cos(om * j + ph).sum()
+        sub = (w * np.cos(om * m + ph)).sum()
+        assert abs(full - sub) < max(2.5 * res, 1e-4) + 1e-9, (om, full, sub)
+    # invalid arguments are refused
+    assert emul.emul_nest_quadrature(8, 4, 2, 12, omega, w.ctypes.data, C.byref(n_used)) < 0
+    assert emul.emul_nest_quadrature(N, 0, 2, 12, omega, w.ctypes.data, C.byref(n_used)) < 0

@@ -12,7 +12,8 @@ from gr_bluetooth_b200 import synth
 fs, fc, nslots = 100e6, 2441e6, 10
 iq, _ = synth.generate(fs, fc, nslots, seed=3, laps=[0x9E8B33, 0x24D952], occupancy=0.1, snr_db=20.0, le_adv_occupancy=0.05)
 first, B = 7, 3
-for kw in (dict(squelch=g.SQUELCH_EAGER), dict(squelch=g.SQUELCH_LAZY), dict(squelch=g.SQUELCH_LAZY, snr_mode=g.SNR_FAST_GUARDED)):
+POLY_ONLY = bool(os.environ.get("SAN_POLY_ONLY"))      # only the throughput mode at 100 Msps and the libbtbb-style search
+for kw in (() if POLY_ONLY else (dict(squelch=g.SQUELCH_EAGER), dict(squelch=g.SQUELCH_LAZY), dict(squelch=g.SQUELCH_LAZY, snr_mode=g.SNR_FAST_GUARDED))):
     for impl in ([1] if os.environ.get("SAN_QUICK") else [0, 1, 2]):
         blk = g.multi_sniffer(fs, fc, 10.0, mm_mode=g.MM_STATELESS, max_slots=B, **kw)
         blk.set_impl(impl)
@@ -35,6 +36,12 @@ for tail in (g.TAIL_LAZY, g.TAIL_FULL):
     hm, _, _ = blk.process(seg, first, B)
     print("poly", tail, len(hits), len(h16), len(hm))
     blk.close()
+blk = g.multi_sniffer(8e6, 2476.5e6, 10.0, mm_mode=g.MM_STATELESS, max_slots=8, search=g.SEARCH_BR | g.SEARCH_BR_BCH, bch=g.bch_any(2))
+print("bch", len(blk.search_bits(np.random.default_rng(2).integers(0, 2, 20000).astype(np.uint8))))
+blk.close()
+if POLY_ONLY:
+    print("done")
+    sys.exit(0)
 for fs2, fc2 in ((30e6, 2414e6), (8e6, 2476.5e6)):
     iq2, _ = synth.generate(fs2, fc2, nslots, seed=4, occupancy=0.2, snr_db=20.0, le_adv_occupancy=0.05)
     blk = g.multi_sniffer(fs2, fc2, 10.0, mm_mode=g.MM_STATELESS, max_slots=B, ddc=g.DDC_POLYPHASE)

@@ -232,4 +232,70 @@ int emul_bch_scan(const uint8_t *symbols, long n, int max_err, uint32_t lap, int
   return found;
 }
 
+// Off-channel energy estimate of one window, the way rx_nest.cu computes it, driven by the PRODUCT's host tables
+// (PfbDesign::design_noise, nest_quadrature) in double precision with plain loops: pre-rotation, fold * M virtual
+// branches over the flat tap array, fold, N1-point and N2-point DFTs at the channel bins, weighted |Z|^2.
+// fold = 0: every output (weights 1).  esum[c] = the estimate of sum_j |y_j|^2 of window b (x[0] = first sample of
+// window 0).  Checks the tables and the index algebra of the folded mode, not the kernel's thread mapping.
+int emul_nest(double fs, double fc, int extra, const float *xf, long n_x, int b, int fold, double *esum)
+{
+  Plan P;
+  if (P.design(fs, fc, 10.0, extra)) return -1;
+  PfbDesign F;
+  if (F.design_noise(P, 5, 16)) return -2;
+  const int M = F.M, N1 = F.N1, N2 = F.N2;
+  const int stride = fold ? 2 * fold : 1, MV = fold ? fold * M : M;
+  std::vector<float> w;
+  if (fold) {
+    if (nest_quadrature(P.n_noise, stride, 2, 12, 2.0 * M_PI * 90e3 * P.D / P.fs, w) < 0) return -3;
+  } else w.assign((size_t)P.n_noise, 1.0f);
+  // outputs of a sequence with period `step` samples between them
+  const long step = (long)stride * P.D;
+  if (fold && step != MV) return -4;
+  for (int c = 0; c < P.nch; c++) esum[c] = 0.0;
+  std::vector<double> vr((size_t)MV), vi((size_t)MV), ur((size_t)M), ui((size_t)M), tr((size_t)N1 * N2), ti((size_t)N1 * N2);
+  for (size_t u = 0; u < w.size(); u++) {
+    const long n0 = (long)b * P.S + P.fns + (long)u * step;
+    for (int r = 0; r < MV; r++) {
+      double ar = 0, ai = 0;
+      for (long k = r; k < P.Nn; k += MV) {                       // flat tap array: virtual branch r holds h'[r + MV q]
+        const long n = n0 + k;
+        if (n >= n_x) return -5;
+        const double ang = -2.0 * M_PI * F.phi * (double)n / M;
+        const double xr = xf[2 * n], xi = xf[2 * n + 1], cs = std::cos(ang), sn = std::sin(ang);
+        const double h = F.hq[(size_t)k];
+        ar += (xr * cs - xi * sn) * h; ai += (xr * sn + xi * cs) * h;
+      }
+      vr[r] = ar; vi[r] = ai;
+    }
+    for (int r = 0; r < M; r++) {
+      double ar = 0, ai = 0;
+      for (int f = 0; f * M + r < MV; f++) { ar += vr[(size_t)f * M + r]; ai += vi[(size_t)f * M + r]; }
+      ur[r] = ar; ui[r] = ai;
+    }
+    for (int k1 = 0; k1 < N1; k1++)
+      for (int n2 = 0; n2 < N2; n2++) {
+        double ar = 0, ai = 0;
+        for (int n1 = 0; n1 < N1; n1++) {
+          const int r = (N2 * n1 + N1 * n2) % M;
+          const double ang = -2.0 * M_PI * (double)((n1 * k1) % N1) / N1;
+          const double cs = std::cos(ang), sn = std::sin(ang);
+          ar += ur[r] * cs - ui[r] * sn; ai += ur[r] * sn + ui[r] * cs;
+        }
+        tr[(size_t)k1 * N2 + n2] = ar; ti[(size_t)k1 * N2 + n2] = ai;
+      }
+    for (int c = 0; c < P.nch; c++) {
+      const int col = F.chan_col[c], k1 = col / F.CPC;
+      double ar = 0, ai = 0;
+      for (int n2 = 0; n2 < N2; n2++) {
+        const cf32 ww = F.WB[(size_t)n2 * F.ncol + col];
+        const double a = tr[(size_t)k1 * N2 + n2], bb = ti[(size_t)k1 * N2 + n2];
+        ar += a * ww.re - bb * ww.im; ai += a * ww.im + bb * ww.re;
+      }
+      esum[c] += (double)w[u] * (ar * ar + ai * ai);
+    }
+  }
+  return 0;
+}
+
 }  // extern "C"

@@ -108,3 +108,22 @@ def test_clock_recovery_is_not_contracted_where_it_rides_in_the_estimator(sass):
     for l in mm:
         if re.search(r"\bFFMA\b", l):
             assert re.search(r", 128, |12582912|1\.0863247", l), l
+
+
+def test_small_block_estimator_and_latency_shaped_clock_recovery(sass):
+    """k_nest2 (three 200-thread blocks per SM): TMA-fed (UBLKCP + mbarrier phase checks), packed FFMA2 tap loop -- 2 chunks
+    x 8 steps x 16 accumulators, twice over (register window offset 0 and 8) -- and within the register budget of three
+    resident blocks.  Its resume role and the stand-alone clock-recovery kernel read the interpolator taps with two
+    16-byte shared loads per step and tie the upper taps to the lower ones with a byte permute; the resume copies
+    16-byte groups from the channel-major demod copy (LDGSTS.128)."""
+    nest2 = body(sass, "k_nest2ILi4ELi100")
+    assert any("UBLKCP" in l for l in nest2) and any("SYNCS.PHASECHK" in l for l in nest2)
+    assert sum(" FFMA2 " in l for l in nest2) >= 2 * 8 * 16
+    assert sum("LDGSTS.E.128" in l for l in nest2) >= 2
+    res = subprocess.run(["cuobjdump", "-res-usage", LIB], capture_output=True, text=True).stdout
+    m = re.search(r"k_nest2ILi4ELi100[^\n]*\n\s*REG:(\d+)", res)
+    assert m and int(m.group(1)) * 200 * 3 <= 65536, m and m.group(1)
+    mm = body(sass, "k_mm_stateless_v2ILi64")
+    assert sum("LDS.128" in l for l in mm) >= 16 and sum(" PRMT " in l for l in mm) >= 32
+    # one rounding per operation survives the load scheduling: 8 FMUL + 8 FADD per step, no FFMA in the interpolation
+    assert sum(" FMUL " in l for l in mm) >= 64 and sum(" FADD " in l for l in mm) >= 64
